@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the volumetric hot path (BASELINE.json metric: voxels/sec, 256x256x32 grid,
+20-class SSC) -- one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2]
+
+A step = one pass of the volumetric forward (stereo cost volume + aggregation, depth_net, MIE,
+lift (x) splat, 3-D encoder + neck, occupancy head, x2 trilinear + argmax) over one synthetic
+stereo pair per GPU (features after the 2-D image backbone).
+  value  : inputs resident in HBM, device-timed (CUDA events), max over ranks.
+  e2e    : the same call with HOST (pinned) feature buffers: H2D of the two feature maps and D2H of
+           the uint8 label volume inside the timed region.
+  roofline: the dominant kernel (occupancy-head conv 384->192 k3 on the 128x128x16 grid, 1.04 TFLOP
+           in one launch) timed alone with CUDA events; FLOP/s against the measured tensor peak.
+  cpu_baseline / --impl reference: the oracle port (oracle/restatement.py, PyTorch CPU fp32, all
+           host threads) on one forward of the same workload.
+Multi-GPU: the path shards by sample (one stereo pair per rank, no data-path collective) -> weak
+scaling; NCCL is used for the barrier and the max-over-ranks reduction only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+VOXELS = {"config1": 128 * 128 * 16, "config2": 256 * 256 * 32, "config0": 64 * 64 * 8, "tiny": 32 * 32 * 8,
+          "config4": 512 * 512 * 64}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(VOXELS))
+    ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"])
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the forward in a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi, during the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline = the oracle port (the one place bench.py may execute oracle/)
+# ------------------------------------------------------------------------------------------
+def cpu_forward_factory(workload: str, seed: int = 0):
+    from oracle import restatement as O
+    from stereoscene_b200 import presets, synth
+    model, mc = presets.build(workload)
+    synth.randomize_weights_(model, seed)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    del model
+    xl, xr = synth.stereo_features(1, mc["input_size"], 8, seed=seed)
+    left, right, calib = synth.kitti_calibration(1, mc["input_size"])
+    gc = mc["model"]["img_view_transformer"]["grid_config"]
+
+    def run():
+        with torch.no_grad():
+            return O.volumetric_forward(sd, xl, xr, left, right, calib, gc, mc["input_size"], mc["occ_size"])
+    return run
+
+
+def time_cpu(workload: str, steps: int, warmup: int, budget_s: float):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run = cpu_forward_factory(workload)
+    t0 = time.perf_counter()
+    run()                                           # first pass doubles as warm-up and cost estimate
+    est = time.perf_counter() - t0
+    done_warm = 1
+    while done_warm < warmup and (done_warm + steps) * est < budget_s:
+        run(); done_warm += 1
+    n = max(1, min(steps, int((budget_s - done_warm * est) / max(est, 1e-6))))
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter(); run(); ts.append(time.perf_counter() - t0)
+    per = statistics.median(ts)
+    return dict(value=VOXELS[workload] / per, unit="voxels/s", cores=cores, kind="port",
+                sample=f"{n} timed forward(s) of {workload} (B=1, fp32, torch {torch.__version__} CPU, "
+                       f"oracle/restatement.py), {per:.2f} s each", seconds_per_forward=per, steps_run=n)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = time_cpu(args.workload, args.steps, args.warmup, args.cpu_budget_s)
+    line = {
+        "impl": "reference", "metric": "voxels/sec", "value": cb["value"], "unit": "voxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_forward"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: synthetic 1242x375 stereo pair -> "
+                               f"{VOXELS[args.workload]} output voxels, 20 classes, B=1 per step",
+                   "note": "reference has no native/GPU-independent build; its CPU path = PyTorch CPU fp32 "
+                           "(oracle port pinned to the reference's own forward), all host threads"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "steps_run": cb["steps_run"], "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from stereoscene_b200 import cabi, ops, presets, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cabi.load()
+    ops.set_default_math(ops.SS_MATH_3XTF32 if args.math == "3xtf32" else ops.SS_MATH_TF32)
+
+    seed = 0
+    model, mc = presets.build(args.workload)
+    synth.randomize_weights_(model, seed)
+    model = model.to(dev).eval()
+    B = 1                                                   # stereo pairs per rank per step (weak scaling)
+    xl_h, xr_h = synth.stereo_features(B, mc["input_size"], 8, seed=seed + rank, pin=True)
+    left, right, calib = synth.kitti_calibration(B, mc["input_size"], device=dev)
+    xl_d, xr_d = xl_h.to(dev), xr_h.to(dev)
+    occ = mc["occ_size"]
+    labels_h = torch.empty((B, *occ), dtype=torch.uint8).pin_memory()
+
+    def forward(xl, xr):
+        return model.forward_features(xl, xr, left, right, calib, occ_size=occ, want_labels=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also fills the splat-index / packed-weight caches) and launch census -------
+    with torch.no_grad():
+        forward(xl_d, xr_d)
+        torch.cuda.synchronize()
+        n0 = cabi.launch_count()
+        out = forward(xl_d, xr_d)
+        torch.cuda.synchronize()
+        launches_per_step = cabi.launch_count() - n0
+        for _ in range(max(0, args.warmup - 2)):
+            forward(xl_d, xr_d)
+    torch.cuda.synchronize()
+
+    # ---- optional CUDA graph of the device-resident step ---------------------------------------
+    graph = None
+    if not args.no_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s), torch.no_grad():
+                forward(xl_d, xr_d)                       # warm this stream's arena / caches
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(g):
+                gout = forward(xl_d, xr_d)
+            g.replay()
+            torch.cuda.synchronize()
+            if not torch.equal(gout["labels"], out["labels"]) and \
+                    float((gout["labels"] != out["labels"]).float().mean()) > 1e-3:
+                raise RuntimeError("graph replay disagrees with eager run")
+            graph = g
+        except Exception as e:                             # fall back to eager launches, say so
+            if rank == 0:
+                print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); timing eager launches",
+                      file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def step_device():
+        if graph is not None:
+            graph.replay()
+        else:
+            with torch.no_grad():
+                forward(xl_d, xr_d)
+
+    for _ in range(3):
+        step_device()
+    # ---- timed region: device-resident inputs ----------------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+
+    # ---- timed region: end to end from host buffers ---------------------------------------------
+    def step_e2e():
+        with torch.no_grad():
+            a = xl_h.to(dev, non_blocking=True)
+            b = xr_h.to(dev, non_blocking=True)
+            o = forward(a, b)
+            labels_h.copy_(o["labels"], non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    vox = VOXELS[args.workload] * B * world
+    value = vox * args.steps / (ms_dev * 1e-3)
+    e2e = vox * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel, timed alone (CUDA events on the launching stream) -------
+    roof, kernels = dominant_kernel_roofline(model, mc, dev, pk)
+
+    line = {
+        "metric": "voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32(3xtf32)", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: synthetic 1242x375 stereo -> 384x1280 -> 48x160x112 frustum -> "
+                               f"{'x'.join(map(str, occ))} logits, 20 classes, B={B} stereo pair per GPU per step "
+                               "(features after the 2-D image backbone)",
+                   "storage": "fp32 channels-last", "math": args.math, "cuda_graph": graph is not None,
+                   "l2": "no flush: one step streams > 9 GB of activations, >> 126 MB L2",
+                   "parallelism": f"sample-sharded x{world} (no data-path collective)"},
+        "e2e": {"value": e2e, "unit": "voxels/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(xl_h.numel() * 4 + xr_h.numel() * 4), "d2h_bytes_per_step": int(labels_h.numel())},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": kernels,
+        "peaks": pk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = time_cpu(args.workload, 1, 1, 90.0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _time_launches(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e-3
+
+
+def dominant_kernel_roofline(model, mc, dev, pk):
+    """Times individual kernels of the step alone with CUDA events (inputs are > L2 or re-streamed,
+    see notes) and relates ALGORITHMIC flops/bytes to the measured peaks."""
+    from stereoscene_b200 import ops
+    from stereoscene_b200.ops import Vol
+    vt = model.img_view_transformer
+    nx = [int(round(float(v))) for v in vt.nx.detach().cpu()]
+    kernels = []
+    torch.manual_seed(0)
+    # (1) head conv 384->192 k3 on the LSS grid: the single largest launch of the step
+    head = model.pts_bbox_head.occ_convs[0][0]
+    x = torch.randn((1, nx[0], nx[1], nx[2], head.in_channels), device=dev)
+    sc = torch.rand((1, head.in_channels), device=dev) + 0.5
+    sh = torch.randn((1, head.in_channels), device=dev) * 0.1
+    y = torch.empty((1, nx[0], nx[1], nx[2], head.out_channels), device=dev)
+    vin = Vol(x, sc, sh, ops.SS_ACT_RELU)
+
+    def head_conv():
+        ops.arena(dev).reset()
+        ops.conv(vin, head, out=y, want_stats=True)
+    t = _time_launches(head_conv)
+    V = nx[0] * nx[1] * nx[2]
+    flops = 2.0 * V * 27 * head.in_channels * head.out_channels
+    ach = flops / t / 1e12
+    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN=64> (OccHead conv 384->192 k3, 128x128x16)",
+            "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+            "traffic": None, "launch_ms": t * 1e3, "algorithmic_flops": flops,
+            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({pk['source']}); kernel runs TF32 mma.sync, "
+                           "nominal TF32 peak is half the bf16 peak"}
+    kernels.append({"name": "occ_head conv3d 384->192 k3", "bound": "tensor", "ms": t * 1e3, "tflops": ach,
+                    "frac": ach / pk["tflops"]})
+    # (2) full-res 32->32 k3 frustum conv (HBM-bound in the algorithmic accounting: in + out once)
+    D, H, W = vt.D, vt.frustum.shape[1], vt.frustum.shape[2]
+    c32 = vt.stereo_volume_net.dres0[0][0]
+    xv = torch.randn((1, D, H, W, 32), device=dev)
+    yv = torch.empty_like(xv)
+
+    def frustum_conv():
+        ops.arena(dev).reset()
+        ops.conv(Vol(xv), c32, out=yv, want_stats=True)
+    t = _time_launches(frustum_conv)
+    byts = 2.0 * xv.numel() * 4
+    kernels.append({"name": "frustum conv3d 32->32 k3 (112x48x160)", "bound": "hbm", "ms": t * 1e3,
+                    "gbs": byts / t / 1e9, "frac": byts / t / 1e9 / pk["hbm_gbs"],
+                    "tflops": 2.0 * D * H * W * 27 * 32 * 32 / t / 1e12})
+    # (3) gwc + warp (write-bound)
+    fea = torch.randn((2, 1, H, W, 64), device=dev)
+    cal = torch.full((1, 1), 380.3, device=dev)
+    t = _time_launches(lambda: ops.gwc_warp(fea, cal, D, 32))
+    byts = (fea.numel() + D * H * W * 32) * 4.0
+    kernels.append({"name": "gwc_warp", "bound": "hbm", "ms": t * 1e3, "gbs": byts / t / 1e9,
+                    "frac": byts / t / 1e9 / pk["hbm_gbs"]})
+    # (4) lift (x) splat (write-bound)
+    left, _, _ = __import__("stereoscene_b200.synth", fromlist=["x"]).kitti_calibration(1, mc["input_size"], device=dev)
+    idx = vt.splat_index(*[left[k] for k in ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")])
+    dp = torch.softmax(torch.randn((1, D, H, W), device=dev), 1)
+    ft = torch.randn((1, H, W, vt.numC_Trans), device=dev)
+    t = _time_launches(lambda: ops.lift_splat(dp, ft, idx))
+    byts = (dp.numel() + ft.numel() + V * vt.numC_Trans) * 4.0 + idx.order.numel() * 4.0
+    kernels.append({"name": "lift_splat", "bound": "hbm", "ms": t * 1e3, "gbs": byts / t / 1e9,
+                    "frac": byts / t / 1e9 / pk["hbm_gbs"]})
+    # (5) x2 trilinear + argmax (write-bound)
+    lg = torch.randn((1, nx[0], nx[1], nx[2], 20), device=dev)
+    occ = mc["occ_size"]
+    t = _time_launches(lambda: ops.trilinear(lg, occ, want_labels=True))
+    byts = (lg.numel() + occ[0] * occ[1] * occ[2] * 20) * 4.0 + occ[0] * occ[1] * occ[2]
+    kernels.append({"name": "trilinear_x2+argmax", "bound": "hbm", "ms": t * 1e3, "gbs": byts / t / 1e9,
+                    "frac": byts / t / 1e9 / pk["hbm_gbs"]})
+    return roof, kernels
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

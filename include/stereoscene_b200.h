@@ -1,0 +1,190 @@
+/*
+ * stereoscene_b200 -- C ABI of the B200 (sm_100a) volumetric hot path of StereoScene / BRGScene.
+ *
+ * The reference has no native code and no FFI: its hot path is PyTorch module code that reaches
+ * ATen / cuDNN / cuBLAS and ONE external compiled operator (mmdet3d.ops.bev_pool).  The drop-in
+ * boundary is therefore (a) the mmdet3d registry names + module signatures, mirrored in Python by
+ * stereoscene_b200/plugin/*, and (b) this C ABI, which is what those modules (or a maintainer's
+ * ctypes / pybind stub) bind.  Every entry point names the reference code it
+ * replaces (paths relative to /root/reference/projects/mmdet3d_plugin/occupancy/).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless a parameter is documented as host.  The caller owns
+ *     every buffer, including workspaces.  No global state; re-entrant; one stream per call.
+ *   - Volumes are channels-last fp32: x[b][d][h][w][c], c fastest, `ldc` floats between voxels
+ *     (ldc >= C lets a layer write into a channel slice of a concatenation buffer).  This is the
+ *     memory of a torch tensor of logical shape [B,C,D,H,W] in torch.channels_last_3d format.
+ *   - "Pending affine": GroupNorm / BatchNorm(eval) / SE gates are never applied in a pass of
+ *     their own.  A producer writes the raw tensor plus per-(batch,channel) sums; the consumer
+ *     receives per-(batch,channel) scale/shift arrays (float[B*C], NULL = identity) and an
+ *     activation code and applies act(x*scale+shift) while it loads x.
+ *   - Return value: 0 on success, a negative SS_ERR_* code otherwise.  Nothing throws.
+ *   - Streams are passed as void* (cudaStream_t).
+ */
+#ifndef STEREOSCENE_B200_H
+#define STEREOSCENE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_OK 0
+#define SS_ERR_INVALID_ARGUMENT (-1)   /* bad shape / unsupported configuration */
+#define SS_ERR_CUDA (-2)               /* a CUDA runtime call failed; see ss_last_error_string() */
+#define SS_ERR_WORKSPACE (-3)          /* caller-provided workspace too small */
+
+#define SS_ACT_NONE 0
+#define SS_ACT_RELU 1
+#define SS_ACT_GELU 2                  /* exact erf GELU (nn.GELU default) */
+
+#define SS_MATH_TF32 0                 /* tensor-core TF32 multiply, fp32 accumulate */
+#define SS_MATH_3XTF32 1               /* error-compensated split (hi/lo) TF32: ~fp32 accuracy */
+
+/* ABI version of this header; ss_abi_version() of the library must match. */
+#define SS_ABI_VERSION 1
+int ss_abi_version(void);
+/* Text of the last CUDA error seen by the calling thread (host pointer, never NULL). */
+const char* ss_last_error_string(void);
+/* Number of kernel launches issued through this library by the calling process so far. */
+long long ss_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense 3-D / 2-D convolution family (implicit GEMM on tensor cores).
+ * Replaces every nn.Conv3d / nn.ConvTranspose3d / nn.Conv2d on the path:
+ *   image2bev/ViewTransformerLSSVoxel.py:38-58 (stereofeature_net), :66-69 (convbn_3d),
+ *   :73-88 (hourglass), :167-187 (dres0/1, classif3_*), :239-241 (MIE redir1/2),
+ *   image2bev/attention.py:93-112 (CA3D), backbones/resnet3d.py:18-32, 143-148, 196-198,
+ *   necks/second_fpn_3d.py:53-59, dense_heads/occhead.py:100-107.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ss_conv3d_desc {
+    int32_t B;                        /* batch */
+    int32_t Din, Hin, Win, Cin;       /* input volume (2-D conv: Din = 1, kd = 1) */
+    int32_t Dout, Hout, Wout, Cout;   /* output volume */
+    int32_t kd, kh, kw;               /* kernel extent, each in {1,2,3,4} */
+    int32_t sd, sh, sw;               /* stride */
+    int32_t pd, ph, pw;               /* padding */
+    int32_t dd, dh, dw;               /* dilation (ordinary convolution only) */
+    int32_t transposed;               /* 1 = ConvTranspose semantics (output_padding is implied by Dout) */
+    int32_t in_ldc, out_ldc;          /* floats between consecutive voxels of x / y */
+    int32_t in_act;                   /* SS_ACT_NONE | SS_ACT_RELU, applied after the pending affine of x */
+    int32_t out_act;                  /* SS_ACT_*, applied after bias, before the statistics and the store */
+    int32_t math;                     /* SS_MATH_* */
+    int32_t cout_packed;              /* Cout rounded up to a multiple of 8: row length of w_packed */
+} ss_conv3d_desc;
+
+/* w_packed: float[taps][Cin][cout_packed], taps = kd*kh*kw in (kd,kh,kw) row-major order, i.e.
+ *   Conv:          w_packed[t][ci][co] = weight[co][ci][kd][kh][kw]
+ *   ConvTranspose: w_packed[t][ci][co] = weight[ci][co][kd][kh][kw]      (columns >= Cout are zero)
+ * bias: float[Cout] or NULL.  in_scale / in_shift: float[B*Cin] or NULL (pending affine of x).
+ * stats: double[B][Cout][2] or NULL; the kernel ADDS sum(y) and sum(y*y) over the voxels of each
+ *        (batch, output channel); the caller zeroes it beforehand. */
+int ss_conv3d_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_scale, const float* in_shift,
+                  const float* w_packed, const float* bias, float* y, double* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Normalisation bookkeeping on [B,C] vectors (the volume itself is never touched).
+ * ------------------------------------------------------------------------------------------- */
+/* GroupNorm (torch.nn.GroupNorm, eps inside the sqrt) from the sums a producer accumulated:
+ * scale[b,c] = gamma[c]*rstd[b,g], shift[b,c] = beta[c] - mean[b,g]*scale[b,c].
+ * Replaces the nn.GroupNorm layers built by build_norm_layer (ViewTransformerLSSVoxel.py:31,69;
+ * attention.py:96,111; stereoscene.py:55).  count = voxels per (batch, channel).
+ * scale/shift are written with row stride ld_out (>= C) at column offset 0. */
+int ss_gn_finalize(const double* stats, const float* gamma, const float* beta, int B, int C, int groups,
+                   double count, float eps, float* scale, float* shift, int ld_out, void* stream);
+
+/* CA3D squeeze-excite folded into the pending affine (attention.py:98-107, 113-118):
+ * pool[b,c] = scale*mean_raw + shift (mean of the GroupNorm output), s = GELU(W2*GELU(W1*pool+b1)+b2),
+ * then scale *= sigmoid(s), shift *= sigmoid(s) in place.  W1: [Cmid][C], W2: [C][Cmid]. */
+int ss_ca3d_gate(const double* stats, double count, float* scale, float* shift, const float* w1, const float* b1,
+                 const float* w2, const float* b2, int B, int C, int Cmid, void* stream);
+
+/* out = act( alpha * A(x) + A(r) ), A(t) = act_t(t*scale_t + shift_t), on [B][V][C] channels-last
+ * volumes.  r may be NULL (no second operand); alpha is a DEVICE pointer to one float or NULL (=1).
+ * Replaces the residual joins ViewTransformerLSSVoxel.py:94-95, 215, 234 and resnet3d.py:62-63. */
+int ss_affine_join_fwd(const float* x, const float* x_scale, const float* x_shift, int x_act,
+                       const float* r, const float* r_scale, const float* r_shift, int r_act,
+                       const float* alpha, int out_act, int B, long long V, int C,
+                       int x_ldc, int r_ldc, int out_ldc, float* out, void* stream);
+
+/* Softmax over the depth axis of a [B][D][P] volume (P = H*W pixels, contiguous), batch strides
+ * in floats.  Replaces F.softmax(dim=1) at ViewTransformerLSSVoxel.py:222, 267 and
+ * ViewTransformerLSSBEVDepth.py:107-108. */
+int ss_softmax_d_fwd(const float* x, long long x_batch_stride, float* y, long long y_batch_stride,
+                     int B, int D, int P, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stereo cost volume: group-wise correlation fused with the disparity->depth-bin resampling.
+ * Replaces build_gwc_volume + groupwise_correlation + warp (ViewTransformerLSSVoxel.py:97-114,
+ * 128-156); the [B,G,maxdisp,H,W] disparity volume is never materialised.
+ *   fea:  float[2B][H][W][C] channels-last features, left = batches [0,B), right = [B,2B)
+ *   i0:   int32[B][K], w0/w1: float[B][K]: per depth bin k the lower disparity index floor(p) and
+ *         the two linear-interpolation weights (host code mirrors the reference's coordinate
+ *         arithmetic; indices outside [0, maxdisp-1] contribute zero)
+ *   out:  float[B][K][H][W][G] channels-last cost volume
+ * ------------------------------------------------------------------------------------------- */
+int ss_gwc_warp_fwd(const float* fea, const int32_t* i0, const float* w0, const float* w1, float* out,
+                    int B, int C, int G, int H, int W, int K, int maxdisp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BRI: confidence-weighted cross-volume attention (attention.py:58-86), flash-style: the
+ * [N,N] energy / attention matrices are never materialised.
+ *   q, kv: float[B][D][N] (N = H*W tokens);  params: DEVICE float[7] = wq,bq,wk,bk,wv,bv,gamma
+ *   out[b][d][n*out_ld + 0] = gamma * sum_j V[d,j]*softmax_j(E[n,:])[j]*conf[j] + kv[b][d][n]
+ *   conf_ws: float[B*N] workspace (conf[j] = max_d softmax_d q[:,j]).
+ * ------------------------------------------------------------------------------------------- */
+int ss_bri_attn_fwd(const float* q, const float* kv, const float* params, float* conf_ws, float* out,
+                    int out_ld, int B, int D, int N, int math, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LSS lift (x) splat.
+ * ------------------------------------------------------------------------------------------- */
+/* Voxel-index path of voxel_pooling (ViewTransformerLSSVoxel.py:441-451), bit-exact:
+ * idx = trunc((geom - (bx - dx/2)) / dx) per axis in fp32, keep iff 0 <= idx < n per axis.
+ *   geom: float[B][P][3] ego-frame points (P = D*H*W frustum points per sample)
+ *   dx3, bx3: HOST float[3] voxel size and first-voxel centre (the module's dx / bx buffers)
+ *   coords: int32[B*P][4] = (ix,iy,iz, kept ? 1 : 0), written for every point (may be NULL)
+ *   order: int32[B*P] point ids sorted by voxel rank ((b*nx+ix)*ny+iy)*nz+iz, stable in point id;
+ *          dropped points are sorted to the end
+ *   voxel_start: int32[B*nx*ny*nz + 1] CSR offsets into `order`
+ *   ws / ws_bytes: workspace (query the size with ss_splat_index_workspace_bytes). */
+size_t ss_splat_index_workspace_bytes(long long n_points);
+int ss_splat_build_index(const float* geom, const float* dx3, const float* bx3, int nx, int ny, int nz,
+                         int B, long long P, int32_t* coords, int32_t* order, int32_t* voxel_start,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* Fused lift (outer product, ViewTransformerLSSVoxel.py:517-519) + per-voxel sum (bev_pool):
+ *   out[b][x][y][z][c] = sum over the voxel's points n=(d,h,w), in ascending point id, of
+ *                        depth_prob[b][d][h][w] * img_feat[b][h][w][c]
+ * (fp32 multiply then add, no fma, so the sum reproduces a sequential CPU accumulation bit for bit).
+ * The [B,N,D,H,W,C] lifted volume is never materialised; every voxel is written exactly once. */
+int ss_lift_splat_fwd(const float* depth_prob, const float* img_feat, const int32_t* order,
+                      const int32_t* voxel_start, float* out, int B, int D, int H, int W, int C,
+                      int nx, int ny, int nz, void* stream);
+
+/* Exact operator-level drop-in for mmdet3d.ops.bev_pool.bev_pool (call site
+ * ViewTransformerLSSVoxel.py:473): feats float[N][C], coords int64[N][4] = (x,y,z,b) all inside the
+ * grid; out float[B][C][D][H][W] with D=nz, H=nx, W=ny (NCDHW, contiguous); empty voxels are 0.
+ * ws sized by ss_bev_pool_workspace_bytes(N, B*D*H*W). */
+size_t ss_bev_pool_workspace_bytes(long long n_points, long long n_voxels);
+int ss_bev_pool_fwd(const float* feats, const int64_t* coords, long long N, int C, int B, int D, int H, int W,
+                    float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Trilinear resize of channels-last logits, align_corners=False (F.interpolate semantics,
+ * detectors/bevdepth_occupancy.py:293-294).  x: [B][Di][Hi][Wi][C] -> y: [B][Do][Ho][Wo][C].
+ * labels (optional, may be NULL): uint8[B][Do][Ho][Wo] = argmax over C of y (first maximum).
+ * ------------------------------------------------------------------------------------------- */
+int ss_trilinear_fwd(const float* x, float* y, uint8_t* labels, int B, int C, int Di, int Hi, int Wi,
+                     int Do, int Ho, int Wo, void* stream);
+
+/* Layout helpers: NCHW/NCDHW <-> channels-last copies ([B][C][V] <-> [B][V][C]). */
+int ss_nchw_to_nhwc(const float* x, float* y, int B, int C, long long V, int out_ldc, void* stream);
+int ss_nhwc_to_nchw(const float* x, float* y, int B, int C, long long V, int in_ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEREOSCENE_B200_H */

@@ -123,6 +123,15 @@ def main():
         json.dump(spec, f, indent=0, sort_keys=True)
     del full
 
+    # ---- the model dict of the shipped config, as OUR loader reads the reference's file
+    from stereoscene_b200.config import Config
+    cfg = Config.fromfile(os.path.join(R.REF_ROOT, "projects/configs/occupancy/semantickitti/stereoscene.py"))
+    data_dir = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "stereoscene_b200", "data")
+    os.makedirs(data_dir, exist_ok=True)
+    with open(os.path.join(data_dir, "stereoscene_model_cfg.json"), "w") as f:
+        json.dump(dict(model=cfg.to_dict()["model"], occ_size=cfg.occ_size, point_cloud_range=cfg.point_cloud_range,
+                       lss_downsample=cfg.lss_downsample, class_names=cfg.class_names), f, indent=1)
+
     # ---- tiny geometry: every stage boundary
     model = build_reference_model(TINY)
     synth.randomize_weights_(model, TINY["seed"])

@@ -1,0 +1,88 @@
+"""ctypes binding of include/stereoscene_b200.h.
+
+The product path has no fallback: if ``libstereoscene_b200.so`` is missing or its ABI version
+does not match, importing an op raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+ABI_VERSION = 1
+
+SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU = 0, 1, 2
+SS_MATH_TF32, SS_MATH_3XTF32 = 0, 1
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "B", "Din", "Hin", "Win", "Cin", "Dout", "Hout", "Wout", "Cout",
+        "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw", "dd", "dh", "dw",
+        "transposed", "in_ldc", "out_ldc", "in_act", "out_act", "math", "cout_packed")]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+_vp, _i, _ll, _d, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); exactly the declarations of include/stereoscene_b200.h
+SIGNATURES = {
+    "ss_abi_version": (_i, []),
+    "ss_last_error_string": (C.c_char_p, []),
+    "ss_launch_count": (_ll, []),
+    "ss_conv3d_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ss_gn_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _f, _vp, _vp, _i, _vp]),
+    "ss_ca3d_gate": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ss_affine_join_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _i, _vp, _vp]),
+    "ss_softmax_d_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "ss_gwc_warp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ss_bri_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ss_splat_index_workspace_bytes": (_sz, [_ll]),
+    "ss_splat_build_index": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ss_lift_splat_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ss_bev_pool_workspace_bytes": (_sz, [_ll, _ll]),
+    "ss_bev_pool_fwd": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "ss_trilinear_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ss_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
+    "ss_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
+}
+
+_lib = None
+
+
+def load(path: str | None = None):
+    """Load the shared library (once) and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or os.environ.get("STEREOSCENE_B200_LIB") or _build.library_path()
+    if not os.path.exists(path):
+        raise NativeLibraryError(
+            f"{path} not found: the CUDA extension is not built. Run `python -m stereoscene_b200._build` "
+            "(or __graft_entry__.build()). There is no CPU / PyTorch fallback for the hot path.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError(f"{path} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ss_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI mismatch: library {lib.ss_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().ss_last_error_string().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().ss_launch_count())

@@ -1,0 +1,236 @@
+// Normalisation bookkeeping, residual joins, depth softmax and layout helpers.
+//
+// GroupNorm / BatchNorm(eval) / SE gates are "pending affines": the producer conv leaves
+// per-(batch,channel) sums, ss_gn_finalize turns them into scale/shift vectors on [B,C], and
+// the *consumer* applies act(x*scale+shift) while loading.  The only full-volume elementwise
+// kernel left is the residual join, which has to materialise its result anyway.
+#include "common.cuh"
+
+namespace ss {
+
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int B, int C, int groups, double count,
+                                   float eps, float* __restrict__ scale, float* __restrict__ shift, int ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i % C;
+    const int cpg = C / groups, g0 = (c / cpg) * cpg;
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+        s += stats[((size_t)b * C + g0 + k) * 2 + 0];
+        q += stats[((size_t)b * C + g0 + k) * 2 + 1];
+    }
+    const double n = count * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = __ldg(gamma + c) * rstd;
+    scale[(size_t)b * ld + c] = sc;
+    shift[(size_t)b * ld + c] = __ldg(beta + c) - (float)mean * sc;
+}
+
+// one CTA per batch sample; C <= 1024, Cmid <= 128
+__global__ void ca3d_gate_kernel(const double* __restrict__ stats, double count, float* __restrict__ scale,
+                                 float* __restrict__ shift, const float* __restrict__ w1,
+                                 const float* __restrict__ b1, const float* __restrict__ w2,
+                                 const float* __restrict__ b2, int C, int Cmid) {
+    extern __shared__ float sm[];
+    float* pool = sm;          // [C]
+    float* hid = sm + C;       // [Cmid]
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float mean_raw = (float)(stats[((size_t)b * C + c) * 2] / count);
+        pool[c] = fmaf(scale[(size_t)b * C + c], mean_raw, shift[(size_t)b * C + c]);
+    }
+    __syncthreads();
+    for (int m = threadIdx.x; m < Cmid; m += blockDim.x) {
+        float a = __ldg(b1 + m);
+        for (int c = 0; c < C; ++c) a = fmaf(__ldg(w1 + (size_t)m * C + c), pool[c], a);
+        hid[m] = gelu_erf(a);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = __ldg(b2 + c);
+        for (int m = 0; m < Cmid; ++m) a = fmaf(__ldg(w2 + (size_t)c * Cmid + m), hid[m], a);
+        const float gate = 1.0f / (1.0f + expf(-gelu_erf(a)));
+        scale[(size_t)b * C + c] *= gate;
+        shift[(size_t)b * C + c] *= gate;
+    }
+}
+
+// out = act( alpha * A(x) + A(r) ); 4 channels per thread when VEC
+template <bool VEC>
+__global__ void affine_join_kernel(const float* __restrict__ x, const float* __restrict__ xs,
+                                   const float* __restrict__ xh, int x_act, const float* __restrict__ r,
+                                   const float* __restrict__ rs, const float* __restrict__ rh, int r_act,
+                                   const float* __restrict__ alpha_p, int out_act, long long V, int C,
+                                   int x_ldc, int r_ldc, int out_ldc, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const float alpha = alpha_p ? __ldg(alpha_p) : 1.0f;
+    constexpr int W = VEC ? 4 : 1;
+    const int cw = C / W;
+    const long long total = V * cw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long v = i / cw;
+        const int c = (int)(i % cw) * W;
+        const size_t vox = (size_t)b * V + v;
+        float xv[W], rv[W];
+        if (VEC) {
+            float4 t4 = ldg_f4(x + vox * x_ldc + c);
+            xv[0] = t4.x; xv[1] = t4.y; xv[2] = t4.z; xv[3] = t4.w;
+            if (r) {
+                float4 u4 = ldg_f4(r + vox * r_ldc + c);
+                rv[0] = u4.x; rv[1] = u4.y; rv[2] = u4.z; rv[3] = u4.w;
+            }
+        } else {
+            xv[0] = __ldg(x + vox * x_ldc + c);
+            if (r) rv[0] = __ldg(r + vox * r_ldc + c);
+        }
+        float o[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            float a = xv[k];
+            if (xs) a = fmaf(a, __ldg(xs + (size_t)b * C + c + k), __ldg(xh + (size_t)b * C + c + k));
+            a = apply_act(a, x_act) * alpha;
+            if (r) {
+                float e = rv[k];
+                if (rs) e = fmaf(e, __ldg(rs + (size_t)b * C + c + k), __ldg(rh + (size_t)b * C + c + k));
+                a += apply_act(e, r_act);
+            }
+            o[k] = apply_act(a, out_act);
+        }
+        if (VEC) *reinterpret_cast<float4*>(out + vox * out_ldc + c) = make_float4(o[0], o[1], o[2], o[3]);
+        else out[vox * out_ldc + c] = o[0];
+    }
+}
+
+// softmax over D of x[b][d][p]; one thread per pixel column, coalesced across p.
+__global__ void softmax_d_kernel(const float* __restrict__ x, long long xbs, float* __restrict__ y, long long ybs,
+                                 int D, int P) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (p >= P) return;
+    const float* xp = x + (size_t)b * xbs + p;
+    float m = -INFINITY;
+    for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(xp + (size_t)d * P));
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s += expf(__ldg(xp + (size_t)d * P) - m);
+    const float inv = 1.0f / s;
+    float* yp = y + (size_t)b * ybs + p;
+    for (int d = 0; d < D; ++d) yp[(size_t)d * P] = expf(__ldg(xp + (size_t)d * P) - m) * inv;
+}
+
+// [B][C][V] -> [B][V][ldc] via a 32x32 shared-memory transpose
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, long long V, int ldc) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const long long v0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j;
+        const long long v = v0 + threadIdx.x;
+        if (c < C && v < V) tile[j][threadIdx.x] = __ldg(x + ((size_t)b * C + c) * V + v);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const long long v = v0 + j;
+        const int c = c0 + threadIdx.x;
+        if (c < C && v < V) y[((size_t)b * V + v) * ldc + c] = tile[threadIdx.x][j];
+    }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C, long long V, int ldc) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const long long v0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const long long v = v0 + j;
+        const int c = c0 + threadIdx.x;
+        if (c < C && v < V) tile[j][threadIdx.x] = __ldg(x + ((size_t)b * V + v) * ldc + c);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j;
+        const long long v = v0 + threadIdx.x;
+        if (c < C && v < V) y[((size_t)b * C + c) * V + v] = tile[threadIdx.x][j];
+    }
+}
+
+}  // namespace ss
+
+using namespace ss;
+
+extern "C" int ss_gn_finalize(const double* stats, const float* gamma, const float* beta, int B, int C, int groups,
+                              double count, float eps, float* scale, float* shift, int ld_out, void* stream) {
+    SS_REQUIRE(stats && gamma && beta && scale && shift, "ss_gn_finalize: null pointer");
+    SS_REQUIRE(B > 0 && C > 0 && groups > 0 && C % groups == 0 && ld_out >= C && count > 0, "ss_gn_finalize: shape");
+    const int n = B * C;
+    gn_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, gamma, beta, B, C, groups, count, eps,
+                                                                          scale, shift, ld_out);
+    return check_launch("gn_finalize_kernel");
+}
+
+extern "C" int ss_ca3d_gate(const double* stats, double count, float* scale, float* shift, const float* w1,
+                            const float* b1, const float* w2, const float* b2, int B, int C, int Cmid, void* stream) {
+    SS_REQUIRE(stats && scale && shift && w1 && b1 && w2 && b2, "ss_ca3d_gate: null pointer");
+    SS_REQUIRE(B > 0 && C > 0 && C <= 1024 && Cmid > 0 && Cmid <= 128 && count > 0, "ss_ca3d_gate: shape");
+    ca3d_gate_kernel<<<B, 128, (C + Cmid) * sizeof(float), (cudaStream_t)stream>>>(stats, count, scale, shift, w1, b1,
+                                                                                   w2, b2, C, Cmid);
+    return check_launch("ca3d_gate_kernel");
+}
+
+extern "C" int ss_affine_join_fwd(const float* x, const float* x_scale, const float* x_shift, int x_act,
+                                  const float* r, const float* r_scale, const float* r_shift, int r_act,
+                                  const float* alpha, int out_act, int B, long long V, int C, int x_ldc, int r_ldc,
+                                  int out_ldc, float* out, void* stream) {
+    SS_REQUIRE(x && out, "ss_affine_join_fwd: null pointer");
+    SS_REQUIRE(B > 0 && B <= 65535 && V > 0 && C > 0, "ss_affine_join_fwd: shape");
+    SS_REQUIRE((x_scale == nullptr) == (x_shift == nullptr) && (r_scale == nullptr) == (r_shift == nullptr),
+               "ss_affine_join_fwd: scale/shift must come together");
+    const bool vec = (C % 4 == 0) && (x_ldc % 4 == 0) && (out_ldc % 4 == 0) && (!r || r_ldc % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                       reinterpret_cast<uintptr_t>(r)) & 15) == 0;
+    const long long total = V * (vec ? C / 4 : C);
+    const int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    const long long cap = 148LL * 16;     // grid-stride: 16 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)B);
+    if (vec)
+        affine_join_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(x, x_scale, x_shift, x_act, r, r_scale, r_shift,
+                                                                            r_act, alpha, out_act, V, C, x_ldc, r_ldc,
+                                                                            out_ldc, out);
+    else
+        affine_join_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(x, x_scale, x_shift, x_act, r, r_scale, r_shift,
+                                                                             r_act, alpha, out_act, V, C, x_ldc, r_ldc,
+                                                                             out_ldc, out);
+    return check_launch("affine_join_kernel");
+}
+
+extern "C" int ss_softmax_d_fwd(const float* x, long long x_batch_stride, float* y, long long y_batch_stride, int B,
+                                int D, int P, void* stream) {
+    SS_REQUIRE(x && y, "ss_softmax_d_fwd: null pointer");
+    SS_REQUIRE(B > 0 && B <= 65535 && D > 0 && P > 0, "ss_softmax_d_fwd: shape");
+    dim3 grid((P + 127) / 128, B);
+    softmax_d_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, x_batch_stride, y, y_batch_stride, D, P);
+    return check_launch("softmax_d_kernel");
+}
+
+extern "C" int ss_nchw_to_nhwc(const float* x, float* y, int B, int C, long long V, int out_ldc, void* stream) {
+    SS_REQUIRE(x && y && B > 0 && B <= 65535 && C > 0 && V > 0 && out_ldc >= C, "ss_nchw_to_nhwc: arguments");
+    dim3 grid((unsigned)((V + 31) / 32), (C + 31) / 32, B), block(32, 8);
+    SS_REQUIRE((C + 31) / 32 <= 65535, "ss_nchw_to_nhwc: too many channels");
+    nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, C, V, out_ldc);
+    return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int ss_nhwc_to_nchw(const float* x, float* y, int B, int C, long long V, int in_ldc, void* stream) {
+    SS_REQUIRE(x && y && B > 0 && B <= 65535 && C > 0 && V > 0 && in_ldc >= C, "ss_nhwc_to_nchw: arguments");
+    dim3 grid((unsigned)((V + 31) / 32), (C + 31) / 32, B), block(32, 8);
+    SS_REQUIRE((C + 31) / 32 <= 65535, "ss_nhwc_to_nchw: too many channels");
+    nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, C, V, in_ldc);
+    return check_launch("nhwc_to_nchw_kernel");
+}

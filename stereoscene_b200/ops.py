@@ -1,0 +1,514 @@
+"""Tensor-level wrappers over the C ABI (include/stereoscene_b200.h).
+
+PyTorch is used here for device memory, streams and views only; every arithmetic step of the
+hot path is a call into libstereoscene_b200.so.  There is no fallback: a CPU tensor, a wrong
+dtype or a missing library raises.
+
+Data model
+----------
+``Vol`` is a channels-last volume ``data[B,D,H,W,C]`` (possibly a channel slice of a wider
+buffer) together with a *pending affine*: per-(batch,channel) ``scale``/``shift`` and an
+activation that the consumer applies while loading, i.e. the logical value of the volume is
+``act(data*scale+shift)``.  GroupNorm, eval-mode BatchNorm, SE gates and the CA3D gate are all
+expressed this way, so no normalisation pass over a volume ever runs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import cabi
+from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_TF32  # noqa: F401
+
+_DEFAULT_MATH = SS_MATH_TF32
+
+
+def set_default_math(mode: int):
+    """SS_MATH_TF32 (fast) or SS_MATH_3XTF32 (split-TF32, ~fp32 accuracy) for conv / BRI energy."""
+    global _DEFAULT_MATH
+    assert mode in (SS_MATH_TF32, SS_MATH_3XTF32)
+    _DEFAULT_MATH = mode
+
+
+def default_math() -> int:
+    return _DEFAULT_MATH
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda_f32(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+
+
+def _vol_ldc(t: torch.Tensor, name: str) -> int:
+    """Voxel stride of a [B,D,H,W,C] tensor that is a channel slice of a contiguous buffer."""
+    _need_cuda_f32(t, name)
+    if t.dim() != 5:
+        raise RuntimeError(f"{name}: expected [B,D,H,W,C], got {tuple(t.shape)}")
+    B, D, H, W, Cc = t.shape
+    sb, sd, sh, sw, sc = t.stride()
+    ldc = sw if W > 1 else (sh if H > 1 else (sd if D > 1 else (sb if B > 1 else Cc)))
+    ok = (sc == 1 or Cc == 1) and (W == 1 or sw == ldc) and (H == 1 or sh == W * ldc) and \
+         (D == 1 or sd == H * W * ldc) and (B == 1 or sb == D * H * W * ldc) and ldc >= Cc
+    if not ok:
+        raise RuntimeError(f"{name}: not a channels-last volume (shape {tuple(t.shape)}, stride {t.stride()})")
+    return int(ldc)
+
+
+@dataclass
+class Vol:
+    data: torch.Tensor                      # [B,D,H,W,C]
+    scale: Optional[torch.Tensor] = None    # [B,C] contiguous
+    shift: Optional[torch.Tensor] = None
+    act: int = SS_ACT_NONE
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def C(self) -> int:
+        return self.data.shape[-1]
+
+    @property
+    def is_plain(self) -> bool:
+        return self.scale is None and self.act == SS_ACT_NONE
+
+    def plain(self) -> torch.Tensor:
+        """The logical value as a contiguous [B,D,H,W,C] tensor (materialises if pending)."""
+        if self.is_plain:
+            return self.data
+        return join(self, None, out_act=SS_ACT_NONE)
+
+    def ncdhw(self) -> torch.Tensor:
+        """Logical [B,C,D,H,W] view (channels_last_3d memory) -- the reference's tensor layout."""
+        return self.plain().permute(0, 4, 1, 2, 3)
+
+
+class StatsArena:
+    """Zero-initialised double[B][C][2] blocks for the per-channel sums, handed out from one pool
+    that is cleared with a single memset per forward."""
+
+    def __init__(self, device, capacity=1 << 16):
+        self.device = device
+        self.capacity = capacity
+        self.pool = torch.zeros(capacity, dtype=torch.float64, device=device)
+        self.used = 0
+
+    def reset(self):
+        if self.used:
+            self.pool[: self.used].zero_()
+        self.used = 0
+
+    def take(self, B: int, Cc: int) -> torch.Tensor:
+        n = B * Cc * 2
+        if self.used + n > self.capacity:
+            # grow: a fresh zeroed pool (old blocks stay alive through their views)
+            self.capacity = max(self.capacity * 2, n * 2)
+            self.pool = torch.zeros(self.capacity, dtype=torch.float64, device=self.device)
+            self.used = 0
+        blk = self.pool[self.used: self.used + n].view(B, Cc, 2)
+        self.used += n
+        return blk
+
+
+_arenas = {}
+
+
+def arena(device) -> StatsArena:
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    a = _arenas.get(key)
+    if a is None:
+        a = _arenas[key] = StatsArena(device)
+    return a
+
+
+# ------------------------------------------------------------------------------------------
+# convolution family
+# ------------------------------------------------------------------------------------------
+def _triple(v) -> Tuple[int, int, int]:
+    if isinstance(v, int):
+        return (v, v, v)
+    v = tuple(int(a) for a in v)
+    if len(v) == 2:
+        return (1,) + v if False else (v[0], v[1], -1)   # never used; 2-D handled by caller
+    return v
+
+
+class PackedConv:
+    """Geometry + weights of one Conv3d / ConvTranspose3d / Conv2d in the kernel's layout
+    (float[taps][Cin][Cout_padded]); built once from the nn.Module that owns the parameter (so the
+    state_dict stays the reference's) and refreshed if the parameter is reassigned or modified."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.module = module
+        m = module
+        if isinstance(m, torch.nn.Conv2d):
+            self.k = (1,) + tuple(m.kernel_size); self.s = (1,) + tuple(m.stride)
+            self.p = (0,) + tuple(m.padding); self.d = (1,) + tuple(m.dilation)
+            self.transposed = False; self.outpad = (0, 0, 0)
+        elif isinstance(m, torch.nn.ConvTranspose3d):
+            self.k = tuple(m.kernel_size); self.s = tuple(m.stride); self.p = tuple(m.padding)
+            self.d = tuple(m.dilation); self.transposed = True; self.outpad = tuple(m.output_padding)
+        elif isinstance(m, torch.nn.Conv3d):
+            self.k = tuple(m.kernel_size); self.s = tuple(m.stride); self.p = tuple(m.padding)
+            self.d = tuple(m.dilation); self.transposed = False; self.outpad = (0, 0, 0)
+        else:
+            raise TypeError(type(m))
+        if m.groups != 1:
+            raise RuntimeError("grouped convolution is not on the hot path")
+        self.Cin, self.Cout = m.in_channels, m.out_channels
+        self.CoutP = (self.Cout + 7) // 8 * 8
+        self._key = None
+        self._w = None
+
+    def weights(self) -> torch.Tensor:
+        w = self.module.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self._key:
+            with torch.no_grad():
+                wd = w.detach()
+                if wd.dim() == 4:
+                    wd = wd.unsqueeze(2)
+                if self.transposed:          # [Cin,Cout,kd,kh,kw] -> [kd,kh,kw,Cin,Cout]
+                    pk = wd.permute(2, 3, 4, 0, 1)
+                else:                        # [Cout,Cin,kd,kh,kw] -> [kd,kh,kw,Cin,Cout]
+                    pk = wd.permute(2, 3, 4, 1, 0)
+                pk = pk.reshape(-1, self.Cin, self.Cout).float()
+                if self.CoutP != self.Cout:
+                    pk = torch.nn.functional.pad(pk, (0, self.CoutP - self.Cout))
+                self._w = pk.contiguous()
+            self._key = key
+        return self._w
+
+    def out_size(self, din: Sequence[int]) -> Tuple[int, int, int]:
+        out = []
+        for i in range(3):
+            if self.transposed:
+                out.append((din[i] - 1) * self.s[i] - 2 * self.p[i] + self.d[i] * (self.k[i] - 1) + self.outpad[i] + 1)
+            else:
+                out.append((din[i] + 2 * self.p[i] - self.d[i] * (self.k[i] - 1) - 1) // self.s[i] + 1)
+        return tuple(out)
+
+
+_packed_cache = {}
+
+
+def packed(module: torch.nn.Module) -> PackedConv:
+    pc = _packed_cache.get(id(module))
+    if pc is None or pc.module is not module:
+        pc = _packed_cache[id(module)] = PackedConv(module)
+    return pc
+
+
+def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, out_act: int = SS_ACT_NONE,
+         want_stats: bool = False, math_mode: Optional[int] = None, use_bias: bool = True):
+    """y = act_out(conv(act_in(x*scale+shift)) + bias); returns (y [B,D',H',W',Cout], stats or None).
+    ``out`` may be a channel slice of a concatenation buffer."""
+    lib = cabi.load()
+    pc = packed(module)
+    xin = x.data
+    in_ldc = _vol_ldc(xin, "conv input")
+    B, Din, Hin, Win, Cin = xin.shape
+    if Cin != pc.Cin:
+        raise RuntimeError(f"conv: input has {Cin} channels, layer expects {pc.Cin}")
+    Do, Ho, Wo = pc.out_size((Din, Hin, Win))
+    if out is None:
+        out = torch.empty((B, Do, Ho, Wo, pc.Cout), dtype=torch.float32, device=xin.device)
+    elif tuple(out.shape) != (B, Do, Ho, Wo, pc.Cout):
+        raise RuntimeError(f"conv: out has shape {tuple(out.shape)}, expected {(B, Do, Ho, Wo, pc.Cout)}")
+    out_ldc = _vol_ldc(out, "conv output")
+    stats = arena(xin.device).take(B, pc.Cout) if want_stats else None
+    bias = module.bias if (use_bias and module.bias is not None) else None
+    if x.scale is not None:
+        if tuple(x.scale.shape) != (B, Cin) or not x.scale.is_contiguous() or not x.shift.is_contiguous():
+            raise RuntimeError("conv: pending affine must be contiguous [B,Cin]")
+    d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
+                      1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act,
+                      _DEFAULT_MATH if math_mode is None else math_mode, pc.CoutP)
+    rc = lib.ss_conv3d_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights().data_ptr(),
+                           _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
+    cabi.check(rc, "ss_conv3d_fwd")
+    return out, stats
+
+
+def voxels_per_channel(t: torch.Tensor) -> int:
+    return int(t.shape[1] * t.shape[2] * t.shape[3])
+
+
+def gn_pending(y: torch.Tensor, stats: torch.Tensor, gn: torch.nn.GroupNorm, act: int = SS_ACT_NONE,
+               scale_out: Optional[torch.Tensor] = None, shift_out: Optional[torch.Tensor] = None) -> Vol:
+    """Turn a producer's sums into the pending GroupNorm(+activation) of its raw output."""
+    lib = cabi.load()
+    B, Cc = stats.shape[0], stats.shape[1]
+    if scale_out is None:
+        ss = torch.empty((2, B, Cc), dtype=torch.float32, device=y.device)
+        scale_out, shift_out = ss[0], ss[1]
+    ld = scale_out.stride(0) if B > 1 else max(Cc, scale_out.stride(0))
+    rc = lib.ss_gn_finalize(stats.data_ptr(), gn.weight.data_ptr(), gn.bias.data_ptr(), B, Cc, gn.num_groups,
+                            float(voxels_per_channel(y)), float(gn.eps), scale_out.data_ptr(), shift_out.data_ptr(),
+                            int(ld), _stream())
+    cabi.check(rc, "ss_gn_finalize")
+    return Vol(y, scale_out, shift_out, act)
+
+
+_bn_cache = {}
+
+
+def bn_pending(y: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, act: int = SS_ACT_NONE) -> Vol:
+    """Eval-mode BatchNorm as a pending affine from the running statistics (host-side, cached:
+    it depends on parameters only)."""
+    B = y.shape[0]
+    key = (id(bn), B, bn.weight.data_ptr(), bn.weight._version, bn.bias._version, bn.running_mean._version,
+           bn.running_var._version, bn.weight.device)
+    hit = _bn_cache.get(id(bn))
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            sc = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+            sh = bn.bias.detach().float() - bn.running_mean.float() * sc
+            hit = (key, sc.unsqueeze(0).repeat(B, 1).contiguous(), sh.unsqueeze(0).repeat(B, 1).contiguous())
+        _bn_cache[id(bn)] = hit
+    return Vol(y, hit[1], hit[2], act)
+
+
+def ca3d_gate(v: Vol, stats: torch.Tensor, conv_reduce: torch.nn.Conv3d, conv_expand: torch.nn.Conv3d) -> Vol:
+    """Fold sigmoid(GELU(expand(GELU(reduce(avgpool(v)))))) into v's pending affine (in place)."""
+    lib = cabi.load()
+    B, Cc = v.scale.shape
+    rc = lib.ss_ca3d_gate(stats.data_ptr(), float(voxels_per_channel(v.data)), v.scale.data_ptr(), v.shift.data_ptr(),
+                          conv_reduce.weight.data_ptr(), conv_reduce.bias.data_ptr(), conv_expand.weight.data_ptr(),
+                          conv_expand.bias.data_ptr(), B, Cc, conv_reduce.out_channels, _stream())
+    cabi.check(rc, "ss_ca3d_gate")
+    return v
+
+
+def join(x: Vol, r: Optional[Vol], out_act: int = SS_ACT_NONE, alpha: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(alpha * x + r) on logical values (x, r pending volumes); plain [B,D,H,W,C] result."""
+    lib = cabi.load()
+    xd = x.data
+    x_ldc = _vol_ldc(xd, "join x")
+    B, D, H, W, Cc = xd.shape
+    r_ldc = 0
+    if r is not None:
+        if tuple(r.data.shape) != tuple(xd.shape):
+            raise RuntimeError(f"join: shapes differ {tuple(xd.shape)} vs {tuple(r.data.shape)}")
+        r_ldc = _vol_ldc(r.data, "join r")
+    if out is None:
+        out = torch.empty((B, D, H, W, Cc), dtype=torch.float32, device=xd.device)
+    out_ldc = _vol_ldc(out, "join out")
+    rc = lib.ss_affine_join_fwd(xd.data_ptr(), _ptr(x.scale), _ptr(x.shift), x.act,
+                                _ptr(r.data if r is not None else None), _ptr(r.scale if r is not None else None),
+                                _ptr(r.shift if r is not None else None), r.act if r is not None else 0,
+                                _ptr(alpha.detach() if alpha is not None else None), out_act, B, D * H * W, Cc,
+                                x_ldc, r_ldc, out_ldc, out.data_ptr(), _stream())
+    cabi.check(rc, "ss_affine_join_fwd")
+    return out
+
+
+def softmax_d(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Softmax over dim 1 of x[B,D,...pixels...] whose per-sample block [D,P] is contiguous
+    (a channel slice x[:, :D] of a wider NCHW tensor is fine)."""
+    lib = cabi.load()
+    _need_cuda_f32(x, "softmax_d")
+    B, D = x.shape[0], x.shape[1]
+    P = int(math.prod(x.shape[2:]))
+    if not x[0].is_contiguous():
+        raise RuntimeError("softmax_d: per-sample [D,P] block must be contiguous")
+    if out is None:
+        out = torch.empty((B, D) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    rc = lib.ss_softmax_d_fwd(x.data_ptr(), x.stride(0) if B > 1 else D * P, out.data_ptr(),
+                              out.stride(0) if B > 1 else D * P, B, D, P, _stream())
+    cabi.check(rc, "ss_softmax_d_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# stereo cost volume
+# ------------------------------------------------------------------------------------------
+def disparity_taps(calib: torch.Tensor, n_bins: int, down: int = 1):
+    """Host-side mirror of the reference's sampling-coordinate arithmetic (warp,
+    ViewTransformerLSSVoxel.py:139-150, then grid_sample's align_corners un-normalisation), kept
+    in fp32 torch ops so the taps are the reference's to the last bit.  Returns
+    (i0 int32 [B,K], w0 float [B,K], w1 float [B,K])."""
+    B = calib.shape[0]
+    D = n_bins
+    k = torch.arange(1, 1 + n_bins // down, dtype=torch.float32, device=calib.device)
+    xx = (calib.reshape(B, -1)[:, :1].float() / (down * 4.0)) / k[None, :]
+    xn = 2.0 * xx / max(D - 1, 1) - 1.0
+    pos = ((xn + 1.0) / 2.0) * (D - 1)
+    f = torch.floor(pos)
+    w1 = pos - f
+    w0 = (f + 1.0) - pos
+    i0 = f.clamp(-2.0, float(D + 1)).to(torch.int32)
+    return i0.contiguous(), w0.contiguous(), w1.contiguous()
+
+
+def gwc_warp(fea: torch.Tensor, calib: torch.Tensor, maxdisp: int, groups: int) -> torch.Tensor:
+    """fea [2B,1,H,W,C] channels-last stereo features (left then right) -> cost volume
+    [B,K=maxdisp,H,W,G]."""
+    lib = cabi.load()
+    _need_cuda_f32(fea, "gwc_warp")
+    if not fea.is_contiguous():
+        raise RuntimeError("gwc_warp: features must be contiguous channels-last")
+    B2, _, H, W, Cc = fea.shape
+    B = B2 // 2
+    i0, w0, w1 = disparity_taps(calib.to(fea.device), maxdisp)
+    out = torch.empty((B, maxdisp, H, W, groups), dtype=torch.float32, device=fea.device)
+    rc = lib.ss_gwc_warp_fwd(fea.data_ptr(), i0.data_ptr(), w0.data_ptr(), w1.data_ptr(), out.data_ptr(),
+                             B, Cc, groups, H, W, maxdisp, maxdisp, _stream())
+    cabi.check(rc, "ss_gwc_warp_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# BRI attention
+# ------------------------------------------------------------------------------------------
+def bri_attention(q: torch.Tensor, kv: torch.Tensor, params: torch.Tensor, out: torch.Tensor, out_ld: int,
+                  math_mode: Optional[int] = None):
+    """q, kv: contiguous [B,D,H,W]; params: device float[7] (wq,bq,wk,bk,wv,bv,gamma);
+    out: buffer written at out[b,d,n*out_ld]."""
+    lib = cabi.load()
+    _need_cuda_f32(q, "bri q"); _need_cuda_f32(kv, "bri kv")
+    if not (q.is_contiguous() and kv.is_contiguous()):
+        raise RuntimeError("bri_attention: q / kv must be contiguous [B,D,H,W]")
+    B, D = q.shape[0], q.shape[1]
+    N = int(math.prod(q.shape[2:]))
+    conf = torch.empty((B, N), dtype=torch.float32, device=q.device)
+    rc = lib.ss_bri_attn_fwd(q.data_ptr(), kv.data_ptr(), params.data_ptr(), conf.data_ptr(), out.data_ptr(), out_ld,
+                             B, D, N, _DEFAULT_MATH if math_mode is None else math_mode, _stream())
+    cabi.check(rc, "ss_bri_attn_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# lift + splat
+# ------------------------------------------------------------------------------------------
+@dataclass
+class SplatIndex:
+    order: torch.Tensor          # int32 [B*P]
+    voxel_start: torch.Tensor    # int32 [B*nx*ny*nz + 1]
+    coords: Optional[torch.Tensor]   # int32 [B*P,4] (ix,iy,iz,kept)
+    nx: int
+    ny: int
+    nz: int
+    B: int
+    P: int
+
+
+def splat_build_index(geom: torch.Tensor, dx, bx, nx: Sequence[int], want_coords: bool = False) -> SplatIndex:
+    """geom [B,...,3] ego-frame frustum points -> sorted point index (calibration-only)."""
+    lib = cabi.load()
+    _need_cuda_f32(geom, "splat geom")
+    B = geom.shape[0]
+    g = geom.reshape(B, -1, 3).contiguous()
+    P = g.shape[1]
+    n = [int(round(float(v))) for v in nx]
+    dxh = (C.c_float * 3)(*[float(v) for v in dx])
+    bxh = (C.c_float * 3)(*[float(v) for v in bx])
+    total = B * P
+    nvox = B * n[0] * n[1] * n[2]
+    order = torch.empty(total, dtype=torch.int32, device=geom.device)
+    start = torch.empty(nvox + 1, dtype=torch.int32, device=geom.device)
+    coords = torch.empty((total, 4), dtype=torch.int32, device=geom.device) if want_coords else None
+    wsb = int(lib.ss_splat_index_workspace_bytes(total))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=geom.device)
+    rc = lib.ss_splat_build_index(g.data_ptr(), dxh, bxh, n[0], n[1], n[2], B, P, _ptr(coords), order.data_ptr(),
+                                  start.data_ptr(), ws.data_ptr(), wsb, _stream())
+    cabi.check(rc, "ss_splat_build_index")
+    return SplatIndex(order, start, coords, n[0], n[1], n[2], B, P)
+
+
+def lift_splat(depth_prob: torch.Tensor, img_feat: torch.Tensor, index: SplatIndex) -> torch.Tensor:
+    """depth_prob [B,D,H,W], img_feat [B,H,W,C] (channels-last) -> bev [B,X,Y,Z,C]."""
+    lib = cabi.load()
+    _need_cuda_f32(depth_prob, "lift depth_prob"); _need_cuda_f32(img_feat, "lift img_feat")
+    if not (depth_prob.is_contiguous() and img_feat.is_contiguous()):
+        raise RuntimeError("lift_splat: inputs must be contiguous")
+    B, D, H, W = depth_prob.shape
+    Cc = img_feat.shape[-1]
+    if index.B != B or index.P != D * H * W:
+        raise RuntimeError("lift_splat: index was built for a different frustum")
+    out = torch.empty((B, index.nx, index.ny, index.nz, Cc), dtype=torch.float32, device=depth_prob.device)
+    rc = lib.ss_lift_splat_fwd(depth_prob.data_ptr(), img_feat.data_ptr(), index.order.data_ptr(),
+                               index.voxel_start.data_ptr(), out.data_ptr(), B, D, H, W, Cc, index.nx, index.ny,
+                               index.nz, _stream())
+    cabi.check(rc, "ss_lift_splat_fwd")
+    return out
+
+
+def bev_pool(feats: torch.Tensor, coords: torch.Tensor, B, D, H, W) -> torch.Tensor:
+    """Drop-in for ``mmdet3d.ops.bev_pool.bev_pool`` (same argument meaning; B/D/H/W may be 0-d
+    tensors as at the reference call site): returns [B,C,D,H,W]."""
+    lib = cabi.load()
+    B, D, H, W = int(B), int(D), int(H), int(W)
+    _need_cuda_f32(feats, "bev_pool feats")
+    if coords.dtype != torch.int64 or not coords.is_cuda:
+        raise RuntimeError("bev_pool: coords must be a CUDA int64 tensor [N,4]")
+    feats = feats.contiguous()
+    coords = coords.contiguous()
+    N, Cc = feats.shape[0], feats.shape[1] if feats.dim() == 2 else 0
+    if feats.dim() != 2 or coords.shape != (N, 4):
+        raise RuntimeError(f"bev_pool: expected feats [N,C] and coords [N,4], got {tuple(feats.shape)}, {tuple(coords.shape)}")
+    out = torch.empty((B, Cc, D, H, W), dtype=torch.float32, device=feats.device)
+    wsb = int(lib.ss_bev_pool_workspace_bytes(max(N, 1), B * D * H * W))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=feats.device)
+    rc = lib.ss_bev_pool_fwd(feats.data_ptr(), coords.data_ptr(), N, Cc, B, D, H, W, out.data_ptr(), ws.data_ptr(), wsb,
+                             _stream())
+    cabi.check(rc, "ss_bev_pool_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# resize + layout
+# ------------------------------------------------------------------------------------------
+def trilinear(x: torch.Tensor, size: Sequence[int], want_labels: bool = False):
+    """x [B,Di,Hi,Wi,C] channels-last -> ([B,Do,Ho,Wo,C], labels uint8 [B,Do,Ho,Wo] or None)."""
+    lib = cabi.load()
+    _need_cuda_f32(x, "trilinear")
+    if not x.is_contiguous():
+        raise RuntimeError("trilinear: input must be contiguous channels-last")
+    B, Di, Hi, Wi, Cc = x.shape
+    Do, Ho, Wo = (int(s) for s in size)
+    y = torch.empty((B, Do, Ho, Wo, Cc), dtype=torch.float32, device=x.device)
+    labels = torch.empty((B, Do, Ho, Wo), dtype=torch.uint8, device=x.device) if want_labels else None
+    rc = lib.ss_trilinear_fwd(x.data_ptr(), y.data_ptr(), _ptr(labels), B, Cc, Di, Hi, Wi, Do, Ho, Wo, _stream())
+    cabi.check(rc, "ss_trilinear_fwd")
+    return y, labels
+
+
+def to_channels_last(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,*spatial] contiguous (NCHW / NCDHW) -> [B,*spatial,C] contiguous."""
+    lib = cabi.load()
+    _need_cuda_f32(x, "to_channels_last")
+    x = x.contiguous()
+    B, Cc = x.shape[0], x.shape[1]
+    V = int(math.prod(x.shape[2:]))
+    y = torch.empty((B,) + tuple(x.shape[2:]) + (Cc,), dtype=torch.float32, device=x.device)
+    cabi.check(lib.ss_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), B, Cc, V, Cc, _stream()), "ss_nchw_to_nhwc")
+    return y
+
+
+def to_channels_first(x: torch.Tensor) -> torch.Tensor:
+    """[B,*spatial,C] contiguous -> [B,C,*spatial] contiguous."""
+    lib = cabi.load()
+    _need_cuda_f32(x, "to_channels_first")
+    x = x.contiguous()
+    B, Cc = x.shape[0], x.shape[-1]
+    V = int(math.prod(x.shape[1:-1]))
+    y = torch.empty((B, Cc) + tuple(x.shape[1:-1]), dtype=torch.float32, device=x.device)
+    cabi.check(lib.ss_nhwc_to_nchw(x.data_ptr(), y.data_ptr(), B, Cc, V, Cc, _stream()), "ss_nhwc_to_nchw")
+    return y

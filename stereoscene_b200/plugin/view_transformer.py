@@ -1,0 +1,454 @@
+"""``ViewTransformerLiftSplatShootVoxel`` -- B200-native replacement, same registry name, ctor
+kwargs, ``forward`` contract and state_dict keys as the reference module
+(projects/mmdet3d_plugin/occupancy/image2bev/ViewTransformerLSSVoxel.py:273-526 and its bases in
+ViewTransformerLSSBEVDepth.py:74-156, 567-659).
+
+forward(input: list) -> (bev_feat [B,C,X,Y,Z], depth_prob [B*N,D,fH,fW]):
+  input[0:8]  = left  (x[B,1,Cin,fH,fW], rots, trans, intrins, post_rots, post_trans, bda, mlp_input)
+  input[8:16] = right (same layout), input[16] = calib [B,1] (focal * baseline); trailing items ignored.
+
+Stages and the kernels that run them (all through the C ABI, stereoscene_b200.ops):
+  (i)   stereo: reduce conv + pending GN/ReLU/SE gate + 1x1 conv -> ss_gwc_warp_fwd ->
+        5 full-res convs + 3 hourglasses (ss_conv3d_fwd with pending affines, ss_affine_join_fwd)
+        -> ss_softmax_d_fwd
+  (N1)  depth_net: adjacent component ("next" row): PyTorch/cuDNN modules for now
+  (iii) MIE: 2 x ss_bri_attn_fwd -> redir1 -> hourglass -> CA3D (gate folded into a pending affine,
+        ss_ca3d_gate) -> redir2 -> ss_softmax_d_fwd
+  (ii)  lift (x) splat: ss_splat_build_index (calibration-only, cached) + ss_lift_splat_fwd
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..ops import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, Vol
+from ..registry import NECKS
+from .layers import HourglassParams, MlpParams, SEParams, conv_gn, conv_gn3d, hourglass
+
+
+# ------------------------------------------------------------------------------------------
+# parameter containers of the stereo branch and the MIE block
+# ------------------------------------------------------------------------------------------
+class StereoFeatureParams(nn.Module):
+    """keys: reduce_conv.{0,1}, depth_mlp, depth_se, depth_conv.0 (ViewTransformerLSSVoxel.py:32-58)."""
+
+    def __init__(self, cin, mid, cout, cam):
+        super().__init__()
+        self.reduce_conv = nn.Sequential(nn.Conv2d(cin, mid, 3, 1, 1), nn.GroupNorm(2, mid), nn.ReLU())
+        self.bn = nn.Identity()
+        self.depth_mlp = MlpParams(cam, mid, mid)
+        self.depth_se = SEParams(mid)
+        self.depth_conv = nn.Sequential(nn.Conv2d(mid, cout, 1, 1, 0))
+
+
+class StereoVolumeParams(nn.Module):
+    """``GwcNet_volume_encoder`` tree (ViewTransformerLSSVoxel.py:158-203)."""
+
+    def __init__(self, maxdisp, out_c=32, cin=640):
+        super().__init__()
+        self.maxdisp = maxdisp
+        self.num_groups = 32
+        self.feature_withcam = StereoFeatureParams(cin, 128, 64, 30)
+        relu = lambda: nn.ReLU(inplace=True)     # noqa: E731  (index placeholders: keys 0 / 2)
+        self.dres0 = nn.Sequential(conv_gn3d(32, 32, 3, 1, 1), relu(), conv_gn3d(32, 32, 3, 1, 1), relu())
+        self.dres1 = nn.Sequential(conv_gn3d(32, 32, 3, 1, 1), relu(), conv_gn3d(32, 32, 3, 1, 1))
+        self.dres2 = HourglassParams(32)
+        self.dres3 = HourglassParams(32)
+        self.dres4 = HourglassParams(32)
+        self.classif3_1 = nn.Sequential(conv_gn3d(32, out_c, 3, 1, 1), relu())
+        self.classif3_2 = nn.Sequential(nn.Conv3d(out_c, 1, 3, padding=1, stride=1, bias=False))
+        # the reference re-initialises every Conv2d/Conv3d of this sub-net (VT:189-203)
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Conv3d)):
+                n = math.prod(m.kernel_size) * m.out_channels
+                nn.init.normal_(m.weight, 0.0, math.sqrt(2.0 / n))
+            elif isinstance(m, nn.Linear):
+                nn.init.zeros_(m.bias)
+
+
+class AttentionParams(nn.Module):
+    """keys: query_conv, key_conv, value_conv (1x1x1, one channel), gamma (attention.py:45-56)."""
+
+    def __init__(self, in_dim=1):
+        super().__init__()
+        if in_dim != 1:
+            raise NotImplementedError("BRI attention is defined on single-channel depth volumes (in_dim=1)")
+        self.query_conv = nn.Conv3d(in_dim, in_dim, 1)
+        self.key_conv = nn.Conv3d(in_dim, in_dim, 1)
+        self.value_conv = nn.Conv3d(in_dim, in_dim, 1)
+        self.gamma = nn.Parameter(torch.zeros(1))
+
+    def packed(self) -> torch.Tensor:
+        """device float[7] = wq,bq,wk,bk,wv,bv,gamma for ss_bri_attn_fwd."""
+        return torch.cat([self.query_conv.weight.view(1), self.query_conv.bias.view(1),
+                          self.key_conv.weight.view(1), self.key_conv.bias.view(1),
+                          self.value_conv.weight.view(1), self.value_conv.bias.view(1),
+                          self.gamma.view(1)]).detach().float().contiguous()
+
+
+class CA3DParams(nn.Module):
+    """keys: conv1.{0,2}, conv2.{0,2}, conv.{0,2} (attention.py:90-112)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Sequential(nn.Conv3d(c, c, 3, 1, 1), nn.GELU(), nn.GroupNorm(1, c))
+        self.conv2 = nn.Sequential(nn.Conv3d(c, c // 8, 1), nn.GELU(), nn.Conv3d(c // 8, c, 1), nn.GELU())
+        self.conv = nn.Sequential(nn.Conv3d(c, c, 3, 1, 1), nn.GELU(), nn.GroupNorm(1, c))
+
+
+class ResidualParams(nn.Module):
+    """keys: alpha, fn.* (ViewTransformerLSSVoxel.py:227-234)."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+        self.alpha = nn.Parameter(torch.zeros(1))
+
+
+class VolumeInteractionParams(nn.Module):
+    """MIE block tree (ViewTransformerLSSVoxel.py:236-246)."""
+
+    def __init__(self):
+        super().__init__()
+        self.redir1 = nn.Conv3d(2, 32, 3, 1, 1)
+        self.dres1 = HourglassParams(32)
+        self.redir2 = nn.Conv3d(32, 1, 3, 1, 1)
+        self.lss2stereo = AttentionParams(1)
+        self.stereo2lss = AttentionParams(1)
+        self.CA3D = ResidualParams(CA3DParams(32))
+
+
+# ------------------------------------------------------------------------------------------
+# DepthNet (adjacent component, row N1 of SURVEY.md section 8f): PyTorch modules on cuDNN for now
+# ------------------------------------------------------------------------------------------
+class BasicBlock2d(nn.Module):
+    """mmdet 2.14 BasicBlock (conv3x3-BN-ReLU-conv3x3-BN + identity, ReLU)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(c)
+        self.conv2 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(c)
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        return F.relu(self.bn2(self.conv2(y)) + x)
+
+
+class _ASPPBranch(nn.Module):
+    def __init__(self, cin, cout, k, dilation):
+        super().__init__()
+        self.atrous_conv = nn.Conv2d(cin, cout, k, padding=0 if k == 1 else dilation, dilation=dilation, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+
+    def forward(self, x):
+        return F.relu(self.bn(self.atrous_conv(x)))
+
+
+class ASPP(nn.Module):
+    """ViewTransformerLSSBEVDepth.py:343-414."""
+
+    def __init__(self, cin, mid):
+        super().__init__()
+        self.aspp1 = _ASPPBranch(cin, mid, 1, 1)
+        self.aspp2 = _ASPPBranch(cin, mid, 3, 6)
+        self.aspp3 = _ASPPBranch(cin, mid, 3, 12)
+        self.aspp4 = _ASPPBranch(cin, mid, 3, 18)
+        self.global_avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)), nn.Conv2d(cin, mid, 1, bias=False),
+                                             nn.GroupNorm(2, mid), nn.ReLU())
+        self.conv1 = nn.Conv2d(mid * 5, mid, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(mid)
+        self.dropout = nn.Dropout(0.5)
+
+    def forward(self, x):
+        g = self.global_avg_pool(x).expand(-1, -1, x.shape[2], x.shape[3])
+        y = torch.cat((self.aspp1(x), self.aspp2(x), self.aspp3(x), self.aspp4(x), g), dim=1)
+        return self.dropout(F.relu(self.bn1(self.conv1(y))))
+
+
+class DCN(nn.Module):
+    """mmcv DeformConv2dPack semantics (no bias; offsets from a zero-initialised 3x3 conv),
+    ViewTransformerLSSBEVDepth.py:490-498."""
+
+    def __init__(self, cin, cout, k=3, padding=1, groups=4):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin // groups, k, k))
+        nn.init.kaiming_uniform_(self.weight, nonlinearity="relu")
+        self.conv_offset = nn.Conv2d(cin, 2 * k * k, k, 1, padding, bias=True)
+        nn.init.zeros_(self.conv_offset.weight)
+        nn.init.zeros_(self.conv_offset.bias)
+        self.padding = padding
+
+    def forward(self, x):
+        from torchvision.ops import deform_conv2d
+        return deform_conv2d(x, self.conv_offset(x), self.weight, None, 1, self.padding, 1)
+
+
+class DepthNet(nn.Module):
+    """ViewTransformerLSSBEVDepth.py:457-517.  Output channels: [0:D] depth logits, [D:D+ctx]
+    context features."""
+
+    def __init__(self, cin, mid, ctx, depth, cam_channels=27):
+        super().__init__()
+        self.reduce_conv = nn.Sequential(nn.Conv2d(cin, mid, 3, 1, 1), nn.GroupNorm(2, mid), nn.ReLU(inplace=True))
+        self.context_conv = nn.Conv2d(mid, ctx, 1)
+        self.bn = nn.GroupNorm(2, cam_channels)
+        self.depth_mlp = MlpParams(cam_channels, mid, mid)
+        self.depth_se = SEParams(mid)
+        self.context_mlp = MlpParams(cam_channels, mid, mid)
+        self.context_se = SEParams(mid)
+        self.depth_conv = nn.Sequential(BasicBlock2d(mid), BasicBlock2d(mid), BasicBlock2d(mid), ASPP(mid, mid),
+                                        DCN(mid, mid, 3, 1, 4), nn.Conv2d(mid, depth, 1))
+
+    def forward(self, x, mlp_input):
+        m = self.bn(mlp_input.reshape(-1, mlp_input.shape[-1]))
+        x = self.reduce_conv(x)
+        context = self.context_conv(self.context_se(x, self.context_mlp(m)[..., None, None]))
+        depth = self.depth_conv(self.depth_se(x, self.depth_mlp(m)[..., None, None]))
+        return torch.cat([depth, context], dim=1)
+
+
+# ------------------------------------------------------------------------------------------
+# the view transformer
+# ------------------------------------------------------------------------------------------
+def gen_dx_bx(xbound, ybound, zbound):
+    """ViewTransformerLSSBEVDepth.py:27-31 (fp32 rounding of the stored buffers is part of the
+    voxel-index contract)."""
+    rows = [xbound, ybound, zbound]
+    dx = torch.Tensor([r[2] for r in rows])
+    bx = torch.Tensor([r[0] + r[2] / 2.0 for r in rows])
+    nx = torch.Tensor([(r[1] - r[0]) / r[2] for r in rows])
+    return dx, bx, nx
+
+
+@NECKS.register_module()
+class ViewTransformerLiftSplatShootVoxel(nn.Module):
+    def __init__(self, loss_depth_weight, semkitti=False, imgseg=False, imgseg_class=20, lift_with_imgseg=False,
+                 point_cloud_range=None, loss_seg_weight=1.0, loss_depth_type="bce", point_xyz_channel=0,
+                 point_xyz_mode="cat", cam_channels=27, loss_depth_reg_weight=0.0, use_voxel_net=False,
+                 grid_config=None, data_config=None, numC_input=512, numC_Trans=64, downsample=16,
+                 accelerate=False, use_bev_pool=True, vp_megvii=False, vp_stero=False, init_cfg=None, **kwargs):
+        super().__init__()
+        if imgseg or lift_with_imgseg:
+            raise NotImplementedError("imgseg auxiliary head is not part of the stereoscene.py path")
+        if point_xyz_channel > 0 or point_xyz_mode == "add":
+            raise NotImplementedError("point_xyz encoder is dead code for stereoscene.py (point_xyz_channel=0)")
+        if use_voxel_net or vp_megvii or accelerate:
+            raise NotImplementedError("use_voxel_net / vp_megvii / accelerate are not used by stereoscene.py")
+        if grid_config is None:
+            grid_config = {"xbound": [-51.2, 51.2, 0.8], "ybound": [-51.2, 51.2, 0.8], "zbound": [-10.0, 10.0, 20.0],
+                           "dbound": [1.0, 60.0, 1.0]}
+        self.grid_config = grid_config
+        dx, bx, nx = gen_dx_bx(grid_config["xbound"], grid_config["ybound"], grid_config["zbound"])
+        self.dx = nn.Parameter(dx, requires_grad=False)
+        self.bx = nn.Parameter(bx, requires_grad=False)
+        self.nx = nn.Parameter(nx, requires_grad=False)
+        self.data_config = data_config if data_config is not None else {"input_size": (256, 704)}
+        self.downsample = downsample
+        self.frustum = self.create_frustum()
+        self.D = self.frustum.shape[0]
+        self.numC_input, self.numC_Trans = numC_input, numC_Trans
+        self.cam_channels = cam_channels
+        self.loss_depth_weight = loss_depth_weight
+        self.loss_depth_reg_weight = loss_depth_reg_weight
+        self.loss_depth_type = loss_depth_type
+        self.cam_depth_range = grid_config["dbound"]
+        self.semkitti, self.imgseg = semkitti, imgseg
+        self.point_xyz_channel, self.point_xyz_mode = point_xyz_channel, point_xyz_mode
+        self.depth_net = DepthNet(numC_input, numC_input, numC_Trans, self.D, cam_channels=cam_channels)
+        self.stereo_volume_net = StereoVolumeParams(maxdisp=self.D, out_c=32, cin=numC_input)
+        self.volume_interaction = VolumeInteractionParams()
+        self.forward_dic = {}
+        self.cache_splat_index = True
+        self._index_cache = None
+        self.stage_outputs = None          # set to a dict to capture per-stage tensors (tests)
+
+    # ---- geometry (ViewTransformerLSSBEVDepth.py:107-156, 604-659) --------------------------
+    def get_depth_dist(self, x):
+        return ops.softmax_d(x) if x.is_cuda else x.softmax(dim=1)
+
+    def create_frustum(self):
+        H, W = self.data_config["input_size"]
+        fH, fW = H // self.downsample, W // self.downsample
+        ds = torch.arange(*self.grid_config["dbound"], dtype=torch.float).view(-1, 1, 1).expand(-1, fH, fW)
+        D = ds.shape[0]
+        xs = torch.linspace(0, W - 1, fW, dtype=torch.float).view(1, 1, fW).expand(D, fH, fW)
+        ys = torch.linspace(0, H - 1, fH, dtype=torch.float).view(1, fH, 1).expand(D, fH, fW)
+        return nn.Parameter(torch.stack((xs, ys, ds), -1), requires_grad=False)
+
+    def get_geometry(self, rots, trans, intrins, post_rots, post_trans, bda):
+        """Frustum points in the ego frame, [B,N,D,fH,fW,3].  Small (3 floats per frustum point)
+        and calibration-only: kept in PyTorch so it is the reference's arithmetic."""
+        B, N, _ = trans.shape
+        pts = self.frustum - post_trans.view(B, N, 1, 1, 1, 3)
+        pts = torch.inverse(post_rots).view(B, N, 1, 1, 1, 3, 3).matmul(pts.unsqueeze(-1))
+        pts = torch.cat((pts[..., :2, :] * pts[..., 2:3, :], pts[..., 2:3, :]), 5)
+        if intrins.shape[3] == 4:          # KITTI: 4x4 with the projection shift in column 3
+            pts = pts - intrins[:, :, :3, 3].view(B, N, 1, 1, 1, 3, 1)
+            intrins = intrins[:, :, :3, :3]
+        comb = rots.matmul(torch.inverse(intrins))
+        pts = comb.view(B, N, 1, 1, 1, 3, 3).matmul(pts).squeeze(-1)
+        pts = pts + trans.view(B, N, 1, 1, 1, 3)
+        if bda.shape[-1] == 4:
+            pts = torch.cat((pts, torch.ones_like(pts[..., :1])), dim=-1)
+            pts = bda.view(B, 1, 1, 1, 1, 4, 4).matmul(pts.unsqueeze(-1)).squeeze(-1)[..., :3]
+        else:
+            pts = bda.view(B, 1, 1, 1, 1, 3, 3).matmul(pts.unsqueeze(-1)).squeeze(-1)
+        return pts
+
+    def get_mlp_input(self, rot, tran, intrin, post_rot, post_tran, bda=None):
+        B, N = rot.shape[:2]
+        if bda is None:
+            bda = torch.eye(3).to(rot).view(1, 3, 3).repeat(B, 1, 1)
+        bda = bda.view(B, 1, *bda.shape[-2:]).repeat(1, N, 1, 1)
+        if intrin.shape[-1] == 4:
+            items = [intrin[:, :, 0, 0], intrin[:, :, 1, 1], intrin[:, :, 0, 2], intrin[:, :, 1, 2],
+                     intrin[:, :, 0, 3], intrin[:, :, 1, 3], intrin[:, :, 2, 3]]
+        else:
+            items = [intrin[:, :, 0, 0], intrin[:, :, 1, 1], intrin[:, :, 0, 2], intrin[:, :, 1, 2]]
+        items += [post_rot[:, :, 0, 0], post_rot[:, :, 0, 1], post_tran[:, :, 0], post_rot[:, :, 1, 0],
+                  post_rot[:, :, 1, 1], post_tran[:, :, 1], bda[:, :, 0, 0], bda[:, :, 0, 1], bda[:, :, 1, 0],
+                  bda[:, :, 1, 1], bda[:, :, 2, 2]]
+        mlp_input = torch.stack(items, dim=-1)
+        if bda.shape[-1] == 4:
+            mlp_input = torch.cat((mlp_input, bda[:, :, :3, -1]), dim=2)
+        sensor2ego = torch.cat([rot, tran.reshape(B, N, 3, 1)], dim=-1).reshape(B, N, -1)
+        return torch.cat([mlp_input, sensor2ego], dim=-1)
+
+    # ---- depth supervision (training helper; ViewTransformerLSSVoxel.py:349-416) -------------
+    def get_downsampled_gt_depth(self, gt_depths):
+        B, N, H, W = gt_depths.shape
+        ds = self.downsample
+        g = gt_depths.view(B * N, H // ds, ds, W // ds, ds, 1).permute(0, 1, 3, 5, 2, 4).contiguous().view(-1, ds * ds)
+        g = torch.where(g == 0.0, 1e5 * torch.ones_like(g), g).min(dim=-1).values.view(B * N, H // ds, W // ds)
+        lo, _, step = self.grid_config["dbound"]
+        g = (g - (lo - step / 2)) / step
+        vals = g.clone()
+        g = torch.where((g < self.D + 1) & (g >= 0.0), g, torch.zeros_like(g))
+        return vals, F.one_hot(g.long(), num_classes=self.D + 1).view(-1, self.D + 1)[:, 1:].float()
+
+    def get_depth_loss(self, depth_labels, depth_preds):
+        if self.loss_depth_type != "bce":
+            raise NotImplementedError("only the 'bce' depth loss is used by stereoscene.py")
+        _, labels = self.get_downsampled_gt_depth(depth_labels)
+        preds = depth_preds.permute(0, 2, 3, 1).contiguous().view(-1, self.D)
+        fg = labels.max(dim=1).values > 0.0
+        loss = F.binary_cross_entropy(preds[fg].float(), labels[fg], reduction="none").sum() / max(1.0, float(fg.sum()))
+        return self.loss_depth_weight * loss
+
+    # ---- (i) stereo branch ------------------------------------------------------------------
+    def stereo_features(self, feat_left, feat_right, mlp_left, mlp_right) -> torch.Tensor:
+        """stereofeature_net on the batched pair -> channels-last [2B,1,fH,fW,64]."""
+        net = self.stereo_volume_net.feature_withcam
+        x = ops.to_channels_last(torch.cat([feat_left, feat_right], 0)).unsqueeze(1)     # [2B,1,H,W,Cin]
+        m = torch.cat([mlp_left, mlp_right], 0).reshape(-1, mlp_left.shape[-1])
+        v = conv_gn(Vol(x), net.reduce_conv, SS_ACT_RELU)
+        # SE gate > 0, so relu(gn(y)) * g == relu(gn(y) * g): fold it into the pending affine
+        gate = net.depth_se.gate(net.depth_mlp(m))
+        v = Vol(v.data, (v.scale * gate).contiguous(), (v.shift * gate).contiguous(), SS_ACT_RELU)
+        fea, _ = ops.conv(v, net.depth_conv[0])
+        return fea
+
+    def cost_aggregation(self, volume: torch.Tensor) -> torch.Tensor:
+        """ViewTransformerLSSVoxel.py:214-222 on a channels-last cost volume -> stereo depth
+        distribution [B,D,fH,fW]."""
+        net = self.stereo_volume_net
+        c = conv_gn(Vol(volume), net.dres0[0], SS_ACT_RELU)
+        c = conv_gn(c, net.dres0[2], SS_ACT_RELU)
+        r = conv_gn(c, net.dres1[0], SS_ACT_RELU)
+        r = conv_gn(r, net.dres1[2], SS_ACT_NONE)
+        cost0 = ops.join(r, c)
+        o = hourglass(net.dres2, Vol(cost0))
+        o = hourglass(net.dres3, Vol(o))
+        o = hourglass(net.dres4, Vol(o))
+        c31 = conv_gn(Vol(o), net.classif3_1[0], SS_ACT_RELU)
+        c3, _ = ops.conv(c31, net.classif3_2[0])                 # [B,D,H,W,1]
+        return ops.softmax_d(c3.view(c3.shape[:4]))
+
+    def stereo_volume(self, feat_left, feat_right, mlp_left, mlp_right, calib) -> torch.Tensor:
+        fea = self.stereo_features(feat_left, feat_right, mlp_left, mlp_right)
+        if self.stage_outputs is not None:
+            self.stage_outputs["stereo_fea"] = fea
+        vol = ops.gwc_warp(fea, calib, self.stereo_volume_net.maxdisp, self.stereo_volume_net.num_groups)
+        if self.stage_outputs is not None:
+            self.stage_outputs["gwc_warp"] = vol
+        return self.cost_aggregation(vol)
+
+    # ---- (iii) MIE ---------------------------------------------------------------------------
+    def mutual_interactive_ensemble(self, stereo: torch.Tensor, lss: torch.Tensor) -> torch.Tensor:
+        """volume_interaction.forward (ViewTransformerLSSVoxel.py:248-268); stereo, lss: [B,D,H,W]."""
+        vi = self.volume_interaction
+        B, D, H, W = stereo.shape
+        both = torch.empty((B, D, H, W, 2), dtype=torch.float32, device=stereo.device)
+        ops.bri_attention(stereo, lss, vi.lss2stereo.packed(), both[..., 0], 2)      # q = stereo, kv = lss
+        ops.bri_attention(lss, stereo, vi.stereo2lss.packed(), both[..., 1], 2)      # q = lss, kv = stereo
+        x, _ = ops.conv(Vol(both), vi.redir1, out_act=SS_ACT_RELU)
+        x = hourglass(vi.dres1, Vol(x))
+        fn = vi.CA3D.fn
+        d, st = ops.conv(Vol(x), fn.conv1[0], out_act=SS_ACT_GELU, want_stats=True)
+        dv = ops.ca3d_gate(ops.gn_pending(d, st, fn.conv1[2]), st, fn.conv2[0], fn.conv2[2])
+        o, st2 = ops.conv(dv, fn.conv[0], out_act=SS_ACT_GELU, want_stats=True)
+        x2 = ops.join(ops.gn_pending(o, st2, fn.conv[2]), Vol(x), alpha=vi.CA3D.alpha)
+        z, _ = ops.conv(Vol(x2), vi.redir2, out_act=SS_ACT_RELU)
+        if self.stage_outputs is not None:
+            self.stage_outputs.update(bri=both, mie_hourglass=x, mie_ca3d=x2)
+        return ops.softmax_d(z.view(B, D, H, W))
+
+    # ---- (ii) lift + splat -------------------------------------------------------------------
+    def splat_index(self, rots, trans, intrins, post_rots, post_trans, bda) -> ops.SplatIndex:
+        cal = (rots, trans, intrins, post_rots, post_trans, bda)
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in cal) + (self.frustum.data_ptr(),)
+        if self.cache_splat_index and self._index_cache is not None and self._index_cache[0] == key:
+            return self._index_cache[1]
+        geom = self.get_geometry(*cal)
+        if self.stage_outputs is not None:
+            self.stage_outputs["geom"] = geom
+        nx = [int(round(float(v))) for v in self.nx.detach().cpu()]
+        idx = ops.splat_build_index(geom, self.dx.detach().cpu().tolist(), self.bx.detach().cpu().tolist(), nx,
+                                    want_coords=self.stage_outputs is not None)
+        if self.cache_splat_index:
+            self._index_cache = (key, idx)
+        return idx
+
+    def voxel_pooling(self, geom_feats, x):
+        """Reference-signature entry (ViewTransformerLSSVoxel.py:432-476): geom [B,N,D,H,W,3], lifted
+        volume x [B,N,D,H,W,C] -> [B,C,X,Y,Z] through the bev_pool-compatible operator."""
+        B, N, D, H, W, Cc = x.shape
+        nx = [int(round(float(v))) for v in self.nx.detach().cpu()]
+        idx = ops.splat_build_index(geom_feats.reshape(B, -1, 3), self.dx.detach().cpu().tolist(),
+                                    self.bx.detach().cpu().tolist(), nx, want_coords=True)
+        c = idx.coords.long()
+        kept = c[:, 3] > 0
+        batch_ix = torch.arange(B, device=x.device).repeat_interleave(N * D * H * W)
+        coords = torch.stack((c[:, 0], c[:, 1], c[:, 2], batch_ix), 1)[kept]
+        out = ops.bev_pool(x.reshape(-1, Cc)[kept], coords, B, nx[2], nx[0], nx[1])
+        return out.permute(0, 1, 3, 4, 2)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, input):
+        x, rots, trans, intrins, post_rots, post_trans, bda, mlp_input = input[:8]
+        feat_left, mlp_left = input[0].squeeze(1), input[7]
+        feat_right, mlp_right = input[8].squeeze(1), input[15]
+        calib = input[16]
+        ops.arena(x.device).reset()
+
+        stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib)
+
+        B, N, Cin, H, W = x.shape
+        y = self.depth_net(x.reshape(B * N, Cin, H, W), mlp_input)              # adjacent (N1)
+        lss = ops.softmax_d(y[:, :self.D])
+        img_feat = ops.to_channels_last(y[:, self.D:self.D + self.numC_Trans])   # [B*N,H,W,C]
+
+        depth_prob = self.mutual_interactive_ensemble(stereo, lss)
+
+        index = self.splat_index(rots, trans, intrins, post_rots, post_trans, bda)
+        bev = ops.lift_splat(depth_prob, img_feat, index)                         # [B,X,Y,Z,C]
+        if self.stage_outputs is not None:
+            self.stage_outputs.update(stereo_prob=stereo, depth_net=y, lss_prob=lss, depth_prob=depth_prob,
+                                      splat_index=index)
+        return bev.permute(0, 4, 1, 2, 3), depth_prob

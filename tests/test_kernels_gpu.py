@@ -1,0 +1,296 @@
+"""Per-kernel parity: every C-ABI entry point against the CPU oracle on the same seeded inputs.
+
+Tolerances (north star: <= 1e-3 relative fp32, bit-exact for the voxel-index scatter):
+  * SS_MATH_3XTF32 (split TF32, ~fp32):  rel-to-max error <= 2e-5
+  * SS_MATH_TF32   (tensor-core TF32):    rel-to-max error <= 1e-3  (per layer, same inputs)
+  * integer / index paths: exact equality
+"""
+import math
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import restatement as O
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"precise": 2e-5, "tf32": 1e-3}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from stereoscene_b200 import cabi, ops as _ops
+    cabi.load()
+    return _ops
+
+
+def _mode(ops, name):
+    return ops.SS_MATH_3XTF32 if name == "precise" else ops.SS_MATH_TF32
+
+
+def _cl(x):  # NCDHW cpu -> channels-last cuda [B,D,H,W,C]
+    return x.permute(0, 2, 3, 4, 1).contiguous().cuda()
+
+
+def _ncdhw(y):  # channels-last cuda -> NCDHW cpu
+    return y.permute(0, 4, 1, 2, 3).cpu()
+
+
+CONV_CASES = [
+    # name, module factory, input shape [B,C,D,H,W]
+    ("k3s1_32", lambda: nn.Conv3d(32, 32, 3, 1, 1, bias=False), (2, 32, 6, 9, 11)),
+    ("k3s2_32_64", lambda: nn.Conv3d(32, 64, 3, 2, 1, bias=False), (1, 32, 8, 10, 12)),
+    ("k3s1_64_128", lambda: nn.Conv3d(64, 128, 3, 1, 1, bias=False), (1, 64, 4, 6, 10)),
+    ("k3s1_384_192", lambda: nn.Conv3d(384, 192, 3, 1, 1, bias=False), (1, 384, 4, 8, 6)),
+    ("k1_192_20", lambda: nn.Conv3d(192, 20, 1, bias=False), (2, 192, 3, 5, 7)),
+    ("k1s2_128_256", lambda: nn.Conv3d(128, 256, 1, 2, bias=False), (1, 128, 4, 6, 8)),
+    ("k3_32_1", lambda: nn.Conv3d(32, 1, 3, 1, 1, bias=True), (2, 32, 5, 6, 9)),
+    ("k3_2_32_bias", lambda: nn.Conv3d(2, 32, 3, 1, 1, bias=True), (2, 2, 6, 7, 9)),
+    ("tk3s2_128_64", lambda: nn.ConvTranspose3d(128, 64, 3, padding=1, output_padding=1, stride=2, bias=False), (1, 128, 3, 4, 5)),
+    ("tk3s2_64_32", lambda: nn.ConvTranspose3d(64, 32, 3, padding=1, output_padding=1, stride=2, bias=False), (2, 64, 2, 3, 4)),
+    ("tk2s2_256_128", lambda: nn.ConvTranspose3d(256, 128, 2, 2, bias=False), (1, 256, 3, 4, 2)),
+    ("tk4s4_512_128", lambda: nn.ConvTranspose3d(512, 128, 4, 4, bias=False), (1, 512, 2, 3, 1)),
+    ("tk1s1_128_128", lambda: nn.ConvTranspose3d(128, 128, 1, 1, bias=False), (1, 128, 3, 4, 2)),
+]
+
+
+@pytest.mark.parametrize("mode", ["precise", "tf32"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv3d_family(ops, case, mode):
+    name, make, shape = case
+    torch.manual_seed(zlib.crc32(name.encode()) % 1000)
+    m = make()
+    x = torch.randn(shape)
+    want = m(x).detach()
+    mg = make().cuda()
+    mg.load_state_dict(m.state_dict())
+    y, st = ops.conv(ops.Vol(_cl(x)), mg, want_stats=True, math_mode=_mode(ops, mode))
+    torch.cuda.synchronize()
+    assert rel_err(_ncdhw(y), want) < TOL[mode]
+    # epilogue sums feed GroupNorm: compare with the oracle's sums of the same tensor
+    s = want.double().sum(dim=(2, 3, 4))
+    q = (want.double() ** 2).sum(dim=(2, 3, 4))
+    assert rel_err(st[..., 0], s) < 10 * TOL[mode]
+    assert rel_err(st[..., 1], q) < 5 * TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["precise", "tf32"])
+def test_conv2d_dilated_bias_gelu(ops, mode):
+    torch.manual_seed(3)
+    for m in (nn.Conv2d(64, 128, 3, 1, 1), nn.Conv2d(64, 32, 3, padding=6, dilation=6, bias=False), nn.Conv2d(128, 64, 1)):
+        x = torch.randn(2, m.in_channels, 12, 20)
+        want = F.gelu(m(x)).detach()
+        mg = type(m)(m.in_channels, m.out_channels, m.kernel_size, m.stride, m.padding, m.dilation, bias=m.bias is not None).cuda()
+        mg.load_state_dict(m.state_dict())
+        xcl = x.permute(0, 2, 3, 1).contiguous().unsqueeze(1).cuda()          # [B,1,H,W,C]
+        y, _ = ops.conv(ops.Vol(xcl), mg, out_act=ops.SS_ACT_GELU, math_mode=_mode(ops, mode))
+        got = y.squeeze(1).permute(0, 3, 1, 2).cpu()
+        assert rel_err(got, want) < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["precise", "tf32"])
+def test_conv_pending_affine_relu_and_gn_chain(ops, mode):
+    """conv -> GroupNorm -> ReLU -> conv -> GroupNorm, with both norms applied as pending affines,
+    versus the plain PyTorch composition; also writes into a channel slice of a wider buffer."""
+    torch.manual_seed(5)
+    c1, g1 = nn.Conv3d(32, 64, 3, 1, 1, bias=False), nn.GroupNorm(2, 64)
+    c2, g2 = nn.Conv3d(64, 32, 3, 2, 1, bias=True), nn.GroupNorm(32, 32)
+    for g in (g1, g2):
+        nn.init.uniform_(g.weight, 0.5, 1.5); nn.init.normal_(g.bias, 0, 0.2)
+    x = torch.randn(2, 32, 6, 8, 10)
+    want1 = F.relu(g1(c1(x)))
+    want2 = g2(c2(want1)).detach()
+    mods = [m.cuda() for m in (nn.Conv3d(32, 64, 3, 1, 1, bias=False), nn.GroupNorm(2, 64), nn.Conv3d(64, 32, 3, 2, 1, bias=True), nn.GroupNorm(32, 32))]
+    for a, b in zip(mods, (c1, g1, c2, g2)):
+        a.load_state_dict(b.state_dict())
+    ops.arena(torch.device("cuda", 0)).reset()
+    y1, st1 = ops.conv(ops.Vol(_cl(x)), mods[0], want_stats=True, math_mode=_mode(ops, mode))
+    v1 = ops.gn_pending(y1, st1, mods[1], ops.SS_ACT_RELU)
+    wide = torch.full((2, 3, 4, 5, 48), 7.0, device="cuda")
+    y2, st2 = ops.conv(v1, mods[2], out=wide[..., 8:40], want_stats=True, math_mode=_mode(ops, mode))
+    v2 = ops.gn_pending(y2, st2, mods[3])
+    got = _ncdhw(v2.plain())
+    assert rel_err(got, want2) < 3 * TOL[mode]
+    assert rel_err(_ncdhw(v1.plain()), want1.detach()) < 3 * TOL[mode]
+    assert float(wide[..., :8].min()) == 7.0 and float(wide[..., 40:].max()) == 7.0      # neighbours untouched
+
+
+def test_bn_pending_join_and_alpha(ops):
+    torch.manual_seed(6)
+    bn = nn.BatchNorm3d(16).eval()
+    nn.init.uniform_(bn.weight, 0.5, 1.5); nn.init.normal_(bn.bias, 0, 0.2)
+    bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5)
+    x, r = torch.randn(2, 16, 3, 5, 7), torch.randn(2, 16, 3, 5, 7)
+    alpha = torch.tensor([0.37])
+    want = F.relu(alpha * bn(x) + F.relu(r)).detach()
+    got = ops.join(ops.bn_pending(_cl(x), bn.cuda()), ops.Vol(_cl(r), None, None, ops.SS_ACT_RELU),
+                   out_act=ops.SS_ACT_RELU, alpha=alpha.cuda())
+    assert rel_err(_ncdhw(got), want) < 1e-6
+    # scalar (C not a multiple of 4) path
+    x3, r3 = torch.randn(1, 3, 2, 3, 5), torch.randn(1, 3, 2, 3, 5)
+    got3 = ops.join(ops.Vol(_cl(x3)), ops.Vol(_cl(r3)))
+    assert rel_err(_ncdhw(got3), x3 + r3) < 1e-6
+
+
+def test_softmax_over_depth(ops):
+    torch.manual_seed(7)
+    x = torch.randn(2, 240, 6, 10) * 3
+    got = ops.softmax_d(x.cuda()[:, :112])             # channel slice of a wider NCHW tensor
+    assert rel_err(got, F.softmax(x[:, :112], dim=1)) < 1e-6
+    assert rel_err(got.sum(1), torch.ones(2, 6, 10)) < 1e-6
+
+
+def test_ca3d_block(ops):
+    """CA3D (attention.py:113-120) with the gate folded into the pending affine."""
+    from stereoscene_b200.plugin.view_transformer import CA3DParams
+    from stereoscene_b200 import synth
+    torch.manual_seed(8)
+    fn = CA3DParams(32)
+    synth.randomize_weights_(fn, 3)
+    sd = {"p." + k: v for k, v in fn.state_dict().items()}
+    x = torch.randn(2, 32, 6, 8, 10)
+    want = O.ca3d(sd, "p", x)
+    fn = fn.cuda()
+    ops.arena(torch.device("cuda", 0)).reset()
+    xv = ops.Vol(_cl(x))
+    d, st = ops.conv(xv, fn.conv1[0], out_act=ops.SS_ACT_GELU, want_stats=True, math_mode=ops.SS_MATH_3XTF32)
+    dv = ops.ca3d_gate(ops.gn_pending(d, st, fn.conv1[2]), st, fn.conv2[0], fn.conv2[2])
+    o, st2 = ops.conv(dv, fn.conv[0], out_act=ops.SS_ACT_GELU, want_stats=True, math_mode=ops.SS_MATH_3XTF32)
+    got = ops.gn_pending(o, st2, fn.conv[2]).plain()
+    assert rel_err(_ncdhw(got), want) < 5e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 8, 16, 48), (1, 64, 6, 40, 112), (1, 32, 4, 12, 20)])
+def test_gwc_warp(ops, shape):
+    """Fused correlation + warp vs build_gwc_volume + warp of the oracle; includes bins whose
+    disparity falls beyond the image / beyond maxdisp (zero) and per-sample calibration."""
+    B, C, H, W, D = shape
+    torch.manual_seed(9)
+    ref, tgt = torch.randn(B, C, H, W), torch.randn(B, C, H, W)
+    calib = torch.tensor([[380.3], [141.0]])[:B]
+    want = O.warp_disparity_to_depth(O.gwc_volume(ref, tgt, D, 32), calib)        # [B,32,D,H,W]
+    fea = torch.cat([ref, tgt], 0).permute(0, 2, 3, 1).contiguous().unsqueeze(1).cuda()
+    got = ops.gwc_warp(fea, calib.cuda(), D, 32)                                   # [B,D,H,W,32]
+    assert rel_err(got.permute(0, 4, 1, 2, 3), want) < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["precise", "tf32"])
+@pytest.mark.parametrize("dims", [(2, 48, 8, 16), (1, 112, 6, 23), (1, 20, 5, 13)])
+def test_bri_attention(ops, mode, dims):
+    B, D, H, W = dims
+    torch.manual_seed(10)
+    q = F.softmax(torch.randn(B, D, H, W) * 2, dim=1)
+    kv = F.softmax(torch.randn(B, D, H, W) * 2, dim=1)
+    sd = {"a.query_conv.weight": torch.tensor(6.5).view(1, 1, 1, 1, 1), "a.query_conv.bias": torch.tensor([0.1]),
+          "a.key_conv.weight": torch.tensor(5.5).view(1, 1, 1, 1, 1), "a.key_conv.bias": torch.tensor([-0.05]),
+          "a.value_conv.weight": torch.tensor(1.3).view(1, 1, 1, 1, 1), "a.value_conv.bias": torch.tensor([0.02]),
+          "a.gamma": torch.tensor([0.5])}
+    want = O.bri_attention(sd, "a", q.unsqueeze(1), kv.unsqueeze(1)).squeeze(1)
+    params = torch.tensor([6.5, 0.1, 5.5, -0.05, 1.3, 0.02, 0.5]).cuda()
+    both = torch.zeros(B, D, H, W, 2, device="cuda")
+    ops.bri_attention(q.cuda(), kv.cuda(), params, both[..., 1], 2, math_mode=_mode(ops, mode))
+    assert rel_err(both[..., 1], want) < (2e-5 if mode == "precise" else 1e-3)
+    assert float(both[..., 0].abs().max()) == 0.0
+
+
+def _frustum_case(B=2, input_size=(64, 128), dbound=(2.0, 26.0, 0.5), grid=((0.0, 51.2, 3.2), (-25.6, 25.6, 3.2), (-2.0, 4.4, 1.6))):
+    from stereoscene_b200 import synth
+    left, _, _ = synth.kitti_calibration(B, input_size)
+    fr = O.create_frustum(input_size, 8, list(dbound))
+    geom = O.get_geometry(fr, left["rots"], left["trans"], left["intrins"], left["post_rots"], left["post_trans"], left["bda"])
+    dx, bx, nx = O.gen_dx_bx(*[list(g) for g in grid])
+    return geom, dx, bx, nx
+
+
+def test_voxel_index_bit_exact(ops):
+    geom, dx, bx, nx = _frustum_case()
+    # add adversarial points: exactly on voxel faces, slightly negative, far outside, huge
+    extra = torch.tensor([[0.0, -25.6, -2.0], [-1e-3, 0.0, 0.0], [-3.19, 0.1, 0.1], [51.2, 25.6, 4.4],
+                          [3.2, -22.4, -0.4], [1e9, -1e9, 3.0], [51.199997, 25.599998, 4.3999996]])
+    g = geom.reshape(2, -1, 3)
+    g[0, :extra.shape[0]] = extra
+    want_idx, want_kept = O.voxel_indices(g, dx, bx, nx)
+    idx = ops.splat_build_index(g.cuda(), dx.tolist(), bx.tolist(), nx.tolist(), want_coords=True)
+    c = idx.coords.cpu()
+    assert torch.equal(c[:, 3].bool(), want_kept)
+    inside = want_kept
+    assert torch.equal(c[inside, :3].long(), want_idx[inside])
+    # CSR structure: counts per voxel equal the oracle's histogram; order is stable in point id
+    n = [int(v) for v in nx.tolist()]
+    P = g.shape[1]
+    b_ix = torch.arange(2).repeat_interleave(P)
+    rank = ((b_ix * n[0] + want_idx[:, 0]) * n[1] + want_idx[:, 1]) * n[2] + want_idx[:, 2]
+    hist = torch.bincount(rank[inside], minlength=2 * n[0] * n[1] * n[2])
+    start = idx.voxel_start.cpu().long()
+    assert torch.equal(start[1:] - start[:-1], hist)
+    order = idx.order.cpu().long()[: int(inside.sum())]
+    assert torch.equal(rank[order], torch.sort(rank[inside], stable=True)[0])
+    seg_sorted = torch.sort(rank[inside], stable=True)[1]
+    assert torch.equal(order, torch.nonzero(inside).flatten()[seg_sorted])
+
+
+def test_lift_splat_matches_oracle(ops):
+    geom, dx, bx, nx = _frustum_case()
+    B, _, D, H, W, _ = geom.shape
+    torch.manual_seed(11)
+    dp = F.softmax(torch.randn(B, D, H, W), dim=1)
+    feat = torch.randn(B, 128, H, W)
+    want = O.lift_splat(dp, feat, geom, dx, bx, nx)                                  # [B,C,X,Y,Z]
+    idx = ops.splat_build_index(geom.reshape(B, -1, 3).cuda(), dx.tolist(), bx.tolist(), nx.tolist())
+    got = ops.lift_splat(dp.cuda(), feat.permute(0, 2, 3, 1).contiguous().cuda(), idx)    # [B,X,Y,Z,C]
+    got = got.permute(0, 4, 1, 2, 3).cpu()
+    assert torch.equal(got != 0, want != 0)                    # occupancy mask: exact
+    assert rel_err(got, want) < 1e-6
+    # checksum of checksums: total mass per channel is conserved by the scatter
+    _, kept = O.voxel_indices(geom, dx, bx, nx)
+    lifted = (dp.unsqueeze(1) * feat.unsqueeze(2)).permute(0, 2, 3, 4, 1).reshape(-1, 128)[kept]
+    assert rel_err(got.double().sum(dim=(0, 2, 3, 4)), lifted.double().sum(0)) < 1e-5
+
+
+def test_bev_pool_dropin(ops):
+    """Same call as the reference's bev_pool(x, geom_feats, B, nz, nx, ny) incl. 0-d tensor sizes,
+    ragged occupancy, collisions and an empty point set."""
+    torch.manual_seed(12)
+    B, Dz, Hx, Wy, C, N = 2, 4, 16, 12, 24, 5000
+    coords = torch.stack([torch.randint(0, Hx, (N,)), torch.randint(0, Wy, (N,)), torch.randint(0, Dz, (N,)),
+                          torch.randint(0, B, (N,))], 1)
+    coords[:300] = coords[0]                                   # heavy collision in one voxel
+    feats = torch.randn(N, C)
+    want = O.bev_pool(feats, coords, B, Dz, Hx, Wy)
+    got = ops.bev_pool(feats.cuda(), coords.cuda(), torch.tensor(float(B)), torch.tensor(float(Dz)),
+                       torch.tensor(float(Hx)), torch.tensor(float(Wy)))
+    assert got.shape == want.shape and got.is_contiguous()
+    assert rel_err(got, want) < 1e-6
+    empty = ops.bev_pool(feats[:0].cuda(), coords[:0].cuda(), B, Dz, Hx, Wy)
+    assert float(empty.abs().sum()) == 0.0
+
+
+def test_trilinear_upsample_and_argmax(ops):
+    torch.manual_seed(13)
+    for shape, size in (((2, 20, 8, 8, 4), (16, 16, 8)), ((1, 20, 5, 6, 3), (10, 12, 6)), ((1, 7, 4, 4, 2), (9, 7, 5))):
+        x = torch.randn(shape)
+        want = F.interpolate(x, size=size, mode="trilinear", align_corners=False)
+        got, labels = ops.trilinear(_cl(x), size, want_labels=True)
+        assert rel_err(_ncdhw(got), want) < 1e-6
+        assert torch.equal(labels.cpu().long(), got.argmax(dim=-1).cpu())
+
+
+def test_layout_round_trip(ops):
+    x = torch.randn(2, 37, 5, 9).cuda()
+    y = ops.to_channels_last(x)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.to_channels_first(y), x)
+
+
+def test_errors_are_loud(ops):
+    with pytest.raises(RuntimeError):
+        ops.conv(ops.Vol(torch.randn(1, 2, 2, 2, 32)), nn.Conv3d(32, 32, 3, 1, 1))           # CPU tensor
+    with pytest.raises(RuntimeError):
+        ops.softmax_d(torch.randn(1, 4, 3, 3, dtype=torch.float64).cuda())                     # wrong dtype
+    with pytest.raises(RuntimeError):
+        ops.conv(ops.Vol(torch.randn(1, 2, 2, 2, 16).cuda()), nn.Conv3d(32, 32, 3, 1, 1).cuda())  # channel mismatch

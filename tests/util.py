@@ -1,0 +1,46 @@
+"""Shared helpers for the parity tests."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from stereoscene_b200 import presets, synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_err(a, b) -> float:
+    """max|a-b| / max|b| on float64 numpy views."""
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def golden_tiny():
+    with open(os.path.join(GOLDEN, "golden_tiny.json")) as f:
+        cfg = json.load(f)
+    return cfg, np.load(os.path.join(GOLDEN, "golden_tiny.npz"))
+
+
+def build_model(workload: str, seed: int, device="cpu"):
+    """Our detector for a workload with the seeded key-addressed weights."""
+    model, mc = presets.build(workload)
+    synth.randomize_weights_(model, seed)
+    return model.to(device).eval(), mc
+
+
+def tiny_inputs(cfg, device="cpu"):
+    B = cfg["batch"]
+    xl, xr = synth.stereo_features(B, tuple(cfg["input_size"]), cfg["downsample"], seed=cfg["seed"])
+    left, right, calib = synth.kitti_calibration(B, tuple(cfg["input_size"]))
+    calib = calib * torch.tensor(cfg.get("calib_scale", [1.0] * B)).view(B, 1)
+    mv = lambda d: {k: v.to(device) for k, v in d.items()}   # noqa: E731
+    return xl.to(device), xr.to(device), mv(left), mv(right), calib.to(device)
+
+
+def cpu_state_dict(model):
+    return {k: v.detach().cpu() for k, v in model.state_dict().items()}
