@@ -84,6 +84,16 @@ typedef struct ss_conv3d_desc {
 int ss_conv3d_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_scale, const float* in_shift,
                   const float* w_packed, const float* bias, float* y, double* stats, void* stream);
 
+/* Same contract on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM,
+ * mbarrier-pipelined shared-memory staging with the pending affine applied by the producer warps).
+ * Requirements: Cin % 32 == 0, in_ldc % 4 == 0, x 16-byte aligned, desc->math == SS_MATH_TF32.
+ * w_kmajor: float[taps][cout_packed][Cin] (K-major: the 32-channel chunk of one output channel is one
+ * 128-byte shared-memory row), values pre-rounded to TF32 (round-to-nearest, ties away from zero):
+ *   Conv:          w_kmajor[t][co][ci] = tf32(weight[co][ci][kd][kh][kw])
+ *   ConvTranspose: w_kmajor[t][co][ci] = tf32(weight[ci][co][kd][kh][kw])     (rows >= Cout are zero) */
+int ss_conv3d_tc_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_scale, const float* in_shift,
+                     const float* w_kmajor, const float* bias, float* y, double* stats, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Normalisation bookkeeping on [B,C] vectors (the volume itself is never touched).
  * ------------------------------------------------------------------------------------------- */

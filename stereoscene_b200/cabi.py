@@ -35,6 +35,7 @@ SIGNATURES = {
     "ss_last_error_string": (C.c_char_p, []),
     "ss_launch_count": (_ll, []),
     "ss_conv3d_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ss_conv3d_tc_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_gn_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _f, _vp, _vp, _i, _vp]),
     "ss_ca3d_gate": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ss_affine_join_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _i, _vp, _vp]),

@@ -137,12 +137,14 @@ conv_igemm_kernel(const ConvParams p) {
     constexpr int B_F4 = (BK * BN / 4 + NT - 1) / NT;     // float4 per thread for the weight tile
     float areg[A_REGS];
     float4 breg[B_F4];
+    uint32_t avalid = 0;
 
     auto load_tiles = [&](int step) {
         if (VEC) {
             const int tap = step / kchunks, c0 = (step % kchunks) * BK;
             const int4 tp = taps[tap];
             const int col4 = (tid & 7) * 4;
+            avalid = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = (tid >> 3) + 32 * j;
@@ -153,15 +155,7 @@ conv_igemm_kernel(const ConvParams p) {
                     (unsigned)iw < (unsigned)p.Win) {
                     const size_t vox = ((size_t)(b * p.Din + id) * p.Hin + ih) * p.Win + iw;
                     v = ldg_f4(p.x + vox * p.in_ldc + c0 + col4);
-                    if (has_aff) {
-                        const float4 s = *reinterpret_cast<const float4*>(ssc + c0 + col4);
-                        const float4 h = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + col4);
-                        v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y);
-                        v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
-                    }
-                    if (in_relu) {
-                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                    }
+                    avalid |= 1u << j;           // affine / ReLU are applied at the smem store
                 }
                 areg[4 * j + 0] = v.x; areg[4 * j + 1] = v.y; areg[4 * j + 2] = v.z; areg[4 * j + 3] = v.w;
             }
@@ -213,16 +207,31 @@ conv_igemm_kernel(const ConvParams p) {
         }
     };
 
-    auto store_tiles = [&](int buf) {
+    auto store_tiles = [&](int buf, int step) {
         float* A = As + buf * BM * AS_LD;
         float* Bt = Bs + buf * BK * BS_LD;
         if (VEC) {
             const int col4 = (tid & 7) * 4;
+            const int c0 = (step % kchunks) * BK;
+            float4 s = make_float4(1.f, 1.f, 1.f, 1.f), h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_aff) {
+                s = *reinterpret_cast<const float4*>(ssc + c0 + col4);
+                h = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + col4);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = (tid >> 3) + 32 * j;
-                *reinterpret_cast<float4*>(A + r * AS_LD + col4) =
-                    make_float4(areg[4 * j], areg[4 * j + 1], areg[4 * j + 2], areg[4 * j + 3]);
+                float4 v = make_float4(areg[4 * j], areg[4 * j + 1], areg[4 * j + 2], areg[4 * j + 3]);
+                if (avalid & (1u << j)) {
+                    if (has_aff) {
+                        v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y);
+                        v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
+                    }
+                    if (in_relu) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                }
+                *reinterpret_cast<float4*>(A + r * AS_LD + col4) = v;
             }
         } else {
 #pragma unroll
@@ -290,13 +299,13 @@ conv_igemm_kernel(const ConvParams p) {
 
     // ---- main loop: register-prefetch double buffering ---------------------------------------
     load_tiles(0);
-    store_tiles(0);
+    store_tiles(0, 0);
     __syncthreads();
     for (int step = 0; step < nsteps; ++step) {
         const int buf = step & 1;
         if (step + 1 < nsteps) load_tiles(step + 1);
         compute(buf);
-        if (step + 1 < nsteps) store_tiles(buf ^ 1);
+        if (step + 1 < nsteps) store_tiles(buf ^ 1, step + 1);
         __syncthreads();
     }
 

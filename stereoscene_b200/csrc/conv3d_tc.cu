@@ -1,0 +1,466 @@
+// tcgen05 implicit-GEMM convolution for the tensor-bound layers (Cin % 32 == 0, Cout % 4 == 0).
+//
+// Same contract as conv3d.cu (channels-last fp32 volumes, pending affine + activation applied
+// while the A tile is staged, bias/activation/GroupNorm sums in the epilogue, ordinary / strided /
+// dilated / transposed-by-parity-class gathers) but the multiply runs on the 5th-generation tensor
+// cores:
+//   * operands: TF32 (kind::tf32), staged in shared memory in the canonical K-major SWIZZLE_128B
+//     layout (one 128-byte row = 32 input channels of one voxel / one output channel), values
+//     rounded to TF32 with cvt.rna by the producers (weights are pre-rounded on the host side);
+//   * accumulators: fp32 in TMEM (128 lanes x BN columns), never in registers;
+//   * warp roles: 8 producer warps in two groups that alternate K-steps (global -> registers with
+//     a one-step register prefetch -> affine/ReLU/zero-padding -> swizzled st.shared ->
+//     fence.proxy.async -> mbarrier arrive), 1 MMA warp (one elected lane issues 4 x
+//     tcgen05.mma M128 x N(BN) x K8 per stage and tcgen05.commit's the stage back to the producers),
+//     then the 8 producer warps drain TMEM with tcgen05.ld (32 lanes x 32 columns each), apply
+//     bias / activation, store 128-byte rows and reduce the per-channel sums with a shuffle
+//     butterfly.
+//   * pipeline: STAGES-deep ring of (A 16 KB + B BN*128 B) stages, full/empty mbarriers.
+// The gather cannot be a TMA tile load because the pending affine + ReLU of the producer layer must
+// be applied between HBM and the MMA (that fusion removes a full read+write pass per layer), so
+// staging is done by threads and made visible to the async proxy with fence.proxy.async.
+#include "common.cuh"
+
+namespace ss {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                  // floats per K step = one 128-byte swizzle row
+constexpr int TC_PRODUCERS = 256;          // 8 warps, two groups of 4
+constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_MAX_TAPS = 64;
+
+struct ConvParams;                         // defined in conv3d.cu (same layout, redeclared below)
+
+struct TcParams {
+    int B, Din, Hin, Win, Cin, Dout, Hout, Wout, Cout, CoutP;
+    int kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw;
+    int transposed, in_ldc, out_ldc, in_act, out_act;
+    int cls_d, cls_h, cls_w;
+    const float* x;
+    const float* in_scale;
+    const float* in_shift;
+    const float* wk;        // [taps][CoutP][Cin]  (K-major, TF32-rounded)
+    const float* bias;
+    float* y;
+    double* stats;
+};
+
+__host__ __device__ inline int tc_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], TF32 in, FP32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
+// [0,14), LBO>>4 in [16,30) (=1 for swizzled K-major), SBO>>4 in [32,46) (8 rows x 128 B = 1024 B),
+// version=1 in [46,48), layout_type=2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: c_format F32 (1) at [4,6), a/b format TF32 (2) at
+// [7,10)/[10,13), K-major A and B, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct TcCfg {
+    static constexpr int STAGES = (BN >= 256) ? 3 : 4;
+    static constexpr int A_BYTES = TC_BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int B_F4 = BN * 8 / 128;      // float4 per producer thread for the weight tile
+    static constexpr bool PREFETCH_B = (BN <= 128); // wider tiles load the weight rows just in time (registers)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const TcParams p) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte aligned stage ring (SWIZZLE_128B atoms are 1024 B)
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* aux = ring + STAGES * Cfg::STAGE_BYTES;
+    int4* rowinfo = reinterpret_cast<int4*>(aux);                         // [128]
+    int4* taps = rowinfo + TC_BM;                                          // [TC_MAX_TAPS]
+    double* sstat = reinterpret_cast<double*>(taps + TC_MAX_TAPS);         // [BN][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * BN);          // full[STAGES], empty[STAGES], accum
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    int* s_ntaps = reinterpret_cast<int*>(tmem_slot + 1);
+    float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [Cin] scale, [Cin] shift
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncls = p.cls_d * p.cls_h * p.cls_w;
+    const int b = blockIdx.z / ncls, cls = blockIdx.z % ncls;
+    const int rd = cls / (p.cls_h * p.cls_w), rh = (cls / p.cls_w) % p.cls_h, rw = cls % p.cls_w;
+    const int n0 = blockIdx.y * BN;
+    const int Dc = (p.Dout - rd + p.cls_d - 1) / p.cls_d, Hc = (p.Hout - rh + p.cls_h - 1) / p.cls_h,
+              Wc = (p.Wout - rw + p.cls_w - 1) / p.cls_w;
+    const int Mc = Dc * Hc * Wc;
+    const int isd = p.transposed ? 1 : p.sd, ish = p.transposed ? 1 : p.sh, isw = p.transposed ? 1 : p.sw;
+    const int m_base = blockIdx.x * TC_BM;
+    if (m_base >= Mc) return;
+
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+
+    // ---- per-CTA setup ------------------------------------------------------------------------
+    if (tid == 0) {
+        int n = 0;
+        for (int a = 0; a < p.kd; ++a)
+            for (int c = 0; c < p.kh; ++c)
+                for (int e = 0; e < p.kw; ++e) {
+                    int od, oh, ow;
+                    if (p.transposed) {
+                        const int vd = rd + p.pd - a, vh = rh + p.ph - c, vw = rw + p.pw - e;
+                        if (((vd % p.sd) + p.sd) % p.sd || ((vh % p.sh) + p.sh) % p.sh || ((vw % p.sw) + p.sw) % p.sw) continue;
+                        od = tc_floordiv(vd, p.sd); oh = tc_floordiv(vh, p.sh); ow = tc_floordiv(vw, p.sw);
+                    } else {
+                        od = a * p.dd - p.pd; oh = c * p.dh - p.ph; ow = e * p.dw - p.pw;
+                    }
+                    taps[n++] = make_int4(od, oh, ow, (a * p.kh + c) * p.kw + e);
+                }
+        *s_ntaps = n;
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 128);      // one producer group (128 threads) fills a stage
+            mbar_init(empty0 + 8 * s, 1);       // released by one tcgen05.commit
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (tid < TC_BM) {
+        const int m = m_base + tid;
+        int4 ri = make_int4(0, 0, 0, -1);
+        if (m < Mc) {
+            const int qd = m / (Hc * Wc), rem = m % (Hc * Wc);
+            const int qh = rem / Wc, qw = rem % Wc;
+            const int od = qd * p.cls_d + rd, oh = qh * p.cls_h + rh, ow = qw * p.cls_w + rw;
+            ri = make_int4(qd * isd, qh * ish, qw * isw, ((b * p.Dout + od) * p.Hout + oh) * p.Wout + ow);
+        }
+        rowinfo[tid] = ri;
+    }
+    for (int i = tid; i < 2 * BN; i += TC_THREADS) sstat[i] = 0.0;
+    const bool has_aff = (p.in_scale != nullptr);
+    if (has_aff)
+        for (int i = tid; i < p.Cin; i += TC_THREADS) {
+            ssc[i] = __ldg(p.in_scale + (size_t)b * p.Cin + i);
+            ssc[p.Cin + i] = __ldg(p.in_shift + (size_t)b * p.Cin + i);
+        }
+    if (warp == TC_PRODUCERS / 32) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ntaps = *s_ntaps;
+    const int kchunks = p.Cin / TC_BK;
+    const int nsteps = ntaps * kchunks;
+    const uint32_t ring_u32 = smem_u32(ring);
+
+    if (warp < TC_PRODUCERS / 32) {
+        // ======================= PRODUCERS: two groups alternate K steps =======================
+        const int grp = warp >> 2;                 // 0 / 1
+        const int pt = tid & 127;                  // thread within the group
+        const int chunk = pt & 7;                  // 16-byte chunk of the 128-byte row
+        const int rbase = pt >> 3;                 // rows rbase + 16 j
+        const bool in_relu = (p.in_act == SS_ACT_RELU);
+        // two named register sets (compile-time indexed) for the one-step prefetch
+        float4 a0[8], a1[8];
+        float4 b0[Cfg::B_F4], b1[Cfg::PREFETCH_B ? Cfg::B_F4 : 1];
+        uint32_t m0 = 0, m1 = 0;
+
+        auto load_b = [&](int step, float4 (&bb)[Cfg::B_F4]) {
+            const int tap = step / kchunks, c0 = (step % kchunks) * TC_BK;
+            const float* wrow = p.wk + ((size_t)taps[tap].w * p.CoutP) * p.Cin + c0 + chunk * 4;
+#pragma unroll
+            for (int j = 0; j < Cfg::B_F4; ++j) {
+                const int n = n0 + rbase + 16 * j;
+                bb[j] = (n < p.CoutP) ? ldg_f4(wrow + (size_t)n * p.Cin) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto load_a = [&](int step, float4 (&ab)[8], uint32_t& mk) {
+            const int tap = step / kchunks, c0 = (step % kchunks) * TC_BK;
+            const int4 tp = taps[tap];
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int4 ri = rowinfo[rbase + 16 * j];
+                const int id = ri.x + tp.x, ih = ri.y + tp.y, iw = ri.z + tp.z;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ri.w >= 0 && (unsigned)id < (unsigned)p.Din && (unsigned)ih < (unsigned)p.Hin &&
+                    (unsigned)iw < (unsigned)p.Win) {
+                    const size_t vox = ((size_t)(b * p.Din + id) * p.Hin + ih) * p.Win + iw;
+                    v = ldg_f4(p.x + vox * p.in_ldc + c0 + chunk * 4);
+                    mask |= 1u << j;
+                }
+                ab[j] = v;
+            }
+            mk = mask;
+        };
+        auto store_stage = [&](int step, float4 (&ab)[8], float4 (&bb)[Cfg::B_F4], uint32_t mask) {
+            const int slot = step % STAGES;
+            const uint32_t use = (uint32_t)(step / STAGES);
+            if (!Cfg::PREFETCH_B) load_b(step, bb);
+            mbar_wait(empty0 + 8 * slot, (use & 1u) ^ 1u);
+            const int c0 = (step % kchunks) * TC_BK;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_aff) {
+                sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
+                sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
+            }
+            unsigned char* a_dst = ring + slot * Cfg::STAGE_BYTES;
+            unsigned char* b_dst = a_dst + Cfg::A_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 v = ab[j];
+                if (mask & (1u << j)) {
+                    if (has_aff) {
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    }
+                    if (in_relu) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                }
+                const int r = rbase + 16 * j;
+                uint4 t;
+                t.x = f2tf32(v.x); t.y = f2tf32(v.y); t.z = f2tf32(v.z); t.w = f2tf32(v.w);
+                *reinterpret_cast<uint4*>(a_dst + r * 128 + ((chunk ^ (r & 7)) << 4)) = t;
+            }
+#pragma unroll
+            for (int j = 0; j < Cfg::B_F4; ++j) {
+                const int n = rbase + 16 * j;
+                *reinterpret_cast<float4*>(b_dst + n * 128 + ((chunk ^ (n & 7)) << 4)) = bb[j];
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(full0 + 8 * slot);
+        };
+
+        int step = grp;
+        if (step < nsteps) {
+            load_a(step, a0, m0);
+            if (Cfg::PREFETCH_B) load_b(step, b0);
+        }
+        while (step < nsteps) {
+            if (step + 2 < nsteps) {
+                load_a(step + 2, a1, m1);
+                if constexpr (Cfg::PREFETCH_B) load_b(step + 2, b1);
+            }
+            store_stage(step, a0, b0, m0);
+            step += 2;
+            if (step >= nsteps) break;
+            if (step + 2 < nsteps) {
+                load_a(step + 2, a0, m0);
+                if constexpr (Cfg::PREFETCH_B) load_b(step + 2, b0);
+            }
+            if constexpr (Cfg::PREFETCH_B) store_stage(step, a1, b1, m1);
+            else store_stage(step, a1, b0, m1);
+            step += 2;
+        }
+    } else {
+        // ======================= MMA ISSUER (one elected lane) ===================================
+        constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+        for (int step = 0; step < nsteps; ++step) {
+            const int slot = step % STAGES;
+            const uint32_t use = (uint32_t)(step / STAGES);
+            mbar_wait(full0 + 8 * slot, use & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = ring_u32 + slot * Cfg::STAGE_BYTES;
+                const uint64_t adesc = make_smem_desc(a_addr);
+                const uint64_t bdesc = make_smem_desc(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)      // 8 TF32 = 32 bytes per MMA: advance start by 32 B
+                    umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (step | k) ? 1u : 0u);
+                umma_commit(empty0 + 8 * slot);            // frees the stage when these MMAs retire
+                if (step == nsteps - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ======================= EPILOGUE: 8 warps drain TMEM ========================================
+    if (warp < TC_PRODUCERS / 32) {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int half = warp >> 2;                    // column half handled by this warp
+        const int row = q * 32 + lane;
+        const int ov = rowinfo[row].w;
+        constexpr int CHUNKS = BN / 32;
+        constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
+        const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+#pragma unroll 1
+        for (int ci = half * CPH; ci < min(CHUNKS, (half + 1) * CPH); ++ci) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ci * 32), r);
+            const int cbase = n0 + ci * 32;
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                float f = __uint_as_float(r[k]);
+                const int c = cbase + k;
+                if (p.bias && c < p.Cout) f += __ldg(p.bias + c);
+                v[k] = apply_act(f, p.out_act);
+            }
+            if (ov >= 0) {
+                float* dst = p.y + (size_t)ov * p.out_ldc + cbase;
+                if (vec_ok && cbase + 32 <= p.Cout) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cbase + k < p.Cout) dst[k] = v[k];
+                }
+            }
+            if (p.stats) {
+                float s[32], qq[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { s[k] = (ov >= 0) ? v[k] : 0.f; qq[k] = s[k] * s[k]; }
+                // butterfly: after the 5 rounds lane L holds the column-(L) total over the warp's 32 rows
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float send_s = up ? s[i] : s[i + off], keep_s = up ? s[i + off] : s[i];
+                        const float send_q = up ? qq[i] : qq[i + off], keep_q = up ? qq[i + off] : qq[i];
+                        s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                        qq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+                    }
+                }
+                atomicAdd(&sstat[2 * (ci * 32 + lane) + 0], (double)s[0]);
+                atomicAdd(&sstat[2 * (ci * 32 + lane) + 1], (double)qq[0]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (p.stats) {
+        for (int i = tid; i < BN; i += TC_THREADS) {
+            const int c = n0 + i;
+            if (c < p.Cout) {
+                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 0, sstat[2 * i + 0]);
+                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 1, sstat[2 * i + 1]);
+            }
+        }
+    }
+    if (warp == TC_PRODUCERS / 32) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BN>
+static int launch_tc(const TcParams& p, cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + TC_BM * sizeof(int4) + TC_MAX_TAPS * sizeof(int4) +
+                  2 * BN * sizeof(double) + (2 * Cfg::STAGES + 1) * sizeof(uint64_t) + 16 + 2 * (size_t)p.Cin * sizeof(float) + 32;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        SS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int ncls = p.cls_d * p.cls_h * p.cls_w;
+    const int Dc = (p.Dout + p.cls_d - 1) / p.cls_d, Hc = (p.Hout + p.cls_h - 1) / p.cls_h, Wc = (p.Wout + p.cls_w - 1) / p.cls_w;
+    const long long Mc = (long long)Dc * Hc * Wc;
+    dim3 grid((unsigned)((Mc + TC_BM - 1) / TC_BM), (unsigned)((p.CoutP + BN - 1) / BN), (unsigned)(p.B * ncls));
+    conv_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(p);
+    return check_launch("conv_tc_kernel");
+}
+
+}  // namespace ss
+
+// wk: float[taps][cout_packed][Cin], K-major, values already rounded to TF32.
+extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                                const float* w_kmajor, const float* bias, float* y, double* stats, void* stream) {
+    using namespace ss;
+    SS_REQUIRE(d && x && w_kmajor && y, "ss_conv3d_tc_fwd: null pointer");
+    SS_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0, "ss_conv3d_tc_fwd: empty shape");
+    SS_REQUIRE(d->Cin % TC_BK == 0 && d->in_ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+               "ss_conv3d_tc_fwd: needs Cin % 32 == 0 and 16-byte aligned channels-last input");
+    SS_REQUIRE(d->kd >= 1 && d->kd <= 4 && d->kh >= 1 && d->kh <= 4 && d->kw >= 1 && d->kw <= 4, "ss_conv3d_tc_fwd: kernel extent");
+    SS_REQUIRE(d->cout_packed >= d->Cout && d->cout_packed % 8 == 0, "ss_conv3d_tc_fwd: cout_packed");
+    SS_REQUIRE(d->in_ldc >= d->Cin && d->out_ldc >= d->Cout, "ss_conv3d_tc_fwd: ldc");
+    SS_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "ss_conv3d_tc_fwd: scale/shift must come together");
+    SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_tc_fwd: in_act");
+    SS_REQUIRE(d->Cin <= 4096, "ss_conv3d_tc_fwd: Cin limited to 4096");
+    SS_REQUIRE((long long)d->B * d->Dout * d->Hout * d->Wout < (1ll << 31), "ss_conv3d_tc_fwd: output too large");
+    SS_REQUIRE(d->math == SS_MATH_TF32, "ss_conv3d_tc_fwd: TF32 only (use ss_conv3d_fwd for 3xTF32)");
+    if (d->transposed) SS_REQUIRE(d->dd == 1 && d->dh == 1 && d->dw == 1, "ss_conv3d_tc_fwd: dilated transposed conv unsupported");
+    TcParams p;
+    p.B = d->B; p.Din = d->Din; p.Hin = d->Hin; p.Win = d->Win; p.Cin = d->Cin;
+    p.Dout = d->Dout; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout; p.CoutP = d->cout_packed;
+    p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
+    p.pd = d->pd; p.ph = d->ph; p.pw = d->pw; p.dd = d->dd; p.dh = d->dh; p.dw = d->dw;
+    p.transposed = d->transposed; p.in_ldc = d->in_ldc; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
+    p.cls_d = d->transposed ? d->sd : 1; p.cls_h = d->transposed ? d->sh : 1; p.cls_w = d->transposed ? d->sw : 1;
+    p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.wk = w_kmajor; p.bias = bias; p.y = y; p.stats = stats;
+    SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int cp = d->cout_packed;
+    if (cp <= 32) return launch_tc<32>(p, st);
+    if (cp <= 64) return launch_tc<64>(p, st);
+    if (cp <= 128) return launch_tc<128>(p, st);
+    if (cp <= 192) return launch_tc<192>(p, st);
+    return launch_tc<256>(p, st);
+}

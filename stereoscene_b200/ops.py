@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -25,6 +26,14 @@ from . import cabi
 from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_TF32  # noqa: F401
 
 _DEFAULT_MATH = SS_MATH_TF32
+_USE_TCGEN05 = os.environ.get("STEREOSCENE_B200_NO_TCGEN05", "0") != "1"
+
+
+def use_tcgen05(flag: bool):
+    """Route eligible convolutions through the tcgen05 kernel (default) or keep every layer on the
+    mma.sync kernel (used by tests to cross-check the two implementations)."""
+    global _USE_TCGEN05
+    _USE_TCGEN05 = bool(flag)
 
 
 def set_default_math(mode: int):
@@ -139,15 +148,6 @@ def arena(device) -> StatsArena:
 # ------------------------------------------------------------------------------------------
 # convolution family
 # ------------------------------------------------------------------------------------------
-def _triple(v) -> Tuple[int, int, int]:
-    if isinstance(v, int):
-        return (v, v, v)
-    v = tuple(int(a) for a in v)
-    if len(v) == 2:
-        return (1,) + v if False else (v[0], v[1], -1)   # never used; 2-D handled by caller
-    return v
-
-
 class PackedConv:
     """Geometry + weights of one Conv3d / ConvTranspose3d / Conv2d in the kernel's layout
     (float[taps][Cin][Cout_padded]); built once from the nn.Module that owns the parameter (so the
@@ -174,6 +174,8 @@ class PackedConv:
         self.CoutP = (self.Cout + 7) // 8 * 8
         self._key = None
         self._w = None
+        self._kkey = None
+        self._wk = None
 
     def weights(self) -> torch.Tensor:
         w = self.module.weight
@@ -193,6 +195,25 @@ class PackedConv:
                 self._w = pk.contiguous()
             self._key = key
         return self._w
+
+    def weights_kmajor(self) -> torch.Tensor:
+        """float[taps][Cout_padded][Cin], rounded to TF32 (nearest, ties away) -- tcgen05 B operand."""
+        w = self.module.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self._kkey:
+            with torch.no_grad():
+                wd = w.detach()
+                if wd.dim() == 4:
+                    wd = wd.unsqueeze(2)
+                pk = wd.permute(2, 3, 4, 1, 0) if self.transposed else wd.permute(2, 3, 4, 0, 1)   # [k,k,k,Cout,Cin]
+                pk = pk.reshape(-1, self.Cout, self.Cin).float()
+                if self.CoutP != self.Cout:
+                    pk = torch.nn.functional.pad(pk, (0, 0, 0, self.CoutP - self.Cout))
+                bits = pk.contiguous().view(torch.int32)
+                bits = (bits + 0x1000) & ~0x1FFF                      # cvt.rna.tf32.f32 on the magnitude bits
+                self._wk = bits.view(torch.float32).contiguous()
+            self._kkey = key
+        return self._wk
 
     def out_size(self, din: Sequence[int]) -> Tuple[int, int, int]:
         out = []
@@ -236,12 +257,19 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     if x.scale is not None:
         if tuple(x.scale.shape) != (B, Cin) or not x.scale.is_contiguous() or not x.shift.is_contiguous():
             raise RuntimeError("conv: pending affine must be contiguous [B,Cin]")
+    mm = _DEFAULT_MATH if math_mode is None else math_mode
     d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
-                      1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act,
-                      _DEFAULT_MATH if math_mode is None else math_mode, pc.CoutP)
-    rc = lib.ss_conv3d_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights().data_ptr(),
-                           _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
-    cabi.check(rc, "ss_conv3d_fwd")
+                      1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
+    tc = (_USE_TCGEN05 and mm == SS_MATH_TF32 and Cin % 32 == 0 and pc.Cout % 4 == 0 and pc.Cout >= 32
+          and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
+    if tc:
+        rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights_kmajor().data_ptr(),
+                                  _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
+        cabi.check(rc, "ss_conv3d_tc_fwd")
+    else:
+        rc = lib.ss_conv3d_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights().data_ptr(),
+                               _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
+        cabi.check(rc, "ss_conv3d_fwd")
     return out, stats
 
 

@@ -440,7 +440,9 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib)
 
         B, N, Cin, H, W = x.shape
-        y = self.depth_net(x.reshape(B * N, Cin, H, W), mlp_input)              # adjacent (N1)
+        # adjacent component (N1) on cuDNN: follow the selected math mode (TF32 allowed only in TF32 mode)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=ops.default_math() == ops.SS_MATH_TF32):
+            y = self.depth_net(x.reshape(B * N, Cin, H, W), mlp_input)
         lss = ops.softmax_d(y[:, :self.D])
         img_feat = ops.to_channels_last(y[:, self.D:self.D + self.numC_Trans])   # [B*N,H,W,C]
 

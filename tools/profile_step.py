@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Profiling harness for ncu (B200_PROFILING.md): runs warm-up steps, then ONE step (or one named
+kernel) between cudaProfilerStart/Stop so `ncu --profile-from-start off` sees exactly that region.
+
+  ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file gpurun_out/launches.csv python tools/profile_step.py --what step
+  ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/head \
+      python tools/profile_step.py --what head_conv
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from stereoscene_b200 import ops, presets, synth  # noqa: E402
+from stereoscene_b200.ops import Vol  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat"])
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--math", default="tf32")
+    ap.add_argument("--reps", type=int, default=1)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    ops.set_default_math(ops.SS_MATH_3XTF32 if a.math == "3xtf32" else ops.SS_MATH_TF32)
+    model, mc = presets.build(a.workload)
+    synth.randomize_weights_(model, 0)
+    model = model.to(dev).eval()
+    xl, xr = synth.stereo_features(1, mc["input_size"], 8, seed=0, device=dev)
+    left, right, calib = synth.kitti_calibration(1, mc["input_size"], device=dev)
+    vt = model.img_view_transformer
+    nx = [int(round(float(v))) for v in vt.nx.detach().cpu()]
+    D, H, W = vt.D, vt.frustum.shape[1], vt.frustum.shape[2]
+
+    if a.what == "step":
+        fn = lambda: model.forward_features(xl, xr, left, right, calib, occ_size=mc["occ_size"], want_labels=True)   # noqa: E731
+    elif a.what == "head_conv":
+        head = model.pts_bbox_head.occ_convs[0][0]
+        x = torch.randn((1, nx[0], nx[1], nx[2], 384), device=dev)
+        sc, sh = torch.rand((1, 384), device=dev) + 0.5, torch.randn((1, 384), device=dev) * 0.1
+        y = torch.empty((1, nx[0], nx[1], nx[2], 192), device=dev)
+        fn = lambda: ops.conv(Vol(x, sc, sh, ops.SS_ACT_RELU), head, out=y, want_stats=True)    # noqa: E731
+    elif a.what == "enc_conv":
+        c = model.img_bev_encoder_backbone.layers[0][0].conv1
+        x = torch.randn((1, nx[0], nx[1], nx[2], 128), device=dev)
+        fn = lambda: ops.conv(Vol(x), c, want_stats=True)     # noqa: E731
+    elif a.what == "frustum_conv":
+        c = vt.stereo_volume_net.dres0[0][0]
+        x = torch.randn((1, D, H, W, 32), device=dev)
+        fn = lambda: ops.conv(Vol(x), c, want_stats=True)     # noqa: E731
+    elif a.what == "bri":
+        q = torch.softmax(torch.randn((1, D, H, W), device=dev), 1)
+        kv = torch.softmax(torch.randn((1, D, H, W), device=dev), 1)
+        out = torch.empty((1, D, H, W, 2), device=dev)
+        p = vt.volume_interaction.lss2stereo.packed()
+        fn = lambda: ops.bri_attention(q, kv, p, out[..., 0], 2)     # noqa: E731
+    elif a.what == "gwc":
+        fea = torch.randn((2, 1, H, W, 64), device=dev)
+        fn = lambda: ops.gwc_warp(fea, calib, D, 32)     # noqa: E731
+    else:
+        idx = vt.splat_index(*[left[k] for k in ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")])
+        dp = torch.softmax(torch.randn((1, D, H, W), device=dev), 1)
+        ft = torch.randn((1, H, W, 128), device=dev)
+        fn = lambda: ops.lift_splat(dp, ft, idx)     # noqa: E731
+
+    with torch.no_grad():
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(a.reps):
+            fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    print("profiled", a.what)
+
+
+if __name__ == "__main__":
+    main()
