@@ -143,9 +143,11 @@ int ss_gwc_warp_fwd(const float* fea, const int32_t* i0, const float* w0, const 
  * [N,N] energy / attention matrices are never materialised.
  *   q, kv: float[B][D][N] (N = H*W tokens);  params: DEVICE float[7] = wq,bq,wk,bk,wv,bv,gamma
  *   out[b][d][n*out_ld + 0] = gamma * sum_j V[d,j]*softmax_j(E[n,:])[j]*conf[j] + kv[b][d][n]
- *   conf_ws: float[B*N] workspace (conf[j] = max_d softmax_d q[:,j]).
+ *   ws: workspace of ss_bri_workspace_bytes(B, D, N) bytes (conf[j] = max_d softmax_d q[:,j] and, when
+ *       the keys are split across CTAs to fill the GPU, the per-split partial softmax states).
  * ------------------------------------------------------------------------------------------- */
-int ss_bri_attn_fwd(const float* q, const float* kv, const float* params, float* conf_ws, float* out,
+size_t ss_bri_workspace_bytes(int B, int D, int N);
+int ss_bri_attn_fwd(const float* q, const float* kv, const float* params, float* ws, size_t ws_bytes, float* out,
                     int out_ld, int B, int D, int N, int math, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

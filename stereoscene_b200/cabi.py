@@ -41,7 +41,8 @@ SIGNATURES = {
     "ss_affine_join_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _i, _vp, _vp]),
     "ss_softmax_d_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "ss_gwc_warp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "ss_bri_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ss_bri_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ss_bri_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _i, _i, _i, _vp]),
     "ss_splat_index_workspace_bytes": (_sz, [_ll]),
     "ss_splat_build_index": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ss_lift_splat_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -38,7 +38,8 @@ __global__ void bri_conf_kernel(const float* __restrict__ q, float* __restrict__
 template <int DP, bool PRECISE>   // DP = D rounded up to a multiple of 8
 __global__ void __launch_bounds__(ATT_THREADS)
 bri_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ params,
-                const float* __restrict__ conf, float* __restrict__ out, int out_ld, int D, int N) {
+                const float* __restrict__ conf, float* __restrict__ out, int out_ld, int D, int N, int keys_per_split,
+                float* __restrict__ part_ml, float* __restrict__ part_o) {
     extern __shared__ __align__(16) float sm[];
     float* Qs = sm;                          // [DP][QK_LD]
     float* Ks = Qs + DP * QK_LD;             // [DP][QK_LD]
@@ -72,17 +73,21 @@ bri_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, const
     float* Pw = Ps + warp * 16 * P_LD;
     const int m0 = warp * 16;
 
-    for (int j0 = 0; j0 < N; j0 += BKEY) {
+    // key split (flash-decoding): blockIdx.z owns keys [j_begin, j_end); partial (m, l, O) are merged by
+    // bri_combine_kernel when gridDim.z > 1
+    const int j_begin = blockIdx.z * keys_per_split;
+    const int j_end = min(N, j_begin + keys_per_split);
+    for (int j0 = j_begin; j0 < j_end; j0 += BKEY) {
         __syncthreads();                      // previous tile fully consumed (also covers Qs on entry)
         for (int idx = tid; idx < DP * BKEY; idx += ATT_THREADS) {
             const int d = idx / BKEY, j = idx % BKEY;
             float kvv = 0.f;
-            const bool ok = (d < D && j0 + j < N);
+            const bool ok = (d < D && j0 + j < j_end);
             if (ok) kvv = __ldg(kvb + (size_t)d * N + j0 + j);
             Ks[d * QK_LD + j] = ok ? fmaf(wk, kvv, bk) : 0.f;
             Vs[d * V_LD + j] = ok ? fmaf(wv, kvv, bv) : 0.f;
         }
-        if (tid < BKEY) cs[tid] = (j0 + tid < N) ? __ldg(conf + (size_t)b * N + j0 + tid) : 0.f;
+        if (tid < BKEY) cs[tid] = (j0 + tid < j_end) ? __ldg(conf + (size_t)b * N + j0 + tid) : 0.f;
         __syncthreads();
 
         // ---- S = Q^T K  (16 x 64 per warp)
@@ -121,8 +126,8 @@ bri_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, const
 #pragma unroll
             for (int nf = 0; nf < BKEY / 8; ++nf) {
                 const int j = j0 + nf * 8 + 2 * t;
-                if (j >= N) s_acc[nf][2 * h] = -INFINITY;
-                if (j + 1 >= N) s_acc[nf][2 * h + 1] = -INFINITY;
+                if (j >= j_end) s_acc[nf][2 * h] = -INFINITY;
+                if (j + 1 >= j_end) s_acc[nf][2 * h + 1] = -INFINITY;
                 mx = fmaxf(mx, fmaxf(s_acc[nf][2 * h], s_acc[nf][2 * h + 1]));
             }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -160,63 +165,128 @@ bri_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, const
         __syncwarp();
     }
 
-    // ---- epilogue: normalise, gamma-residual, store
+    // ---- epilogue: normalise, gamma-residual, store (or write the split's partial state)
+    const bool split = gridDim.z > 1;
+    const size_t pbase = ((size_t)blockIdx.z * gridDim.y + b);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int i = i0 + m0 + g + 8 * h;
         if (i >= N) continue;
-        const float inv = 1.0f / l_run[h];
+        if (split) {
+            if (t == 0) {
+                part_ml[(pbase * 2 + 0) * N + i] = m_run[h];
+                part_ml[(pbase * 2 + 1) * N + i] = l_run[h];
+            }
 #pragma unroll
-        for (int nf = 0; nf < NFO; ++nf) {
+            for (int nf = 0; nf < NFO; ++nf)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int d = nf * 8 + 2 * t + e;
-                if (d < D) {
-                    const float res = __ldg(kvb + (size_t)d * N + i);
-                    out[((size_t)b * D * N + (size_t)d * N + i) * out_ld] = fmaf(gamma, o_acc[nf][2 * h + e] * inv, res);
+                for (int e = 0; e < 2; ++e) {
+                    const int d = nf * 8 + 2 * t + e;
+                    if (d < D) part_o[(pbase * D + d) * N + i] = o_acc[nf][2 * h + e];
+                }
+        } else {
+            const float inv = 1.0f / l_run[h];
+#pragma unroll
+            for (int nf = 0; nf < NFO; ++nf) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int d = nf * 8 + 2 * t + e;
+                    if (d < D) {
+                        const float res = __ldg(kvb + (size_t)d * N + i);
+                        out[((size_t)b * D * N + (size_t)d * N + i) * out_ld] = fmaf(gamma, o_acc[nf][2 * h + e] * inv, res);
+                    }
                 }
             }
         }
     }
 }
 
+// merge the key splits: out = gamma * (sum_s O_s e^{m_s-m}) / (sum_s l_s e^{m_s-m}) + kv
+__global__ void bri_combine_kernel(const float* __restrict__ part_ml, const float* __restrict__ part_o,
+                                   const float* __restrict__ kv, const float* __restrict__ params,
+                                   float* __restrict__ out, int out_ld, int B, int D, int N, int KS) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.z;
+    if (i >= N) return;
+    float m = -INFINITY;
+    for (int s = 0; s < KS; ++s) m = fmaxf(m, part_ml[(((size_t)s * B + b) * 2 + 0) * N + i]);
+    float w[8];
+    float l = 0.f;
+    for (int s = 0; s < KS; ++s) {
+        w[s] = expf(part_ml[(((size_t)s * B + b) * 2 + 0) * N + i] - m);
+        l += w[s] * part_ml[(((size_t)s * B + b) * 2 + 1) * N + i];
+    }
+    const float gamma = __ldg(params + 6), inv = 1.0f / l;
+    for (int d = blockIdx.y; d < D; d += gridDim.y) {
+        float o = 0.f;
+        for (int s = 0; s < KS; ++s) o += w[s] * part_o[(((size_t)s * B + b) * D + d) * N + i];
+        out[((size_t)b * D * N + (size_t)d * N + i) * out_ld] = fmaf(gamma, o * inv, __ldg(kv + ((size_t)b * D + d) * N + i));
+    }
+}
+
+static int bri_key_splits(int B, int N) {
+    // enough CTAs for ~2 waves of 2 CTAs/SM; at most 8 splits, each a multiple of the key tile
+    const int qtiles = (N + BQ - 1) / BQ;
+    int ks = 1;
+    while (ks < 8 && (long long)qtiles * B * ks < 2 * 2 * 148 && (N / (ks * 2)) >= 4 * BKEY) ks *= 2;
+    return ks;
+}
+
 template <int DP>
 static int launch_bri(const float* q, const float* kv, const float* params, const float* conf, float* out, int out_ld,
-                      int B, int D, int N, bool precise, cudaStream_t st) {
+                      int B, int D, int N, bool precise, int KS, float* part_ml, float* part_o, cudaStream_t st) {
     const size_t smem = (size_t)(2 * DP * QK_LD + DP * V_LD + 4 * 16 * P_LD + BKEY) * sizeof(float);
-    dim3 grid((N + BQ - 1) / BQ, B);
+    const int kps = ((N + KS - 1) / KS + BKEY - 1) / BKEY * BKEY;
+    dim3 grid((N + BQ - 1) / BQ, B, KS);
     static thread_local bool configured = false;
     if (!configured) {
         SS_CUDA(cudaFuncSetAttribute(bri_attn_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SS_CUDA(cudaFuncSetAttribute(bri_attn_kernel<DP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    if (precise) {
-        bri_attn_kernel<DP, true><<<grid, ATT_THREADS, smem, st>>>(q, kv, params, conf, out, out_ld, D, N);
-    } else {
-        bri_attn_kernel<DP, false><<<grid, ATT_THREADS, smem, st>>>(q, kv, params, conf, out, out_ld, D, N);
-    }
-    return check_launch("bri_attn_kernel");
+    if (precise)
+        bri_attn_kernel<DP, true><<<grid, ATT_THREADS, smem, st>>>(q, kv, params, conf, out, out_ld, D, N, kps, part_ml, part_o);
+    else
+        bri_attn_kernel<DP, false><<<grid, ATT_THREADS, smem, st>>>(q, kv, params, conf, out, out_ld, D, N, kps, part_ml, part_o);
+    int rc = check_launch("bri_attn_kernel");
+    if (rc || KS == 1) return rc;
+    dim3 cgrid((N + 127) / 128, min(D, 8), B);
+    bri_combine_kernel<<<cgrid, 128, 0, st>>>(part_ml, part_o, kv, params, out, out_ld, B, D, N, KS);
+    return check_launch("bri_combine_kernel");
 }
 
 }  // namespace ss
 
-extern "C" int ss_bri_attn_fwd(const float* q, const float* kv, const float* params, float* conf_ws, float* out,
-                               int out_ld, int B, int D, int N, int math, void* stream) {
+extern "C" size_t ss_bri_workspace_bytes(int B, int D, int N) {
+    const int ks = ss::bri_key_splits(B, N);
+    size_t fl = (size_t)B * N;                                   // conf
+    if (ks > 1) fl += (size_t)ks * B * N * (2 + D);              // partial (m, l) and O
+    return fl * sizeof(float);
+}
+
+extern "C" int ss_bri_attn_fwd(const float* q, const float* kv, const float* params, float* ws, size_t ws_bytes,
+                               float* out, int out_ld, int B, int D, int N, int math, void* stream) {
     using namespace ss;
-    SS_REQUIRE(q && kv && params && conf_ws && out, "ss_bri_attn_fwd: null pointer");
+    SS_REQUIRE(q && kv && params && ws && out, "ss_bri_attn_fwd: null pointer");
     SS_REQUIRE(B > 0 && B <= 65535 && D > 0 && D <= 128 && N > 0 && out_ld >= 1, "ss_bri_attn_fwd: shape (D <= 128)");
+    if (ws_bytes < ss_bri_workspace_bytes(B, D, N)) return SS_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    const int KS = bri_key_splits(B, N);
+    float* conf_ws = ws;
+    float* part_ml = ws + (size_t)B * N;
+    float* part_o = part_ml + (size_t)KS * B * N * 2;
     dim3 cgrid((N + 127) / 128, B);
     bri_conf_kernel<<<cgrid, 128, 0, st>>>(q, conf_ws, D, N);
     int rc = check_launch("bri_conf_kernel");
     if (rc) return rc;
     const bool precise = (math == SS_MATH_3XTF32);
     const int dp = (D + 7) / 8 * 8;
-    if (dp <= 32) return launch_bri<32>(q, kv, params, conf_ws, out, out_ld, B, D, N, precise, st);
-    if (dp <= 48) return launch_bri<48>(q, kv, params, conf_ws, out, out_ld, B, D, N, precise, st);
-    if (dp <= 64) return launch_bri<64>(q, kv, params, conf_ws, out, out_ld, B, D, N, precise, st);
-    if (dp <= 96) return launch_bri<96>(q, kv, params, conf_ws, out, out_ld, B, D, N, precise, st);
-    if (dp <= 112) return launch_bri<112>(q, kv, params, conf_ws, out, out_ld, B, D, N, precise, st);
-    return launch_bri<128>(q, kv, params, conf_ws, out, out_ld, B, D, N, precise, st);
+#define SS_BRI(DPV) return launch_bri<DPV>(q, kv, params, conf_ws, out, out_ld, B, D, N, precise, KS, part_ml, part_o, st)
+    if (dp <= 32) SS_BRI(32);
+    if (dp <= 48) SS_BRI(48);
+    if (dp <= 64) SS_BRI(64);
+    if (dp <= 96) SS_BRI(96);
+    if (dp <= 112) SS_BRI(112);
+    SS_BRI(128);
+#undef SS_BRI
 }

@@ -8,13 +8,13 @@
 //     layout (one 128-byte row = 32 input channels of one voxel / one output channel), values
 //     rounded to TF32 with cvt.rna by the producers (weights are pre-rounded on the host side);
 //   * accumulators: fp32 in TMEM (128 lanes x BN columns), never in registers;
-//   * warp roles: 8 producer warps in two groups that alternate K-steps (global -> registers with
-//     a one-step register prefetch -> affine/ReLU/zero-padding -> swizzled st.shared ->
-//     fence.proxy.async -> mbarrier arrive), 1 MMA warp (one elected lane issues 4 x
-//     tcgen05.mma M128 x N(BN) x K8 per stage and tcgen05.commit's the stage back to the producers),
-//     then the 8 producer warps drain TMEM with tcgen05.ld (32 lanes x 32 columns each), apply
-//     bias / activation, store 128-byte rows and reduce the per-channel sums with a shuffle
-//     butterfly.
+//   * warp roles: 8 producer warps stream every K-step with cp.async (16-byte LDGSTS straight into
+//     the swizzled stage, zero-fill for padding rows, PREFETCH stages in flight per thread), then
+//     fix up their own chunks in place (pending affine, ReLU, cvt.rna.tf32), fence.proxy.async and
+//     arrive on the stage's mbarrier; 1 MMA warp (one elected lane issues 4 x tcgen05.mma
+//     M128 x N(BN) x K8 per stage and tcgen05.commit's the stage back to the producers); finally the
+//     8 producer warps drain TMEM with tcgen05.ld (32 lanes x 32 columns each), apply bias /
+//     activation, store 128-byte rows and reduce the per-channel sums with a shuffle butterfly.
 //   * pipeline: STAGES-deep ring of (A 16 KB + B BN*128 B) stages, full/empty mbarriers.
 // The gather cannot be a TMA tile load because the pending affine + ReLU of the producer layer must
 // be applied between HBM and the MMA (that fusion removes a full read+write pass per layer), so
@@ -72,6 +72,18 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// 16-byte async copy global -> shared (L2 only); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// same, allocating in L1: the 27 taps of a 3x3x3 stencil re-read the same voxel rows within a few steps
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
@@ -123,17 +135,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES = (BN >= 256) ? 3 : 4;
+    static constexpr int STAGES = BN >= 256 ? 4 : BN >= 192 ? 5 : BN >= 128 ? 6 : 4;
+    static constexpr int PREFETCH = STAGES - 2;     // cp.async groups in flight per producer thread
+    static constexpr int MIN_CTAS = BN <= 64 ? 2 : 1;
     static constexpr int A_BYTES = TC_BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    static constexpr int B_F4 = BN * 8 / 128;      // float4 per producer thread for the weight tile
-    static constexpr bool PREFETCH_B = (BN <= 128); // wider tiles load the weight rows just in time (registers)
+    static constexpr int B_CH = BN * 8 / 256;       // 16-byte chunks of the weight tile per producer thread
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::MIN_CTAS)
 conv_tc_kernel(const TcParams p) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -181,7 +194,7 @@ conv_tc_kernel(const TcParams p) {
                 }
         *s_ntaps = n;
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 128);      // one producer group (128 threads) fills a stage
+            mbar_init(full0 + 8 * s, TC_PRODUCERS);   // every producer thread arrives once per stage
             mbar_init(empty0 + 8 * s, 1);       // released by one tcgen05.commit
         }
         mbar_init(accum_bar, 1);
@@ -216,61 +229,58 @@ conv_tc_kernel(const TcParams p) {
     const uint32_t ring_u32 = smem_u32(ring);
 
     if (warp < TC_PRODUCERS / 32) {
-        // ======================= PRODUCERS: two groups alternate K steps =======================
-        const int grp = warp >> 2;                 // 0 / 1
-        const int pt = tid & 127;                  // thread within the group
-        const int chunk = pt & 7;                  // 16-byte chunk of the 128-byte row
-        const int rbase = pt >> 3;                 // rows rbase + 16 j
+        // ======================= PRODUCERS: cp.async ring, PREFETCH stages in flight ================
+        constexpr int PF = Cfg::PREFETCH;
+        const int chunk = tid & 7;                 // 16-byte chunk of the 128-byte row
+        const int rbase = tid >> 3;                // rows rbase + 32 j
         const bool in_relu = (p.in_act == SS_ACT_RELU);
-        // two named register sets (compile-time indexed) for the one-step prefetch
-        float4 a0[8], a1[8];
-        float4 b0[Cfg::B_F4], b1[Cfg::PREFETCH_B ? Cfg::B_F4 : 1];
-        uint32_t m0 = 0, m1 = 0;
+        uint32_t hist = 0;                         // validity masks of the in-flight steps, 4 bits each
 
-        auto load_b = [&](int step, float4 (&bb)[Cfg::B_F4]) {
-            const int tap = step / kchunks, c0 = (step % kchunks) * TC_BK;
-            const float* wrow = p.wk + ((size_t)taps[tap].w * p.CoutP) * p.Cin + c0 + chunk * 4;
-#pragma unroll
-            for (int j = 0; j < Cfg::B_F4; ++j) {
-                const int n = n0 + rbase + 16 * j;
-                bb[j] = (n < p.CoutP) ? ldg_f4(wrow + (size_t)n * p.Cin) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        auto load_a = [&](int step, float4 (&ab)[8], uint32_t& mk) {
-            const int tap = step / kchunks, c0 = (step % kchunks) * TC_BK;
-            const int4 tp = taps[tap];
-            uint32_t mask = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int4 ri = rowinfo[rbase + 16 * j];
-                const int id = ri.x + tp.x, ih = ri.y + tp.y, iw = ri.z + tp.z;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ri.w >= 0 && (unsigned)id < (unsigned)p.Din && (unsigned)ih < (unsigned)p.Hin &&
-                    (unsigned)iw < (unsigned)p.Win) {
-                    const size_t vox = ((size_t)(b * p.Din + id) * p.Hin + ih) * p.Win + iw;
-                    v = ldg_f4(p.x + vox * p.in_ldc + c0 + chunk * 4);
-                    mask |= 1u << j;
-                }
-                ab[j] = v;
-            }
-            mk = mask;
-        };
-        auto store_stage = [&](int step, float4 (&ab)[8], float4 (&bb)[Cfg::B_F4], uint32_t mask) {
+        auto issue = [&](int step) {
             const int slot = step % STAGES;
             const uint32_t use = (uint32_t)(step / STAGES);
-            if (!Cfg::PREFETCH_B) load_b(step, bb);
             mbar_wait(empty0 + 8 * slot, (use & 1u) ^ 1u);
-            const int c0 = (step % kchunks) * TC_BK;
+            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;      // taps innermost: L1 reuse of the voxel rows
+            const int4 tp = taps[tap];
+            const uint32_t a_dst = ring_u32 + slot * Cfg::STAGE_BYTES;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = rbase + 32 * j;
+                const int4 ri = rowinfo[r];
+                const int id = ri.x + tp.x, ih = ri.y + tp.y, iw = ri.z + tp.z;
+                const bool ok = ri.w >= 0 && (unsigned)id < (unsigned)p.Din && (unsigned)ih < (unsigned)p.Hin &&
+                                (unsigned)iw < (unsigned)p.Win;
+                const size_t vox = ok ? ((size_t)(b * p.Din + id) * p.Hin + ih) * p.Win + iw : 0;
+                cp_async16_ca(a_dst + r * 128 + ((chunk ^ (r & 7)) << 4), p.x + vox * p.in_ldc + c0 + chunk * 4, ok ? 16u : 0u);
+                mask |= (ok ? 1u : 0u) << j;
+            }
+            const float* wrow = p.wk + ((size_t)tp.w * p.CoutP) * p.Cin + c0 + chunk * 4;
+            const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+#pragma unroll
+            for (int j = 0; j < Cfg::B_CH; ++j) {
+                const int n = rbase + 32 * j;
+                const bool ok = (n0 + n) < p.CoutP;
+                cp_async16(b_dst + n * 128 + ((chunk ^ (n & 7)) << 4), wrow + (size_t)(ok ? n0 + n : 0) * p.Cin, ok ? 16u : 0u);
+            }
+            hist |= mask << (4 * (step % 8));
+        };
+        auto finish = [&](int step) {              // this thread's chunks of `step` have landed
+            const int slot = step % STAGES;
+            const int c0 = (step / ntaps) * TC_BK;
+            const uint32_t mask = (hist >> (4 * (step % 8))) & 15u;
+            hist &= ~(15u << (4 * (step % 8)));
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_aff) {
                 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
                 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
             }
             unsigned char* a_dst = ring + slot * Cfg::STAGE_BYTES;
-            unsigned char* b_dst = a_dst + Cfg::A_BYTES;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 v = ab[j];
+            for (int j = 0; j < 4; ++j) {
+                const int r = rbase + 32 * j;
+                float4* ptr = reinterpret_cast<float4*>(a_dst + r * 128 + ((chunk ^ (r & 7)) << 4));
+                float4 v = *ptr;
                 if (mask & (1u << j)) {
                     if (has_aff) {
                         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
@@ -280,40 +290,21 @@ conv_tc_kernel(const TcParams p) {
                         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                     }
                 }
-                const int r = rbase + 16 * j;
                 uint4 t;
                 t.x = f2tf32(v.x); t.y = f2tf32(v.y); t.z = f2tf32(v.z); t.w = f2tf32(v.w);
-                *reinterpret_cast<uint4*>(a_dst + r * 128 + ((chunk ^ (r & 7)) << 4)) = t;
-            }
-#pragma unroll
-            for (int j = 0; j < Cfg::B_F4; ++j) {
-                const int n = rbase + 16 * j;
-                *reinterpret_cast<float4*>(b_dst + n * 128 + ((chunk ^ (n & 7)) << 4)) = bb[j];
+                *reinterpret_cast<uint4*>(ptr) = t;
             }
             fence_proxy_async_smem();
             mbar_arrive(full0 + 8 * slot);
         };
 
-        int step = grp;
-        if (step < nsteps) {
-            load_a(step, a0, m0);
-            if (Cfg::PREFETCH_B) load_b(step, b0);
-        }
-        while (step < nsteps) {
-            if (step + 2 < nsteps) {
-                load_a(step + 2, a1, m1);
-                if constexpr (Cfg::PREFETCH_B) load_b(step + 2, b1);
+        for (int s = 0; s < nsteps + PF; ++s) {
+            if (s < nsteps) issue(s);
+            cp_async_commit();
+            if (s >= PF) {
+                cp_async_wait<PF>();
+                finish(s - PF);
             }
-            store_stage(step, a0, b0, m0);
-            step += 2;
-            if (step >= nsteps) break;
-            if (step + 2 < nsteps) {
-                load_a(step + 2, a0, m0);
-                if constexpr (Cfg::PREFETCH_B) load_b(step + 2, b0);
-            }
-            if constexpr (Cfg::PREFETCH_B) store_stage(step, a1, b1, m1);
-            else store_stage(step, a1, b0, m1);
-            step += 2;
         }
     } else {
         // ======================= MMA ISSUER (one elected lane) ===================================

@@ -415,8 +415,9 @@ def bri_attention(q: torch.Tensor, kv: torch.Tensor, params: torch.Tensor, out: 
         raise RuntimeError("bri_attention: q / kv must be contiguous [B,D,H,W]")
     B, D = q.shape[0], q.shape[1]
     N = int(math.prod(q.shape[2:]))
-    conf = torch.empty((B, N), dtype=torch.float32, device=q.device)
-    rc = lib.ss_bri_attn_fwd(q.data_ptr(), kv.data_ptr(), params.data_ptr(), conf.data_ptr(), out.data_ptr(), out_ld,
+    wsb = int(lib.ss_bri_workspace_bytes(B, D, N))
+    ws = torch.empty(wsb // 4, dtype=torch.float32, device=q.device)
+    rc = lib.ss_bri_attn_fwd(q.data_ptr(), kv.data_ptr(), params.data_ptr(), ws.data_ptr(), wsb, out.data_ptr(), out_ld,
                              B, D, N, _DEFAULT_MATH if math_mode is None else math_mode, _stream())
     cabi.check(rc, "ss_bri_attn_fwd")
     return out

@@ -189,6 +189,17 @@ class DCN(nn.Module):
         return deform_conv2d(x, self.conv_offset(x), self.weight, None, 1, self.padding, 1)
 
 
+def _group_norm_wide(x, gn: nn.GroupNorm):
+    """GroupNorm with few groups over a large map: torch's native kernel launches one CTA per
+    (sample, group) -- 2 CTAs here -- so the moments are taken with a split reduction instead."""
+    B, Cc = x.shape[:2]
+    xv = x.reshape(B, gn.num_groups, -1)
+    var, mean = torch.var_mean(xv, dim=2, unbiased=False, keepdim=True)
+    y = ((xv - mean) * torch.rsqrt(var + gn.eps)).view_as(x)
+    shp = (1, Cc) + (1,) * (x.dim() - 2)
+    return y * gn.weight.view(shp) + gn.bias.view(shp)
+
+
 class DepthNet(nn.Module):
     """ViewTransformerLSSBEVDepth.py:457-517.  Output channels: [0:D] depth logits, [D:D+ctx]
     context features."""
@@ -207,7 +218,7 @@ class DepthNet(nn.Module):
 
     def forward(self, x, mlp_input):
         m = self.bn(mlp_input.reshape(-1, mlp_input.shape[-1]))
-        x = self.reduce_conv(x)
+        x = torch.relu_(_group_norm_wide(self.reduce_conv[0](x), self.reduce_conv[1]))
         context = self.context_conv(self.context_se(x, self.context_mlp(m)[..., None, None]))
         depth = self.depth_conv(self.depth_se(x, self.depth_mlp(m)[..., None, None]))
         return torch.cat([depth, context], dim=1)
