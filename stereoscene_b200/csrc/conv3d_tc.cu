@@ -1,45 +1,45 @@
-// tcgen05 implicit-GEMM convolution for the tensor-bound layers (Cin % 32 == 0, Cout % 4 == 0).
+// tcgen05 + TMA implicit-GEMM convolution for the tensor-bound layers (Cin % 32 == 0, Cout % 4 == 0).
 //
-// Same contract as conv3d.cu (channels-last fp32 volumes, pending affine + activation applied
-// while the A tile is staged, bias/activation/GroupNorm sums in the epilogue, ordinary / strided /
-// dilated / transposed-by-parity-class gathers) but the multiply runs on the 5th-generation tensor
-// cores:
-//   * operands: TF32 (kind::tf32), staged in shared memory in the canonical K-major SWIZZLE_128B
-//     layout (one 128-byte row = 32 input channels of one voxel / one output channel), values
-//     rounded to TF32 with cvt.rna by the producers (weights are pre-rounded on the host side);
-//   * accumulators: fp32 in TMEM (128 lanes x BN columns), never in registers;
-//   * warp roles: 8 producer warps stream every K-step with cp.async (16-byte LDGSTS straight into
-//     the swizzled stage, zero-fill for padding rows, PREFETCH stages in flight per thread), then
-//     fix up their own chunks in place (pending affine, ReLU, cvt.rna.tf32), fence.proxy.async and
-//     arrive on the stage's mbarrier; 1 MMA warp (one elected lane issues 4 x tcgen05.mma
-//     M128 x N(BN) x K8 per stage and tcgen05.commit's the stage back to the producers); finally the
-//     8 producer warps drain TMEM with tcgen05.ld (32 lanes x 32 columns each), apply bias /
-//     activation, store 128-byte rows and reduce the per-channel sums with a shuffle butterfly.
-//   * pipeline: STAGES-deep ring of (A 16 KB + B BN*128 B) stages, full/empty mbarriers.
-// The gather cannot be a TMA tile load because the pending affine + ReLU of the producer layer must
-// be applied between HBM and the MMA (that fusion removes a full read+write pass per layer), so
-// staging is done by threads and made visible to the async proxy with fence.proxy.async.
+// Same contract as conv3d.cu (channels-last fp32 volumes, pending affine + activation of the
+// producer layer applied on the way in, bias / activation / GroupNorm sums in the epilogue,
+// ordinary / strided / dilated / transposed-by-parity-class gathers), built the Blackwell way:
+//   * One CTA owns a 128-voxel OUTPUT BOX (TD x TH x TW voxels, chosen per layer) x BN channels.
+//     For every K step (tap, 32-channel chunk) ONE thread issues two TMA tile loads:
+//       A: cp.async.bulk.tensor.5d over the NDHWC input (box 32ch x TW x TH x TD x 1, traversal
+//          stride = conv stride, start = box origin*stride + tap offset; out-of-bounds = zero fill,
+//          which IS the conv zero padding; data type TFLOAT32 so the TMA unit rounds to TF32),
+//       B: cp.async.bulk.tensor.2d over the K-major weights [tap*CoutP + n][Cin] (box 32 x BN),
+//     both landing in the canonical K-major SWIZZLE_128B layout (one 128-byte row = 32 channels of
+//     one voxel / one output channel) and signalling the stage's mbarrier with complete_tx bytes.
+//   * If the input carries a pending affine / ReLU (the previous layer's GroupNorm etc.), 8 fix-up
+//     warps apply it IN PLACE on the landed A tile (OOB rows stay zero), fence.proxy.async, and
+//     hand the stage to the MMA warp; plain inputs go TMA -> tensor core with no thread touching
+//     the data.
+//   * One elected lane issues 4 x tcgen05.mma (kind::tf32, M128 x N(BN) x K8) per stage into a TMEM
+//     accumulator (128 lanes x BN fp32 columns) and tcgen05.commit's the stage back to the TMA
+//     producer; after the last K step the 8 warps drain TMEM with tcgen05.ld (32 lanes x 32 columns),
+//     add bias / activation, store 128-byte rows and reduce per-channel sums with a shuffle butterfly.
+//   * STAGES-deep smem ring (A 16 KB + B BN*128 B per stage), full / ready / empty mbarriers.
+#include <cuda.h>
 #include "common.cuh"
 
 namespace ss {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                  // floats per K step = one 128-byte swizzle row
-constexpr int TC_PRODUCERS = 256;          // 8 warps, two groups of 4
-constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_WORKERS = 256;            // 8 fix-up / epilogue warps
+constexpr int TC_THREADS = TC_WORKERS + 64;   // + TMA warp + MMA warp
 constexpr int TC_MAX_TAPS = 64;
-
-struct ConvParams;                         // defined in conv3d.cu (same layout, redeclared below)
 
 struct TcParams {
     int B, Din, Hin, Win, Cin, Dout, Hout, Wout, Cout, CoutP;
     int kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw;
-    int transposed, in_ldc, out_ldc, in_act, out_act;
+    int transposed, out_ldc, in_act, out_act;
     int cls_d, cls_h, cls_w;
-    const float* x;
+    int TD, TH, TW;            // output box of one CTA (TD*TH*TW == 128)
+    int nTD, nTH, nTW;         // boxes per class grid (sized for the largest class)
     const float* in_scale;
     const float* in_shift;
-    const float* wk;        // [taps][CoutP][Cin]  (K-major, TF32-rounded)
     const float* bias;
     float* y;
     double* stats;
@@ -55,6 +55,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -72,17 +75,20 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// 16-byte async copy global -> shared (L2 only); src_bytes = 0 zero-fills the destination
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+// TMA tile loads (global -> shared, completion on an mbarrier via complete_tx::bytes)
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
-// same, allocating in L1: the 27 taps of a 3x3x3 stencil re-read the same voxel rows within a few steps
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
 
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
@@ -136,29 +142,26 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 template <int BN>
 struct TcCfg {
     static constexpr int STAGES = BN >= 256 ? 4 : BN >= 192 ? 5 : BN >= 128 ? 6 : 4;
-    static constexpr int PREFETCH = STAGES - 2;     // cp.async groups in flight per producer thread
     static constexpr int MIN_CTAS = BN <= 64 ? 2 : 1;
     static constexpr int A_BYTES = TC_BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    static constexpr int B_CH = BN * 8 / 256;       // 16-byte chunks of the weight tile per producer thread
 };
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::MIN_CTAS)
-conv_tc_kernel(const TcParams p) {
+conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned stage ring (SWIZZLE_128B atoms are 1024 B)
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* aux = ring + STAGES * Cfg::STAGE_BYTES;
-    int4* rowinfo = reinterpret_cast<int4*>(aux);                         // [128]
-    int4* taps = rowinfo + TC_BM;                                          // [TC_MAX_TAPS]
+    int4* taps = reinterpret_cast<int4*>(aux);                             // [TC_MAX_TAPS]
     double* sstat = reinterpret_cast<double*>(taps + TC_MAX_TAPS);         // [BN][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * BN);          // full[STAGES], empty[STAGES], accum
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * BN);          // full[S], ready[S], empty[S], accum
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
     int* s_ntaps = reinterpret_cast<int*>(tmem_slot + 1);
     float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [Cin] scale, [Cin] shift
 
@@ -169,12 +172,17 @@ conv_tc_kernel(const TcParams p) {
     const int n0 = blockIdx.y * BN;
     const int Dc = (p.Dout - rd + p.cls_d - 1) / p.cls_d, Hc = (p.Hout - rh + p.cls_h - 1) / p.cls_h,
               Wc = (p.Wout - rw + p.cls_w - 1) / p.cls_w;
-    const int Mc = Dc * Hc * Wc;
     const int isd = p.transposed ? 1 : p.sd, ish = p.transposed ? 1 : p.sh, isw = p.transposed ? 1 : p.sw;
-    const int m_base = blockIdx.x * TC_BM;
-    if (m_base >= Mc) return;
+    // output box of this CTA in class-grid coordinates
+    const int tw_i = blockIdx.x % p.nTW, th_i = (blockIdx.x / p.nTW) % p.nTH, td_i = blockIdx.x / (p.nTW * p.nTH);
+    const int q0d = td_i * p.TD, q0h = th_i * p.TH, q0w = tw_i * p.TW;
+    if (q0d >= Dc || q0h >= Hc || q0w >= Wc) return;          // smaller parity classes have fewer boxes (uniform per CTA)
 
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+    const uint32_t full0 = smem_u32(bars), ready0 = smem_u32(bars + STAGES), empty0 = smem_u32(bars + 2 * STAGES),
+                   accum_bar = smem_u32(bars + 3 * STAGES);
+    const bool has_aff = (p.in_scale != nullptr);
+    const bool in_relu = (p.in_act == SS_ACT_RELU);
+    const bool fixup = has_aff || in_relu;
 
     // ---- per-CTA setup ------------------------------------------------------------------------
     if (tid == 0) {
@@ -194,31 +202,22 @@ conv_tc_kernel(const TcParams p) {
                 }
         *s_ntaps = n;
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, TC_PRODUCERS);   // every producer thread arrives once per stage
-            mbar_init(empty0 + 8 * s, 1);       // released by one tcgen05.commit
+            mbar_init(full0 + 8 * s, 1);              // one arrive.expect_tx by the TMA thread (+ tx bytes)
+            mbar_init(ready0 + 8 * s, TC_WORKERS);    // every fix-up thread arrives once per stage
+            mbar_init(empty0 + 8 * s, 1);             // released by one tcgen05.commit
         }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
-    }
-    if (tid < TC_BM) {
-        const int m = m_base + tid;
-        int4 ri = make_int4(0, 0, 0, -1);
-        if (m < Mc) {
-            const int qd = m / (Hc * Wc), rem = m % (Hc * Wc);
-            const int qh = rem / Wc, qw = rem % Wc;
-            const int od = qd * p.cls_d + rd, oh = qh * p.cls_h + rh, ow = qw * p.cls_w + rw;
-            ri = make_int4(qd * isd, qh * ish, qw * isw, ((b * p.Dout + od) * p.Hout + oh) * p.Wout + ow);
-        }
-        rowinfo[tid] = ri;
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
     }
     for (int i = tid; i < 2 * BN; i += TC_THREADS) sstat[i] = 0.0;
-    const bool has_aff = (p.in_scale != nullptr);
     if (has_aff)
         for (int i = tid; i < p.Cin; i += TC_THREADS) {
             ssc[i] = __ldg(p.in_scale + (size_t)b * p.Cin + i);
             ssc[p.Cin + i] = __ldg(p.in_shift + (size_t)b * p.Cin + i);
         }
-    if (warp == TC_PRODUCERS / 32) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+    if (warp == TC_WORKERS / 32 + 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -228,91 +227,30 @@ conv_tc_kernel(const TcParams p) {
     const int nsteps = ntaps * kchunks;
     const uint32_t ring_u32 = smem_u32(ring);
 
-    if (warp < TC_PRODUCERS / 32) {
-        // ======================= PRODUCERS: cp.async ring, PREFETCH stages in flight ================
-        constexpr int PF = Cfg::PREFETCH;
-        const int chunk = tid & 7;                 // 16-byte chunk of the 128-byte row
-        const int rbase = tid >> 3;                // rows rbase + 32 j
-        const bool in_relu = (p.in_act == SS_ACT_RELU);
-        uint32_t hist = 0;                         // validity masks of the in-flight steps, 4 bits each
-
-        auto issue = [&](int step) {
-            const int slot = step % STAGES;
-            const uint32_t use = (uint32_t)(step / STAGES);
-            mbar_wait(empty0 + 8 * slot, (use & 1u) ^ 1u);
-            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;      // taps innermost: L1 reuse of the voxel rows
-            const int4 tp = taps[tap];
-            const uint32_t a_dst = ring_u32 + slot * Cfg::STAGE_BYTES;
-            uint32_t mask = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = rbase + 32 * j;
-                const int4 ri = rowinfo[r];
-                const int id = ri.x + tp.x, ih = ri.y + tp.y, iw = ri.z + tp.z;
-                const bool ok = ri.w >= 0 && (unsigned)id < (unsigned)p.Din && (unsigned)ih < (unsigned)p.Hin &&
-                                (unsigned)iw < (unsigned)p.Win;
-                const size_t vox = ok ? ((size_t)(b * p.Din + id) * p.Hin + ih) * p.Win + iw : 0;
-                cp_async16_ca(a_dst + r * 128 + ((chunk ^ (r & 7)) << 4), p.x + vox * p.in_ldc + c0 + chunk * 4, ok ? 16u : 0u);
-                mask |= (ok ? 1u : 0u) << j;
-            }
-            const float* wrow = p.wk + ((size_t)tp.w * p.CoutP) * p.Cin + c0 + chunk * 4;
-            const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-#pragma unroll
-            for (int j = 0; j < Cfg::B_CH; ++j) {
-                const int n = rbase + 32 * j;
-                const bool ok = (n0 + n) < p.CoutP;
-                cp_async16(b_dst + n * 128 + ((chunk ^ (n & 7)) << 4), wrow + (size_t)(ok ? n0 + n : 0) * p.Cin, ok ? 16u : 0u);
-            }
-            hist |= mask << (4 * (step % 8));
-        };
-        auto finish = [&](int step) {              // this thread's chunks of `step` have landed
-            const int slot = step % STAGES;
-            const int c0 = (step / ntaps) * TC_BK;
-            const uint32_t mask = (hist >> (4 * (step % 8))) & 15u;
-            hist &= ~(15u << (4 * (step % 8)));
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_aff) {
-                sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
-                sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
-            }
-            unsigned char* a_dst = ring + slot * Cfg::STAGE_BYTES;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = rbase + 32 * j;
-                float4* ptr = reinterpret_cast<float4*>(a_dst + r * 128 + ((chunk ^ (r & 7)) << 4));
-                float4 v = *ptr;
-                if (mask & (1u << j)) {
-                    if (has_aff) {
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                    }
-                    if (in_relu) {
-                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                    }
-                }
-                uint4 t;
-                t.x = f2tf32(v.x); t.y = f2tf32(v.y); t.z = f2tf32(v.z); t.w = f2tf32(v.w);
-                *reinterpret_cast<uint4*>(ptr) = t;
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(full0 + 8 * slot);
-        };
-
-        for (int s = 0; s < nsteps + PF; ++s) {
-            if (s < nsteps) issue(s);
-            cp_async_commit();
-            if (s >= PF) {
-                cp_async_wait<PF>();
-                finish(s - PF);
+    if (warp == TC_WORKERS / 32) {
+        // ======================= TMA PRODUCER (one lane) =========================================
+        if (lane == 0) {
+            for (int step = 0; step < nsteps; ++step) {
+                const int slot = step % STAGES;
+                const uint32_t use = (uint32_t)(step / STAGES);
+                mbar_wait(empty0 + 8 * slot, (use & 1u) ^ 1u);
+                const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;     // taps innermost: the box stays hot in L2
+                const int4 tp = taps[tap];
+                const uint32_t a_dst = ring_u32 + slot * Cfg::STAGE_BYTES;
+                const uint32_t bar = full0 + 8 * slot;
+                mbar_arrive_expect_tx(bar, Cfg::STAGE_BYTES);
+                tma_load_5d(a_dst, &tmA, bar, c0, q0w * isw + tp.z, q0h * ish + tp.y, q0d * isd + tp.x, b);
+                tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, bar, c0, tp.w * p.CoutP + n0);
             }
         }
-    } else {
-        // ======================= MMA ISSUER (one elected lane) ===================================
+    } else if (warp == TC_WORKERS / 32 + 1) {
+        // ======================= MMA ISSUER (one lane) ===========================================
         constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+        const uint32_t wait0 = fixup ? ready0 : full0;
         for (int step = 0; step < nsteps; ++step) {
             const int slot = step % STAGES;
             const uint32_t use = (uint32_t)(step / STAGES);
-            mbar_wait(full0 + 8 * slot, use & 1u);
+            mbar_wait(wait0 + 8 * slot, use & 1u);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_addr = ring_u32 + slot * Cfg::STAGE_BYTES;
@@ -326,16 +264,69 @@ conv_tc_kernel(const TcParams p) {
             }
             __syncwarp();
         }
+    } else if (fixup) {
+        // ======================= FIX-UP WARPS: pending affine / ReLU in place ====================
+        const int chunk = tid & 7;                 // 16-byte chunk of the 128-byte row
+        const int rbase = tid >> 3;                // rows rbase + 32 j
+        int ld[4], lh[4], lw[4];                   // input coordinates of this thread's rows at tap offset 0
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = rbase + 32 * j;
+            lw[j] = (q0w + r % p.TW) * isw;
+            lh[j] = (q0h + (r / p.TW) % p.TH) * ish;
+            ld[j] = (q0d + r / (p.TW * p.TH)) * isd;
+        }
+        for (int step = 0; step < nsteps; ++step) {
+            const int slot = step % STAGES;
+            const uint32_t use = (uint32_t)(step / STAGES);
+            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
+            const int4 tp = taps[tap];
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_aff) {
+                sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
+                sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
+            }
+            mbar_wait(full0 + 8 * slot, use & 1u);
+            unsigned char* a_dst = ring + slot * Cfg::STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = rbase + 32 * j;
+                // zero padding must stay zero: only rows whose tap lands inside the input are touched
+                const bool ok = (unsigned)(ld[j] + tp.x) < (unsigned)p.Din && (unsigned)(lh[j] + tp.y) < (unsigned)p.Hin &&
+                                (unsigned)(lw[j] + tp.z) < (unsigned)p.Win;
+                if (ok) {
+                    float4* ptr = reinterpret_cast<float4*>(a_dst + r * 128 + ((chunk ^ (r & 7)) << 4));
+                    float4 v = *ptr;
+                    if (has_aff) {
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    }
+                    if (in_relu) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                    uint4 t;
+                    t.x = f2tf32(v.x); t.y = f2tf32(v.y); t.z = f2tf32(v.z); t.w = f2tf32(v.w);
+                    *reinterpret_cast<uint4*>(ptr) = t;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(ready0 + 8 * slot);
+        }
     }
 
     // ======================= EPILOGUE: 8 warps drain TMEM ========================================
-    if (warp < TC_PRODUCERS / 32) {
+    if (warp < TC_WORKERS / 32) {
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int half = warp >> 2;                    // column half handled by this warp
         const int row = q * 32 + lane;
-        const int ov = rowinfo[row].w;
+        const int qd = q0d + row / (p.TW * p.TH), qh = q0h + (row / p.TW) % p.TH, qw = q0w + row % p.TW;
+        int ov = -1;
+        if (qd < Dc && qh < Hc && qw < Wc) {
+            const int od = qd * p.cls_d + rd, oh = qh * p.cls_h + rh, ow = qw * p.cls_w + rw;
+            ov = ((b * p.Dout + od) * p.Hout + oh) * p.Wout + ow;
+        }
         constexpr int CHUNKS = BN / 32;
         constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
@@ -395,27 +386,87 @@ conv_tc_kernel(const TcParams p) {
             }
         }
     }
-    if (warp == TC_PRODUCERS / 32) {
+    if (warp == TC_WORKERS / 32 + 1) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// choose the 128-voxel output box: powers of two, maximise the fraction of useful rows, prefer a long W
+static void choose_box(int Dc, int Hc, int Wc, int sd, int sh, int sw, int& TD, int& TH, int& TW) {
+    double best = -1.0;
+    for (int tw = 128; tw >= 1; tw >>= 1)
+        for (int th = 128 / tw; th >= 1; th >>= 1) {
+            const int td = 128 / (tw * th);
+            if (tw * sw > 256 || th * sh > 256 || td * sd > 256) continue;       // TMA box limit
+            auto eff = [](int n, int t) { return (double)n / (double)(((n + t - 1) / t) * t); };
+            const double u = eff(Dc, td) * eff(Hc, th) * eff(Wc, tw) + 1e-6 * tw;
+            if (u > best) { best = u; TD = td; TH = th; TW = tw; }
+        }
+}
+
 template <int BN>
-static int launch_tc(const TcParams& p, cudaStream_t st) {
+static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, int ntaps_total, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
-    size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + TC_BM * sizeof(int4) + TC_MAX_TAPS * sizeof(int4) +
-                  2 * BN * sizeof(double) + (2 * Cfg::STAGES + 1) * sizeof(uint64_t) + 16 + 2 * (size_t)p.Cin * sizeof(float) + 32;
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return set_arg_error("ss_conv3d_tc_fwd: cuTensorMapEncodeTiled is not available from the driver");
+    const int ncls = p.cls_d * p.cls_h * p.cls_w;
+    const int Dc = (p.Dout + p.cls_d - 1) / p.cls_d, Hc = (p.Hout + p.cls_h - 1) / p.cls_h, Wc = (p.Wout + p.cls_w - 1) / p.cls_w;
+    const int isd = p.transposed ? 1 : p.sd, ish = p.transposed ? 1 : p.sh, isw = p.transposed ? 1 : p.sw;
+    choose_box(Dc, Hc, Wc, isd, ish, isw, p.TD, p.TH, p.TW);
+    p.nTD = (Dc + p.TD - 1) / p.TD; p.nTH = (Hc + p.TH - 1) / p.TH; p.nTW = (Wc + p.TW - 1) / p.TW;
+
+    alignas(64) CUtensorMap tmA, tmB;
+    {   // A: NDHWC input, 5-D (C, W, H, D, B)
+        cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.Din, (cuuint64_t)p.B};
+        cuuint64_t gstr[4] = {(cuuint64_t)in_ldc * 4, (cuuint64_t)p.Win * in_ldc * 4, (cuuint64_t)p.Hin * p.Win * in_ldc * 4,
+                              (cuuint64_t)p.Din * p.Hin * p.Win * in_ldc * 4};
+        cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * isw), (cuuint32_t)(p.TH * ish), (cuuint32_t)(p.TD * isd), 1};
+        cuuint32_t estr[5] = {1, (cuuint32_t)isw, (cuuint32_t)ish, (cuuint32_t)isd, 1};
+        // plain input: TFLOAT32 (the TMA unit rounds fp32 -> tf32); pending affine: raw FLOAT32, the fix-up
+        // warps round once, after the affine
+        const bool fixup = (p.in_scale != nullptr) || (p.in_act == SS_ACT_RELU);
+        CUresult r = encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_arg_error("ss_conv3d_tc_fwd: cuTensorMapEncodeTiled(A) failed");
+    }
+    {   // B: K-major weights [taps*CoutP][Cin]
+        cuuint64_t gdim[2] = {(cuuint64_t)p.Cin, (cuuint64_t)ntaps_total * p.CoutP};
+        cuuint64_t gstr[1] = {(cuuint64_t)p.Cin * 4};
+        cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wk), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_arg_error("ss_conv3d_tc_fwd: cuTensorMapEncodeTiled(B) failed");
+    }
+    size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + TC_MAX_TAPS * sizeof(int4) + 2 * BN * sizeof(double) +
+                  (3 * Cfg::STAGES + 1) * sizeof(uint64_t) + 16 + 2 * (size_t)p.Cin * sizeof(float) + 32;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         SS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int ncls = p.cls_d * p.cls_h * p.cls_w;
-    const int Dc = (p.Dout + p.cls_d - 1) / p.cls_d, Hc = (p.Hout + p.cls_h - 1) / p.cls_h, Wc = (p.Wout + p.cls_w - 1) / p.cls_w;
-    const long long Mc = (long long)Dc * Hc * Wc;
-    dim3 grid((unsigned)((Mc + TC_BM - 1) / TC_BM), (unsigned)((p.CoutP + BN - 1) / BN), (unsigned)(p.B * ncls));
-    conv_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(p);
+    dim3 grid((unsigned)(p.nTD * p.nTH * p.nTW), (unsigned)((p.CoutP + BN - 1) / BN), (unsigned)(p.B * ncls));
+    conv_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(p, tmA, tmB);
     return check_launch("conv_tc_kernel");
 }
 
@@ -429,7 +480,9 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     SS_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0, "ss_conv3d_tc_fwd: empty shape");
     SS_REQUIRE(d->Cin % TC_BK == 0 && d->in_ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                "ss_conv3d_tc_fwd: needs Cin % 32 == 0 and 16-byte aligned channels-last input");
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(w_kmajor) & 15) == 0, "ss_conv3d_tc_fwd: weights must be 16-byte aligned");
     SS_REQUIRE(d->kd >= 1 && d->kd <= 4 && d->kh >= 1 && d->kh <= 4 && d->kw >= 1 && d->kw <= 4, "ss_conv3d_tc_fwd: kernel extent");
+    SS_REQUIRE(d->sd >= 1 && d->sd <= 8 && d->sh >= 1 && d->sh <= 8 && d->sw >= 1 && d->sw <= 8, "ss_conv3d_tc_fwd: stride");
     SS_REQUIRE(d->cout_packed >= d->Cout && d->cout_packed % 8 == 0, "ss_conv3d_tc_fwd: cout_packed");
     SS_REQUIRE(d->in_ldc >= d->Cin && d->out_ldc >= d->Cout, "ss_conv3d_tc_fwd: ldc");
     SS_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "ss_conv3d_tc_fwd: scale/shift must come together");
@@ -443,15 +496,16 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     p.Dout = d->Dout; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout; p.CoutP = d->cout_packed;
     p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
     p.pd = d->pd; p.ph = d->ph; p.pw = d->pw; p.dd = d->dd; p.dh = d->dh; p.dw = d->dw;
-    p.transposed = d->transposed; p.in_ldc = d->in_ldc; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
+    p.transposed = d->transposed; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
     p.cls_d = d->transposed ? d->sd : 1; p.cls_h = d->transposed ? d->sh : 1; p.cls_w = d->transposed ? d->sw : 1;
-    p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.wk = w_kmajor; p.bias = bias; p.y = y; p.stats = stats;
+    p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int cp = d->cout_packed;
-    if (cp <= 32) return launch_tc<32>(p, st);
-    if (cp <= 64) return launch_tc<64>(p, st);
-    if (cp <= 128) return launch_tc<128>(p, st);
-    if (cp <= 192) return launch_tc<192>(p, st);
-    return launch_tc<256>(p, st);
+    const int ntaps_total = d->kd * d->kh * d->kw;
+    if (cp <= 32) return launch_tc<32>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+    if (cp <= 64) return launch_tc<64>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+    if (cp <= 128) return launch_tc<128>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+    if (cp <= 192) return launch_tc<192>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+    return launch_tc<256>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
 }
