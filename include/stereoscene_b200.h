@@ -192,6 +192,16 @@ int ss_bev_pool_fwd(const float* feats, const int64_t* coords, long long N, int 
 int ss_trilinear_fwd(const float* x, float* y, uint8_t* labels, int B, int C, int Di, int Hi, int Wi,
                      int Do, int Ho, int Wo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Deformable-convolution sampling (mmcv DeformConv2dPack / torchvision deform_conv2d semantics,
+ * deform_groups = 1), DepthNet's DCN layer (image2bev/ViewTransformerLSSBEVDepth.py:490-498).
+ *   x: [B][H][W][C] channels-last;  offsets: [B][2*kh*kw][Ho][Wo] (NCHW: 2t = dy, 2t+1 = dx)
+ *   out: [B][Ho][Wo][groups][kh*kw][C/groups]  -- the im2col rows of each group, ready for a 1x1
+ *        ss_conv3d_tc_fwd per group with K = kh*kw*C/groups.
+ * ------------------------------------------------------------------------------------------- */
+int ss_deform_sample_fwd(const float* x, const float* offsets, float* out, int B, int H, int W, int C,
+                         int groups, int kh, int kw, int stride, int pad, int dil, void* stream);
+
 /* Layout helpers: NCHW/NCDHW <-> channels-last copies ([B][C][V] <-> [B][V][C]). */
 int ss_nchw_to_nhwc(const float* x, float* y, int B, int C, long long V, int out_ldc, void* stream);
 int ss_nhwc_to_nchw(const float* x, float* y, int B, int C, long long V, int in_ldc, void* stream);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "ss_bev_pool_workspace_bytes": (_sz, [_ll, _ll]),
     "ss_bev_pool_fwd": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ss_trilinear_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ss_deform_sample_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ss_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
     "ss_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
 }

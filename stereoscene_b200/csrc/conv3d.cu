@@ -403,6 +403,11 @@ static int dispatch_conv(const ConvParams& p, bool precise, bool vec, cudaStream
 
 }  // namespace ss
 
+namespace ss {
+int try_conv_cout1(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                   const float* w_packed, const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
+}
+
 extern "C" int ss_conv3d_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                              const float* w_packed, const float* bias, float* y, double* stats, void* stream) {
     using namespace ss;
@@ -434,6 +439,10 @@ extern "C" int ss_conv3d_fwd(const ss_conv3d_desc* d, const float* x, const floa
     const bool vec = (d->Cin % BK == 0) && (d->in_ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const bool precise = (d->math == SS_MATH_3XTF32);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {   // single-output-channel layers are bandwidth problems: FMA-pipe kernel (fp32 exact)
+        int rc1 = 0;
+        if (try_conv_cout1(d, x, in_scale, in_shift, w_packed, bias, y, stats, st, &rc1)) return rc1;
+    }
     const int cp = d->cout_packed;
     if (cp <= 8) return dispatch_conv<8, 8, 1>(p, precise, vec, st);
     if (cp <= 16) return dispatch_conv<16, 8, 1>(p, precise, vec, st);

@@ -268,19 +268,32 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
         // ======================= FIX-UP WARPS: pending affine / ReLU in place ====================
         const int chunk = tid & 7;                 // 16-byte chunk of the 128-byte row
         const int rbase = tid >> 3;                // rows rbase + 32 j
-        int ld[4], lh[4], lw[4];                   // input coordinates of this thread's rows at tap offset 0
+        // per-row validity of every tap (bit t = tap t lands inside the input): zero padding written by
+        // the TMA unit must stay zero, so only in-bounds rows are transformed
+        unsigned long long vmask[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = rbase + 32 * j;
-            lw[j] = (q0w + r % p.TW) * isw;
-            lh[j] = (q0h + (r / p.TW) % p.TH) * ish;
-            ld[j] = (q0d + r / (p.TW * p.TH)) * isd;
+            const int iw = (q0w + r % p.TW) * isw, ih = (q0h + (r / p.TW) % p.TH) * ish, id = (q0d + r / (p.TW * p.TH)) * isd;
+            unsigned long long m = 0;
+            for (int t = 0; t < ntaps; ++t) {
+                const int4 tp = taps[t];
+                const bool ok = (unsigned)(id + tp.x) < (unsigned)p.Din && (unsigned)(ih + tp.y) < (unsigned)p.Hin &&
+                                (unsigned)(iw + tp.z) < (unsigned)p.Win;
+                m |= (unsigned long long)(ok ? 1 : 0) << t;
+            }
+            vmask[j] = m;
+        }
+        uint32_t roff[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = rbase + 32 * j;
+            roff[j] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
         }
         for (int step = 0; step < nsteps; ++step) {
             const int slot = step % STAGES;
             const uint32_t use = (uint32_t)(step / STAGES);
             const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
-            const int4 tp = taps[tap];
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_aff) {
                 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
@@ -288,26 +301,18 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             }
             mbar_wait(full0 + 8 * slot, use & 1u);
             unsigned char* a_dst = ring + slot * Cfg::STAGE_BYTES;
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(a_dst + roff[j]);     // 4 independent loads
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int r = rbase + 32 * j;
-                // zero padding must stay zero: only rows whose tap lands inside the input are touched
-                const bool ok = (unsigned)(ld[j] + tp.x) < (unsigned)p.Din && (unsigned)(lh[j] + tp.y) < (unsigned)p.Hin &&
-                                (unsigned)(lw[j] + tp.z) < (unsigned)p.Win;
-                if (ok) {
-                    float4* ptr = reinterpret_cast<float4*>(a_dst + r * 128 + ((chunk ^ (r & 7)) << 4));
-                    float4 v = *ptr;
-                    if (has_aff) {
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                    }
-                    if (in_relu) {
-                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                    }
-                    uint4 t;
-                    t.x = f2tf32(v.x); t.y = f2tf32(v.y); t.z = f2tf32(v.z); t.w = f2tf32(v.w);
-                    *reinterpret_cast<uint4*>(ptr) = t;
-                }
+                const bool ok = (vmask[j] >> tap) & 1ull;
+                float4 w = v[j];
+                w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+                if (in_relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+                uint4 t;
+                t.x = ok ? f2tf32(w.x) : 0u; t.y = ok ? f2tf32(w.y) : 0u; t.z = ok ? f2tf32(w.z) : 0u; t.w = ok ? f2tf32(w.w) : 0u;
+                *reinterpret_cast<uint4*>(a_dst + roff[j]) = t;
             }
             fence_proxy_async_smem();
             mbar_arrive(ready0 + 8 * slot);
@@ -507,5 +512,12 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     if (cp <= 64) return launch_tc<64>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
     if (cp <= 128) return launch_tc<128>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
     if (cp <= 192) return launch_tc<192>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+    {   // wide layers on small grids: 256-column tiles leave most SMs idle, 128-column tiles double the CTA count
+        const int ncls = p.cls_d * p.cls_h * p.cls_w;
+        const long long rows = ((long long)(p.Dout + p.cls_d - 1) / p.cls_d) * ((p.Hout + p.cls_h - 1) / p.cls_h) *
+                               ((p.Wout + p.cls_w - 1) / p.cls_w);
+        const long long ctas256 = ((rows + TC_BM - 1) / TC_BM) * ((cp + 255) / 256) * p.B * ncls;
+        if (ctas256 < 2 * 148 && cp % 128 == 0) return launch_tc<128>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+    }
     return launch_tc<256>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
 }

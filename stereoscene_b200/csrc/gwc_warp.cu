@@ -13,7 +13,7 @@
 namespace ss {
 
 constexpr int GW_THREADS = 256;
-constexpr int GW_KCHUNK = 16;
+constexpr int GW_KCHUNK = 8;
 
 // fea: [2B][H][W][C]; CTA = (k-chunk, h, b)
 template <int CPG>
@@ -36,36 +36,40 @@ gwc_warp_kernel(const float* __restrict__ fea, const int32_t* __restrict__ i0p, 
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr float inv_cpg = 1.0f / CPG;
-    const int total = kn * W;
-    for (int idx = warp; idx < total; idx += GW_THREADS / 32) {
-        const int kk = idx / W, w = idx % W;
+    // each warp takes whole depth bins: the two disparity taps are loop constants, lanes = groups
+    for (int kk = warp; kk < kn; kk += GW_THREADS / 32) {
         const int k = k0 + kk;
         const int i0 = __ldg(i0p + b * K + k);
         const float a0 = __ldg(w0p + b * K + k), a1 = __ldg(w1p + b * K + k);
         const int i1 = i0 + 1;
-        const bool v0ok = (i0 >= 0 && i0 < maxdisp && w - i0 >= 0);
-        const bool v1ok = (i1 >= 0 && i1 < maxdisp && w - i1 >= 0);
+        const bool t0 = (i0 >= 0 && i0 < maxdisp), t1 = (i1 >= 0 && i1 < maxdisp);
+        float* orow = out + ((((size_t)b * K + k) * H + h) * W) * G;
         for (int g = lane; g < G; g += 32) {
-            float r[CPG];
+            const float* rg = sref + g * CPG;
+            const float* tg = stgt + g * CPG;
+#pragma unroll 4
+            for (int w = 0; w < W; ++w) {
+                float r[CPG];
 #pragma unroll
-            for (int c = 0; c < CPG; ++c) r[c] = sref[w * C + g * CPG + c];
-            float acc = 0.f;
-            bool any = false;
-            if (v0ok) {
-                float s = 0.f;
+                for (int c = 0; c < CPG; ++c) r[c] = rg[w * C + c];
+                float acc = 0.f;
+                bool any = false;
+                if (t0 && w >= i0) {
+                    float s = 0.f;
 #pragma unroll
-                for (int c = 0; c < CPG; ++c) s += r[c] * stgt[(w - i0) * C + g * CPG + c];
-                acc = (s * inv_cpg) * a0;
-                any = true;
+                    for (int c = 0; c < CPG; ++c) s += r[c] * tg[(w - i0) * C + c];
+                    acc = (s * inv_cpg) * a0;
+                    any = true;
+                }
+                if (t1 && w >= i1) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int c = 0; c < CPG; ++c) s += r[c] * tg[(w - i1) * C + c];
+                    const float tv = (s * inv_cpg) * a1;
+                    acc = any ? acc + tv : tv;
+                }
+                __stcs(orow + (size_t)w * G + g, acc);
             }
-            if (v1ok) {
-                float s = 0.f;
-#pragma unroll
-                for (int c = 0; c < CPG; ++c) s += r[c] * stgt[(w - i1) * C + g * CPG + c];
-                const float tv = (s * inv_cpg) * a1;
-                acc = any ? acc + tv : tv;
-            }
-            __stcs(out + ((((size_t)b * K + k) * H + h) * W + w) * G + g, acc);
         }
     }
 }

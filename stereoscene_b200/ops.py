@@ -501,6 +501,24 @@ def bev_pool(feats: torch.Tensor, coords: torch.Tensor, B, D, H, W) -> torch.Ten
     return out
 
 
+def deform_sample(x: torch.Tensor, offsets: torch.Tensor, groups: int, k: int, stride: int, pad: int, dil: int):
+    """x [B,H,W,C] channels-last, offsets [B,2*k*k,Ho,Wo] NCHW -> S [B,Ho,Wo,groups,k*k,C/groups]."""
+    lib = cabi.load()
+    _need_cuda_f32(x, "deform_sample x"); _need_cuda_f32(offsets, "deform_sample offsets")
+    if not (x.is_contiguous() and offsets.is_contiguous()):
+        raise RuntimeError("deform_sample: inputs must be contiguous")
+    B, H, W, Cc = x.shape
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    if tuple(offsets.shape) != (B, 2 * k * k, Ho, Wo):
+        raise RuntimeError(f"deform_sample: offsets shape {tuple(offsets.shape)}, expected {(B, 2 * k * k, Ho, Wo)}")
+    out = torch.empty((B, Ho, Wo, groups, k * k, Cc // groups), dtype=torch.float32, device=x.device)
+    rc = lib.ss_deform_sample_fwd(x.data_ptr(), offsets.data_ptr(), out.data_ptr(), B, H, W, Cc, groups, k, k, stride, pad,
+                                  dil, _stream())
+    cabi.check(rc, "ss_deform_sample_fwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # resize + layout
 # ------------------------------------------------------------------------------------------

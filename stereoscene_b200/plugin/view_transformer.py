@@ -173,7 +173,9 @@ class ASPP(nn.Module):
 
 class DCN(nn.Module):
     """mmcv DeformConv2dPack semantics (no bias; offsets from a zero-initialised 3x3 conv),
-    ViewTransformerLSSBEVDepth.py:490-498."""
+    ViewTransformerLSSBEVDepth.py:490-498.  Sampling runs in ss_deform_sample_fwd, the grouped GEMM
+    on the tcgen05 conv kernel (one 1x1 conv per group over the sampled rows); on a CPU tensor the
+    module falls back to nothing -- it raises, like the rest of the hot path."""
 
     def __init__(self, cin, cout, k=3, padding=1, groups=4):
         super().__init__()
@@ -182,11 +184,43 @@ class DCN(nn.Module):
         self.conv_offset = nn.Conv2d(cin, 2 * k * k, k, 1, padding, bias=True)
         nn.init.zeros_(self.conv_offset.weight)
         nn.init.zeros_(self.conv_offset.bias)
-        self.padding = padding
+        self.padding, self.groups, self.k = padding, groups, k
+        object.__setattr__(self, "_gconvs", None)      # per-group 1x1 weight holders (not parameters)
+        object.__setattr__(self, "_gkey", None)
+
+    def _group_convs(self):
+        w = self.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self._gkey:
+            G, k = self.groups, self.k
+            cout_g, cin_g = w.shape[0] // G, w.shape[1]
+            with torch.no_grad():
+                # [G][cout_g][cin_g][k*k] -> [G][cout_g][k*k][cin_g]: K index = tap * cin_g + channel
+                wm = w.detach().view(G, cout_g, cin_g, k * k).permute(0, 1, 3, 2).reshape(G, cout_g, k * k * cin_g)
+                convs = []
+                for g in range(G):
+                    c = nn.Conv3d(k * k * cin_g, cout_g, 1, bias=False).to(w.device)
+                    c.weight.copy_(wm[g].view(cout_g, -1, 1, 1, 1))
+                    c.weight.requires_grad_(False)
+                    convs.append(c)
+            object.__setattr__(self, "_gconvs", convs)
+            object.__setattr__(self, "_gkey", key)
+        return self._gconvs
 
     def forward(self, x):
-        from torchvision.ops import deform_conv2d
-        return deform_conv2d(x, self.conv_offset(x), self.weight, None, 1, self.padding, 1)
+        """x: [B,C,H,W] -> [B,Cout,H,W] (channels_last memory)."""
+        B, Cc, H, W = x.shape
+        off = self.conv_offset(x).contiguous()
+        xcl = ops.to_channels_last(x)                                           # [B,H,W,C]
+        S = ops.deform_sample(xcl, off, self.groups, self.k, 1, self.padding, 1)  # [B,H,W,G,k*k,C/G]
+        G = self.groups
+        S5 = S.view(B, 1, H, W, G, -1)
+        cout = self.weight.shape[0]
+        out = torch.empty((B, 1, H, W, cout), dtype=torch.float32, device=x.device)
+        cg = cout // G
+        for g, conv in enumerate(self._group_convs()):
+            ops.conv(ops.Vol(S5[..., g, :]), conv, out=out[..., g * cg:(g + 1) * cg])
+        return out.squeeze(1).permute(0, 3, 1, 2)
 
 
 def _group_norm_wide(x, gn: nn.GroupNorm):

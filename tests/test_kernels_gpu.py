@@ -107,6 +107,23 @@ def test_tcgen05_conv_agrees_with_mma_sync(ops, case):
     assert rel_err(st1[..., 1], st0[..., 1]) < 2e-3
 
 
+def test_single_output_channel_conv(ops):
+    """32 -> 1 k3 layers (classif3_2 / MIE redir2) run on the FMA-pipe kernel: pending affine + ReLU in,
+    bias + ReLU out, W not a multiple of the 8-voxel segment."""
+    torch.manual_seed(21)
+    for cin, shape in ((32, (2, 32, 5, 7, 13)), (64, (1, 64, 3, 4, 21))):
+        m = nn.Conv3d(cin, 1, 3, 1, 1, bias=True)
+        x = torch.randn(shape)
+        sc, sh = torch.rand(shape[0], cin) + 0.5, torch.randn(shape[0], cin) * 0.3
+        xin = F.relu(x * sc[:, :, None, None, None] + sh[:, :, None, None, None])
+        want = F.relu(m(xin)).detach()
+        mg = nn.Conv3d(cin, 1, 3, 1, 1, bias=True).cuda()
+        mg.load_state_dict(m.state_dict())
+        y, _ = ops.conv(ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU), mg, out_act=ops.SS_ACT_RELU,
+                        math_mode=ops.SS_MATH_TF32)
+        assert rel_err(_ncdhw(y), want) < 1e-5
+
+
 @pytest.mark.parametrize("mode", ["precise", "tf32"])
 def test_conv2d_dilated_bias_gelu(ops, mode):
     torch.manual_seed(3)
@@ -296,6 +313,30 @@ def test_bev_pool_dropin(ops):
     assert rel_err(got, want) < 1e-6
     empty = ops.bev_pool(feats[:0].cuda(), coords[:0].cuda(), B, Dz, Hx, Wy)
     assert float(empty.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["precise", "tf32"])
+def test_deformable_conv(ops, mode):
+    """DCN (mmcv DeformConv2dPack semantics) = ss_deform_sample_fwd + grouped GEMM, against
+    torchvision's deform_conv2d on the CPU with non-trivial offsets (incl. samples outside the map)."""
+    from torchvision.ops import deform_conv2d
+    from stereoscene_b200.plugin.view_transformer import DCN
+    torch.manual_seed(14)
+    m = DCN(128, 128, 3, 1, 4)
+    nn.init.normal_(m.conv_offset.weight, 0, 0.05)
+    nn.init.normal_(m.conv_offset.bias, 0, 1.5)
+    x = torch.randn(2, 128, 9, 14)
+    with torch.no_grad():
+        want = deform_conv2d(x, m.conv_offset(x), m.weight, None, 1, 1, 1)
+    mg = m.cuda()
+    ops.set_default_math(_mode(ops, mode))
+    try:
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            got = mg(x.cuda())
+    finally:
+        ops.set_default_math(ops.SS_MATH_TF32)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TOL[mode]
 
 
 def test_trilinear_upsample_and_argmax(ops):
