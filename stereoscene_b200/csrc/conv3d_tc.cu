@@ -12,9 +12,11 @@
 //     both landing in the canonical K-major SWIZZLE_128B layout (one 128-byte row = 32 channels of
 //     one voxel / one output channel) and signalling the stage's mbarrier with complete_tx bytes.
 //   * If the input carries a pending affine / ReLU (the previous layer's GroupNorm etc.), 8 fix-up
-//     warps apply it IN PLACE on the landed A tile (OOB rows stay zero), fence.proxy.async, and
-//     hand the stage to the MMA warp; plain inputs go TMA -> tensor core with no thread touching
-//     the data.
+//     warps read the landed A tile from shared memory once, apply the affine in registers (OOB rows
+//     stay zero), round to TF32 and write it into a small ring of TENSOR-MEMORY columns
+//     (tcgen05.st, lane = voxel row); the MMA then takes A from TMEM and B from shared memory, so
+//     the fix-up adds no shared-memory write and removes the MMA's A read.  Plain inputs go
+//     TMA -> shared memory -> tensor core with no thread touching the data.
 //   * One elected lane issues 4 x tcgen05.mma (kind::tf32, M128 x N(BN) x K8) per stage into a TMEM
 //     accumulator (128 lanes x BN fp32 columns) and tcgen05.commit's the stage back to the TMA
 //     producer; after the last K step the 8 warps drain TMEM with tcgen05.ld (32 lanes x 32 columns),
@@ -108,6 +110,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand in tensor memory (lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -146,7 +166,10 @@ struct TcCfg {
     static constexpr int A_BYTES = TC_BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int ACC_COLS = (BN + 31) / 32 * 32;            // accumulator columns
+    static constexpr int A_COL0 = ACC_COLS;                          // A-operand ring: STAGES x 32 columns
+    static constexpr int TMEM_NEED = ACC_COLS + STAGES * TC_BK;
+    static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;   // power of two >= need (2 CTAs/SM at 256)
 };
 
 template <int BN>
@@ -256,65 +279,67 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
                 const uint32_t a_addr = ring_u32 + slot * Cfg::STAGE_BYTES;
                 const uint64_t adesc = make_smem_desc(a_addr);
                 const uint64_t bdesc = make_smem_desc(a_addr + Cfg::A_BYTES);
+                if (fixup) {                              // A from the TMEM ring written by the fix-up warps
+                    const uint32_t a_tmem = tmem_base + (uint32_t)(Cfg::A_COL0 + slot * TC_BK);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k)      // 8 TF32 = 32 bytes per MMA: advance start by 32 B
-                    umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (step | k) ? 1u : 0u);
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        umma_tf32_ts(tmem_base, a_tmem + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), idesc, (step | k) ? 1u : 0u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)  // 8 TF32 = 32 bytes per MMA: advance start by 32 B
+                        umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (step | k) ? 1u : 0u);
+                }
                 umma_commit(empty0 + 8 * slot);            // frees the stage when these MMAs retire
                 if (step == nsteps - 1) umma_commit(accum_bar);
             }
             __syncwarp();
         }
     } else if (fixup) {
-        // ======================= FIX-UP WARPS: pending affine / ReLU in place ====================
-        const int chunk = tid & 7;                 // 16-byte chunk of the 128-byte row
-        const int rbase = tid >> 3;                // rows rbase + 32 j
-        // per-row validity of every tap (bit t = tap t lands inside the input): zero padding written by
-        // the TMA unit must stay zero, so only in-bounds rows are transformed
-        unsigned long long vmask[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = rbase + 32 * j;
+        // ======================= FIX-UP WARPS: smem -> registers (affine, ReLU, TF32) -> TMEM ======
+        const int q = warp & 3;                    // TMEM lane quarter of this warp
+        const int half = warp >> 2;                // K half: channels [16*half, 16*half+16) of the 32-channel chunk
+        const int r = q * 32 + lane;               // voxel row of this thread
+        // validity of every tap for this row (bit t = tap t lands inside the input): the zero padding
+        // written by the TMA unit must stay zero
+        unsigned long long vmask = 0;
+        {
             const int iw = (q0w + r % p.TW) * isw, ih = (q0h + (r / p.TW) % p.TH) * ish, id = (q0d + r / (p.TW * p.TH)) * isd;
-            unsigned long long m = 0;
             for (int t = 0; t < ntaps; ++t) {
                 const int4 tp = taps[t];
                 const bool ok = (unsigned)(id + tp.x) < (unsigned)p.Din && (unsigned)(ih + tp.y) < (unsigned)p.Hin &&
                                 (unsigned)(iw + tp.z) < (unsigned)p.Win;
-                m |= (unsigned long long)(ok ? 1 : 0) << t;
+                vmask |= (unsigned long long)(ok ? 1 : 0) << t;
             }
-            vmask[j] = m;
         }
         uint32_t roff[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = rbase + 32 * j;
-            roff[j] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
-        }
+        for (int j = 0; j < 4; ++j) roff[j] = (uint32_t)(r * 128 + (((half * 4 + j) ^ (r & 7)) << 4));
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::A_COL0 + half * 16);
         for (int step = 0; step < nsteps; ++step) {
             const int slot = step % STAGES;
             const uint32_t use = (uint32_t)(step / STAGES);
-            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_aff) {
-                sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
-                sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
-            }
+            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK + half * 16;
             mbar_wait(full0 + 8 * slot, use & 1u);
-            unsigned char* a_dst = ring + slot * Cfg::STAGE_BYTES;
+            const unsigned char* a_src = ring + slot * Cfg::STAGE_BYTES;
             float4 v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(a_dst + roff[j]);     // 4 independent loads
+            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(a_src + roff[j]);
+            const bool ok = (vmask >> tap) & 1ull;
+            uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const bool ok = (vmask[j] >> tap) & 1ull;
                 float4 w = v[j];
-                w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+                if (has_aff) {
+                    const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + 4 * j);          // warp-uniform: broadcast
+                    const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + 4 * j);
+                    w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+                }
                 if (in_relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
-                uint4 t;
-                t.x = ok ? f2tf32(w.x) : 0u; t.y = ok ? f2tf32(w.y) : 0u; t.z = ok ? f2tf32(w.z) : 0u; t.w = ok ? f2tf32(w.w) : 0u;
-                *reinterpret_cast<uint4*>(a_dst + roff[j]) = t;
+                o[4 * j + 0] = ok ? f2tf32(w.x) : 0u; o[4 * j + 1] = ok ? f2tf32(w.y) : 0u;
+                o[4 * j + 2] = ok ? f2tf32(w.z) : 0u; o[4 * j + 3] = ok ? f2tf32(w.w) : 0u;
             }
-            fence_proxy_async_smem();
+            tmem_st16(t_row + (uint32_t)(slot * TC_BK), o);
+            tc_fence_before();
             mbar_arrive(ready0 + 8 * slot);
         }
     }
