@@ -292,9 +292,8 @@ def run_ours(args):
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop()
 
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    from stereoscene_b200 import sharding
+    t = sharding.max_over_ranks(torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev))
     ms_dev, ms_e2e = float(t[0]), float(t[1])
 
     if rank != 0:
@@ -303,9 +302,8 @@ def run_ours(args):
         return
 
     pk = peaks()
-    vox = VOXELS[args.workload] * B * world
-    value = vox * args.steps / (ms_dev * 1e-3)
-    e2e = vox * args.steps / (ms_e2e * 1e-3)
+    value = sharding.whole_job_voxels_per_s(VOXELS[args.workload], B, world, args.steps, ms_dev)
+    e2e = sharding.whole_job_voxels_per_s(VOXELS[args.workload], B, world, args.steps, ms_e2e)
 
     # ---- roofline of the dominant kernel, timed alone (CUDA events on the launching stream) -------
     roof, kernels = dominant_kernel_roofline(model, mc, dev, pk)
