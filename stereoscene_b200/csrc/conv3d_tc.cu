@@ -119,6 +119,15 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -226,7 +235,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
         *s_ntaps = n;
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);              // one arrive.expect_tx by the TMA thread (+ tx bytes)
-            mbar_init(ready0 + 8 * s, TC_WORKERS);    // every fix-up thread arrives once per stage
+            mbar_init(ready0 + 8 * s, TC_WORKERS / 2);   // one fix-up group (4 warps) arrives per stage
             mbar_init(empty0 + 8 * s, 1);             // released by one tcgen05.commit
         }
         mbar_init(accum_bar, 1);
@@ -296,8 +305,10 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
         }
     } else if (fixup) {
         // ======================= FIX-UP WARPS: smem -> registers (affine, ReLU, TF32) -> TMEM ======
+        // two groups of 4 warps alternate K steps, so each group has two stage times to hide the
+        // barrier wake-up, shared-memory and tcgen05.st latencies
         const int q = warp & 3;                    // TMEM lane quarter of this warp
-        const int half = warp >> 2;                // K half: channels [16*half, 16*half+16) of the 32-channel chunk
+        const int grp = warp >> 2;                 // handles steps with step % 2 == grp
         const int r = q * 32 + lane;               // voxel row of this thread
         // validity of every tap for this row (bit t = tap t lands inside the input): the zero padding
         // written by the TMA unit must stay zero
@@ -311,34 +322,38 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
                 vmask |= (unsigned long long)(ok ? 1 : 0) << t;
             }
         }
-        uint32_t roff[4];
+        uint32_t roff[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) roff[j] = (uint32_t)(r * 128 + (((half * 4 + j) ^ (r & 7)) << 4));
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::A_COL0 + half * 16);
-        for (int step = 0; step < nsteps; ++step) {
+        for (int j = 0; j < 8; ++j) roff[j] = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::A_COL0;
+        for (int step = grp; step < nsteps; step += 2) {
             const int slot = step % STAGES;
             const uint32_t use = (uint32_t)(step / STAGES);
-            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK + half * 16;
+            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
             mbar_wait(full0 + 8 * slot, use & 1u);
             const unsigned char* a_src = ring + slot * Cfg::STAGE_BYTES;
-            float4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(a_src + roff[j]);
             const bool ok = (vmask >> tap) & 1ull;
-            uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 w = v[j];
-                if (has_aff) {
-                    const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + 4 * j);          // warp-uniform: broadcast
-                    const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + 4 * j);
-                    w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+            for (int hh = 0; hh < 2; ++hh) {       // two halves of 16 channels: 4 loads in flight, one tcgen05.st each
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(a_src + roff[hh * 4 + j]);
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 w = v[j];
+                    if (has_aff) {
+                        const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + hh * 16 + 4 * j);     // warp-uniform: broadcast
+                        const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + hh * 16 + 4 * j);
+                        w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+                    }
+                    if (in_relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+                    o[4 * j + 0] = ok ? f2tf32(w.x) : 0u; o[4 * j + 1] = ok ? f2tf32(w.y) : 0u;
+                    o[4 * j + 2] = ok ? f2tf32(w.z) : 0u; o[4 * j + 3] = ok ? f2tf32(w.w) : 0u;
                 }
-                if (in_relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
-                o[4 * j + 0] = ok ? f2tf32(w.x) : 0u; o[4 * j + 1] = ok ? f2tf32(w.y) : 0u;
-                o[4 * j + 2] = ok ? f2tf32(w.z) : 0u; o[4 * j + 3] = ok ? f2tf32(w.w) : 0u;
+                tmem_st16_nowait(t_row + (uint32_t)(slot * TC_BK + hh * 16), o);
             }
-            tmem_st16(t_row + (uint32_t)(slot * TC_BK), o);
+            tmem_st_wait();
             tc_fence_before();
             mbar_arrive(ready0 + 8 * slot);
         }

@@ -260,8 +260,9 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     mm = _DEFAULT_MATH if math_mode is None else math_mode
     d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
                       1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
-    tc = (_USE_TCGEN05 and mm == SS_MATH_TF32 and Cin % 32 == 0 and pc.Cout % 4 == 0 and pc.Cout >= 32
-          and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
+    # single-output-channel layers ride the tensor-core kernel too (N padded to 32): it is faster than the FMA kernel
+    tc = (_USE_TCGEN05 and mm == SS_MATH_TF32 and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout == 1)
+          and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0 and not (pc.Cout == 1 and want_stats))
     if tc:
         rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights_kmajor().data_ptr(),
                                   _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
