@@ -1,0 +1,432 @@
+// "Marching" tcgen05 convolution for the HBM-bound 32-channel 3x3x3 layers of the frustum volume
+// (dres0/dres1/classif3_1, CA3D, the 32->1 logit convs: ViewTransformerLSSVoxel.py:167-187, 239-241,
+// attention.py:93-112).  Algorithmic intensity of these layers is ~216 FLOP/B, i.e. they are bound by
+// reading the input once and writing the output once -- IF the 27-fold stencil reuse happens on chip.
+//
+// Design (persistent, one CTA per SM):
+//   * weights of all 27 taps stay RESIDENT in shared memory (27 x 32 x 128 B = 108 KB, K-major
+//     SWIZZLE_128B, loaded once per CTA by TMA);
+//   * a CTA owns a column of 16(h) x 8(w) output voxels and MARCHES along d.  Input planes (one TMA 5-D
+//     box of 18 x 10 halo voxels x 32 channels = 22.5 KB, out-of-bounds zero fill = conv padding) live
+//     in a 4-slot ring; every plane is loaded once and used by the 3 output planes that touch it;
+//   * the A operand of tap (kd,kh,kw) is NOT re-staged: it is the same plane slot addressed through a
+//     UMMA shared-memory descriptor whose start is shifted by (kh*10 + kw) rows and whose
+//     stride-byte-offset is the halo line pitch (10 rows = 1280 B).  The 128-byte swizzle is a function
+//     of the absolute shared-memory address (verified on B200 by tools/probes/umma_shift_probe.cu), so
+//     row-shifted starts and a non-1024 SBO are legal;
+//   * accumulators are double-buffered in TMEM: the epilogue of tile i (tcgen05.ld, bias, activation,
+//     GroupNorm sums, stores) overlaps the MMAs of tile i+1;
+//   * a pending affine / ReLU of the producer layer is applied once per plane, in place, by 4 fix-up
+//     warps (padding stays zero) -- amortised over the 27 taps x 3 planes that read it.
+// L2->SM traffic per output tile: one 22.5 KB plane (vs 27 x 20 KB for the per-tap box kernel).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ss {
+
+constexpr int MR_TH = 16, MR_TW = 8;                 // output tile (h, w); M = 128 rows
+constexpr int MR_HH = MR_TH + 2, MR_HW = MR_TW + 2;  // halo plane
+constexpr int MR_PLANE_ROWS = MR_HH * MR_HW;         // 180
+constexpr int MR_PLANE_BYTES = 23 * 1024;            // 180 * 128 = 23040, padded to a multiple of 1024
+constexpr int MR_NP = 4;                             // plane ring slots
+constexpr int MR_TAPS = 27;
+constexpr int MR_BN = 32;
+constexpr int MR_W_BYTES = MR_TAPS * MR_BN * 128;    // 110592
+constexpr int MR_THREADS = 8 * 32 + 64;              // 4 epilogue warps, 4 fix-up warps, producer warp, MMA warp
+
+struct MarchParams {
+    int B, D, H, W, Cout, out_ldc, in_act, out_act;
+    int nTH, nTW;
+    long long total_tiles;                           // B * nTH * nTW * D
+    const float* in_scale;
+    const float* in_shift;
+    const float* bias;
+    float* y;
+    double* stats;
+};
+
+// ---- PTX wrappers (same as conv3d_tc.cu; kept local to this translation unit) ------------------
+__device__ __forceinline__ uint32_t m_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void m_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void m_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void m_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void m_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MWAIT_DONE;\n\t"
+        "bra MWAIT_LOOP;\n\t"
+        "MWAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void m_tma_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void m_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void m_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void m_umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void m_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major SWIZZLE_128B descriptor with an explicit stride-byte-offset (8-row group pitch)
+__device__ __forceinline__ uint64_t m_desc(uint32_t saddr, uint32_t sbo_bytes) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// flat tile id -> (b, column, d); tiles of one column are consecutive in d (the marching axis)
+struct TileCoord { int b, th, tw, d; };
+__device__ __forceinline__ TileCoord decode_tile(long long t, const MarchParams& p) {
+    TileCoord c;
+    c.d = (int)(t % p.D);
+    long long col = t / p.D;
+    c.tw = (int)(col % p.nTW);
+    c.th = (int)((col / p.nTW) % p.nTH);
+    c.b = (int)(col / ((long long)p.nTW * p.nTH));
+    return c;
+}
+
+__global__ void __launch_bounds__(MR_THREADS, 1)
+conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* wres = base;                                   // resident weights
+    unsigned char* planes = base + MR_W_BYTES;                    // MR_NP plane slots (MR_W_BYTES is a multiple of 1024)
+    unsigned char* aux = planes + MR_NP * MR_PLANE_BYTES;
+    double* sstat = reinterpret_cast<double*>(aux);               // [2][32][2] (per accumulator buffer)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * 64);
+    // barriers: w_full, p_full[NP], p_ready[NP], p_empty[NP], t_full[2], t_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * MR_NP + 4);
+    float* ssc = reinterpret_cast<float*>(tmem_slot + 4);         // [B? no: per batch reloaded] scale[32], shift[32]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t w_full = m_smem_u32(bars), p_full0 = m_smem_u32(bars + 1), p_ready0 = m_smem_u32(bars + 1 + MR_NP),
+                   p_empty0 = m_smem_u32(bars + 1 + 2 * MR_NP), t_full0 = m_smem_u32(bars + 1 + 3 * MR_NP),
+                   t_empty0 = m_smem_u32(bars + 1 + 3 * MR_NP + 2);
+    const bool has_aff = (p.in_scale != nullptr);
+    const bool in_relu = (p.in_act == SS_ACT_RELU);
+    const bool fixup = has_aff || in_relu;
+
+    // this CTA's contiguous range of flat tiles
+    const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
+    const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+
+    if (tid == 0) {
+        m_mbar_init(w_full, 1);
+        for (int s = 0; s < MR_NP; ++s) {
+            m_mbar_init(p_full0 + 8 * s, 1);
+            m_mbar_init(p_ready0 + 8 * s, 128);
+            m_mbar_init(p_empty0 + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            m_mbar_init(t_full0 + 8 * a, 1);
+            m_mbar_init(t_empty0 + 8 * a, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    }
+    for (int i = tid; i < 2 * 64; i += MR_THREADS) sstat[i] = 0.0;
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(m_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t planes_u32 = m_smem_u32(planes), wres_u32 = m_smem_u32(wres);
+
+    // The plane stream: for every maximal run of consecutive tiles of one column [d0, d1) the planes
+    // d0-1 .. d1 are loaded in order; tile d uses stream planes (d-d0), +1, +2.  All roles walk the
+    // same runs, so a global plane counter L gives slot = L % NP and the barrier parity.
+    if (warp == 8) {
+        // ======================= TMA PRODUCER ====================================================
+        if (lane == 0 && t_begin < t_end) {
+            m_mbar_expect_tx(w_full, MR_W_BYTES);
+            for (int i = 0; i < 4; ++i)          // 864 weight rows in 4 boxes of 216 rows
+                m_tma_2d(wres_u32 + i * 216 * 128, &tmW, w_full, 0, i * 216);
+            long long L = 0;
+            long long t = t_begin;
+            while (t < t_end) {
+                const TileCoord c = decode_tile(t, p);
+                const int run = (int)min((long long)(p.D - c.d), t_end - t);     // tiles of this column handled here
+                for (int s = 0; s < run + 2; ++s, ++L) {
+                    const int slot = (int)(L % MR_NP);
+                    const uint32_t use = (uint32_t)(L / MR_NP);
+                    m_mbar_wait(p_empty0 + 8 * slot, (use & 1u) ^ 1u);
+                    const uint32_t bar = p_full0 + 8 * slot;
+                    m_mbar_expect_tx(bar, MR_PLANE_ROWS * 128);
+                    m_tma_5d(planes_u32 + slot * MR_PLANE_BYTES, &tmA, bar, 0, c.tw * MR_TW - 1, c.th * MR_TH - 1, c.d - 1 + s, c.b);
+                }
+                t += run;
+            }
+        }
+    } else if (warp == 9) {
+        // ======================= MMA ISSUER ======================================================
+        if (t_begin < t_end) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MR_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            m_mbar_wait(w_full, 0);
+            const uint32_t rdy0 = fixup ? p_ready0 : p_full0;
+            long long L = 0, tile_n = 0;
+            long long t = t_begin;
+            while (t < t_end) {
+                const TileCoord c = decode_tile(t, p);
+                const int run = (int)min((long long)(p.D - c.d), t_end - t);
+                // planes L, L+1 of this run must have landed before the first tile; each tile then waits for one more
+                for (int s = 0; s < 2; ++s) {
+                    const long long Ls = L + s;
+                    m_mbar_wait(rdy0 + 8 * (int)(Ls % MR_NP), (uint32_t)(Ls / MR_NP) & 1u);
+                }
+                for (int i = 0; i < run; ++i, ++tile_n) {
+                    const long long Ln = L + i + 2;
+                    m_mbar_wait(rdy0 + 8 * (int)(Ln % MR_NP), (uint32_t)(Ln / MR_NP) & 1u);
+                    const int acc = (int)(tile_n & 1);
+                    m_mbar_wait(t_empty0 + 8 * acc, ((uint32_t)(tile_n >> 1) & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MR_BN);
+#pragma unroll 1
+                        for (int a = 0; a < 3; ++a) {
+                            const uint32_t pl = planes_u32 + (uint32_t)((L + i + a) % MR_NP) * MR_PLANE_BYTES;
+#pragma unroll
+                            for (int ce = 0; ce < 9; ++ce) {
+                                const uint32_t a_addr = pl + (uint32_t)(((ce / 3) * MR_HW + (ce % 3)) * 128);
+                                const uint64_t adesc = m_desc(a_addr, MR_HW * 128);
+                                const uint64_t bdesc = m_desc(wres_u32 + (uint32_t)((a * 9 + ce) * MR_BN * 128), 1024);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    m_umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (a | ce | k) ? 1u : 0u);
+                            }
+                        }
+                        m_umma_commit(t_full0 + 8 * acc);                              // accumulator ready for the epilogue
+                        m_umma_commit(p_empty0 + 8 * (int)((L + i) % MR_NP));           // oldest plane no longer needed
+                        if (i == run - 1) {                                             // end of the run: release the last two planes
+                            m_umma_commit(p_empty0 + 8 * (int)((L + i + 1) % MR_NP));
+                            m_umma_commit(p_empty0 + 8 * (int)((L + i + 2) % MR_NP));
+                        }
+                    }
+                    __syncwarp();
+                }
+                L += run + 2;
+                t += run;
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================= FIX-UP WARPS (4..7): pending affine / ReLU once per plane, in place ==
+        if (fixup && t_begin < t_end) {
+            const int ft = tid - 128;                  // 0..127
+            long long L = 0;
+            long long t = t_begin;
+            int cur_b = -1;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int chunk = ft & 7;                  // 16-byte chunk (4 channels) handled by this thread
+            while (t < t_end) {
+                const TileCoord c = decode_tile(t, p);
+                const int run = (int)min((long long)(p.D - c.d), t_end - t);
+                if (has_aff && c.b != cur_b) {
+                    cur_b = c.b;
+                    sc = ldg_f4(p.in_scale + (size_t)c.b * 32 + chunk * 4);
+                    sh = ldg_f4(p.in_shift + (size_t)c.b * 32 + chunk * 4);
+                }
+                for (int s = 0; s < run + 2; ++s, ++L) {
+                    const int slot = (int)(L % MR_NP);
+                    m_mbar_wait(p_full0 + 8 * slot, (uint32_t)(L / MR_NP) & 1u);
+                    const int dpl = c.d - 1 + s;
+                    if ((unsigned)dpl < (unsigned)p.D) {           // planes outside the volume are all padding
+                        unsigned char* pl = planes + slot * MR_PLANE_BYTES;
+                        for (int r = ft >> 3; r < MR_PLANE_ROWS; r += 16) {
+                            const int hh = c.th * MR_TH - 1 + r / MR_HW, ww = c.tw * MR_TW - 1 + r % MR_HW;
+                            if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
+                                float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
+                                float4 v = *ptr;
+                                if (has_aff) {
+                                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                                    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                                }
+                                if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                                uint4 o;
+                                o.x = f2tf32(v.x); o.y = f2tf32(v.y); o.z = f2tf32(v.z); o.w = f2tf32(v.w);
+                                *reinterpret_cast<uint4*>(ptr) = o;
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    m_mbar_arrive(p_ready0 + 8 * slot);
+                }
+                t += run;
+            }
+        }
+    } else {
+        // ======================= EPILOGUE WARPS (0..3) ===========================================
+        const int q = warp;
+        const int row = q * 32 + lane;
+        const int lh = row / MR_TW, lw = row % MR_TW;
+        const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) && p.Cout == 32;
+        long long tile_n = 0;
+        double run_s = 0.0, run_q = 0.0;               // lane = channel: sums of this warp's 32 rows over all tiles
+        int run_b = -1;
+        auto flush = [&]() {
+            if (p.stats && run_b >= 0 && lane < p.Cout) {
+                atomicAdd(p.stats + ((size_t)run_b * p.Cout + lane) * 2 + 0, run_s);
+                atomicAdd(p.stats + ((size_t)run_b * p.Cout + lane) * 2 + 1, run_q);
+            }
+            run_s = 0.0; run_q = 0.0;
+        };
+        for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
+            const TileCoord c = decode_tile(t, p);
+            if (c.b != run_b) { flush(); run_b = c.b; }
+            const int acc = (int)(tile_n & 1);
+            m_mbar_wait(t_full0 + 8 * acc, (uint32_t)(tile_n >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[32];
+            m_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MR_BN), r);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            m_mbar_arrive(t_empty0 + 8 * acc);                     // accumulator may be overwritten
+            const int oh = c.th * MR_TH + lh, ow = c.tw * MR_TW + lw;
+            const bool valid = oh < p.H && ow < p.W;
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                float f = __uint_as_float(r[k]);
+                if (p.bias && k < p.Cout) f += __ldg(p.bias + k);
+                v[k] = apply_act(f, p.out_act);
+            }
+            if (valid) {
+                float* dst = p.y + ((((size_t)c.b * p.D + c.d) * p.H + oh) * p.W + ow) * p.out_ldc;
+                if (vec_ok) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (k < p.Cout) dst[k] = v[k];
+                }
+            }
+            if (p.stats) {
+                float s[32], qq[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { s[k] = valid ? v[k] : 0.f; qq[k] = s[k] * s[k]; }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float send_s = up ? s[i] : s[i + off], keep_s = up ? s[i + off] : s[i];
+                        const float send_q = up ? qq[i] : qq[i + off], keep_q = up ? qq[i + off] : qq[i];
+                        s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                        qq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+                    }
+                }
+                run_s += (double)s[0];
+                run_q += (double)qq[0];
+            }
+        }
+        flush();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+typedef CUresult (*MEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// returns 1 if the layer was handled by the marching kernel
+int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                     const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
+    if (d->transposed || d->Cin != 32 || d->cout_packed > 32 || d->kd != 3 || d->kh != 3 || d->kw != 3) return 0;
+    if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
+    if (d->pd != 1 || d->ph != 1 || d->pw != 1 || d->Win < 8 || d->Hin < 8 || d->Din < 3) return 0;
+    if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win || d->math != SS_MATH_TF32) return 0;
+    static MEncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) return 0;
+        encode = reinterpret_cast<MEncodeTiledFn>(ptr);
+    }
+    if (d->cout_packed != 32) return 0;                              // Cout < 32 layers arrive padded to 32 weight rows
+    MarchParams p;
+    p.B = d->B; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cout = d->Cout; p.out_ldc = d->out_ldc;
+    p.in_act = d->in_act; p.out_act = d->out_act;
+    p.nTH = (p.H + MR_TH - 1) / MR_TH; p.nTW = (p.W + MR_TW - 1) / MR_TW;
+    p.total_tiles = (long long)p.B * p.nTH * p.nTW * p.D;
+    p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
+    alignas(64) CUtensorMap tmA, tmW;
+    {
+        cuuint64_t gdim[5] = {32, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B};
+        cuuint64_t gstr[4] = {(cuuint64_t)d->in_ldc * 4, (cuuint64_t)p.W * d->in_ldc * 4, (cuuint64_t)p.H * p.W * d->in_ldc * 4,
+                              (cuuint64_t)p.D * p.H * p.W * d->in_ldc * 4};
+        cuuint32_t box[5] = {32, MR_HW, MR_HH, 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        if (encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_march32: tensor map A"); return 1; }
+    }
+    {
+        cuuint64_t gdim[2] = {32, (cuuint64_t)MR_TAPS * 32};
+        cuuint64_t gstr[1] = {32 * 4};
+        cuuint32_t box[2] = {32, 216};
+        cuuint32_t estr[2] = {1, 1};
+        if (encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_kmajor), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_march32: tensor map W"); return 1; }
+    }
+    const size_t smem = 1024 + MR_W_BYTES + MR_NP * MR_PLANE_BYTES + 2 * 64 * sizeof(double) + 32 * sizeof(uint64_t) + 64 + 64 * sizeof(float);
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_march32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { *rc = set_cuda_error(e, "conv_march32 smem attribute"); return 1; }
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)min((long long)sms, p.total_tiles);
+    conv_march32_kernel<<<grid, MR_THREADS, smem, st>>>(p, tmA, tmW);
+    *rc = check_launch("conv_march32_kernel");
+    return 1;
+}
+
+}  // namespace ss

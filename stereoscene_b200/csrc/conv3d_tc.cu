@@ -517,6 +517,11 @@ static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, i
 
 }  // namespace ss
 
+namespace ss {
+int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                     const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
+}
+
 // wk: float[taps][cout_packed][Cin], K-major, values already rounded to TF32.
 extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                                 const float* w_kmajor, const float* bias, float* y, double* stats, void* stream) {
@@ -546,6 +551,10 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {   // 32-channel 3x3x3 stride-1 layers: persistent marching kernel (halo planes + resident weights)
+        int rcm = 0;
+        if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
+    }
     const int cp = d->cout_packed;
     const int ntaps_total = d->kd * d->kh * d->kw;
     if (cp <= 32) return launch_tc<32>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);

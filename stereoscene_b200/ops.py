@@ -171,7 +171,8 @@ class PackedConv:
         if m.groups != 1:
             raise RuntimeError("grouped convolution is not on the hot path")
         self.Cin, self.Cout = m.in_channels, m.out_channels
-        self.CoutP = (self.Cout + 7) // 8 * 8
+        # rows of the packed weight matrices: narrow layers are padded to one 32-column tensor-core tile
+        self.CoutP = 32 if self.Cout <= 32 else (self.Cout + 7) // 8 * 8
         self._key = None
         self._w = None
         self._kkey = None
@@ -261,8 +262,8 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
                       1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
     # single-output-channel layers ride the tensor-core kernel too (N padded to 32): it is faster than the FMA kernel
-    tc = (_USE_TCGEN05 and mm == SS_MATH_TF32 and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout == 1)
-          and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0 and not (pc.Cout == 1 and want_stats))
+    tc = (_USE_TCGEN05 and mm == SS_MATH_TF32 and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
+          and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
     if tc:
         rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights_kmajor().data_ptr(),
                                   _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())

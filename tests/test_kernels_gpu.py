@@ -57,6 +57,8 @@ CONV_CASES = [
     ("tk2s2_256_128", lambda: nn.ConvTranspose3d(256, 128, 2, 2, bias=False), (1, 256, 3, 4, 2)),
     ("tk4s4_512_128", lambda: nn.ConvTranspose3d(512, 128, 4, 4, bias=False), (1, 512, 2, 3, 1)),
     ("tk1s1_128_128", lambda: nn.ConvTranspose3d(128, 128, 1, 1, bias=False), (1, 128, 3, 4, 2)),
+    ("k3s1_32_march", lambda: nn.Conv3d(32, 32, 3, 1, 1, bias=True), (2, 32, 11, 21, 19)),
+    ("k3s1_32_march_big", lambda: nn.Conv3d(32, 32, 3, 1, 1, bias=False), (1, 32, 40, 48, 40)),
     ("k3s1_256_512", lambda: nn.Conv3d(256, 512, 3, 1, 1, bias=False), (1, 256, 3, 5, 6)),
     ("k3s1_128_128_big", lambda: nn.Conv3d(128, 128, 3, 1, 1, bias=True), (2, 128, 9, 12, 16)),
 ]
@@ -121,7 +123,7 @@ def test_single_output_channel_conv(ops):
         mg.load_state_dict(m.state_dict())
         y, _ = ops.conv(ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU), mg, out_act=ops.SS_ACT_RELU,
                         math_mode=ops.SS_MATH_TF32)
-        assert rel_err(_ncdhw(y), want) < 1e-5
+        assert rel_err(_ncdhw(y), want) < 1e-3
 
 
 @pytest.mark.parametrize("mode", ["precise", "tf32"])
