@@ -1,0 +1,399 @@
+// Halo-resident tcgen05 convolution for the tensor-bound 3x3x3 stride-1 layers with wide channels
+// (3-D encoder blocks, occupancy head, hourglass conv2: resnet3d.py:18-32, occhead.py:100-107,
+// ViewTransformerLSSVoxel.py:75-76).
+//
+// The per-tap box kernel (conv3d_tc.cu) re-fetches a 16 KB A box per tap and is bound by L2->SM
+// bandwidth.  Here a CTA owns 256 output voxels (32 h x 8 w at one depth plane d, two M=128 tiles that
+// share every weight tile) and, per 32-channel chunk, loads the three input planes d-1, d, d+1 ONCE
+// (TMA 5-D box of 34 x 10 halo voxels, out-of-bounds zero fill = conv padding, 42.5 KB) into a 3-slot
+// ring.  The A operand of tap (kd,kh,kw) / M-tile mt is the same plane addressed through a UMMA
+// descriptor whose start is shifted by ((16 mt + kh) * 10 + kw) rows with stride-byte-offset = the
+// halo line pitch (1280 B) -- legal because the 128-byte swizzle is a function of the absolute smem
+// address (tools/probes/umma_shift_probe.cu).  Weight tiles (BN x 128 B per tap) stream through their
+// own TMA ring and are used by both M-tiles, so L2->SM traffic per MMA drops ~4-6x and the kernel
+// becomes tensor-pipe bound.  Pending affine / ReLU: applied once per landed plane, in place, by the 8
+// worker warps (padding stays zero).  Accumulators: 2 x BN fp32 columns in TMEM.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ss {
+
+constexpr int HL_TH = 32, HL_TW = 8;
+constexpr int HL_HH = HL_TH + 2, HL_HW = HL_TW + 2;
+constexpr int HL_PLANE_ROWS = HL_HH * HL_HW;          // 340
+constexpr int HL_PLANE_BYTES = 43 * 1024;             // 340*128 = 43520 -> padded to a multiple of 1024
+constexpr int HL_NPL = 3;
+constexpr int HL_WORKERS = 256;
+constexpr int HL_THREADS = HL_WORKERS + 96;           // + A producer, MMA, B producer warps
+
+struct HaloParams {
+    int B, D, H, W, Cin, Cout, CoutP, out_ldc, in_act, out_act;
+    int nTH, nTW;
+    const float* in_scale;
+    const float* in_shift;
+    const float* bias;
+    float* y;
+    double* stats;
+};
+
+__device__ __forceinline__ uint32_t h_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void h_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void h_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void h_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void h_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "HWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra HWAIT_DONE;\n\t"
+        "bra HWAIT_LOOP;\n\t"
+        "HWAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void h_tma_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void h_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void h_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void h_umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void h_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t h_desc(uint32_t saddr, uint32_t sbo_bytes) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <int BN>
+struct HaloCfg {
+    static constexpr int SB = BN >= 256 ? 2 : BN >= 192 ? 3 : 4;       // weight-tile ring depth
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+    using Cfg = HaloCfg<BN>;
+    constexpr int SB = Cfg::SB;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* planes = base;                                            // HL_NPL plane slots
+    unsigned char* bring = base + HL_NPL * HL_PLANE_BYTES;                   // SB weight tiles
+    unsigned char* aux = bring + SB * Cfg::B_BYTES;
+    double* sstat = reinterpret_cast<double*>(aux);                          // [BN][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * BN);            // pa_full[3] pa_ready[3] pa_empty[3] pb_full[SB] pb_empty[SB] accum
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * HL_NPL + 2 * SB + 1);
+    float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // scale[Cin], shift[Cin]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.y * BN;
+    // tile decode: blockIdx.x = ((b * D + d) * nTH + th) * nTW + tw
+    const int tw_i = blockIdx.x % p.nTW, th_i = (blockIdx.x / p.nTW) % p.nTH;
+    const int d = (blockIdx.x / (p.nTW * p.nTH)) % p.D, b = blockIdx.x / (p.nTW * p.nTH * p.D);
+    const int h0 = th_i * HL_TH, w0 = tw_i * HL_TW;
+
+    const uint32_t pa_full0 = h_smem_u32(bars), pa_ready0 = h_smem_u32(bars + HL_NPL), pa_empty0 = h_smem_u32(bars + 2 * HL_NPL),
+                   pb_full0 = h_smem_u32(bars + 3 * HL_NPL), pb_empty0 = h_smem_u32(bars + 3 * HL_NPL + SB),
+                   accum_bar = h_smem_u32(bars + 3 * HL_NPL + 2 * SB);
+    const bool has_aff = (p.in_scale != nullptr);
+    const bool in_relu = (p.in_act == SS_ACT_RELU);
+    const bool fixup = has_aff || in_relu;
+    const int kchunks = p.Cin / 32;
+
+    if (tid == 0) {
+        for (int s = 0; s < HL_NPL; ++s) {
+            h_mbar_init(pa_full0 + 8 * s, 1);
+            h_mbar_init(pa_ready0 + 8 * s, HL_WORKERS);
+            h_mbar_init(pa_empty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < SB; ++s) {
+            h_mbar_init(pb_full0 + 8 * s, 1);
+            h_mbar_init(pb_empty0 + 8 * s, 1);
+        }
+        h_mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    for (int i = tid; i < 2 * BN; i += HL_THREADS) sstat[i] = 0.0;
+    if (has_aff)
+        for (int i = tid; i < p.Cin; i += HL_THREADS) {
+            ssc[i] = __ldg(p.in_scale + (size_t)b * p.Cin + i);
+            ssc[p.Cin + i] = __ldg(p.in_shift + (size_t)b * p.Cin + i);
+        }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(h_smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t planes_u32 = h_smem_u32(planes), bring_u32 = h_smem_u32(bring);
+
+    if (warp == 8) {
+        // ======================= A PRODUCER: 3 planes per 32-channel chunk ==========================
+        if (lane == 0) {
+            for (int L = 0; L < kchunks * 3; ++L) {
+                const int slot = L % HL_NPL;
+                const uint32_t use = (uint32_t)(L / HL_NPL);
+                h_mbar_wait(pa_empty0 + 8 * slot, (use & 1u) ^ 1u);
+                const uint32_t bar = pa_full0 + 8 * slot;
+                h_mbar_expect_tx(bar, HL_PLANE_ROWS * 128);
+                h_tma_5d(planes_u32 + slot * HL_PLANE_BYTES, &tmA, bar, (L / 3) * 32, w0 - 1, h0 - 1, d - 1 + (L % 3), b);
+            }
+        }
+    } else if (warp == 10) {
+        // ======================= B PRODUCER: one weight tile per (chunk, tap) =======================
+        if (lane == 0) {
+            for (int L = 0; L < kchunks * 27; ++L) {
+                const int slot = L % SB;
+                const uint32_t use = (uint32_t)(L / SB);
+                h_mbar_wait(pb_empty0 + 8 * slot, (use & 1u) ^ 1u);
+                const uint32_t bar = pb_full0 + 8 * slot;
+                h_mbar_expect_tx(bar, Cfg::B_BYTES);
+                h_tma_2d(bring_u32 + slot * Cfg::B_BYTES, &tmB, bar, (L / 27) * 32, (L % 27) * p.CoutP + n0);
+            }
+        }
+    } else if (warp == 9) {
+        // ======================= MMA ISSUER ========================================================
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t rdy0 = fixup ? pa_ready0 : pa_full0;
+        int Lb = 0;
+        for (int Lp = 0; Lp < kchunks * 3; ++Lp) {
+            const int pslot = Lp % HL_NPL;
+            h_mbar_wait(rdy0 + 8 * pslot, (uint32_t)(Lp / HL_NPL) & 1u);
+            const uint32_t pl = planes_u32 + pslot * HL_PLANE_BYTES;
+            for (int ce = 0; ce < 9; ++ce, ++Lb) {
+                const int bslot = Lb % SB;
+                h_mbar_wait(pb_full0 + 8 * bslot, (uint32_t)(Lb / SB) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint64_t bdesc = h_desc(bring_u32 + bslot * Cfg::B_BYTES, 1024);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint32_t a_addr = pl + (uint32_t)(((mt * 16 + ce / 3) * HL_HW + (ce % 3)) * 128);
+                        const uint64_t adesc = h_desc(a_addr, HL_HW * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            h_umma_tf32(tmem_base + (uint32_t)(mt * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                        (Lp | ce | k) ? 1u : 0u);
+                    }
+                    h_umma_commit(pb_empty0 + 8 * bslot);
+                    if (ce == 8) h_umma_commit(pa_empty0 + 8 * pslot);
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) h_umma_commit(accum_bar);
+        __syncwarp();
+    } else if (fixup) {
+        // ======================= WORKERS: pending affine / ReLU, once per landed plane, in place =====
+        for (int L = 0; L < kchunks * 3; ++L) {
+            const int slot = L % HL_NPL;
+            h_mbar_wait(pa_full0 + 8 * slot, (uint32_t)(L / HL_NPL) & 1u);
+            const int dpl = d - 1 + (L % 3), c0 = (L / 3) * 32;
+            if ((unsigned)dpl < (unsigned)p.D) {
+                unsigned char* pl = planes + slot * HL_PLANE_BYTES;
+                for (int idx = tid; idx < HL_PLANE_ROWS * 8; idx += HL_WORKERS) {
+                    const int r = idx >> 3, chunk = idx & 7;
+                    const int hh = h0 - 1 + r / HL_HW, ww = w0 - 1 + r % HL_HW;
+                    if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
+                        float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
+                        float4 v = *ptr;
+                        if (has_aff) {
+                            const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
+                            const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
+                            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        }
+                        if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        uint4 o;
+                        o.x = f2tf32(v.x); o.y = f2tf32(v.y); o.z = f2tf32(v.z); o.w = f2tf32(v.w);
+                        *reinterpret_cast<uint4*>(ptr) = o;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            h_mbar_arrive(pa_ready0 + 8 * slot);
+        }
+    }
+
+    // ======================= EPILOGUE: 8 warps, warp = (M-tile, lane quarter) =======================
+    if (warp < HL_WORKERS / 32) {
+        h_mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3, mt = warp >> 2;
+        const int row = q * 32 + lane;
+        const int oh = h0 + mt * 16 + row / HL_TW, ow = w0 + row % HL_TW;
+        const bool valid = oh < p.H && ow < p.W;
+        const size_t ov = (((size_t)b * p.D + d) * p.H + oh) * p.W + ow;
+        const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+#pragma unroll 1
+        for (int ci = 0; ci < BN / 32; ++ci) {
+            uint32_t r[32];
+            h_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + ci * 32), r);
+            const int cbase = n0 + ci * 32;
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                float f = __uint_as_float(r[k]);
+                const int c = cbase + k;
+                if (p.bias && c < p.Cout) f += __ldg(p.bias + c);
+                v[k] = apply_act(f, p.out_act);
+            }
+            if (valid) {
+                float* dst = p.y + ov * p.out_ldc + cbase;
+                if (vec_ok && cbase + 32 <= p.Cout) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cbase + k < p.Cout) dst[k] = v[k];
+                }
+            }
+            if (p.stats) {
+                float s[32], qq[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { s[k] = valid ? v[k] : 0.f; qq[k] = s[k] * s[k]; }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float send_s = up ? s[i] : s[i + off], keep_s = up ? s[i + off] : s[i];
+                        const float send_q = up ? qq[i] : qq[i + off], keep_q = up ? qq[i + off] : qq[i];
+                        s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                        qq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+                    }
+                }
+                atomicAdd(&sstat[2 * (ci * 32 + lane) + 0], (double)s[0]);
+                atomicAdd(&sstat[2 * (ci * 32 + lane) + 1], (double)qq[0]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (p.stats) {
+        for (int i = tid; i < BN; i += HL_THREADS) {
+            const int c = n0 + i;
+            if (c < p.Cout) {
+                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 0, sstat[2 * i + 0]);
+                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 1, sstat[2 * i + 1]);
+            }
+        }
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*HEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int BN>
+static int launch_halo(const HaloParams& p, const CUtensorMap& tmA, const float* wk, HEncodeTiledFn encode, cudaStream_t st) {
+    using Cfg = HaloCfg<BN>;
+    alignas(64) CUtensorMap tmB;
+    cuuint64_t gdim[2] = {(cuuint64_t)p.Cin, (cuuint64_t)27 * p.CoutP};
+    cuuint64_t gstr[1] = {(cuuint64_t)p.Cin * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    if (encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wk), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return set_arg_error("conv_halo: tensor map B");
+    const size_t smem = 1024 + (size_t)HL_NPL * HL_PLANE_BYTES + (size_t)Cfg::SB * Cfg::B_BYTES + 2 * BN * sizeof(double) +
+                        (3 * HL_NPL + 2 * Cfg::SB + 1) * sizeof(uint64_t) + 16 + 32 + 2 * (size_t)p.Cin * sizeof(float);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        SS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)((long long)p.B * p.D * p.nTH * p.nTW), (unsigned)((p.CoutP + BN - 1) / BN), 1);
+    conv_halo_kernel<BN><<<grid, HL_THREADS, smem, st>>>(p, tmA, tmB);
+    return check_launch("conv_halo_kernel");
+}
+
+// returns 1 if the layer was handled here
+int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
+                  const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
+    if (d->transposed || d->Cin % 32 != 0 || d->cout_packed < 64 || d->kd != 3 || d->kh != 3 || d->kw != 3) return 0;
+    if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
+    if (d->pd != 1 || d->ph != 1 || d->pw != 1 || d->math != SS_MATH_TF32) return 0;
+    if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
+    const int nTH = (d->Hin + HL_TH - 1) / HL_TH, nTW = (d->Win + HL_TW - 1) / HL_TW;
+    const double eff = (double)d->Hin * d->Win / ((double)nTH * HL_TH * nTW * HL_TW);
+    if (eff < 0.7) return 0;                                       // too many wasted rows: the box kernel picks a better tile
+    if ((long long)d->B * d->Din * nTH * nTW > 0x7fffffffLL) return 0;
+    static HEncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) return 0;
+        encode = reinterpret_cast<HEncodeTiledFn>(ptr);
+    }
+    HaloParams p;
+    p.B = d->B; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cin = d->Cin; p.Cout = d->Cout; p.CoutP = d->cout_packed;
+    p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act; p.nTH = nTH; p.nTW = nTW;
+    p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
+    alignas(64) CUtensorMap tmA;
+    cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B};
+    cuuint64_t gstr[4] = {(cuuint64_t)d->in_ldc * 4, (cuuint64_t)p.W * d->in_ldc * 4, (cuuint64_t)p.H * p.W * d->in_ldc * 4,
+                          (cuuint64_t)p.D * p.H * p.W * d->in_ldc * 4};
+    cuuint32_t box[5] = {32, HL_HW, HL_HH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim, gstr, box,
+               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_halo: tensor map A"); return 1; }
+    const int cp = d->cout_packed;
+    if (cp <= 64) *rc = launch_halo<64>(p, tmA, w_kmajor, encode, st);
+    else if (cp <= 128) *rc = launch_halo<128>(p, tmA, w_kmajor, encode, st);
+    else if (cp <= 192) *rc = launch_halo<192>(p, tmA, w_kmajor, encode, st);
+    else {
+        // 256-column tiles halve the A traffic per FLOP but leave SMs idle on small grids
+        const long long ctas256 = (long long)p.B * p.D * nTH * nTW * ((cp + 255) / 256);
+        if (cp % 128 == 0 && (cp % 256 != 0 || ctas256 < 2 * 148)) *rc = launch_halo<128>(p, tmA, w_kmajor, encode, st);
+        else *rc = launch_halo<256>(p, tmA, w_kmajor, encode, st);
+    }
+    return 1;
+}
+
+}  // namespace ss

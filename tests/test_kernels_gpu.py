@@ -59,6 +59,10 @@ CONV_CASES = [
     ("tk1s1_128_128", lambda: nn.ConvTranspose3d(128, 128, 1, 1, bias=False), (1, 128, 3, 4, 2)),
     ("k3s1_32_march", lambda: nn.Conv3d(32, 32, 3, 1, 1, bias=True), (2, 32, 11, 21, 19)),
     ("k3s1_32_march_big", lambda: nn.Conv3d(32, 32, 3, 1, 1, bias=False), (1, 32, 40, 48, 40)),
+    ("k3s1_128_128_halo", lambda: nn.Conv3d(128, 128, 3, 1, 1, bias=True), (1, 128, 5, 40, 16)),
+    ("k3s1_384_192_halo", lambda: nn.Conv3d(384, 192, 3, 1, 1, bias=False), (1, 384, 3, 32, 8)),
+    ("k3s1_64_64_halo", lambda: nn.Conv3d(64, 64, 3, 1, 1, bias=False), (2, 64, 4, 24, 24)),
+    ("k3s1_256_256_halo", lambda: nn.Conv3d(256, 256, 3, 1, 1, bias=False), (1, 256, 3, 64, 8)),
     ("k3s1_256_512", lambda: nn.Conv3d(256, 512, 3, 1, 1, bias=False), (1, 256, 3, 5, 6)),
     ("k3s1_128_128_big", lambda: nn.Conv3d(128, 128, 3, 1, 1, bias=True), (2, 128, 9, 12, 16)),
 ]
