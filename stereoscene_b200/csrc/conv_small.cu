@@ -100,3 +100,4 @@ int try_conv_cout1(const ss_conv3d_desc* d, const float* x, const float* in_scal
 }
 
 }  // namespace ss
+

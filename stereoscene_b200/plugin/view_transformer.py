@@ -254,7 +254,16 @@ class DepthNet(nn.Module):
         m = self.bn(mlp_input.reshape(-1, mlp_input.shape[-1]))
         x = torch.relu_(_group_norm_wide(self.reduce_conv[0](x), self.reduce_conv[1]))
         context = self.context_conv(self.context_se(x, self.context_mlp(m)[..., None, None]))
-        depth = self.depth_conv(self.depth_se(x, self.depth_mlp(m)[..., None, None]))
+        d = self.depth_se(x, self.depth_mlp(m)[..., None, None])
+        for i in range(4):                                         # 3 BasicBlocks + ASPP (cuDNN)
+            d = self.depth_conv[i](d)
+        d = self.depth_conv[4](d)                                  # DCN: own kernels, channels-last result
+        if d.is_cuda:                                              # final 1x1 conv on the tcgen05 kernel, straight from channels-last
+            dcl = d.permute(0, 2, 3, 1).unsqueeze(1)               # [B,1,H,W,C] view of the DCN output
+            y, _ = ops.conv(ops.Vol(dcl), self.depth_conv[5])
+            depth = ops.to_channels_first(y.squeeze(1))
+        else:
+            depth = self.depth_conv[5](d)
         return torch.cat([depth, context], dim=1)
 
 

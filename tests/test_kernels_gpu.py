@@ -130,6 +130,20 @@ def test_single_output_channel_conv(ops):
         assert rel_err(_ncdhw(y), want) < 1e-3
 
 
+def test_few_input_channel_conv(ops):
+    """Conv3d 2 -> 32 k3 + bias + ReLU (MIE redir1): generic K = tap*Cin path, input as a channel slice."""
+    torch.manual_seed(22)
+    m = nn.Conv3d(2, 32, 3, 1, 1, bias=True)
+    x = torch.rand(2, 2, 6, 9, 13)
+    want = F.relu(m(x)).detach()
+    mg = nn.Conv3d(2, 32, 3, 1, 1, bias=True).cuda()
+    mg.load_state_dict(m.state_dict())
+    wide = torch.zeros(2, 6, 9, 13, 4, device="cuda")
+    wide[..., 1:3] = _cl(x)                                   # input as a channel slice (ldc = 4)
+    y, _ = ops.conv(ops.Vol(wide[..., 1:3]), mg, out_act=ops.SS_ACT_RELU, math_mode=ops.SS_MATH_TF32)
+    assert rel_err(_ncdhw(y), want) < 1e-3
+
+
 @pytest.mark.parametrize("mode", ["precise", "tf32"])
 def test_conv2d_dilated_bias_gelu(ops, mode):
     torch.manual_seed(3)
