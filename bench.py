@@ -34,6 +34,8 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+HEAD_CONV_DRAM_BYTES = 630678016   # ncu --set full of conv_halo_kernel<192> (profiles/r01_head_conv_halo_ncu_full_raw.csv): 456.5 MB read + 174.1 MB written per launch
+
 VOXELS = {"config1": 128 * 128 * 16, "config2": 256 * 256 * 32, "config0": 64 * 64 * 8, "tiny": 32 * 32 * 8,
           "config4": 512 * 512 * 64}
 
@@ -372,11 +374,15 @@ def dominant_kernel_roofline(model, mc, dev, pk):
     V = nx[0] * nx[1] * nx[2]
     flops = 2.0 * V * 27 * head.in_channels * head.out_channels
     ach = flops / t / 1e12
-    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN=64> (OccHead conv 384->192 k3, 128x128x16)",
+    roof = {"bound": "tensor", "kernel": "conv_halo_kernel<192> (OccHead conv 384->192 k3 on the 128x128x16 grid; "
+                                         "TMA halo planes + tcgen05.mma kind::tf32, TMEM accumulators)",
             "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-            "traffic": None, "launch_ms": t * 1e3, "algorithmic_flops": flops,
-            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({pk['source']}); kernel runs TF32 mma.sync, "
-                           "nominal TF32 peak is half the bf16 peak"}
+            "traffic": HEAD_CONV_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01_head_conv_halo_ncu_full_raw.csv "
+                                                                "(dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+            "launch_ms": t * 1e3, "algorithmic_flops": flops,
+            "algorithmic_bytes": (x.numel() + y.numel()) * 4.0,
+            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({pk['source']}); the kernel multiplies in TF32, whose "
+                           "nominal peak is half the bf16 peak, so frac 0.5 = TF32 speed of light"}
     kernels.append({"name": "occ_head conv3d 384->192 k3", "bound": "tensor", "ms": t * 1e3, "tflops": ach,
                     "frac": ach / pk["tflops"]})
     # (2) full-res 32->32 k3 frustum conv (HBM-bound in the algorithmic accounting: in + out once)
