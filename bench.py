@@ -191,6 +191,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cabi.load()
     ops.set_default_math(ops.SS_MATH_3XTF32 if args.math == "3xtf32" else ops.SS_MATH_TF32)
