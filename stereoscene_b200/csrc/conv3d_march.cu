@@ -25,14 +25,22 @@
 namespace ss {
 
 constexpr int MR_TH = 16, MR_TW = 8;                 // output tile (h, w); M = 128 rows
-constexpr int MR_HH = MR_TH + 2, MR_HW = MR_TW + 2;  // halo plane
-constexpr int MR_PLANE_ROWS = MR_HH * MR_HW;         // 180
-constexpr int MR_PLANE_BYTES = 23 * 1024;            // 180 * 128 = 23040, padded to a multiple of 1024
 constexpr int MR_NP = 4;                             // plane ring slots
-constexpr int MR_TAPS = 27;
 constexpr int MR_BN = 32;
-constexpr int MR_W_BYTES = MR_TAPS * MR_BN * 128;    // 110592
 constexpr int MR_THREADS = 8 * 32 + 64;              // 4 epilogue warps, 4 fix-up warps, producer warp, MMA warp
+
+// KS = kernel extent per axis (3: 3x3x3 pad 1; 1: 1x1x1, e.g. the hourglass redir1 layers)
+template <int KS>
+struct MarchCfg {
+    static constexpr int PAD = (KS - 1) / 2;
+    static constexpr int HH = MR_TH + KS - 1, HW = MR_TW + KS - 1;     // halo plane
+    static constexpr int PLANE_ROWS = HH * HW;                        // 180 / 128
+    static constexpr int PLANE_BYTES = (PLANE_ROWS * 128 + 1023) / 1024 * 1024;
+    static constexpr int TAPS = KS * KS * KS;
+    static constexpr int W_BYTES = TAPS * MR_BN * 128;                // 110592 / 4096
+    static constexpr int W_BOX_ROWS = KS == 3 ? 216 : 32;             // weight rows per TMA box
+    static constexpr int W_BOXES = TAPS * MR_BN / W_BOX_ROWS;
+};
 
 struct MarchParams {
     int B, D, H, W, Cout, out_ldc, in_act, out_act;
@@ -120,8 +128,12 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const MarchParams&
     return c;
 }
 
+template <int KS>
 __global__ void __launch_bounds__(MR_THREADS, 1)
 conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
+    using Cfg = MarchCfg<KS>;
+    constexpr int MR_HW = Cfg::HW, MR_PLANE_ROWS = Cfg::PLANE_ROWS, MR_PLANE_BYTES = Cfg::PLANE_BYTES, MR_W_BYTES = Cfg::W_BYTES;
+    constexpr int PAD = Cfg::PAD;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* wres = base;                                   // resident weights
@@ -131,7 +143,6 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * 64);
     // barriers: w_full, p_full[NP], p_ready[NP], p_empty[NP], t_full[2], t_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * MR_NP + 4);
-    float* ssc = reinterpret_cast<float*>(tmem_slot + 4);         // [B? no: per batch reloaded] scale[32], shift[32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t w_full = m_smem_u32(bars), p_full0 = m_smem_u32(bars + 1), p_ready0 = m_smem_u32(bars + 1 + MR_NP),
@@ -178,20 +189,20 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
         // ======================= TMA PRODUCER ====================================================
         if (lane == 0 && t_begin < t_end) {
             m_mbar_expect_tx(w_full, MR_W_BYTES);
-            for (int i = 0; i < 4; ++i)          // 864 weight rows in 4 boxes of 216 rows
-                m_tma_2d(wres_u32 + i * 216 * 128, &tmW, w_full, 0, i * 216);
+            for (int i = 0; i < Cfg::W_BOXES; ++i)          // weight rows in boxes of W_BOX_ROWS rows
+                m_tma_2d(wres_u32 + i * Cfg::W_BOX_ROWS * 128, &tmW, w_full, 0, i * Cfg::W_BOX_ROWS);
             long long L = 0;
             long long t = t_begin;
             while (t < t_end) {
                 const TileCoord c = decode_tile(t, p);
                 const int run = (int)min((long long)(p.D - c.d), t_end - t);     // tiles of this column handled here
-                for (int s = 0; s < run + 2; ++s, ++L) {
+                for (int s = 0; s < run + KS - 1; ++s, ++L) {
                     const int slot = (int)(L % MR_NP);
                     const uint32_t use = (uint32_t)(L / MR_NP);
                     m_mbar_wait(p_empty0 + 8 * slot, (use & 1u) ^ 1u);
                     const uint32_t bar = p_full0 + 8 * slot;
                     m_mbar_expect_tx(bar, MR_PLANE_ROWS * 128);
-                    m_tma_5d(planes_u32 + slot * MR_PLANE_BYTES, &tmA, bar, 0, c.tw * MR_TW - 1, c.th * MR_TH - 1, c.d - 1 + s, c.b);
+                    m_tma_5d(planes_u32 + slot * MR_PLANE_BYTES, &tmA, bar, 0, c.tw * MR_TW - PAD, c.th * MR_TH - PAD, c.d - PAD + s, c.b);
                 }
                 t += run;
             }
@@ -207,13 +218,13 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
             while (t < t_end) {
                 const TileCoord c = decode_tile(t, p);
                 const int run = (int)min((long long)(p.D - c.d), t_end - t);
-                // planes L, L+1 of this run must have landed before the first tile; each tile then waits for one more
-                for (int s = 0; s < 2; ++s) {
+                // the first KS-1 planes of this run must have landed before the first tile; each tile then waits for one more
+                for (int s = 0; s < KS - 1; ++s) {
                     const long long Ls = L + s;
                     m_mbar_wait(rdy0 + 8 * (int)(Ls % MR_NP), (uint32_t)(Ls / MR_NP) & 1u);
                 }
                 for (int i = 0; i < run; ++i, ++tile_n) {
-                    const long long Ln = L + i + 2;
+                    const long long Ln = L + i + KS - 1;
                     m_mbar_wait(rdy0 + 8 * (int)(Ln % MR_NP), (uint32_t)(Ln / MR_NP) & 1u);
                     const int acc = (int)(tile_n & 1);
                     m_mbar_wait(t_empty0 + 8 * acc, ((uint32_t)(tile_n >> 1) & 1u) ^ 1u);
@@ -221,13 +232,13 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                     if (lane == 0) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MR_BN);
 #pragma unroll 1
-                        for (int a = 0; a < 3; ++a) {
+                        for (int a = 0; a < KS; ++a) {
                             const uint32_t pl = planes_u32 + (uint32_t)((L + i + a) % MR_NP) * MR_PLANE_BYTES;
 #pragma unroll
-                            for (int ce = 0; ce < 9; ++ce) {
-                                const uint32_t a_addr = pl + (uint32_t)(((ce / 3) * MR_HW + (ce % 3)) * 128);
+                            for (int ce = 0; ce < KS * KS; ++ce) {
+                                const uint32_t a_addr = pl + (uint32_t)(((ce / KS) * MR_HW + (ce % KS)) * 128);
                                 const uint64_t adesc = m_desc(a_addr, MR_HW * 128);
-                                const uint64_t bdesc = m_desc(wres_u32 + (uint32_t)((a * 9 + ce) * MR_BN * 128), 1024);
+                                const uint64_t bdesc = m_desc(wres_u32 + (uint32_t)((a * KS * KS + ce) * MR_BN * 128), 1024);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
                                     m_umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (a | ce | k) ? 1u : 0u);
@@ -235,14 +246,13 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                         }
                         m_umma_commit(t_full0 + 8 * acc);                              // accumulator ready for the epilogue
                         m_umma_commit(p_empty0 + 8 * (int)((L + i) % MR_NP));           // oldest plane no longer needed
-                        if (i == run - 1) {                                             // end of the run: release the last two planes
-                            m_umma_commit(p_empty0 + 8 * (int)((L + i + 1) % MR_NP));
-                            m_umma_commit(p_empty0 + 8 * (int)((L + i + 2) % MR_NP));
+                        if (i == run - 1) {                                             // end of the run: release the remaining planes
+                            for (int s = 1; s < KS; ++s) m_umma_commit(p_empty0 + 8 * (int)((L + i + s) % MR_NP));
                         }
                     }
                     __syncwarp();
                 }
-                L += run + 2;
+                L += run + KS - 1;
                 t += run;
             }
         }
@@ -263,14 +273,14 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                     sc = ldg_f4(p.in_scale + (size_t)c.b * 32 + chunk * 4);
                     sh = ldg_f4(p.in_shift + (size_t)c.b * 32 + chunk * 4);
                 }
-                for (int s = 0; s < run + 2; ++s, ++L) {
+                for (int s = 0; s < run + KS - 1; ++s, ++L) {
                     const int slot = (int)(L % MR_NP);
                     m_mbar_wait(p_full0 + 8 * slot, (uint32_t)(L / MR_NP) & 1u);
-                    const int dpl = c.d - 1 + s;
+                    const int dpl = c.d - PAD + s;
                     if ((unsigned)dpl < (unsigned)p.D) {           // planes outside the volume are all padding
                         unsigned char* pl = planes + slot * MR_PLANE_BYTES;
                         for (int r = ft >> 3; r < MR_PLANE_ROWS; r += 16) {
-                            const int hh = c.th * MR_TH - 1 + r / MR_HW, ww = c.tw * MR_TW - 1 + r % MR_HW;
+                            const int hh = c.th * MR_TH - PAD + r / MR_HW, ww = c.tw * MR_TW - PAD + r % MR_HW;
                             if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
                                 float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
                                 float4 v = *ptr;
@@ -370,12 +380,53 @@ typedef CUresult (*MEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+template <int KS>
+static int launch_march(const MarchParams& p, const ss_conv3d_desc* d, const float* x, const float* w_kmajor, bool fixup,
+                        MEncodeTiledFn encode, cudaStream_t st) {
+    using Cfg = MarchCfg<KS>;
+    alignas(64) CUtensorMap tmA, tmW;
+    {
+        cuuint64_t gdim[5] = {32, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B};
+        cuuint64_t gstr[4] = {(cuuint64_t)d->in_ldc * 4, (cuuint64_t)p.W * d->in_ldc * 4, (cuuint64_t)p.H * p.W * d->in_ldc * 4,
+                              (cuuint64_t)p.D * p.H * p.W * d->in_ldc * 4};
+        cuuint32_t box[5] = {32, (cuuint32_t)Cfg::HW, (cuuint32_t)Cfg::HH, 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        if (encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return set_arg_error("conv_march32: tensor map A");
+    }
+    {
+        cuuint64_t gdim[2] = {32, (cuuint64_t)Cfg::TAPS * 32};
+        cuuint64_t gstr[1] = {32 * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)Cfg::W_BOX_ROWS};
+        cuuint32_t estr[2] = {1, 1};
+        if (encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_kmajor), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return set_arg_error("conv_march32: tensor map W");
+    }
+    const size_t smem = 1024 + Cfg::W_BYTES + MR_NP * Cfg::PLANE_BYTES + 2 * 64 * sizeof(double) + 32 * sizeof(uint64_t) + 64 + 64 * sizeof(float);
+    static thread_local bool configured = false;
+    if (!configured) {
+        SS_CUDA(cudaFuncSetAttribute(conv_march32_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)min((long long)sms, p.total_tiles);
+    conv_march32_kernel<KS><<<grid, MR_THREADS, smem, st>>>(p, tmA, tmW);
+    return check_launch("conv_march32_kernel");
+}
+
 // returns 1 if the layer was handled by the marching kernel
 int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                      const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
-    if (d->transposed || d->Cin != 32 || d->cout_packed > 32 || d->kd != 3 || d->kh != 3 || d->kw != 3) return 0;
+    if (d->transposed || d->Cin != 32 || d->cout_packed != 32) return 0;      // Cout < 32 layers arrive padded to 32 weight rows
+    const bool k3 = d->kd == 3 && d->kh == 3 && d->kw == 3 && d->pd == 1 && d->ph == 1 && d->pw == 1;
+    const bool k1 = d->kd == 1 && d->kh == 1 && d->kw == 1 && d->pd == 0 && d->ph == 0 && d->pw == 0;
+    if (!k3 && !k1) return 0;
     if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
-    if (d->pd != 1 || d->ph != 1 || d->pw != 1 || d->Win < 8 || d->Hin < 8 || d->Din < 3) return 0;
+    if (d->Win < 8 || d->Hin < 8 || d->Din < 3) return 0;
     if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win || d->math != SS_MATH_TF32) return 0;
     static MEncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -385,7 +436,6 @@ int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_sc
             qres != cudaDriverEntryPointSuccess) return 0;
         encode = reinterpret_cast<MEncodeTiledFn>(ptr);
     }
-    if (d->cout_packed != 32) return 0;                              // Cout < 32 layers arrive padded to 32 weight rows
     MarchParams p;
     p.B = d->B; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cout = d->Cout; p.out_ldc = d->out_ldc;
     p.in_act = d->in_act; p.out_act = d->out_act;
@@ -393,39 +443,7 @@ int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_sc
     p.total_tiles = (long long)p.B * p.nTH * p.nTW * p.D;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
-    alignas(64) CUtensorMap tmA, tmW;
-    {
-        cuuint64_t gdim[5] = {32, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B};
-        cuuint64_t gstr[4] = {(cuuint64_t)d->in_ldc * 4, (cuuint64_t)p.W * d->in_ldc * 4, (cuuint64_t)p.H * p.W * d->in_ldc * 4,
-                              (cuuint64_t)p.D * p.H * p.W * d->in_ldc * 4};
-        cuuint32_t box[5] = {32, MR_HW, MR_HH, 1, 1};
-        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        if (encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim,
-                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_march32: tensor map A"); return 1; }
-    }
-    {
-        cuuint64_t gdim[2] = {32, (cuuint64_t)MR_TAPS * 32};
-        cuuint64_t gstr[1] = {32 * 4};
-        cuuint32_t box[2] = {32, 216};
-        cuuint32_t estr[2] = {1, 1};
-        if (encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_kmajor), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_march32: tensor map W"); return 1; }
-    }
-    const size_t smem = 1024 + MR_W_BYTES + MR_NP * MR_PLANE_BYTES + 2 * 64 * sizeof(double) + 32 * sizeof(uint64_t) + 64 + 64 * sizeof(float);
-    static thread_local bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_march32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { *rc = set_cuda_error(e, "conv_march32 smem attribute"); return 1; }
-        configured = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = (unsigned)min((long long)sms, p.total_tiles);
-    conv_march32_kernel<<<grid, MR_THREADS, smem, st>>>(p, tmA, tmW);
-    *rc = check_launch("conv_march32_kernel");
+    *rc = k3 ? launch_march<3>(p, d, x, w_kmajor, fixup, encode, st) : launch_march<1>(p, d, x, w_kmajor, fixup, encode, st);
     return 1;
 }
 

@@ -258,12 +258,9 @@ class DepthNet(nn.Module):
         for i in range(4):                                         # 3 BasicBlocks + ASPP (cuDNN)
             d = self.depth_conv[i](d)
         d = self.depth_conv[4](d)                                  # DCN: own kernels, channels-last result
-        if d.is_cuda:                                              # final 1x1 conv on the tcgen05 kernel, straight from channels-last
-            dcl = d.permute(0, 2, 3, 1).unsqueeze(1)               # [B,1,H,W,C] view of the DCN output
-            y, _ = ops.conv(ops.Vol(dcl), self.depth_conv[5])
-            depth = ops.to_channels_first(y.squeeze(1))
-        else:
-            depth = self.depth_conv[5](d)
+        dcl = d.permute(0, 2, 3, 1).unsqueeze(1)                   # [B,1,H,W,C] view of the DCN output
+        y, _ = ops.conv(ops.Vol(dcl), self.depth_conv[5])          # final 1x1 conv on the tcgen05 kernel
+        depth = ops.to_channels_first(y.squeeze(1))
         return torch.cat([depth, context], dim=1)
 
 
@@ -324,7 +321,7 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
 
     # ---- geometry (ViewTransformerLSSBEVDepth.py:107-156, 604-659) --------------------------
     def get_depth_dist(self, x):
-        return ops.softmax_d(x) if x.is_cuda else x.softmax(dim=1)
+        return ops.softmax_d(x)
 
     def create_frustum(self):
         H, W = self.data_config["input_size"]

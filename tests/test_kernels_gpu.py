@@ -58,6 +58,7 @@ CONV_CASES = [
     ("tk4s4_512_128", lambda: nn.ConvTranspose3d(512, 128, 4, 4, bias=False), (1, 512, 2, 3, 1)),
     ("tk1s1_128_128", lambda: nn.ConvTranspose3d(128, 128, 1, 1, bias=False), (1, 128, 3, 4, 2)),
     ("k3s1_32_march", lambda: nn.Conv3d(32, 32, 3, 1, 1, bias=True), (2, 32, 11, 21, 19)),
+    ("k1_32_32_march", lambda: nn.Conv3d(32, 32, 1, bias=True), (2, 32, 9, 20, 17)),
     ("k3s1_32_march_big", lambda: nn.Conv3d(32, 32, 3, 1, 1, bias=False), (1, 32, 40, 48, 40)),
     ("k3s1_128_128_halo", lambda: nn.Conv3d(128, 128, 3, 1, 1, bias=True), (1, 128, 5, 40, 16)),
     ("k3s1_384_192_halo", lambda: nn.Conv3d(384, 192, 3, 1, 1, bias=False), (1, 384, 3, 32, 8)),
