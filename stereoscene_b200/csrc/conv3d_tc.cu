@@ -520,6 +520,8 @@ static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, i
 namespace ss {
 int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                      const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
+int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
+                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
 int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
 }
@@ -558,6 +560,8 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
         if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
         // wide 3x3x3 stride-1 layers: halo-resident kernel (planes loaded once per chunk, two M tiles per weight tile)
         if (try_conv_halo(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
+        // stride-2 transposed 3x3x3 layers: one CTA per input tile computes all 8 output parity classes
+        if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
     }
     const int cp = d->cout_packed;
     const int ntaps_total = d->kd * d->kh * d->kw;

@@ -64,6 +64,8 @@ CONV_CASES = [
     ("k3s1_384_192_halo", lambda: nn.Conv3d(384, 192, 3, 1, 1, bias=False), (1, 384, 3, 32, 8)),
     ("k3s1_64_64_halo", lambda: nn.Conv3d(64, 64, 3, 1, 1, bias=False), (2, 64, 4, 24, 24)),
     ("k3s1_256_256_halo", lambda: nn.Conv3d(256, 256, 3, 1, 1, bias=False), (1, 256, 3, 64, 8)),
+    ("tk3s2_64_32_tp", lambda: nn.ConvTranspose3d(64, 32, 3, padding=1, output_padding=1, stride=2, bias=False), (1, 64, 5, 16, 16)),
+    ("tk3s2_128_64_tp", lambda: nn.ConvTranspose3d(128, 64, 3, padding=1, output_padding=1, stride=2, bias=True), (2, 128, 3, 12, 24)),
     ("k3s1_256_512", lambda: nn.Conv3d(256, 512, 3, 1, 1, bias=False), (1, 256, 3, 5, 6)),
     ("k3s1_128_128_big", lambda: nn.Conv3d(128, 128, 3, 1, 1, bias=True), (2, 128, 9, 12, 16)),
 ]
