@@ -276,24 +276,60 @@ def run_ours(args):
     ms_dev = e0.elapsed_time(e1)
 
     # ---- timed region: end to end from host buffers ---------------------------------------------
-    def step_e2e():
+    # public serving API (stereoscene_b200.runtime.VolumetricEngine): pinned host features -> H2D on a copy
+    # stream -> CUDA-graph forward -> D2H of the uint8 label volume, double-buffered so the copies of
+    # neighbouring pairs overlap the compute.  Falls back to the eager public call if graphs are disabled.
+    e2e_mode = "engine(graph+overlapped copies)"
+    eng = None
+    if not args.no_graph:
+        try:
+            from stereoscene_b200.runtime import VolumetricEngine
+            eng = VolumetricEngine(model, left, right, calib, occ, tuple(xl_h.shape), device=dev)
+        except Exception as e:
+            if rank == 0:
+                print(f"[bench] VolumetricEngine unavailable ({type(e).__name__}: {e}); e2e uses eager calls", file=sys.stderr)
+            eng = None
+
+    def step_e2e_eager():
         with torch.no_grad():
             a = xl_h.to(dev, non_blocking=True)
             b = xr_h.to(dev, non_blocking=True)
             o = forward(a, b)
             labels_h.copy_(o["labels"], non_blocking=True)
 
-    for _ in range(2):
-        step_e2e()
+    def run_e2e(n):
+        if eng is not None:
+            for _ in eng.stream((xl_h, xr_h) for _ in range(n)):
+                pass
+            cur = torch.cuda.current_stream()
+            for ev in eng.d2h_done:
+                cur.wait_event(ev)
+        else:
+            for _ in range(n):
+                step_e2e_eager()
+
+    if eng is None:
+        e2e_mode = "eager forward_features()"
+    run_e2e(3)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        step_e2e()
+    if eng is not None:                      # make the engine's streams start after the start event
+        eng.copy_stream.wait_event(f0)
+        eng.compute_stream.wait_event(f0)
+    run_e2e(args.steps)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop()
+    if eng is not None and rank == 0:
+        # the engine's labels must be the eager forward's labels
+        same = float((eng.infer(xl_h, xr_h).to(dev) != out["labels"]).float().mean())
+        if same > 1e-3:
+            raise SystemExit(f"engine output disagrees with the eager forward ({same:.3e} of labels differ)")
+
+    # ---- per-stage split under the reference's stage names (bevdepth_occupancy.py:63-79, 103-122) ----
+    stage_ms = stage_breakdown(model, xl_d, xr_d, left, right, calib, occ)
 
     from stereoscene_b200 import sharding
     t = sharding.max_over_ranks(torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev))
@@ -323,6 +359,8 @@ def run_ours(args):
                    "parallelism": f"sample-sharded x{world} (no data-path collective)"},
         "e2e": {"value": e2e, "unit": "voxels/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(xl_h.numel() * 4 + xr_h.numel() * 4), "d2h_bytes_per_step": int(labels_h.numel())},
+        "e2e_mode": e2e_mode,
+        "stage_ms": stage_ms,
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
@@ -336,6 +374,34 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stage_breakdown(model, xl, xr, left, right, calib, occ, iters=5):
+    """Eager per-stage device times (CUDA events), reference stage names."""
+    from stereoscene_b200 import ops
+    vt = model.img_view_transformer
+    keys = ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    acc = [0.0] * 4
+    with torch.no_grad():
+        for it in range(iters + 1):
+            ml = vt.get_mlp_input(*[left[k] for k in keys]); mr = vt.get_mlp_input(*[right[k] for k in keys])
+            ev[0].record()
+            bev, _ = vt([xl] + [left[k] for k in keys] + [ml] + [xr] + [right[k] for k in keys] + [mr] + [calib, None, None])
+            ev[1].record()
+            levels = model.img_bev_encoder_backbone.forward_vol(ops.Vol(bev.permute(0, 2, 3, 4, 1)))
+            ev[2].record()
+            neck = model.img_bev_encoder_neck.forward_vol(levels)
+            ev[3].record()
+            logits = model.pts_bbox_head.forward_voxel_vol([neck])[0]
+            ops.trilinear(logits, occ, want_labels=True)
+            ev[4].record()
+            torch.cuda.synchronize()
+            if it:
+                for i in range(4):
+                    acc[i] += ev[i].elapsed_time(ev[i + 1])
+    names = ("view_transformer", "bev_encoder", "bev_neck", "occ_head+upsample")
+    return {n: a / iters for n, a in zip(names, acc)}
 
 
 def _time_launches(fn, iters=10, warm=3):

@@ -5,7 +5,7 @@
 // The per-tap box kernel (conv3d_tc.cu) re-fetches a 16 KB A box per tap and is bound by L2->SM
 // bandwidth.  Here a CTA owns 256 output voxels (32 h x 8 w at one depth plane d, two M=128 tiles that
 // share every weight tile) and, per 32-channel chunk, loads the three input planes d-1, d, d+1 ONCE
-// (TMA 5-D box of 34 x 10 halo voxels, out-of-bounds zero fill = conv padding, 42.5 KB) into a 3-slot
+// (TMA 5-D box of 34 x 10 halo voxels, out-of-bounds zero fill = conv padding, 42.5 KB) into a 2-slot
 // ring.  The A operand of tap (kd,kh,kw) / M-tile mt is the same plane addressed through a UMMA
 // descriptor whose start is shifted by ((16 mt + kh) * 10 + kw) rows with stride-byte-offset = the
 // halo line pitch (1280 B) -- legal because the 128-byte swizzle is a function of the absolute smem
@@ -22,7 +22,7 @@ constexpr int HL_TH = 32, HL_TW = 8;
 constexpr int HL_HH = HL_TH + 2, HL_HW = HL_TW + 2;
 constexpr int HL_PLANE_ROWS = HL_HH * HL_HW;          // 340
 constexpr int HL_PLANE_BYTES = 43 * 1024;             // 340*128 = 43520 -> padded to a multiple of 1024
-constexpr int HL_NPL = 3;
+constexpr int HL_NPL = 2;                             // plane ring (a plane lasts 9 taps x 8 MMAs: one slot of prefetch suffices)
 constexpr int HL_WORKERS = 256;
 constexpr int HL_THREADS = HL_WORKERS + 96;           // + A producer, MMA, B producer warps
 
@@ -99,7 +99,9 @@ __device__ __forceinline__ uint64_t h_desc(uint32_t saddr, uint32_t sbo_bytes) {
 
 template <int BN>
 struct HaloCfg {
-    static constexpr int SB = BN >= 256 ? 2 : BN >= 192 ? 3 : 4;       // weight-tile ring depth
+    // weight-tile ring depth: a tile is consumed in 8 MMAs (~64 BN/128 x 8 cycles), far less than the TMA
+    // round trip, so the ring has to hold several microseconds of tiles
+    static constexpr int SB = BN >= 256 ? 4 : BN >= 192 ? 5 : BN >= 128 ? 8 : 12;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };

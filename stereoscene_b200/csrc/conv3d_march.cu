@@ -165,7 +165,7 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
         }
         for (int a = 0; a < 2; ++a) {
             m_mbar_init(t_full0 + 8 * a, 1);
-            m_mbar_init(t_empty0 + 8 * a, 128);
+            m_mbar_init(t_empty0 + 8 * a, fixup ? 128 : 256);   // plain inputs: all 8 worker warps drain TMEM
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -256,9 +256,9 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                 t += run;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && fixup) {
         // ======================= FIX-UP WARPS (4..7): pending affine / ReLU once per plane, in place ==
-        if (fixup && t_begin < t_end) {
+        if (t_begin < t_end) {
             const int ft = tid - 128;                  // 0..127
             long long L = 0;
             long long t = t_begin;
@@ -302,8 +302,11 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
             }
         }
     } else {
-        // ======================= EPILOGUE WARPS (0..3) ===========================================
-        const int q = warp;
+        // ======================= EPILOGUE WARPS (0..3, plus 4..7 when there is no fix-up work) =======
+        const int q = warp & 3;
+        const int nsplit = fixup ? 1 : 2;              // warps sharing a lane quarter split the 32 columns
+        const int cpart = fixup ? 0 : (warp >> 2);
+        const int ncol = 32 / nsplit, col0 = cpart * ncol;
         const int row = q * 32 + lane;
         const int lh = row / MR_TW, lw = row % MR_TW;
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) && p.Cout == 32;
@@ -311,9 +314,12 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
         double run_s = 0.0, run_q = 0.0;               // lane = channel: sums of this warp's 32 rows over all tiles
         int run_b = -1;
         auto flush = [&]() {
-            if (p.stats && run_b >= 0 && lane < p.Cout) {
-                atomicAdd(p.stats + ((size_t)run_b * p.Cout + lane) * 2 + 0, run_s);
-                atomicAdd(p.stats + ((size_t)run_b * p.Cout + lane) * 2 + 1, run_q);
+            if (p.stats && run_b >= 0) {
+                const int ch = (nsplit == 1) ? lane : col0 + (lane & 15);
+                if (ch < p.Cout && (nsplit == 1 || lane < 16)) {
+                    atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 0, run_s);
+                    atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 1, run_q);
+                }
             }
             run_s = 0.0; run_q = 0.0;
         };
@@ -324,7 +330,19 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
             m_mbar_wait(t_full0 + 8 * acc, (uint32_t)(tile_n >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t r[32];
-            m_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MR_BN), r);
+            if (nsplit == 1) {
+                m_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MR_BN), r);
+            } else {
+                uint32_t r16[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MR_BN + col0);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]), "=r"(r16[6]), "=r"(r16[7]),
+                               "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]), "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { r[k] = r16[k]; r[16 + k] = 0u; }
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             m_mbar_arrive(t_empty0 + 8 * acc);                     // accumulator may be overwritten
             const int oh = c.th * MR_TH + lh, ow = c.tw * MR_TW + lw;
@@ -333,24 +351,28 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 float f = __uint_as_float(r[k]);
-                if (p.bias && k < p.Cout) f += __ldg(p.bias + k);
+                const int ch = col0 + k;
+                if (p.bias && k < ncol && ch < p.Cout) f += __ldg(p.bias + ch);
                 v[k] = apply_act(f, p.out_act);
             }
             if (valid) {
-                float* dst = p.y + ((((size_t)c.b * p.D + c.d) * p.H + oh) * p.W + ow) * p.out_ldc;
+                float* dst = p.y + ((((size_t)c.b * p.D + c.d) * p.H + oh) * p.W + ow) * p.out_ldc + col0;
                 if (vec_ok) {
 #pragma unroll
-                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                    for (int k = 0; k < 32; k += 4)
+                        if (k < ncol) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 32; ++k)
-                        if (k < p.Cout) dst[k] = v[k];
+                        if (k < ncol && col0 + k < p.Cout) dst[k] = v[k];
                 }
             }
             if (p.stats) {
                 float s[32], qq[32];
 #pragma unroll
-                for (int k = 0; k < 32; ++k) { s[k] = valid ? v[k] : 0.f; qq[k] = s[k] * s[k]; }
+                for (int k = 0; k < 32; ++k) { s[k] = (valid && k < ncol) ? v[k] : 0.f; qq[k] = s[k] * s[k]; }
+                // butterfly over the 32 rows of the warp; with 16 columns per warp the upper half is zero and
+                // lane L (< 16) ends up with column col0 + L, lanes >= 16 with zeros
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     const bool up = (lane & off) != 0;

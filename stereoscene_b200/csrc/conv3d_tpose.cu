@@ -19,7 +19,7 @@ constexpr int TP_HH = TP_TH + 1, TP_HW = TP_TW + 1;
 constexpr int TP_PLANE_ROWS = TP_HH * TP_HW;           // 153
 constexpr int TP_PLANE_BYTES = 20 * 1024;              // 153*128 = 19584 -> padded
 constexpr int TP_NPL = 4;                              // plane ring: 2 planes per chunk, one chunk of prefetch
-constexpr int TP_SB = 8;                               // weight-tile ring
+constexpr int TP_SB_BYTES = 24 * 1024;                 // weight-tile ring (small, so that two CTAs fit on an SM when BN = 32)
 constexpr int TP_WORKERS = 256;
 constexpr int TP_THREADS = TP_WORKERS + 96;
 
@@ -112,9 +112,10 @@ __device__ __forceinline__ int tpose_build_table(int* tab) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(TP_THREADS, 1)
+__global__ void __launch_bounds__(TP_THREADS, BN <= 32 ? 2 : 1)
 conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     constexpr int B_BYTES = BN * 128;
+    constexpr int TP_SB = TP_SB_BYTES / B_BYTES;
     constexpr int TMEM_COLS = 8 * BN <= 256 ? 256 : 512;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -350,6 +351,7 @@ static int launch_tpose(const TposeParams& p, const CUtensorMap& tmA, const floa
     if (encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wk), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return set_arg_error("conv_tpose: tensor map B");
+    constexpr int TP_SB = TP_SB_BYTES / (BN * 128);
     const size_t smem = 1024 + (size_t)TP_NPL * TP_PLANE_BYTES + (size_t)TP_SB * BN * 128 + 2 * BN * sizeof(double) +
                         (3 * TP_NPL + 2 * TP_SB + 1) * sizeof(uint64_t) + 16 + 32 * sizeof(int) + 32 + 2 * (size_t)p.Cin * sizeof(float);
     static thread_local size_t configured = 0;
