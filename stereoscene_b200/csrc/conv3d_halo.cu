@@ -121,7 +121,8 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * HL_NPL + 2 * SB + 1);
     float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // scale[Cin], shift[Cin]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = uniform_warp_index();
     const int n0 = blockIdx.y * BN;
     // tile decode: blockIdx.x = ((b * D + d) * nTH + th) * nTW + tw
     const int tw_i = blockIdx.x % p.nTW, th_i = (blockIdx.x / p.nTW) % p.nTH;
@@ -168,60 +169,56 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
     const uint32_t planes_u32 = h_smem_u32(planes), bring_u32 = h_smem_u32(bring);
 
     if (warp == 8) {
-        // ======================= A PRODUCER: 3 planes per 32-channel chunk ==========================
-        if (lane == 0) {
-            for (int L = 0; L < kchunks * 3; ++L) {
-                const int slot = L % HL_NPL;
-                const uint32_t use = (uint32_t)(L / HL_NPL);
-                h_mbar_wait(pa_empty0 + 8 * slot, (use & 1u) ^ 1u);
-                const uint32_t bar = pa_full0 + 8 * slot;
-                h_mbar_expect_tx(bar, HL_PLANE_ROWS * 128);
-                h_tma_5d(planes_u32 + slot * HL_PLANE_BYTES, &tmA, bar, (L / 3) * 32, w0 - 1, h0 - 1, d - 1 + (L % 3), b);
-            }
+        // ======================= A PRODUCER: 3 planes per 32-channel chunk (warp-uniform, elected issue) ====
+        for (int L = 0; L < kchunks * 3; ++L) {
+            const int slot = L % HL_NPL;
+            const uint32_t use = (uint32_t)(L / HL_NPL);
+            h_mbar_wait(pa_empty0 + 8 * slot, (use & 1u) ^ 1u);
+            const uint32_t bar = pa_full0 + 8 * slot;
+            mbar_expect_tx_elect(bar, HL_PLANE_ROWS * 128);
+            tma_5d_elect(planes_u32 + slot * HL_PLANE_BYTES, &tmA, bar, (L / 3) * 32, w0 - 1, h0 - 1, d - 1 + (L % 3), b);
+            __syncwarp();
         }
     } else if (warp == 10) {
         // ======================= B PRODUCER: one weight tile per (chunk, tap) =======================
-        if (lane == 0) {
-            for (int L = 0; L < kchunks * 27; ++L) {
-                const int slot = L % SB;
-                const uint32_t use = (uint32_t)(L / SB);
-                h_mbar_wait(pb_empty0 + 8 * slot, (use & 1u) ^ 1u);
-                const uint32_t bar = pb_full0 + 8 * slot;
-                h_mbar_expect_tx(bar, Cfg::B_BYTES);
-                h_tma_2d(bring_u32 + slot * Cfg::B_BYTES, &tmB, bar, (L / 27) * 32, (L % 27) * p.CoutP + n0);
-            }
+        for (int L = 0; L < kchunks * 27; ++L) {
+            const int slot = L % SB;
+            const uint32_t use = (uint32_t)(L / SB);
+            h_mbar_wait(pb_empty0 + 8 * slot, (use & 1u) ^ 1u);
+            const uint32_t bar = pb_full0 + 8 * slot;
+            mbar_expect_tx_elect(bar, Cfg::B_BYTES);
+            tma_2d_elect(bring_u32 + slot * Cfg::B_BYTES, &tmB, bar, (L / 27) * 32, (L % 27) * p.CoutP + n0);
+            __syncwarp();
         }
     } else if (warp == 9) {
-        // ======================= MMA ISSUER ========================================================
+        // ======================= MMA ISSUER (warp-uniform; see common.cuh) ==========================
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t A_HI = umma_desc_hi(HL_HW * 128), B_HI = umma_desc_hi(1024);
         const uint32_t rdy0 = fixup ? pa_ready0 : pa_full0;
         int Lb = 0;
         for (int Lp = 0; Lp < kchunks * 3; ++Lp) {
             const int pslot = Lp % HL_NPL;
             h_mbar_wait(rdy0 + 8 * pslot, (uint32_t)(Lp / HL_NPL) & 1u);
-            const uint32_t pl = planes_u32 + pslot * HL_PLANE_BYTES;
+            const uint32_t a_lo = umma_desc_lo(planes_u32 + pslot * HL_PLANE_BYTES);
+#pragma unroll
             for (int ce = 0; ce < 9; ++ce, ++Lb) {
                 const int bslot = Lb % SB;
                 h_mbar_wait(pb_full0 + 8 * bslot, (uint32_t)(Lb / SB) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint64_t bdesc = h_desc(bring_u32 + bslot * Cfg::B_BYTES, 1024);
+                const uint32_t b_lo = umma_desc_lo(bring_u32 + bslot * Cfg::B_BYTES);
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        const uint32_t a_addr = pl + (uint32_t)(((mt * 16 + ce / 3) * HL_HW + (ce % 3)) * 128);
-                        const uint64_t adesc = h_desc(a_addr, HL_HW * 128);
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint32_t ao = (uint32_t)(((mt * 16 + ce / 3) * HL_HW + (ce % 3)) * 128) >> 4;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            h_umma_tf32(tmem_base + (uint32_t)(mt * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                        (Lp | ce | k) ? 1u : 0u);
-                    }
-                    h_umma_commit(pb_empty0 + 8 * bslot);
-                    if (ce == 8) h_umma_commit(pa_empty0 + 8 * pslot);
+                    for (int k = 0; k < 4; ++k)
+                        umma_ss_tf32<A_HI, B_HI>(tmem_base + (uint32_t)(mt * BN), a_lo + ao + 2 * k, b_lo + 2 * k, idesc, (Lp | ce | k) ? 1u : 0u);
                 }
+                umma_commit_elect(pb_empty0 + 8 * bslot);
+                if (ce == 8) umma_commit_elect(pa_empty0 + 8 * pslot);
                 __syncwarp();
             }
         }
-        if (lane == 0) h_umma_commit(accum_bar);
+        umma_commit_elect(accum_bar);
         __syncwarp();
     } else if (fixup) {
         // ======================= WORKERS: pending affine / ReLU, once per landed plane, in place =====

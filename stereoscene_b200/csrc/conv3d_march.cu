@@ -14,8 +14,14 @@
 //     stride-byte-offset is the halo line pitch (10 rows = 1280 B).  The 128-byte swizzle is a function
 //     of the absolute shared-memory address (verified on B200 by tools/probes/umma_shift_probe.cu), so
 //     row-shifted starts and a non-1024 SBO are legal;
-//   * accumulators are double-buffered in TMEM: the epilogue of tile i (tcgen05.ld, bias, activation,
-//     GroupNorm sums, stores) overlaps the MMAs of tile i+1;
+//   * the three kd taps of one (kh,kw) shift are ONE MMA: an input plane p feeds the output planes p-1, p, p+1
+//     (kd = 2, 1, 0), whose accumulators sit side by side in a 4-slot TMEM ring, and the resident weights
+//     are stored [kh,kw][kd=2|kd=1|kd=0][cout] so that B is one 96-row operand.  N = 96 instead of 32 cuts
+//     the shared-memory operand traffic per FLOP 2.1x (A, the 4 KB plane window, is the dominant read: at
+//     N = 32 the layer is bound by the 128 B/clk tensor-core shared-memory port, not by the MMA rate) and every
+//     plane is consumed by 36 MMAs right after it lands, so the 4-slot plane ring is 3 planes of prefetch;
+//   * the epilogue of output plane d (tcgen05.ld, bias, activation, GroupNorm sums, stores) overlaps the
+//     MMAs of the following planes (ring slot d % 4);
 //   * a pending affine / ReLU of the producer layer is applied once per plane, in place, by 4 fix-up
 //     warps (padding stays zero) -- amortised over the 27 taps x 3 planes that read it.
 // L2->SM traffic per output tile: one 22.5 KB plane (vs 27 x 20 KB for the per-tap box kernel).
@@ -27,6 +33,7 @@ namespace ss {
 constexpr int MR_TH = 16, MR_TW = 8;                 // output tile (h, w); M = 128 rows
 constexpr int MR_NP = 4;                             // plane ring slots
 constexpr int MR_BN = 32;
+constexpr int MR_ACC = 4;                            // TMEM accumulator ring (32 columns each)
 constexpr int MR_THREADS = 8 * 32 + 64;              // 4 epilogue warps, 4 fix-up warps, producer warp, MMA warp
 
 // KS = kernel extent per axis (3: 3x3x3 pad 1; 1: 1x1x1, e.g. the hourglass redir1 layers)
@@ -38,7 +45,7 @@ struct MarchCfg {
     static constexpr int PLANE_BYTES = (PLANE_ROWS * 128 + 1023) / 1024 * 1024;
     static constexpr int TAPS = KS * KS * KS;
     static constexpr int W_BYTES = TAPS * MR_BN * 128;                // 110592 / 4096
-    static constexpr int W_BOX_ROWS = KS == 3 ? 216 : 32;             // weight rows per TMA box
+    static constexpr int W_BOX_ROWS = 32;                             // weight rows per TMA box (one tap)
     static constexpr int W_BOXES = TAPS * MR_BN / W_BOX_ROWS;
 };
 
@@ -85,16 +92,66 @@ __device__ __forceinline__ void m_tma_2d(uint32_t dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void m_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// The MMA warp runs its loops warp-uniformly (all 32 lanes compute the same descriptors, so ptxas keeps them in
+// uniform registers) and only the instruction itself is predicated on the elected lane.  Issuing from inside an
+// `if (lane == 0)` region instead makes ptxas wrap every UTCHMMA in an ELECT / R2UR.BROADCAST loop (~90 clk per MMA),
+// which bounds small-N layers by instruction issue.
+// warp-uniform variants for the producer warp: every lane runs the loop, one elected lane issues
+__device__ __forceinline__ void m_mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+        "}\n" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void m_umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void m_tma_5d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t"
+        "}\n" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void m_tma_2d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t"
+        "}\n" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void m_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t leader) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void m_umma_commit(uint32_t bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(bar), "r"(leader) : "memory");
+}
+// same, with the descriptors given as their (varying) low words; the high words are compile-time constants
+template <uint32_t A_HI, uint32_t B_HI>
+__device__ __forceinline__ void m_umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(A_HI), "n"(B_HI) : "memory");
 }
 __device__ __forceinline__ void m_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -139,15 +196,16 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     unsigned char* wres = base;                                   // resident weights
     unsigned char* planes = base + MR_W_BYTES;                    // MR_NP plane slots (MR_W_BYTES is a multiple of 1024)
     unsigned char* aux = planes + MR_NP * MR_PLANE_BYTES;
-    double* sstat = reinterpret_cast<double*>(aux);               // [2][32][2] (per accumulator buffer)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * 64);
-    // barriers: w_full, p_full[NP], p_ready[NP], p_empty[NP], t_full[2], t_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * MR_NP + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
+    // barriers: w_full, p_full[NP], p_ready[NP], p_empty[NP], t_full[ACC], t_empty[ACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * MR_NP + 2 * MR_ACC);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // provably warp-uniform role index
+    const uint32_t leader = (lane == 0) ? 1u : 0u;
     const uint32_t w_full = m_smem_u32(bars), p_full0 = m_smem_u32(bars + 1), p_ready0 = m_smem_u32(bars + 1 + MR_NP),
                    p_empty0 = m_smem_u32(bars + 1 + 2 * MR_NP), t_full0 = m_smem_u32(bars + 1 + 3 * MR_NP),
-                   t_empty0 = m_smem_u32(bars + 1 + 3 * MR_NP + 2);
+                   t_empty0 = m_smem_u32(bars + 1 + 3 * MR_NP + MR_ACC);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
     const bool fixup = has_aff || in_relu;
@@ -163,7 +221,7 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
             m_mbar_init(p_ready0 + 8 * s, 128);
             m_mbar_init(p_empty0 + 8 * s, 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < MR_ACC; ++a) {
             m_mbar_init(t_full0 + 8 * a, 1);
             m_mbar_init(t_empty0 + 8 * a, fixup ? 128 : 256);   // plain inputs: all 8 worker warps drain TMEM
         }
@@ -171,9 +229,8 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     }
-    for (int i = tid; i < 2 * 64; i += MR_THREADS) sstat[i] = 0.0;
     if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(m_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(m_smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -186,23 +243,26 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     // d0-1 .. d1 are loaded in order; tile d uses stream planes (d-d0), +1, +2.  All roles walk the
     // same runs, so a global plane counter L gives slot = L % NP and the barrier parity.
     if (warp == 8) {
-        // ======================= TMA PRODUCER ====================================================
-        if (lane == 0 && t_begin < t_end) {
-            m_mbar_expect_tx(w_full, MR_W_BYTES);
-            for (int i = 0; i < Cfg::W_BOXES; ++i)          // weight rows in boxes of W_BOX_ROWS rows
-                m_tma_2d(wres_u32 + i * Cfg::W_BOX_ROWS * 128, &tmW, w_full, 0, i * Cfg::W_BOX_ROWS);
-            long long L = 0;
+        // ======================= TMA PRODUCER (warp-uniform; one elected lane issues) ===========
+        if (t_begin < t_end) {
+            m_mbar_expect_tx_elect(w_full, MR_W_BYTES);
+            for (int i = 0; i < Cfg::TAPS; ++i) {           // tap (kd, ce) lands at slot ce*3 + (2-kd): [kd=2|kd=1|kd=0] per shift
+                const int kd = i / (KS * KS), ce = i % (KS * KS);
+                const int pos = KS == 3 ? ce * 3 + (2 - kd) : i;
+                m_tma_2d_elect(wres_u32 + pos * 32 * 128, &tmW, w_full, 0, i * 32);
+            }
+            uint32_t L = 0;
             long long t = t_begin;
             while (t < t_end) {
                 const TileCoord c = decode_tile(t, p);
                 const int run = (int)min((long long)(p.D - c.d), t_end - t);     // tiles of this column handled here
                 for (int s = 0; s < run + KS - 1; ++s, ++L) {
-                    const int slot = (int)(L % MR_NP);
-                    const uint32_t use = (uint32_t)(L / MR_NP);
-                    m_mbar_wait(p_empty0 + 8 * slot, (use & 1u) ^ 1u);
+                    const uint32_t slot = L % MR_NP;
+                    m_mbar_wait(p_empty0 + 8 * slot, ((L / MR_NP) & 1u) ^ 1u);
                     const uint32_t bar = p_full0 + 8 * slot;
-                    m_mbar_expect_tx(bar, MR_PLANE_ROWS * 128);
-                    m_tma_5d(planes_u32 + slot * MR_PLANE_BYTES, &tmA, bar, 0, c.tw * MR_TW - PAD, c.th * MR_TH - PAD, c.d - PAD + s, c.b);
+                    m_mbar_expect_tx_elect(bar, MR_PLANE_ROWS * 128);
+                    m_tma_5d_elect(planes_u32 + slot * MR_PLANE_BYTES, &tmA, bar, 0, c.tw * MR_TW - PAD, c.th * MR_TH - PAD, c.d - PAD + s, c.b);
+                    __syncwarp();
                 }
                 t += run;
             }
@@ -210,49 +270,92 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     } else if (warp == 9) {
         // ======================= MMA ISSUER ======================================================
         if (t_begin < t_end) {
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MR_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
             m_mbar_wait(w_full, 0);
             const uint32_t rdy0 = fixup ? p_ready0 : p_full0;
-            long long L = 0, tile_n = 0;
+            uint32_t L = 0, tile_n = 0;
             long long t = t_begin;
             while (t < t_end) {
                 const TileCoord c = decode_tile(t, p);
                 const int run = (int)min((long long)(p.D - c.d), t_end - t);
-                // the first KS-1 planes of this run must have landed before the first tile; each tile then waits for one more
-                for (int s = 0; s < KS - 1; ++s) {
-                    const long long Ls = L + s;
-                    m_mbar_wait(rdy0 + 8 * (int)(Ls % MR_NP), (uint32_t)(Ls / MR_NP) & 1u);
-                }
-                for (int i = 0; i < run; ++i, ++tile_n) {
-                    const long long Ln = L + i + KS - 1;
-                    m_mbar_wait(rdy0 + 8 * (int)(Ln % MR_NP), (uint32_t)(Ln / MR_NP) & 1u);
-                    const int acc = (int)(tile_n & 1);
-                    m_mbar_wait(t_empty0 + 8 * acc, ((uint32_t)(tile_n >> 1) & 1u) ^ 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (lane == 0) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MR_BN);
-#pragma unroll 1
-                        for (int a = 0; a < KS; ++a) {
-                            const uint32_t pl = planes_u32 + (uint32_t)((L + i + a) % MR_NP) * MR_PLANE_BYTES;
+                if constexpr (KS == 1) {
+                    for (int i = 0; i < run; ++i, ++tile_n, ++L) {
+                        const uint32_t slot = L % MR_NP, acc = tile_n % MR_ACC;
+                        m_mbar_wait(rdy0 + 8 * slot, (L / MR_NP) & 1u);
+                        m_mbar_wait(t_empty0 + 8 * acc, ((tile_n / MR_ACC) & 1u) ^ 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        {
+                            const uint64_t adesc = m_desc(planes_u32 + (uint32_t)slot * MR_PLANE_BYTES, MR_HW * 128);
+                            const uint64_t bdesc = m_desc(wres_u32, 1024);
 #pragma unroll
-                            for (int ce = 0; ce < KS * KS; ++ce) {
-                                const uint32_t a_addr = pl + (uint32_t)(((ce / KS) * MR_HW + (ce % KS)) * 128);
-                                const uint64_t adesc = m_desc(a_addr, MR_HW * 128);
-                                const uint64_t bdesc = m_desc(wres_u32 + (uint32_t)((a * KS * KS + ce) * MR_BN * 128), 1024);
+                            for (int k = 0; k < 4; ++k)
+                                m_umma_tf32(tmem_base + (uint32_t)(acc * MR_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                            idesc0 | ((uint32_t)(MR_BN >> 3) << 17), k ? 1u : 0u, leader);
+                            m_umma_commit(t_full0 + 8 * acc, leader);
+                            m_umma_commit(p_empty0 + 8 * slot, leader);
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    // stream plane s (depth c.d - 1 + s) feeds the output tiles j = s-2, s-1, s of this run through
+                    // kd = 2, 1, 0; tile j (global number tile_n + j) accumulates in TMEM ring slot (tile_n + j) % 4.
+                    // The issue loop is the critical path of this kernel (one thread, ~1 MMA per 50 clk needed):
+                    // everything that varies per MMA is a 32-bit add of a compile-time constant to a descriptor word.
+                    constexpr uint32_t A_HI = ((uint32_t)(MR_HW * 128) >> 4) | (1u << 14) | (2u << 29);
+                    constexpr uint32_t B_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+                    const uint32_t w_lo = ((wres_u32 >> 4) & 0x3FFFu) | (1u << 16);
+                    for (int s = 0; s < run + 2; ++s, ++L) {
+                        const uint32_t slot = L & (MR_NP - 1);
+                        m_mbar_wait(rdy0 + 8 * slot, (L / MR_NP) & 1u);
+                        const int jlo = max(0, s - 2), jhi = min(run - 1, s);
+                        const bool fresh = s <= run - 1;                        // tile s gets its first contribution here
+                        if (fresh) {
+                            const uint32_t n = tile_n + (uint32_t)s;
+                            m_mbar_wait(t_empty0 + 8 * (n & (MR_ACC - 1)), ((n / MR_ACC) & 1u) ^ 1u);
+                        }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_lo = (((planes_u32 + slot * MR_PLANE_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+                        // window [jlo, jhi] -> at most two runs of consecutive ring slots (split at the wrap)
+                        const uint32_t r0 = (tile_n + (uint32_t)jlo) & (MR_ACC - 1);
+                        const int cnt = jhi - jlo + 1;
+                        const int n0 = min(cnt, MR_ACC - (int)r0), n1 = cnt - n0;
+                        const uint32_t d0 = tmem_base + r0 * MR_BN, d1 = tmem_base;
+                        const uint32_t b0 = w_lo + (uint32_t)(2 - (s - jlo)) * 256u, b1 = b0 + (uint32_t)n0 * 256u;   // 32 rows = 256 x 16 B
+                        const uint32_t id0 = idesc0 | ((uint32_t)(n0 * MR_BN >> 3) << 17), id1 = idesc0 | ((uint32_t)(n1 * MR_BN >> 3) << 17);
+                        // first MMA of the plane: tile s (the last of the window) starts from zero, the others accumulate
+                        if (fresh) {
+                            const uint32_t rs = (tile_n + (uint32_t)jhi) & (MR_ACC - 1);
+                            if (cnt > 1) {
+                                const int m0 = min(cnt - 1, MR_ACC - (int)r0), m1 = cnt - 1 - m0;
+                                m_umma_lo<A_HI, B_HI>(d0, a_lo, b0, idesc0 | ((uint32_t)(m0 * MR_BN >> 3) << 17), 1u);
+                                if (m1 > 0) m_umma_lo<A_HI, B_HI>(d1, a_lo, b0 + (uint32_t)m0 * 256u, idesc0 | ((uint32_t)(m1 * MR_BN >> 3) << 17), 1u);
+                            }
+                            m_umma_lo<A_HI, B_HI>(tmem_base + rs * MR_BN, a_lo, b0 + (uint32_t)(cnt - 1) * 256u, idesc0 | ((uint32_t)(MR_BN >> 3) << 17), 0u);
+                        }
+                        if (n1 == 0) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    m_umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (a | ce | k) ? 1u : 0u);
+                            for (int i = 0; i < 36; ++i) {
+                                if (i == 0 && fresh) continue;
+                                const uint32_t ao = (uint32_t)((((i >> 2) / 3) * MR_HW + ((i >> 2) % 3)) * 128 + 32 * (i & 3)) >> 4;
+                                const uint32_t bo = (uint32_t)((i >> 2) * 96 * 128 + 32 * (i & 3)) >> 4;
+                                m_umma_lo<A_HI, B_HI>(d0, a_lo + ao, b0 + bo, id0, 1u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 36; ++i) {
+                                if (i == 0 && fresh) continue;
+                                const uint32_t ao = (uint32_t)((((i >> 2) / 3) * MR_HW + ((i >> 2) % 3)) * 128 + 32 * (i & 3)) >> 4;
+                                const uint32_t bo = (uint32_t)((i >> 2) * 96 * 128 + 32 * (i & 3)) >> 4;
+                                m_umma_lo<A_HI, B_HI>(d0, a_lo + ao, b0 + bo, id0, 1u);
+                                m_umma_lo<A_HI, B_HI>(d1, a_lo + ao, b1 + bo, id1, 1u);
                             }
                         }
-                        m_umma_commit(t_full0 + 8 * acc);                              // accumulator ready for the epilogue
-                        m_umma_commit(p_empty0 + 8 * (int)((L + i) % MR_NP));           // oldest plane no longer needed
-                        if (i == run - 1) {                                             // end of the run: release the remaining planes
-                            for (int s = 1; s < KS; ++s) m_umma_commit(p_empty0 + 8 * (int)((L + i + s) % MR_NP));
-                        }
+                        if (s >= 2) m_umma_commit(t_full0 + 8 * ((tile_n + (uint32_t)s - 2u) & (MR_ACC - 1)), leader);   // tile s-2 is complete
+                        m_umma_commit(p_empty0 + 8 * slot, leader);
+                        __syncwarp();
                     }
-                    __syncwarp();
+                    tile_n += (uint32_t)run;
                 }
-                L += run + KS - 1;
                 t += run;
             }
         }
@@ -311,23 +414,42 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
         const int lh = row / MR_TW, lw = row % MR_TW;
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) && p.Cout == 32;
         long long tile_n = 0;
-        double run_s = 0.0, run_q = 0.0;               // lane = channel: sums of this warp's 32 rows over all tiles
+        // GroupNorm sums: every thread keeps running sums of ITS voxel row over all tiles of the CTA (32 + 32
+        // registers, two FP32 ops per value); the cross-lane transposing butterfly and the double atomics run
+        // once per (CTA, sample) instead of once per tile
+        float acc_s[32], acc_q[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
         int run_b = -1;
         auto flush = [&]() {
             if (p.stats && run_b >= 0) {
+                // butterfly over the 32 rows of the warp: lane L ends up with column L (with 16 columns per warp
+                // the upper half is zero: lane L < 16 holds column col0 + L)
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float send_s = up ? acc_s[i] : acc_s[i + off], keep_s = up ? acc_s[i + off] : acc_s[i];
+                        const float send_q = up ? acc_q[i] : acc_q[i + off], keep_q = up ? acc_q[i + off] : acc_q[i];
+                        acc_s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                        acc_q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+                    }
+                }
                 const int ch = (nsplit == 1) ? lane : col0 + (lane & 15);
                 if (ch < p.Cout && (nsplit == 1 || lane < 16)) {
-                    atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 0, run_s);
-                    atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 1, run_q);
+                    atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 0, (double)acc_s[0]);
+                    atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 1, (double)acc_q[0]);
                 }
             }
-            run_s = 0.0; run_q = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
         };
         for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
             const TileCoord c = decode_tile(t, p);
             if (c.b != run_b) { flush(); run_b = c.b; }
-            const int acc = (int)(tile_n & 1);
-            m_mbar_wait(t_full0 + 8 * acc, (uint32_t)(tile_n >> 1) & 1u);
+            const int acc = (int)(tile_n % MR_ACC);
+            m_mbar_wait(t_full0 + 8 * acc, (uint32_t)(tile_n / MR_ACC) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t r[32];
             if (nsplit == 1) {
@@ -368,24 +490,12 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                 }
             }
             if (p.stats) {
-                float s[32], qq[32];
 #pragma unroll
-                for (int k = 0; k < 32; ++k) { s[k] = (valid && k < ncol) ? v[k] : 0.f; qq[k] = s[k] * s[k]; }
-                // butterfly over the 32 rows of the warp; with 16 columns per warp the upper half is zero and
-                // lane L (< 16) ends up with column col0 + L, lanes >= 16 with zeros
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float send_s = up ? s[i] : s[i + off], keep_s = up ? s[i + off] : s[i];
-                        const float send_q = up ? qq[i] : qq[i + off], keep_q = up ? qq[i + off] : qq[i];
-                        s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-                        qq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-                    }
+                for (int k = 0; k < 32; ++k) {
+                    const float sv = (valid && k < ncol) ? v[k] : 0.f;
+                    acc_s[k] += sv;
+                    acc_q[k] = fmaf(sv, sv, acc_q[k]);
                 }
-                run_s += (double)s[0];
-                run_q += (double)qq[0];
             }
         }
         flush();
@@ -394,7 +504,7 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     __syncthreads();
     if (warp == 9) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
@@ -426,7 +536,7 @@ static int launch_march(const MarchParams& p, const ss_conv3d_desc* d, const flo
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return set_arg_error("conv_march32: tensor map W");
     }
-    const size_t smem = 1024 + Cfg::W_BYTES + MR_NP * Cfg::PLANE_BYTES + 2 * 64 * sizeof(double) + 32 * sizeof(uint64_t) + 64 + 64 * sizeof(float);
+    const size_t smem = 1024 + Cfg::W_BYTES + MR_NP * Cfg::PLANE_BYTES + 32 * sizeof(uint64_t) + 64;
     static thread_local bool configured = false;
     if (!configured) {
         SS_CUDA(cudaFuncSetAttribute(conv_march32_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -197,7 +197,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
     int* s_ntaps = reinterpret_cast<int*>(tmem_slot + 1);
     float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [Cin] scale, [Cin] shift
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = uniform_warp_index();
     const int ncls = p.cls_d * p.cls_h * p.cls_w;
     const int b = blockIdx.z / ncls, cls = blockIdx.z % ncls;
     const int rd = cls / (p.cls_h * p.cls_w), rh = (cls / p.cls_w) % p.cls_h, rw = cls % p.cls_w;
@@ -260,47 +261,44 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
     const uint32_t ring_u32 = smem_u32(ring);
 
     if (warp == TC_WORKERS / 32) {
-        // ======================= TMA PRODUCER (one lane) =========================================
-        if (lane == 0) {
-            for (int step = 0; step < nsteps; ++step) {
-                const int slot = step % STAGES;
-                const uint32_t use = (uint32_t)(step / STAGES);
-                mbar_wait(empty0 + 8 * slot, (use & 1u) ^ 1u);
-                const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;     // taps innermost: the box stays hot in L2
-                const int4 tp = taps[tap];
-                const uint32_t a_dst = ring_u32 + slot * Cfg::STAGE_BYTES;
-                const uint32_t bar = full0 + 8 * slot;
-                mbar_arrive_expect_tx(bar, Cfg::STAGE_BYTES);
-                tma_load_5d(a_dst, &tmA, bar, c0, q0w * isw + tp.z, q0h * ish + tp.y, q0d * isd + tp.x, b);
-                tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, bar, c0, tp.w * p.CoutP + n0);
-            }
+        // ======================= TMA PRODUCER (warp-uniform, elected issue; see common.cuh) =======
+        for (int step = 0; step < nsteps; ++step) {
+            const int slot = step % STAGES;
+            const uint32_t use = (uint32_t)(step / STAGES);
+            mbar_wait(empty0 + 8 * slot, (use & 1u) ^ 1u);
+            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;     // taps innermost: the box stays hot in L2
+            const int4 tp = taps[tap];
+            const uint32_t a_dst = ring_u32 + slot * Cfg::STAGE_BYTES;
+            const uint32_t bar = full0 + 8 * slot;
+            mbar_expect_tx_elect(bar, Cfg::STAGE_BYTES);
+            tma_5d_elect(a_dst, &tmA, bar, c0, q0w * isw + tp.z, q0h * ish + tp.y, q0d * isd + tp.x, b);
+            tma_2d_elect(a_dst + Cfg::A_BYTES, &tmB, bar, c0, tp.w * p.CoutP + n0);
+            __syncwarp();
         }
     } else if (warp == TC_WORKERS / 32 + 1) {
-        // ======================= MMA ISSUER (one lane) ===========================================
+        // ======================= MMA ISSUER (warp-uniform, elected issue) =========================
         constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+        constexpr uint32_t D_HI = umma_desc_hi(1024);
         const uint32_t wait0 = fixup ? ready0 : full0;
         for (int step = 0; step < nsteps; ++step) {
             const int slot = step % STAGES;
             const uint32_t use = (uint32_t)(step / STAGES);
             mbar_wait(wait0 + 8 * slot, use & 1u);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_addr = ring_u32 + slot * Cfg::STAGE_BYTES;
-                const uint64_t adesc = make_smem_desc(a_addr);
-                const uint64_t bdesc = make_smem_desc(a_addr + Cfg::A_BYTES);
-                if (fixup) {                              // A from the TMEM ring written by the fix-up warps
-                    const uint32_t a_tmem = tmem_base + (uint32_t)(Cfg::A_COL0 + slot * TC_BK);
+            const uint32_t a_addr = ring_u32 + slot * Cfg::STAGE_BYTES;
+            const uint32_t a_lo = umma_desc_lo(a_addr), b_lo = umma_desc_lo(a_addr + Cfg::A_BYTES);
+            if (fixup) {                              // A from the TMEM ring written by the fix-up warps
+                const uint32_t a_tmem = tmem_base + (uint32_t)(Cfg::A_COL0 + slot * TC_BK);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k)
-                        umma_tf32_ts(tmem_base, a_tmem + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), idesc, (step | k) ? 1u : 0u);
-                } else {
+                for (int k = 0; k < TC_BK / 8; ++k)
+                    umma_ts_tf32<D_HI>(tmem_base, a_tmem + (uint32_t)(8 * k), b_lo + 2 * k, idesc, (step | k) ? 1u : 0u);
+            } else {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k)  // 8 TF32 = 32 bytes per MMA: advance start by 32 B
-                        umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (step | k) ? 1u : 0u);
-                }
-                umma_commit(empty0 + 8 * slot);            // frees the stage when these MMAs retire
-                if (step == nsteps - 1) umma_commit(accum_bar);
+                for (int k = 0; k < TC_BK / 8; ++k)  // 8 TF32 = 32 bytes per MMA: advance start by 32 B
+                    umma_ss_tf32<D_HI, D_HI>(tmem_base, a_lo + 2 * k, b_lo + 2 * k, idesc, (step | k) ? 1u : 0u);
             }
+            umma_commit_elect(empty0 + 8 * slot);            // frees the stage when these MMAs retire
+            if (step == nsteps - 1) umma_commit_elect(accum_bar);
             __syncwarp();
         }
     } else if (fixup) {

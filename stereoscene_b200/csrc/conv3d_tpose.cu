@@ -96,7 +96,9 @@ __device__ __forceinline__ uint64_t t_desc(uint32_t saddr, uint32_t sbo_bytes) {
 
 // The 27 (class, tap) pairs in issue order.  Per axis: parity 0 -> (kernel 1, offset 0); parity 1 ->
 // (kernel 0, offset 1) then (kernel 2, offset 0).  entry = cls | off_d<<3 | off_h<<4 | off_w<<5 | wtap<<8
-__device__ __forceinline__ int tpose_build_table(int* tab) {
+struct TposeTable { int v[27]; };
+__host__ __device__ constexpr TposeTable tpose_table() {
+    TposeTable t{};
     int n = 0;
     for (int cls = 0; cls < 8; ++cls) {
         const int rd = cls >> 2, rh = (cls >> 1) & 1, rw = cls & 1;
@@ -105,10 +107,10 @@ __device__ __forceinline__ int tpose_build_table(int* tab) {
                 for (int e = 0; e < (rw ? 2 : 1); ++e) {
                     const int kd = rd ? (a ? 2 : 0) : 1, kh = rh ? (c ? 2 : 0) : 1, kw = rw ? (e ? 2 : 0) : 1;
                     const int od = rd ? (a ? 0 : 1) : 0, oh = rh ? (c ? 0 : 1) : 0, ow = rw ? (e ? 0 : 1) : 0;
-                    tab[n++] = cls | (od << 3) | (oh << 4) | (ow << 5) | (((kd * 3 + kh) * 3 + kw) << 8);
+                    t.v[n++] = cls | (od << 3) | (oh << 4) | (ow << 5) | (((kd * 3 + kh) * 3 + kw) << 8);
                 }
     }
-    return n;   // 27
+    return t;   // 27 entries
 }
 
 template <int BN>
@@ -128,7 +130,9 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
     int* tab = reinterpret_cast<int*>(tmem_slot + 4);                        // [27]
     float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tab + 32) + 15) & ~(uintptr_t)15);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = uniform_warp_index();
+    constexpr TposeTable TAB = tpose_table();
     const int tw_i = blockIdx.x % p.nTW, th_i = (blockIdx.x / p.nTW) % p.nTH;
     const int q = (blockIdx.x / (p.nTW * p.nTH)) % p.Din, b = blockIdx.x / (p.nTW * p.nTH * p.Din);
     const int h0 = th_i * TP_TH, w0 = tw_i * TP_TW;
@@ -142,7 +146,7 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
     const int kchunks = p.Cin / 32;
 
     if (tid == 0) {
-        tpose_build_table(tab);
+        for (int i = 0; i < 27; ++i) tab[i] = TAB.v[i];
         for (int s = 0; s < TP_NPL; ++s) {
             t_mbar_init(pa_full0 + 8 * s, 1);
             t_mbar_init(pa_ready0 + 8 * s, TP_WORKERS);
@@ -174,64 +178,67 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
     const uint32_t planes_u32 = t_smem_u32(planes), bring_u32 = t_smem_u32(bring);
 
     if (warp == 8) {
-        // ======================= A PRODUCER: planes q, q+1 per chunk ================================
-        if (lane == 0) {
-            for (int L = 0; L < kchunks * 2; ++L) {
-                const int slot = L % TP_NPL;
-                const uint32_t use = (uint32_t)(L / TP_NPL);
-                t_mbar_wait(pa_empty0 + 8 * slot, (use & 1u) ^ 1u);
-                const uint32_t bar = pa_full0 + 8 * slot;
-                t_mbar_expect_tx(bar, TP_PLANE_ROWS * 128);
-                t_tma_5d(planes_u32 + slot * TP_PLANE_BYTES, &tmA, bar, (L / 2) * 32, w0, h0, q + (L & 1), b);
-            }
+        // ======================= A PRODUCER: planes q, q+1 per chunk (warp-uniform, elected issue) ===
+        for (int L = 0; L < kchunks * 2; ++L) {
+            const int slot = L % TP_NPL;
+            const uint32_t use = (uint32_t)(L / TP_NPL);
+            t_mbar_wait(pa_empty0 + 8 * slot, (use & 1u) ^ 1u);
+            const uint32_t bar = pa_full0 + 8 * slot;
+            mbar_expect_tx_elect(bar, TP_PLANE_ROWS * 128);
+            tma_5d_elect(planes_u32 + slot * TP_PLANE_BYTES, &tmA, bar, (L / 2) * 32, w0, h0, q + (L & 1), b);
+            __syncwarp();
         }
     } else if (warp == 10) {
         // ======================= B PRODUCER: one weight tile per (chunk, class-tap) =================
-        if (lane == 0) {
-            for (int L = 0; L < kchunks * 27; ++L) {
+        int L = 0;
+        for (int ch = 0; ch < kchunks; ++ch) {
+#pragma unroll
+            for (int e = 0; e < 27; ++e, ++L) {
                 const int slot = L % TP_SB;
                 const uint32_t use = (uint32_t)(L / TP_SB);
                 t_mbar_wait(pb_empty0 + 8 * slot, (use & 1u) ^ 1u);
                 const uint32_t bar = pb_full0 + 8 * slot;
-                t_mbar_expect_tx(bar, B_BYTES);
-                t_tma_2d(bring_u32 + slot * B_BYTES, &tmB, bar, (L / 27) * 32, (tab[L % 27] >> 8) * p.CoutP);
+                mbar_expect_tx_elect(bar, B_BYTES);
+                tma_2d_elect(bring_u32 + slot * B_BYTES, &tmB, bar, ch * 32, (TAB.v[e] >> 8) * p.CoutP);
+                __syncwarp();
             }
         }
     } else if (warp == 9) {
-        // ======================= MMA ISSUER ========================================================
+        // ======================= MMA ISSUER (warp-uniform; see common.cuh) ==========================
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t A_HI = umma_desc_hi(TP_HW * 128), B_HI = umma_desc_hi(1024);
         const uint32_t rdy0 = fixup ? pa_ready0 : pa_full0;
         int Lb = 0;
         for (int ch = 0; ch < kchunks; ++ch) {
             const int s0 = (2 * ch) % TP_NPL, s1 = (2 * ch + 1) % TP_NPL;
             t_mbar_wait(rdy0 + 8 * s0, (uint32_t)((2 * ch) / TP_NPL) & 1u);
             t_mbar_wait(rdy0 + 8 * s1, (uint32_t)((2 * ch + 1) / TP_NPL) & 1u);
+            const uint32_t a0_lo = umma_desc_lo(planes_u32 + (uint32_t)s0 * TP_PLANE_BYTES);
+            const uint32_t a1_lo = umma_desc_lo(planes_u32 + (uint32_t)s1 * TP_PLANE_BYTES);
+#pragma unroll
             for (int e = 0; e < 27; ++e, ++Lb) {
                 const int bslot = Lb % TP_SB;
                 t_mbar_wait(pb_full0 + 8 * bslot, (uint32_t)(Lb / TP_SB) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const int ent = tab[e];
-                    const int cls = ent & 7, od = (ent >> 3) & 1, oh = (ent >> 4) & 1, ow = (ent >> 5) & 1;
-                    const uint32_t pl = planes_u32 + (uint32_t)(od ? s1 : s0) * TP_PLANE_BYTES;
-                    const uint64_t adesc = t_desc(pl + (uint32_t)((oh * TP_HW + ow) * 128), TP_HW * 128);
-                    const uint64_t bdesc = t_desc(bring_u32 + bslot * B_BYTES, 1024);
-                    // first MMA into a class accumulator: its first tap of chunk 0 (taps of a class are consecutive)
-                    const bool first_tap = (e == 0) || ((tab[e - 1] & 7) != cls);
+                const int ent = TAB.v[e];
+                const int cls = ent & 7, od = (ent >> 3) & 1, oh = (ent >> 4) & 1, ow = (ent >> 5) & 1;
+                const uint32_t a_lo = (od ? a1_lo : a0_lo) + ((uint32_t)((oh * TP_HW + ow) * 128) >> 4);
+                const uint32_t b_lo = umma_desc_lo(bring_u32 + bslot * B_BYTES);
+                // first MMA into a class accumulator: its first tap of chunk 0 (taps of a class are consecutive)
+                const bool first_tap = (e == 0) || ((TAB.v[e > 0 ? e - 1 : 0] & 7) != cls);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        t_umma_tf32(tmem_base + (uint32_t)(cls * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                    (ch == 0 && first_tap && k == 0) ? 0u : 1u);
-                    t_umma_commit(pb_empty0 + 8 * bslot);
-                    if (e == 26) {
-                        t_umma_commit(pa_empty0 + 8 * s0);
-                        t_umma_commit(pa_empty0 + 8 * s1);
-                    }
+                for (int k = 0; k < 4; ++k)
+                    umma_ss_tf32<A_HI, B_HI>(tmem_base + (uint32_t)(cls * BN), a_lo + 2 * k, b_lo + 2 * k, idesc,
+                                             (ch == 0 && first_tap && k == 0) ? 0u : 1u);
+                umma_commit_elect(pb_empty0 + 8 * bslot);
+                if (e == 26) {
+                    umma_commit_elect(pa_empty0 + 8 * s0);
+                    umma_commit_elect(pa_empty0 + 8 * s1);
                 }
                 __syncwarp();
             }
         }
-        if (lane == 0) t_umma_commit(accum_bar);
+        umma_commit_elect(accum_bar);
         __syncwarp();
     } else if (fixup) {
         // ======================= WORKERS: pending affine / ReLU once per landed plane, in place =====
