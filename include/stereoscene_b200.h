@@ -44,7 +44,7 @@ extern "C" {
 #define SS_MATH_3XTF32 1               /* error-compensated split (hi/lo) TF32: ~fp32 accuracy */
 
 /* ABI version of this header; ss_abi_version() of the library must match. */
-#define SS_ABI_VERSION 1
+#define SS_ABI_VERSION 2
 int ss_abi_version(void);
 /* Text of the last CUDA error seen by the calling thread (host pointer, never NULL). */
 const char* ss_last_error_string(void);
@@ -118,6 +118,12 @@ int ss_affine_join_fwd(const float* x, const float* x_scale, const float* x_shif
                        const float* r, const float* r_scale, const float* r_shift, int r_act,
                        const float* alpha, int out_act, int B, long long V, int C,
                        int x_ldc, int r_ldc, int out_ldc, float* out, void* stream);
+
+/* Per-(batch,channel) sums of a pending volume: stats[b][c][0] += sum_v a, stats[b][c][1] += sum_v a*a with
+ * a = act(x*scale+shift) (double[B][C][2], caller zeroes it).  Serves the global-average-pool branch of
+ * DepthNet's ASPP (image2bev/ViewTransformerLSSBEVDepth.py:373-379, 394) without a pass through ATen. */
+int ss_channel_sums_fwd(const float* x, const float* x_scale, const float* x_shift, int x_act, int B,
+                        long long V, int C, int x_ldc, double* stats, void* stream);
 
 /* Softmax over the depth axis of a [B][D][P] volume (P = H*W pixels, contiguous), batch strides
  * in floats.  Replaces F.softmax(dim=1) at ViewTransformerLSSVoxel.py:222, 267 and

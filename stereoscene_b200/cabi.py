@@ -10,7 +10,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU = 0, 1, 2
 SS_MATH_TF32, SS_MATH_3XTF32 = 0, 1
@@ -39,6 +39,7 @@ SIGNATURES = {
     "ss_gn_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _f, _vp, _vp, _i, _vp]),
     "ss_ca3d_gate": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ss_affine_join_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _i, _vp, _vp]),
+    "ss_channel_sums_fwd": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _i, _vp, _vp]),
     "ss_softmax_d_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "ss_gwc_warp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ss_bri_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -29,6 +29,7 @@ constexpr int HL_THREADS = HL_WORKERS + 96;           // + A producer, MMA, B pr
 struct HaloParams {
     int B, D, H, W, Cin, Cout, CoutP, out_ldc, in_act, out_act;
     int nTH, nTW;
+    int KD;                       // depth taps: 3 (3x3x3, pad 1) or 1 (2-D 3x3 layers, D == 1 planes)
     const float* in_scale;
     const float* in_shift;
     const float* bias;
@@ -136,6 +137,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
     const bool in_relu = (p.in_act == SS_ACT_RELU);
     const bool fixup = has_aff || in_relu;
     const int kchunks = p.Cin / 32;
+    const int KD = p.KD;
 
     if (tid == 0) {
         for (int s = 0; s < HL_NPL; ++s) {
@@ -170,24 +172,25 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
 
     if (warp == 8) {
         // ======================= A PRODUCER: 3 planes per 32-channel chunk (warp-uniform, elected issue) ====
-        for (int L = 0; L < kchunks * 3; ++L) {
+        for (int L = 0; L < kchunks * KD; ++L) {
             const int slot = L % HL_NPL;
             const uint32_t use = (uint32_t)(L / HL_NPL);
             h_mbar_wait(pa_empty0 + 8 * slot, (use & 1u) ^ 1u);
             const uint32_t bar = pa_full0 + 8 * slot;
             mbar_expect_tx_elect(bar, HL_PLANE_ROWS * 128);
-            tma_5d_elect(planes_u32 + slot * HL_PLANE_BYTES, &tmA, bar, (L / 3) * 32, w0 - 1, h0 - 1, d - 1 + (L % 3), b);
+            tma_5d_elect(planes_u32 + slot * HL_PLANE_BYTES, &tmA, bar, (L / KD) * 32, w0 - 1, h0 - 1, d - KD / 2 + (L % KD), b);
             __syncwarp();
         }
     } else if (warp == 10) {
         // ======================= B PRODUCER: one weight tile per (chunk, tap) =======================
-        for (int L = 0; L < kchunks * 27; ++L) {
+        const int ntaps = 9 * KD;
+        for (int L = 0; L < kchunks * ntaps; ++L) {
             const int slot = L % SB;
             const uint32_t use = (uint32_t)(L / SB);
             h_mbar_wait(pb_empty0 + 8 * slot, (use & 1u) ^ 1u);
             const uint32_t bar = pb_full0 + 8 * slot;
             mbar_expect_tx_elect(bar, Cfg::B_BYTES);
-            tma_2d_elect(bring_u32 + slot * Cfg::B_BYTES, &tmB, bar, (L / 27) * 32, (L % 27) * p.CoutP + n0);
+            tma_2d_elect(bring_u32 + slot * Cfg::B_BYTES, &tmB, bar, (L / ntaps) * 32, (L % ntaps) * p.CoutP + n0);
             __syncwarp();
         }
     } else if (warp == 9) {
@@ -196,7 +199,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         constexpr uint32_t A_HI = umma_desc_hi(HL_HW * 128), B_HI = umma_desc_hi(1024);
         const uint32_t rdy0 = fixup ? pa_ready0 : pa_full0;
         int Lb = 0;
-        for (int Lp = 0; Lp < kchunks * 3; ++Lp) {
+        for (int Lp = 0; Lp < kchunks * KD; ++Lp) {
             const int pslot = Lp % HL_NPL;
             h_mbar_wait(rdy0 + 8 * pslot, (uint32_t)(Lp / HL_NPL) & 1u);
             const uint32_t a_lo = umma_desc_lo(planes_u32 + pslot * HL_PLANE_BYTES);
@@ -222,10 +225,10 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         __syncwarp();
     } else if (fixup) {
         // ======================= WORKERS: pending affine / ReLU, once per landed plane, in place =====
-        for (int L = 0; L < kchunks * 3; ++L) {
+        for (int L = 0; L < kchunks * KD; ++L) {
             const int slot = L % HL_NPL;
             h_mbar_wait(pa_full0 + 8 * slot, (uint32_t)(L / HL_NPL) & 1u);
-            const int dpl = d - 1 + (L % 3), c0 = (L / 3) * 32;
+            const int dpl = d - KD / 2 + (L % KD), c0 = (L / KD) * 32;
             if ((unsigned)dpl < (unsigned)p.D) {
                 unsigned char* pl = planes + slot * HL_PLANE_BYTES;
                 for (int idx = tid; idx < HL_PLANE_ROWS * 8; idx += HL_WORKERS) {
@@ -330,7 +333,7 @@ template <int BN>
 static int launch_halo(const HaloParams& p, const CUtensorMap& tmA, const float* wk, HEncodeTiledFn encode, cudaStream_t st) {
     using Cfg = HaloCfg<BN>;
     alignas(64) CUtensorMap tmB;
-    cuuint64_t gdim[2] = {(cuuint64_t)p.Cin, (cuuint64_t)27 * p.CoutP};
+    cuuint64_t gdim[2] = {(cuuint64_t)p.Cin, (cuuint64_t)9 * p.KD * p.CoutP};
     cuuint64_t gstr[1] = {(cuuint64_t)p.Cin * 4};
     cuuint32_t box[2] = {32, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
@@ -352,9 +355,10 @@ static int launch_halo(const HaloParams& p, const CUtensorMap& tmA, const float*
 // returns 1 if the layer was handled here
 int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
-    if (d->transposed || d->Cin % 32 != 0 || d->cout_packed < 64 || d->kd != 3 || d->kh != 3 || d->kw != 3) return 0;
+    if (d->transposed || d->Cin % 32 != 0 || d->cout_packed < 64 || d->kh != 3 || d->kw != 3) return 0;
+    if (!((d->kd == 3 && d->pd == 1) || (d->kd == 1 && d->pd == 0))) return 0;     // 3x3x3, or 2-D 3x3 (one plane per chunk)
     if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
-    if (d->pd != 1 || d->ph != 1 || d->pw != 1 || d->math != SS_MATH_TF32) return 0;
+    if (d->ph != 1 || d->pw != 1 || d->math != SS_MATH_TF32) return 0;
     if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
     const int nTH = (d->Hin + HL_TH - 1) / HL_TH, nTW = (d->Win + HL_TW - 1) / HL_TW;
     const double eff = (double)d->Hin * d->Win / ((double)nTH * HL_TH * nTW * HL_TW);
@@ -370,7 +374,7 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
     }
     HaloParams p;
     p.B = d->B; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cin = d->Cin; p.Cout = d->Cout; p.CoutP = d->cout_packed;
-    p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act; p.nTH = nTH; p.nTW = nTW;
+    p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act; p.nTH = nTH; p.nTW = nTW; p.KD = d->kd;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
     alignas(64) CUtensorMap tmA;

@@ -106,6 +106,31 @@ __global__ void affine_join_kernel(const float* __restrict__ x, const float* __r
     }
 }
 
+// per-(batch,channel) sum and sum of squares of a pending volume act(x*scale+shift): a CTA owns a slab of
+// voxels, a thread owns channels tid, tid+blockDim, ... (consecutive threads read consecutive channels)
+__global__ void channel_sums_kernel(const float* __restrict__ x, const float* __restrict__ xs,
+                                    const float* __restrict__ xh, int act, long long V, int C, int ldc,
+                                    double* __restrict__ stats) {
+    const int b = blockIdx.y;
+    const long long per = (V + gridDim.x - 1) / gridDim.x;
+    const long long v0 = (long long)blockIdx.x * per;
+    const long long v1 = (v0 + per < V) ? v0 + per : V;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sc = xs ? __ldg(xs + (size_t)b * C + c) : 1.0f;
+        const float sh = xs ? __ldg(xh + (size_t)b * C + c) : 0.0f;
+        float s = 0.f, q = 0.f;
+        for (long long v = v0; v < v1; ++v) {
+            const float a = apply_act(fmaf(__ldg(x + ((size_t)b * V + v) * ldc + c), sc, sh), act);
+            s += a;
+            q = fmaf(a, a, q);
+        }
+        if (v1 > v0) {
+            atomicAdd(stats + ((size_t)b * C + c) * 2 + 0, (double)s);
+            atomicAdd(stats + ((size_t)b * C + c) * 2 + 1, (double)q);
+        }
+    }
+}
+
 // softmax over D of x[b][d][p]; one thread per pixel column, coalesced across p.
 __global__ void softmax_d_kernel(const float* __restrict__ x, long long xbs, float* __restrict__ y, long long ybs,
                                  int D, int P) {
@@ -208,6 +233,19 @@ extern "C" int ss_affine_join_fwd(const float* x, const float* x_scale, const fl
                                                                              r_act, alpha, out_act, V, C, x_ldc, r_ldc,
                                                                              out_ldc, out);
     return check_launch("affine_join_kernel");
+}
+
+extern "C" int ss_channel_sums_fwd(const float* x, const float* x_scale, const float* x_shift, int x_act, int B,
+                                   long long V, int C, int x_ldc, double* stats, void* stream) {
+    SS_REQUIRE(x && stats, "ss_channel_sums_fwd: null pointer");
+    SS_REQUIRE(B > 0 && B <= 65535 && V > 0 && C > 0 && x_ldc >= C, "ss_channel_sums_fwd: shape");
+    SS_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), "ss_channel_sums_fwd: scale/shift must come together");
+    long long blocks = (V + 15) / 16;                      // >= 16 voxels per CTA keeps the atomics sparse
+    const long long cap = 148LL * 4;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)B);
+    channel_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_scale, x_shift, x_act, V, C, x_ldc, stats);
+    return check_launch("channel_sums_kernel");
 }
 
 extern "C" int ss_softmax_d_fwd(const float* x, long long x_batch_stride, float* y, long long y_batch_stride, int B,

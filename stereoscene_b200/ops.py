@@ -349,6 +349,19 @@ def join(x: Vol, r: Optional[Vol], out_act: int = SS_ACT_NONE, alpha: Optional[t
     return out
 
 
+def channel_sums(x: Vol) -> torch.Tensor:
+    """double[B,C,2] = (sum, sum of squares) over the voxels of the logical value of a pending volume."""
+    lib = cabi.load()
+    xd = x.data
+    ldc = _vol_ldc(xd, "channel_sums")
+    B, Cc = xd.shape[0], xd.shape[-1]
+    st = arena(xd.device).take(B, Cc)
+    rc = lib.ss_channel_sums_fwd(xd.data_ptr(), _ptr(x.scale), _ptr(x.shift), x.act, B, voxels_per_channel(xd), Cc, ldc,
+                                 st.data_ptr(), _stream())
+    cabi.check(rc, "ss_channel_sums_fwd")
+    return st
+
+
 def softmax_d(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Softmax over dim 1 of x[B,D,...pixels...] whose per-sample block [D,P] is contiguous
     (a channel slice x[:, :D] of a wider NCHW tensor is fine)."""

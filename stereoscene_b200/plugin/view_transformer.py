@@ -11,7 +11,9 @@ Stages and the kernels that run them (all through the C ABI, stereoscene_b200.op
   (i)   stereo: reduce conv + pending GN/ReLU/SE gate + 1x1 conv -> ss_gwc_warp_fwd ->
         5 full-res convs + 3 hourglasses (ss_conv3d_fwd with pending affines, ss_affine_join_fwd)
         -> ss_softmax_d_fwd
-  (N1)  depth_net: adjacent component ("next" row): PyTorch/cuDNN modules for now
+  (N1)  depth_net: reduce conv + pending GN/ReLU/SE gates, 3 BasicBlocks (pending BatchNorm), ASPP
+        (dilated convs into one sliced buffer, pooled branch folded into a per-channel shift), DCN
+        (ss_deform_sample_fwd + grouped GEMM), 1x1 head -- all on ss_conv3d_*_fwd
   (iii) MIE: 2 x ss_bri_attn_fwd -> redir1 -> hourglass -> CA3D (gate folded into a pending affine,
         ss_ca3d_gate) -> redir2 -> ss_softmax_d_fwd
   (ii)  lift (x) splat: ss_splat_build_index (calibration-only, cached) + ss_lift_splat_fwd
@@ -123,8 +125,20 @@ class VolumeInteractionParams(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------
-# DepthNet (adjacent component, row N1 of SURVEY.md section 8f): PyTorch modules on cuDNN for now
+# DepthNet (adjacent component, row N1 of SURVEY.md section 8f) on the same kernels as the rest of
+# the path: every map is a channels-last [B,1,H,W,C] volume, BatchNorm(eval) / GroupNorm / SE gates
+# travel as pending affines, the ASPP concat is a channel-sliced buffer.
 # ------------------------------------------------------------------------------------------
+def _holder(weight: torch.Tensor) -> nn.Conv3d:
+    """A 1x1x1 Conv3d that only carries a derived weight matrix [Cout,Cin] into ops.conv (not a
+    parameter of the model: the state_dict stays the reference's)."""
+    c = nn.Conv3d(weight.shape[1], weight.shape[0], 1, bias=False).to(weight.device)
+    with torch.no_grad():
+        c.weight.copy_(weight.reshape(weight.shape[0], weight.shape[1], 1, 1, 1))
+    c.weight.requires_grad_(False)
+    return c
+
+
 class BasicBlock2d(nn.Module):
     """mmdet 2.14 BasicBlock (conv3x3-BN-ReLU-conv3x3-BN + identity, ReLU)."""
 
@@ -135,9 +149,10 @@ class BasicBlock2d(nn.Module):
         self.conv2 = nn.Conv2d(c, c, 3, padding=1, bias=False)
         self.bn2 = nn.BatchNorm2d(c)
 
-    def forward(self, x):
-        y = F.relu(self.bn1(self.conv1(x)))
-        return F.relu(self.bn2(self.conv2(y)) + x)
+    def forward_vol(self, x: Vol) -> Vol:
+        u1, _ = ops.conv(x, self.conv1)
+        u2, _ = ops.conv(ops.bn_pending(u1, self.bn1, SS_ACT_RELU), self.conv2)
+        return Vol(ops.join(ops.bn_pending(u2, self.bn2), x, out_act=SS_ACT_RELU))
 
 
 class _ASPPBranch(nn.Module):
@@ -146,12 +161,12 @@ class _ASPPBranch(nn.Module):
         self.atrous_conv = nn.Conv2d(cin, cout, k, padding=0 if k == 1 else dilation, dilation=dilation, bias=False)
         self.bn = nn.BatchNorm2d(cout)
 
-    def forward(self, x):
-        return F.relu(self.bn(self.atrous_conv(x)))
-
 
 class ASPP(nn.Module):
-    """ViewTransformerLSSBEVDepth.py:343-414."""
+    """ViewTransformerLSSBEVDepth.py:343-414.  The four atrous branches write their raw outputs into
+    channel slices of one buffer (their BN+ReLU is the pending affine of the fusing 1x1 conv); the
+    global-average-pool branch is constant over the map, so its share of the 1x1 conv is a
+    per-(batch,channel) vector folded into the pending shift of bn1."""
 
     def __init__(self, cin, mid):
         super().__init__()
@@ -164,18 +179,52 @@ class ASPP(nn.Module):
         self.conv1 = nn.Conv2d(mid * 5, mid, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(mid)
         self.dropout = nn.Dropout(0.5)
+        object.__setattr__(self, "_split", None)
+        object.__setattr__(self, "_affine", None)
 
-    def forward(self, x):
-        g = self.global_avg_pool(x).expand(-1, -1, x.shape[2], x.shape[3])
-        y = torch.cat((self.aspp1(x), self.aspp2(x), self.aspp3(x), self.aspp4(x), g), dim=1)
-        return self.dropout(F.relu(self.bn1(self.conv1(y))))
+    def _conv1_split(self):
+        """(holder of conv1's columns for the four branches, its columns for the pooled branch)."""
+        w = self.conv1.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if self._split is None or self._split[0] != key:
+            mid = w.shape[0]
+            w2 = w.detach().flatten(1)
+            object.__setattr__(self, "_split", (key, _holder(w2[:, :4 * mid]), w2[:, 4 * mid:].contiguous()))
+        return self._split[1], self._split[2]
+
+    def _branch_affine(self, raw: torch.Tensor):
+        """BN(eval)+ReLU of the four branches as one [B,4*mid] pending affine (cached)."""
+        vs = [ops.bn_pending(raw, br.bn, SS_ACT_RELU) for br in (self.aspp1, self.aspp2, self.aspp3, self.aspp4)]
+        key = tuple(id(v.scale) for v in vs)
+        if self._affine is None or self._affine[0] != key:
+            object.__setattr__(self, "_affine", (key, torch.cat([v.scale for v in vs], 1).contiguous(),
+                                                 torch.cat([v.shift for v in vs], 1).contiguous(), vs))
+        return self._affine[1], self._affine[2]
+
+    def forward_vol(self, x: Vol) -> Vol:
+        B, _, H, W, _ = x.data.shape
+        mid = self.conv1.out_channels
+        buf = torch.empty((B, 1, H, W, 4 * mid), dtype=torch.float32, device=x.data.device)
+        for i, br in enumerate((self.aspp1, self.aspp2, self.aspp3, self.aspp4)):
+            ops.conv(x, br.atrous_conv, out=buf[..., i * mid:(i + 1) * mid])
+        sc, sh = self._branch_affine(buf)
+        # pooled branch on [B,C] vectors: mean -> 1x1 conv -> GroupNorm -> ReLU (bilinear upsampling of a
+        # 1x1 map with align_corners=True is a broadcast)
+        pooled = (ops.channel_sums(x)[..., 0] / float(H * W)).float()
+        gp = self.global_avg_pool
+        g = torch.relu(F.group_norm(pooled @ gp[1].weight.flatten(1).t(), gp[2].num_groups, gp[2].weight, gp[2].bias,
+                                    gp[2].eps))
+        head, w_pool = self._conv1_split()
+        y, _ = ops.conv(Vol(buf, sc, sh, SS_ACT_RELU), head)
+        bn = ops.bn_pending(y, self.bn1, SS_ACT_RELU)
+        return Vol(y, bn.scale, torch.addcmul(bn.shift, bn.scale, g @ w_pool.t()).contiguous(), SS_ACT_RELU)
 
 
 class DCN(nn.Module):
     """mmcv DeformConv2dPack semantics (no bias; offsets from a zero-initialised 3x3 conv),
-    ViewTransformerLSSBEVDepth.py:490-498.  Sampling runs in ss_deform_sample_fwd, the grouped GEMM
-    on the tcgen05 conv kernel (one 1x1 conv per group over the sampled rows); on a CPU tensor the
-    module falls back to nothing -- it raises, like the rest of the hot path."""
+    ViewTransformerLSSBEVDepth.py:490-498.  Offsets come from the conv kernel in split-TF32 (they are
+    sampling positions), sampling runs in ss_deform_sample_fwd, the grouped GEMM on the tcgen05 conv
+    kernel (one 1x1 conv per group over the sampled rows)."""
 
     def __init__(self, cin, cout, k=3, padding=1, groups=4):
         super().__init__()
@@ -194,44 +243,31 @@ class DCN(nn.Module):
         if key != self._gkey:
             G, k = self.groups, self.k
             cout_g, cin_g = w.shape[0] // G, w.shape[1]
-            with torch.no_grad():
-                # [G][cout_g][cin_g][k*k] -> [G][cout_g][k*k][cin_g]: K index = tap * cin_g + channel
-                wm = w.detach().view(G, cout_g, cin_g, k * k).permute(0, 1, 3, 2).reshape(G, cout_g, k * k * cin_g)
-                convs = []
-                for g in range(G):
-                    c = nn.Conv3d(k * k * cin_g, cout_g, 1, bias=False).to(w.device)
-                    c.weight.copy_(wm[g].view(cout_g, -1, 1, 1, 1))
-                    c.weight.requires_grad_(False)
-                    convs.append(c)
-            object.__setattr__(self, "_gconvs", convs)
+            # [G][cout_g][cin_g][k*k] -> [G][cout_g][k*k][cin_g]: K index = tap * cin_g + channel
+            wm = w.detach().view(G, cout_g, cin_g, k * k).permute(0, 1, 3, 2).reshape(G, cout_g, k * k * cin_g)
+            object.__setattr__(self, "_gconvs", [_holder(wm[g]) for g in range(G)])
             object.__setattr__(self, "_gkey", key)
         return self._gconvs
 
-    def forward(self, x):
-        """x: [B,C,H,W] -> [B,Cout,H,W] (channels_last memory)."""
-        B, Cc, H, W = x.shape
-        off = self.conv_offset(x).contiguous()
-        xcl = ops.to_channels_last(x)                                           # [B,H,W,C]
-        S = ops.deform_sample(xcl, off, self.groups, self.k, 1, self.padding, 1)  # [B,H,W,G,k*k,C/G]
+    def forward_vol(self, x: Vol) -> torch.Tensor:
+        """x: pending [B,1,H,W,C] volume -> plain [B,1,H,W,Cout]."""
+        B, _, H, W, _ = x.data.shape
+        off, _ = ops.conv(x, self.conv_offset, math_mode=ops.SS_MATH_3XTF32)             # [B,1,H,W,2*k*k]
+        off = ops.to_channels_first(off.squeeze(1))                                     # [B,2*k*k,H,W]
+        S = ops.deform_sample(x.plain().squeeze(1), off, self.groups, self.k, 1, self.padding, 1)  # [B,H,W,G,k*k,C/G]
         G = self.groups
         S5 = S.view(B, 1, H, W, G, -1)
         cout = self.weight.shape[0]
-        out = torch.empty((B, 1, H, W, cout), dtype=torch.float32, device=x.device)
+        out = torch.empty((B, 1, H, W, cout), dtype=torch.float32, device=x.data.device)
         cg = cout // G
         for g, conv in enumerate(self._group_convs()):
-            ops.conv(ops.Vol(S5[..., g, :]), conv, out=out[..., g * cg:(g + 1) * cg])
-        return out.squeeze(1).permute(0, 3, 1, 2)
+            ops.conv(Vol(S5[..., g, :]), conv, out=out[..., g * cg:(g + 1) * cg])
+        return out
 
-
-def _group_norm_wide(x, gn: nn.GroupNorm):
-    """GroupNorm with few groups over a large map: torch's native kernel launches one CTA per
-    (sample, group) -- 2 CTAs here -- so the moments are taken with a split reduction instead."""
-    B, Cc = x.shape[:2]
-    xv = x.reshape(B, gn.num_groups, -1)
-    var, mean = torch.var_mean(xv, dim=2, unbiased=False, keepdim=True)
-    y = ((xv - mean) * torch.rsqrt(var + gn.eps)).view_as(x)
-    shp = (1, Cc) + (1,) * (x.dim() - 2)
-    return y * gn.weight.view(shp) + gn.bias.view(shp)
+    def forward(self, x):
+        """Reference tensor contract: x [B,C,H,W] -> [B,Cout,H,W] (channels_last memory)."""
+        y = self.forward_vol(Vol(ops.to_channels_last(x).unsqueeze(1)))
+        return y.squeeze(1).permute(0, 3, 1, 2)
 
 
 class DepthNet(nn.Module):
@@ -250,18 +286,28 @@ class DepthNet(nn.Module):
         self.depth_conv = nn.Sequential(BasicBlock2d(mid), BasicBlock2d(mid), BasicBlock2d(mid), ASPP(mid, mid),
                                         DCN(mid, mid, 3, 1, 4), nn.Conv2d(mid, depth, 1))
 
+    def forward_vol(self, x: torch.Tensor, mlp_input: torch.Tensor):
+        """x: channels-last [B,1,H,W,Cin] -> (depth logits [B,1,H,W,D], context [B,1,H,W,ctx]), both
+        channels-last."""
+        m = self.bn(mlp_input.reshape(-1, mlp_input.shape[-1]))          # GroupNorm on the [B,cam] calibration vector
+        v = conv_gn(Vol(x), self.reduce_conv, SS_ACT_RELU)
+        # SE gates are > 0: relu(gn(y)) * g == relu(gn(y) * g), so each gate is a rescaled pending affine
+        gc = self.context_se.gate(self.context_mlp(m))
+        gd = self.depth_se.gate(self.depth_mlp(m))
+        context, _ = ops.conv(Vol(v.data, (v.scale * gc).contiguous(), (v.shift * gc).contiguous(), SS_ACT_RELU),
+                              self.context_conv)
+        d = Vol(v.data, (v.scale * gd).contiguous(), (v.shift * gd).contiguous(), SS_ACT_RELU)
+        for i in range(3):
+            d = self.depth_conv[i].forward_vol(d)
+        d = self.depth_conv[3].forward_vol(d)
+        d = self.depth_conv[4].forward_vol(d)
+        depth, _ = ops.conv(Vol(d), self.depth_conv[5])
+        return depth, context
+
     def forward(self, x, mlp_input):
-        m = self.bn(mlp_input.reshape(-1, mlp_input.shape[-1]))
-        x = torch.relu_(_group_norm_wide(self.reduce_conv[0](x), self.reduce_conv[1]))
-        context = self.context_conv(self.context_se(x, self.context_mlp(m)[..., None, None]))
-        d = self.depth_se(x, self.depth_mlp(m)[..., None, None])
-        for i in range(4):                                         # 3 BasicBlocks + ASPP (cuDNN)
-            d = self.depth_conv[i](d)
-        d = self.depth_conv[4](d)                                  # DCN: own kernels, channels-last result
-        dcl = d.permute(0, 2, 3, 1).unsqueeze(1)                   # [B,1,H,W,C] view of the DCN output
-        y, _ = ops.conv(ops.Vol(dcl), self.depth_conv[5])          # final 1x1 conv on the tcgen05 kernel
-        depth = ops.to_channels_first(y.squeeze(1))
-        return torch.cat([depth, context], dim=1)
+        """Reference tensor contract: x [B,Cin,H,W] -> [B,D+ctx,H,W]."""
+        depth, context = self.forward_vol(ops.to_channels_last(x).unsqueeze(1), mlp_input)
+        return torch.cat([ops.to_channels_first(depth.squeeze(1)), ops.to_channels_first(context.squeeze(1))], dim=1)
 
 
 # ------------------------------------------------------------------------------------------
@@ -393,10 +439,12 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         return self.loss_depth_weight * loss
 
     # ---- (i) stereo branch ------------------------------------------------------------------
-    def stereo_features(self, feat_left, feat_right, mlp_left, mlp_right) -> torch.Tensor:
-        """stereofeature_net on the batched pair -> channels-last [2B,1,fH,fW,64]."""
+    def stereo_features(self, feat_left, feat_right, mlp_left, mlp_right, pair_cl=None) -> torch.Tensor:
+        """stereofeature_net on the batched pair -> channels-last [2B,1,fH,fW,64].  ``pair_cl`` is the
+        channels-last [2B,1,fH,fW,Cin] copy of cat(left, right) if the caller already made it."""
         net = self.stereo_volume_net.feature_withcam
-        x = ops.to_channels_last(torch.cat([feat_left, feat_right], 0)).unsqueeze(1)     # [2B,1,H,W,Cin]
+        x = pair_cl if pair_cl is not None else \
+            ops.to_channels_last(torch.cat([feat_left, feat_right], 0)).unsqueeze(1)     # [2B,1,H,W,Cin]
         m = torch.cat([mlp_left, mlp_right], 0).reshape(-1, mlp_left.shape[-1])
         v = conv_gn(Vol(x), net.reduce_conv, SS_ACT_RELU)
         # SE gate > 0, so relu(gn(y)) * g == relu(gn(y) * g): fold it into the pending affine
@@ -421,8 +469,8 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         c3, _ = ops.conv(c31, net.classif3_2[0])                 # [B,D,H,W,1]
         return ops.softmax_d(c3.view(c3.shape[:4]))
 
-    def stereo_volume(self, feat_left, feat_right, mlp_left, mlp_right, calib) -> torch.Tensor:
-        fea = self.stereo_features(feat_left, feat_right, mlp_left, mlp_right)
+    def stereo_volume(self, feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl=None) -> torch.Tensor:
+        fea = self.stereo_features(feat_left, feat_right, mlp_left, mlp_right, pair_cl)
         if self.stage_outputs is not None:
             self.stage_outputs["stereo_fea"] = fea
         vol = ops.gwc_warp(fea, calib, self.stereo_volume_net.maxdisp, self.stereo_volume_net.num_groups)
@@ -488,20 +536,24 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         calib = input[16]
         ops.arena(x.device).reset()
 
-        stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib)
-
         B, N, Cin, H, W = x.shape
-        # adjacent component (N1) on cuDNN: follow the selected math mode (TF32 allowed only in TF32 mode)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=ops.default_math() == ops.SS_MATH_TF32):
-            y = self.depth_net(x.reshape(B * N, Cin, H, W), mlp_input)
-        lss = ops.softmax_d(y[:, :self.D])
-        img_feat = ops.to_channels_last(y[:, self.D:self.D + self.numC_Trans])   # [B*N,H,W,C]
+        if N != 1:
+            raise NotImplementedError("the stereo path is defined for one camera per side (N=1)")
+        # one channels-last copy of the feature pair serves the stereo branch (both maps) and depth_net (left)
+        pair_cl = ops.to_channels_last(torch.cat([feat_left, feat_right], 0)).unsqueeze(1)      # [2B,1,H,W,Cin]
+        stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
+
+        depth_cl, ctx_cl = self.depth_net.forward_vol(pair_cl[:B], mlp_input)
+        depth_logits = ops.to_channels_first(depth_cl.squeeze(1))                 # [B,D,H,W]
+        lss = ops.softmax_d(depth_logits)
+        img_feat = ctx_cl.squeeze(1)                                              # [B,H,W,C] channels-last
 
         depth_prob = self.mutual_interactive_ensemble(stereo, lss)
 
         index = self.splat_index(rots, trans, intrins, post_rots, post_trans, bda)
         bev = ops.lift_splat(depth_prob, img_feat, index)                         # [B,X,Y,Z,C]
         if self.stage_outputs is not None:
+            y = torch.cat([depth_logits, ops.to_channels_first(img_feat)], dim=1)
             self.stage_outputs.update(stereo_prob=stereo, depth_net=y, lss_prob=lss, depth_prob=depth_prob,
                                       splat_index=index)
         return bev.permute(0, 4, 1, 2, 3), depth_prob

@@ -161,6 +161,29 @@ def test_conv2d_dilated_bias_gelu(ops, mode):
         assert rel_err(got, want) < TOL[mode]
 
 
+@pytest.mark.parametrize("pending", [False, True])
+def test_conv2d_3x3_wide_halo_kernel(ops, pending):
+    """2-D 3x3 layers with wide channels (DepthNet's BasicBlocks / reduce convs) ride the halo-resident
+    tcgen05 kernel with one plane per channel chunk (kd = 1); plain and pending-affine inputs, a map
+    whose rows do not fill the 32x8 tile, batch 2."""
+    torch.manual_seed(31)
+    m = nn.Conv2d(96, 160, 3, 1, 1, bias=True)
+    x = torch.randn(2, 96, 30, 19)
+    sc, sh = torch.rand(2, 96) + 0.5, torch.randn(2, 96) * 0.3
+    xin = F.relu(x * sc[:, :, None, None] + sh[:, :, None, None]) if pending else x
+    want = m(xin).detach()
+    mg = nn.Conv2d(96, 160, 3, 1, 1, bias=True).cuda()
+    mg.load_state_dict(m.state_dict())
+    xcl = x.permute(0, 2, 3, 1).contiguous().unsqueeze(1).cuda()
+    v = ops.Vol(xcl, sc.cuda(), sh.cuda(), ops.SS_ACT_RELU) if pending else ops.Vol(xcl)
+    ops.arena(torch.device("cuda", 0)).reset()
+    y, st = ops.conv(v, mg, want_stats=True)
+    got = y.squeeze(1).permute(0, 3, 1, 2).cpu()
+    assert rel_err(got, want) < TOL["tf32"]
+    wd = want.double()
+    assert rel_err(st[..., 0], wd.sum(dim=(2, 3))) < 1e-3 and rel_err(st[..., 1], (wd * wd).sum(dim=(2, 3))) < 1e-3
+
+
 @pytest.mark.parametrize("mode", ["precise", "tf32"])
 def test_conv_pending_affine_relu_and_gn_chain(ops, mode):
     """conv -> GroupNorm -> ReLU -> conv -> GroupNorm, with both norms applied as pending affines,
@@ -360,6 +383,54 @@ def test_deformable_conv(ops, mode):
         ops.set_default_math(ops.SS_MATH_TF32)
     assert got.shape == want.shape
     assert rel_err(got, want) < TOL[mode]
+
+
+def test_channel_sums(ops):
+    """ss_channel_sums_fwd: per-(batch,channel) sum / sum of squares of a pending volume, also on a
+    channel slice of a wider buffer."""
+    torch.manual_seed(21)
+    for (B, V, Cc, ld) in ((2, 8 * 16, 640, 640), (1, 77, 33, 40), (3, 5, 4, 4)):
+        wide = torch.randn(B, 1, 1, V, ld)
+        x = wide[..., :Cc]
+        sc, sh = torch.rand(B, Cc) + 0.5, torch.randn(B, Cc) * 0.3
+        a = F.relu(x * sc.view(B, 1, 1, 1, Cc) + sh.view(B, 1, 1, 1, Cc)).double()
+        want = torch.stack((a.sum(dim=(1, 2, 3)), (a * a).sum(dim=(1, 2, 3))), -1)
+        ops.arena(torch.device("cuda", 0)).reset()
+        got = ops.channel_sums(ops.Vol(wide.cuda()[..., :Cc], sc.cuda(), sh.cuda(), ops.SS_ACT_RELU))
+        assert got.dtype == torch.float64 and rel_err(got, want) < 1e-6
+        plain = ops.channel_sums(ops.Vol(wide.cuda()[..., :Cc]))
+        assert rel_err(plain[..., 0], x.double().sum(dim=(1, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["precise", "tf32"])
+def test_depth_net_module(ops, mode):
+    """DepthNet with the reference's tensor contract: 3 BasicBlocks with pending
+    BatchNorm, ASPP (dilations 6/12/18 larger than the map, pooled branch folded into a shift),
+    DCN and the 1x1 heads, against the oracle restatement (pinned to the reference's forward)."""
+    from stereoscene_b200 import presets, synth
+    model, mc = presets.build("tiny")
+    synth.randomize_weights_(model, 11)
+    vt = model.img_view_transformer
+    sd = {"dn." + k: v.detach().cpu().clone() for k, v in vt.depth_net.state_dict().items()}
+    B, H, W = 2, 6, 20
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, vt.numC_input, H, W, generator=g)
+    mlp = torch.randn(B, 1, vt.cam_channels, generator=g)
+    with torch.no_grad():
+        want = O.depth_net(sd, "dn", x, mlp)
+    dn = vt.depth_net.cuda()
+    ops.set_default_math(_mode(ops, mode))
+    try:
+        ops.arena(torch.device("cuda", 0)).reset()
+        with torch.no_grad():
+            got = dn(x.cuda(), mlp.cuda())
+    finally:
+        ops.set_default_math(ops.SS_MATH_TF32)
+    assert got.shape == want.shape
+    D = vt.D
+    tol = 1e-3 if mode == "precise" else 1e-2          # ~12 stacked layers in TF32
+    assert rel_err(got[:, :D], want[:, :D]) < tol
+    assert rel_err(got[:, D:], want[:, D:]) < tol
 
 
 def test_trilinear_upsample_and_argmax(ops):
