@@ -224,6 +224,17 @@ __global__ void bri_combine_kernel(const float* __restrict__ part_ml, const floa
     }
 }
 
+void bri_combine_launch(const float* part_ml, const float* part_o, const float* kv, const float* params, float* out, int out_ld,
+                        int B, int D, int N, int KS, cudaStream_t st) {
+    dim3 cgrid((N + 127) / 128, min(D, 8), B);
+    bri_combine_kernel<<<cgrid, 128, 0, st>>>(part_ml, part_o, kv, params, out, out_ld, B, D, N, KS);
+}
+
+// tcgen05 kernel (bri_attn_tc.cu)
+size_t bri_tc_workspace_floats(int B, int D, int N);
+int try_bri_tc(const float* q, const float* kv, const float* params, float* ws, float* out, int out_ld, int B, int D, int N,
+               cudaStream_t st, int* rc);
+
 static int bri_key_splits(int B, int N) {
     // enough CTAs for ~2 waves of 2 CTAs/SM; at most 8 splits, each a multiple of the key tile
     const int qtiles = (N + BQ - 1) / BQ;
@@ -261,7 +272,8 @@ extern "C" size_t ss_bri_workspace_bytes(int B, int D, int N) {
     const int ks = ss::bri_key_splits(B, N);
     size_t fl = (size_t)B * N;                                   // conf
     if (ks > 1) fl += (size_t)ks * B * N * (2 + D);              // partial (m, l) and O
-    return fl * sizeof(float);
+    const size_t fl_tc = ss::bri_tc_workspace_floats(B, D, N);   // the tcgen05 kernel lays the workspace out its own way
+    return (fl > fl_tc ? fl : fl_tc) * sizeof(float);
 }
 
 extern "C" int ss_bri_attn_fwd(const float* q, const float* kv, const float* params, float* ws, size_t ws_bytes,
@@ -271,6 +283,10 @@ extern "C" int ss_bri_attn_fwd(const float* q, const float* kv, const float* par
     SS_REQUIRE(B > 0 && B <= 65535 && D > 0 && D <= 128 && N > 0 && out_ld >= 1, "ss_bri_attn_fwd: shape (D <= 128)");
     if (ws_bytes < ss_bri_workspace_bytes(B, D, N)) return SS_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    if (math == SS_MATH_TF32 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+        int rct = 0;
+        if (try_bri_tc(q, kv, params, ws, out, out_ld, B, D, N, st, &rct)) return rct;
+    }
     const int KS = bri_key_splits(B, N);
     float* conf_ws = ws;
     float* part_ml = ws + (size_t)B * N;

@@ -271,7 +271,8 @@ def test_gwc_warp(ops, shape):
 
 
 @pytest.mark.parametrize("mode", ["precise", "tf32"])
-@pytest.mark.parametrize("dims", [(2, 48, 8, 16), (1, 112, 6, 23), (1, 20, 5, 13), (1, 48, 16, 48), (2, 112, 24, 80)])
+@pytest.mark.parametrize("dims", [(2, 48, 8, 16), (1, 112, 6, 23), (1, 20, 5, 13), (1, 48, 16, 48), (2, 112, 24, 80),
+                                  (1, 20, 8, 20), (2, 100, 10, 18), (1, 112, 48, 160)])
 def test_bri_attention(ops, mode, dims):
     B, D, H, W = dims
     torch.manual_seed(10)
