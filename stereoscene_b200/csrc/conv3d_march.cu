@@ -185,6 +185,110 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const MarchParams&
     return c;
 }
 
+// Epilogue of one worker warp: NCOL accumulator columns of its 32 voxel rows, for every tile of the CTA.
+// The per-tile body is the critical path of the HBM-bound layers (every tile passes through all worker warps), so
+// everything tile-invariant is hoisted: bias values live in registers, the tile coordinate is advanced
+// incrementally (no 64-bit divisions), the activation switch sits outside the element loops, and the
+// GroupNorm sums are per-thread running sums that are transposed / reduced once per (CTA, sample).
+template <int NCOL>
+__device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t_begin, long long t_end, int q, int lane, int col0,
+                                               uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0) {
+    if (t_begin >= t_end) return;
+    const int row = q * 32 + lane;
+    const int lh = row / MR_TW, lw = row % MR_TW;
+    const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) && p.Cout == 32;
+    const bool want_stats = p.stats != nullptr;
+    const int act = p.out_act;
+    float bias_r[NCOL], acc_s[NCOL], acc_q[NCOL];
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) {
+        bias_r[k] = (p.bias && col0 + k < p.Cout) ? __ldg(p.bias + col0 + k) : 0.f;
+        acc_s[k] = 0.f; acc_q[k] = 0.f;
+    }
+    TileCoord c = decode_tile(t_begin, p);
+    int run_b = c.b;
+    auto flush = [&]() {
+        if (want_stats) {
+            // transposing butterfly over the 32 rows of the warp: lane L ends up with column L of the slice
+            float s[32], qq[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { s[k] = k < NCOL ? acc_s[k % NCOL] : 0.f; qq[k] = k < NCOL ? acc_q[k % NCOL] : 0.f; }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float send_s = up ? s[i] : s[i + off], keep_s = up ? s[i + off] : s[i];
+                    const float send_q = up ? qq[i] : qq[i + off], keep_q = up ? qq[i + off] : qq[i];
+                    s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                    qq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+                }
+            }
+            const int ch = col0 + lane;
+            if (lane < NCOL && ch < p.Cout) {
+                atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 0, (double)s[0]);
+                atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 1, (double)qq[0]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
+    };
+    uint32_t tile_n = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
+        if (c.b != run_b) { flush(); run_b = c.b; }
+        const uint32_t acc = tile_n % MR_ACC;
+        m_mbar_wait(t_full0 + 8 * acc, (tile_n / MR_ACC) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t r[NCOL];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MR_BN + (uint32_t)col0;
+        if constexpr (NCOL == 32) {
+            m_tmem_ld32(taddr, r);
+        } else {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        m_mbar_arrive(t_empty0 + 8 * acc);                     // accumulator may be overwritten
+        float v[NCOL];
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) v[k] = __uint_as_float(r[k]) + bias_r[k];
+        if (act == SS_ACT_RELU) {
+#pragma unroll
+            for (int k = 0; k < NCOL; ++k) v[k] = fmaxf(v[k], 0.f);
+        } else if (act == SS_ACT_GELU) {
+#pragma unroll
+            for (int k = 0; k < NCOL; ++k) v[k] = gelu_erf(v[k]);
+        }
+        const int oh = c.th * MR_TH + lh, ow = c.tw * MR_TW + lw;
+        if (oh < p.H && ow < p.W) {
+            float* dst = p.y + ((((size_t)c.b * p.D + c.d) * p.H + oh) * p.W + ow) * p.out_ldc + col0;
+            if (vec_ok) {
+#pragma unroll
+                for (int k = 0; k < NCOL; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NCOL; ++k)
+                    if (col0 + k < p.Cout) dst[k] = v[k];
+            }
+            if (want_stats) {
+#pragma unroll
+                for (int k = 0; k < NCOL; ++k) { acc_s[k] += v[k]; acc_q[k] = fmaf(v[k], v[k], acc_q[k]); }
+            }
+        }
+        if (++c.d == p.D) {                                     // next flat tile: d fastest, then tw, th, b
+            c.d = 0;
+            if (++c.tw == p.nTW) {
+                c.tw = 0;
+                if (++c.th == p.nTH) { c.th = 0; ++c.b; }
+            }
+        }
+    }
+    flush();
+}
+
 template <int KS>
 __global__ void __launch_bounds__(MR_THREADS, 1)
 conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
@@ -406,99 +510,9 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
         }
     } else {
         // ======================= EPILOGUE WARPS (0..3, plus 4..7 when there is no fix-up work) =======
-        const int q = warp & 3;
-        const int nsplit = fixup ? 1 : 2;              // warps sharing a lane quarter split the 32 columns
-        const int cpart = fixup ? 0 : (warp >> 2);
-        const int ncol = 32 / nsplit, col0 = cpart * ncol;
-        const int row = q * 32 + lane;
-        const int lh = row / MR_TW, lw = row % MR_TW;
-        const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) && p.Cout == 32;
-        long long tile_n = 0;
-        // GroupNorm sums: every thread keeps running sums of ITS voxel row over all tiles of the CTA (32 + 32
-        // registers, two FP32 ops per value); the cross-lane transposing butterfly and the double atomics run
-        // once per (CTA, sample) instead of once per tile
-        float acc_s[32], acc_q[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
-        int run_b = -1;
-        auto flush = [&]() {
-            if (p.stats && run_b >= 0) {
-                // butterfly over the 32 rows of the warp: lane L ends up with column L (with 16 columns per warp
-                // the upper half is zero: lane L < 16 holds column col0 + L)
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float send_s = up ? acc_s[i] : acc_s[i + off], keep_s = up ? acc_s[i + off] : acc_s[i];
-                        const float send_q = up ? acc_q[i] : acc_q[i + off], keep_q = up ? acc_q[i + off] : acc_q[i];
-                        acc_s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-                        acc_q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-                    }
-                }
-                const int ch = (nsplit == 1) ? lane : col0 + (lane & 15);
-                if (ch < p.Cout && (nsplit == 1 || lane < 16)) {
-                    atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 0, (double)acc_s[0]);
-                    atomicAdd(p.stats + ((size_t)run_b * p.Cout + ch) * 2 + 1, (double)acc_q[0]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 32; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
-        };
-        for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
-            const TileCoord c = decode_tile(t, p);
-            if (c.b != run_b) { flush(); run_b = c.b; }
-            const int acc = (int)(tile_n % MR_ACC);
-            m_mbar_wait(t_full0 + 8 * acc, (uint32_t)(tile_n / MR_ACC) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r[32];
-            if (nsplit == 1) {
-                m_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MR_BN), r);
-            } else {
-                uint32_t r16[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MR_BN + col0);
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                             : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]), "=r"(r16[6]), "=r"(r16[7]),
-                               "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]), "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
-                             : "r"(taddr) : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int k = 0; k < 16; ++k) { r[k] = r16[k]; r[16 + k] = 0u; }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            m_mbar_arrive(t_empty0 + 8 * acc);                     // accumulator may be overwritten
-            const int oh = c.th * MR_TH + lh, ow = c.tw * MR_TW + lw;
-            const bool valid = oh < p.H && ow < p.W;
-            float v[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                float f = __uint_as_float(r[k]);
-                const int ch = col0 + k;
-                if (p.bias && k < ncol && ch < p.Cout) f += __ldg(p.bias + ch);
-                v[k] = apply_act(f, p.out_act);
-            }
-            if (valid) {
-                float* dst = p.y + ((((size_t)c.b * p.D + c.d) * p.H + oh) * p.W + ow) * p.out_ldc + col0;
-                if (vec_ok) {
-#pragma unroll
-                    for (int k = 0; k < 32; k += 4)
-                        if (k < ncol) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (k < ncol && col0 + k < p.Cout) dst[k] = v[k];
-                }
-            }
-            if (p.stats) {
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float sv = (valid && k < ncol) ? v[k] : 0.f;
-                    acc_s[k] += sv;
-                    acc_q[k] = fmaf(sv, sv, acc_q[k]);
-                }
-            }
-        }
-        flush();
+        // warps sharing a TMEM lane quarter split the 32 output columns when all 8 worker warps drain
+        if (fixup) march_epilogue<32>(p, t_begin, t_end, warp & 3, lane, 0, tmem_base, t_full0, t_empty0);
+        else march_epilogue<16>(p, t_begin, t_end, warp & 3, lane, (warp >> 2) * 16, tmem_base, t_full0, t_empty0);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -22,11 +22,18 @@ from stereoscene_b200.ops import Vol  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat"])
+    ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat", "redir1x1", "depth_conv", "aspp_dil", "mie_redir1", "frustum_conv_pending"])
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--math", default="tf32")
     ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--time-one", action="store_true")
+    ap.add_argument("--time", action="store_true", help="time every kernel case with CUDA events instead of profiling one")
     a = ap.parse_args()
+    if a.time:
+        import subprocess
+        for w in ("head_conv", "enc_conv", "frustum_conv", "frustum_conv_pending", "redir1x1", "mie_redir1", "depth_conv", "aspp_dil", "bri", "gwc", "splat"):
+            subprocess.run([sys.executable, __file__, "--what", w, "--time-one", "--workload", a.workload])
+        return
     dev = torch.device("cuda", 0)
     ops.set_default_math(ops.SS_MATH_3XTF32 if a.math == "3xtf32" else ops.SS_MATH_TF32)
     model, mc = presets.build(a.workload)
@@ -54,6 +61,27 @@ def main():
         c = vt.stereo_volume_net.dres0[0][0]
         x = torch.randn((1, D, H, W, 32), device=dev)
         fn = lambda: ops.conv(Vol(x), c, want_stats=True)     # noqa: E731
+    elif a.what == "frustum_conv_pending":
+        c = vt.stereo_volume_net.dres0[0][0]
+        x = torch.randn((1, D, H, W, 32), device=dev)
+        sc, sh = torch.rand((1, 32), device=dev) + 0.5, torch.randn((1, 32), device=dev) * 0.1
+        fn = lambda: ops.conv(Vol(x, sc, sh, ops.SS_ACT_RELU), c, want_stats=True)     # noqa: E731
+    elif a.what == "redir1x1":
+        c = vt.stereo_volume_net.dres2.redir1[0]
+        x = torch.randn((1, D, H, W, 32), device=dev)
+        fn = lambda: ops.conv(Vol(x), c, want_stats=True)     # noqa: E731
+    elif a.what == "mie_redir1":
+        c = vt.volume_interaction.redir1
+        x = torch.randn((1, D, H, W, 2), device=dev)
+        fn = lambda: ops.conv(Vol(x), c, out_act=ops.SS_ACT_RELU)     # noqa: E731
+    elif a.what == "depth_conv":
+        c = vt.depth_net.depth_conv[0].conv1
+        x = torch.randn((1, 1, H, W, 640), device=dev)
+        fn = lambda: ops.conv(Vol(x), c)     # noqa: E731
+    elif a.what == "aspp_dil":
+        c = vt.depth_net.depth_conv[3].aspp3.atrous_conv
+        x = torch.randn((1, 1, H, W, 640), device=dev)
+        fn = lambda: ops.conv(Vol(x), c)     # noqa: E731
     elif a.what == "bri":
         q = torch.softmax(torch.randn((1, D, H, W), device=dev), 1)
         kv = torch.softmax(torch.randn((1, D, H, W), device=dev), 1)
@@ -69,6 +97,18 @@ def main():
         ft = torch.randn((1, H, W, 128), device=dev)
         fn = lambda: ops.lift_splat(dp, ft, idx)     # noqa: E731
 
+    if a.time_one:
+        with torch.no_grad():
+            for _ in range(3):
+                ops.arena(dev).reset(); fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                ops.arena(dev).reset(); fn()
+            e1.record(); torch.cuda.synchronize()
+        print(f"[time] {a.what:22s} {e0.elapsed_time(e1) / 20 * 1e3:9.1f} us", flush=True)
+        return
     with torch.no_grad():
         for _ in range(2):
             fn()
