@@ -117,8 +117,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
     unsigned char* planes = base;                                            // HL_NPL plane slots
     unsigned char* bring = base + HL_NPL * HL_PLANE_BYTES;                   // SB weight tiles
     unsigned char* aux = bring + SB * Cfg::B_BYTES;
-    double* sstat = reinterpret_cast<double*>(aux);                          // [BN][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * BN);            // pa_full[3] pa_ready[3] pa_empty[3] pb_full[SB] pb_empty[SB] accum
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * BN * sizeof(double));            // pa_full[3] pa_ready[3] pa_empty[3] pb_full[SB] pb_empty[SB] accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * HL_NPL + 2 * SB + 1);
     float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // scale[Cin], shift[Cin]
 
@@ -154,7 +153,6 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
-    for (int i = tid; i < 2 * BN; i += HL_THREADS) sstat[i] = 0.0;
     if (has_aff)
         for (int i = tid; i < p.Cin; i += HL_THREADS) {
             ssc[i] = __ldg(p.in_scale + (size_t)b * p.Cin + i);
@@ -264,6 +262,13 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         const bool valid = oh < p.H && ow < p.W;
         const size_t ov = (((size_t)b * p.D + d) * p.H + oh) * p.W + ow;
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        // column sums go through a per-warp 32x33 scratch tile (the plane ring is free once accum_bar fired): one
+        // store + one load + two FP ops per value instead of the 5-round shuffle transpose
+        float* scratch = reinterpret_cast<float*>(planes) + warp * (32 * 33);
+        float* part = reinterpret_cast<float*>(planes) + 8 * 32 * 33 + warp * (2 * BN);      // per-warp column sums (no atomics: fixed summation order)
+        const int act = p.out_act;
+        const bool has_bias = p.bias != nullptr;
+        const bool want_stats = p.stats != nullptr;
 #pragma unroll 1
         for (int ci = 0; ci < BN / 32; ++ci) {
             uint32_t r[32];
@@ -271,11 +276,18 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
             const int cbase = n0 + ci * 32;
             float v[32];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                float f = __uint_as_float(r[k]);
-                const int c = cbase + k;
-                if (p.bias && c < p.Cout) f += __ldg(p.bias + c);
-                v[k] = apply_act(f, p.out_act);
+            for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+            if (has_bias) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (cbase + k < p.Cout) v[k] += __ldg(p.bias + cbase + k);
+            }
+            if (act == SS_ACT_RELU) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+            } else if (act == SS_ACT_GELU) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = gelu_erf(v[k]);
             }
             if (valid) {
                 float* dst = p.y + ov * p.out_ldc + cbase;
@@ -288,23 +300,20 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
                         if (cbase + k < p.Cout) dst[k] = v[k];
                 }
             }
-            if (p.stats) {
-                float s[32], qq[32];
+            if (want_stats) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) { s[k] = valid ? v[k] : 0.f; qq[k] = s[k] * s[k]; }
+                for (int k = 0; k < 32; ++k) scratch[lane * 33 + k] = valid ? v[k] : 0.f;
+                __syncwarp();
+                float cs = 0.f, cq = 0.f;
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float send_s = up ? s[i] : s[i + off], keep_s = up ? s[i + off] : s[i];
-                        const float send_q = up ? qq[i] : qq[i + off], keep_q = up ? qq[i + off] : qq[i];
-                        s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-                        qq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-                    }
+                for (int rr = 0; rr < 32; ++rr) {
+                    const float x = scratch[rr * 33 + lane];
+                    cs += x;
+                    cq = fmaf(x, x, cq);
                 }
-                atomicAdd(&sstat[2 * (ci * 32 + lane) + 0], (double)s[0]);
-                atomicAdd(&sstat[2 * (ci * 32 + lane) + 1], (double)qq[0]);
+                __syncwarp();
+                part[2 * (ci * 32 + lane) + 0] = cs;
+                part[2 * (ci * 32 + lane) + 1] = cq;
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -314,8 +323,12 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         for (int i = tid; i < BN; i += HL_THREADS) {
             const int c = n0 + i;
             if (c < p.Cout) {
-                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 0, sstat[2 * i + 0]);
-                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 1, sstat[2 * i + 1]);
+                const float* part0 = reinterpret_cast<const float*>(planes) + 8 * 32 * 33;
+                double ts = 0.0, tq = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { ts += (double)part0[w * 2 * BN + 2 * i + 0]; tq += (double)part0[w * 2 * BN + 2 * i + 1]; }
+                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 0, ts);
+                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 1, tq);
             }
         }
     }

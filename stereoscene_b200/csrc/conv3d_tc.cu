@@ -191,8 +191,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* aux = ring + STAGES * Cfg::STAGE_BYTES;
     int4* taps = reinterpret_cast<int4*>(aux);                             // [TC_MAX_TAPS]
-    double* sstat = reinterpret_cast<double*>(taps + TC_MAX_TAPS);         // [BN][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 2 * BN);          // full[S], ready[S], empty[S], accum
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(taps + TC_MAX_TAPS) + 2 * BN);   // full[S], ready[S], empty[S], accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
     int* s_ntaps = reinterpret_cast<int*>(tmem_slot + 1);
     float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [Cin] scale, [Cin] shift
@@ -244,7 +243,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
-    for (int i = tid; i < 2 * BN; i += TC_THREADS) sstat[i] = 0.0;
     if (has_aff)
         for (int i = tid; i < p.Cin; i += TC_THREADS) {
             ssc[i] = __ldg(p.in_scale + (size_t)b * p.Cin + i);
@@ -373,6 +371,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
         constexpr int CHUNKS = BN / 32;
         constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        // column sums through a per-warp 32x33 scratch tile in the (now idle) operand ring
+        float* scratch = reinterpret_cast<float*>(ring) + warp * (32 * 33);
+        float* part = reinterpret_cast<float*>(ring) + 8 * 32 * 33 + q * (2 * BN);           // per-quarter column sums (no atomics: fixed summation order)
+        const int act = p.out_act;
+        const bool has_bias = p.bias != nullptr;
+        const bool want_stats = p.stats != nullptr;
 #pragma unroll 1
         for (int ci = half * CPH; ci < min(CHUNKS, (half + 1) * CPH); ++ci) {
             uint32_t r[32];
@@ -380,11 +384,18 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             const int cbase = n0 + ci * 32;
             float v[32];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                float f = __uint_as_float(r[k]);
-                const int c = cbase + k;
-                if (p.bias && c < p.Cout) f += __ldg(p.bias + c);
-                v[k] = apply_act(f, p.out_act);
+            for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+            if (has_bias) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (cbase + k < p.Cout) v[k] += __ldg(p.bias + cbase + k);
+            }
+            if (act == SS_ACT_RELU) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+            } else if (act == SS_ACT_GELU) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = gelu_erf(v[k]);
             }
             if (ov >= 0) {
                 float* dst = p.y + (size_t)ov * p.out_ldc + cbase;
@@ -397,24 +408,20 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
                         if (cbase + k < p.Cout) dst[k] = v[k];
                 }
             }
-            if (p.stats) {
-                float s[32], qq[32];
+            if (want_stats) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) { s[k] = (ov >= 0) ? v[k] : 0.f; qq[k] = s[k] * s[k]; }
-                // butterfly: after the 5 rounds lane L holds the column-(L) total over the warp's 32 rows
+                for (int k = 0; k < 32; ++k) scratch[lane * 33 + k] = (ov >= 0) ? v[k] : 0.f;
+                __syncwarp();
+                float cs = 0.f, cq = 0.f;
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float send_s = up ? s[i] : s[i + off], keep_s = up ? s[i + off] : s[i];
-                        const float send_q = up ? qq[i] : qq[i + off], keep_q = up ? qq[i + off] : qq[i];
-                        s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-                        qq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-                    }
+                for (int rr = 0; rr < 32; ++rr) {
+                    const float x = scratch[rr * 33 + lane];
+                    cs += x;
+                    cq = fmaf(x, x, cq);
                 }
-                atomicAdd(&sstat[2 * (ci * 32 + lane) + 0], (double)s[0]);
-                atomicAdd(&sstat[2 * (ci * 32 + lane) + 1], (double)qq[0]);
+                __syncwarp();
+                part[2 * (ci * 32 + lane) + 0] = cs;
+                part[2 * (ci * 32 + lane) + 1] = cq;
             }
         }
         tc_fence_before();
@@ -424,8 +431,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
         for (int i = tid; i < BN; i += TC_THREADS) {
             const int c = n0 + i;
             if (c < p.Cout) {
-                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 0, sstat[2 * i + 0]);
-                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 1, sstat[2 * i + 1]);
+                const float* part0 = reinterpret_cast<const float*>(ring) + 8 * 32 * 33;
+                double ts = 0.0, tq = 0.0;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { ts += (double)part0[w * 2 * BN + 2 * i + 0]; tq += (double)part0[w * 2 * BN + 2 * i + 1]; }
+                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 0, ts);
+                atomicAdd(p.stats + ((size_t)b * p.Cout + c) * 2 + 1, tq);
             }
         }
     }
