@@ -406,6 +406,8 @@ static int dispatch_conv(const ConvParams& p, bool precise, bool vec, cudaStream
 namespace ss {
 int try_conv_cout1(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                    const float* w_packed, const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
+int try_conv_cin_small(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                       const float* w_packed, const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
 }
 
 extern "C" int ss_conv3d_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
@@ -442,6 +444,8 @@ extern "C" int ss_conv3d_fwd(const ss_conv3d_desc* d, const float* x, const floa
     {   // single-output-channel layers are bandwidth problems: FMA-pipe kernel (fp32 exact)
         int rc1 = 0;
         if (try_conv_cout1(d, x, in_scale, in_shift, w_packed, bias, y, stats, st, &rc1)) return rc1;
+        // 1- or 2-channel inputs (MIE redir1): K = 27*Cin fits one warp-level GEMM with the weights in registers
+        if (try_conv_cin_small(d, x, in_scale, in_shift, w_packed, bias, y, stats, st, &rc1)) return rc1;
     }
     const int cp = d->cout_packed;
     if (cp <= 8) return dispatch_conv<8, 8, 1>(p, precise, vec, st);

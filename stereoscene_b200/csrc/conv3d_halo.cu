@@ -29,6 +29,7 @@ constexpr int HL_THREADS = HL_WORKERS + 96;           // + A producer, MMA, B pr
 struct HaloParams {
     int B, D, H, W, Cin, Cout, CoutP, out_ldc, in_act, out_act;
     int nTH, nTW;
+    int sH, sW, swap;             // voxel strides of the kernel's h / w axes; swap = 1: the kernel's (h,w) are the tensor's (w,h)
     int KD;                       // depth taps: 3 (3x3x3, pad 1) or 1 (2-D 3x3 layers, D == 1 planes)
     const float* in_scale;
     const float* in_shift;
@@ -102,7 +103,7 @@ template <int BN>
 struct HaloCfg {
     // weight-tile ring depth: a tile is consumed in 8 MMAs (~64 BN/128 x 8 cycles), far less than the TMA
     // round trip, so the ring has to hold several microseconds of tiles
-    static constexpr int SB = BN >= 256 ? 4 : BN >= 192 ? 5 : BN >= 128 ? 8 : 12;
+    static constexpr int SB = BN >= 256 ? 4 : BN >= 192 ? 5 : BN >= 160 ? 6 : BN >= 128 ? 8 : 12;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
@@ -188,7 +189,10 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
             h_mbar_wait(pb_empty0 + 8 * slot, (use & 1u) ^ 1u);
             const uint32_t bar = pb_full0 + 8 * slot;
             mbar_expect_tx_elect(bar, Cfg::B_BYTES);
-            tma_2d_elect(bring_u32 + slot * Cfg::B_BYTES, &tmB, bar, (L / ntaps) * 32, (L % ntaps) * p.CoutP + n0);
+            // weight tap in the tensor's (kd,kh,kw) order; with swapped axes the kernel's (kh,kw) are the tensor's (kw,kh)
+            const int tl = L % ntaps, ce = tl % 9;
+            const int wt = p.swap ? (tl - ce) + (ce % 3) * 3 + ce / 3 : tl;
+            tma_2d_elect(bring_u32 + slot * Cfg::B_BYTES, &tmB, bar, (L / ntaps) * 32, wt * p.CoutP + n0);
             __syncwarp();
         }
     } else if (warp == 9) {
@@ -260,7 +264,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         const int row = q * 32 + lane;
         const int oh = h0 + mt * 16 + row / HL_TW, ow = w0 + row % HL_TW;
         const bool valid = oh < p.H && ow < p.W;
-        const size_t ov = (((size_t)b * p.D + d) * p.H + oh) * p.W + ow;
+        const size_t ov = ((size_t)b * p.D + d) * p.H * p.W + (size_t)oh * p.sH + (size_t)ow * p.sW;
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         // column sums go through a per-warp 32x33 scratch tile (the plane ring is free once accum_bar fired): one
         // store + one load + two FP ops per value instead of the 5-round shuffle transpose
@@ -373,7 +377,12 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
     if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
     if (d->ph != 1 || d->pw != 1 || d->math != SS_MATH_TF32) return 0;
     if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
-    const int nTH = (d->Hin + HL_TH - 1) / HL_TH, nTW = (d->Win + HL_TW - 1) / HL_TW;
+    // tile orientation: 32 x 8 voxels along (h, w) or, with the axes swapped, along (w, h) -- whichever wastes fewer rows
+    auto tiles_of = [](int Hk, int Wk) { return (long long)((Hk + HL_TH - 1) / HL_TH) * ((Wk + HL_TW - 1) / HL_TW); };
+    const long long t_norm = tiles_of(d->Hin, d->Win), t_swap = tiles_of(d->Win, d->Hin);
+    const int swap = t_swap < t_norm ? 1 : 0;
+    const int Hk = swap ? d->Win : d->Hin, Wk = swap ? d->Hin : d->Win;
+    const int nTH = (Hk + HL_TH - 1) / HL_TH, nTW = (Wk + HL_TW - 1) / HL_TW;
     const double eff = (double)d->Hin * d->Win / ((double)nTH * HL_TH * nTW * HL_TW);
     if (eff < 0.7) return 0;                                       // too many wasted rows: the box kernel picks a better tile
     if ((long long)d->B * d->Din * nTH * nTW > 0x7fffffffLL) return 0;
@@ -386,27 +395,36 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
         encode = reinterpret_cast<HEncodeTiledFn>(ptr);
     }
     HaloParams p;
-    p.B = d->B; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cin = d->Cin; p.Cout = d->Cout; p.CoutP = d->cout_packed;
+    p.B = d->B; p.D = d->Din; p.H = Hk; p.W = Wk; p.Cin = d->Cin; p.Cout = d->Cout; p.CoutP = d->cout_packed;
     p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act; p.nTH = nTH; p.nTW = nTW; p.KD = d->kd;
+    p.swap = swap; p.sH = swap ? 1 : d->Win; p.sW = swap ? d->Win : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
     alignas(64) CUtensorMap tmA;
-    cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B};
-    cuuint64_t gstr[4] = {(cuuint64_t)d->in_ldc * 4, (cuuint64_t)p.W * d->in_ldc * 4, (cuuint64_t)p.H * p.W * d->in_ldc * 4,
-                          (cuuint64_t)p.D * p.H * p.W * d->in_ldc * 4};
+    // tensor map dims in the kernel's order (C, w, h, D, B); the byte strides say which tensor axis each one walks
+    const cuuint64_t str_w = (cuuint64_t)d->in_ldc * 4, str_h = (cuuint64_t)d->Win * d->in_ldc * 4;
+    cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)Wk, (cuuint64_t)Hk, (cuuint64_t)p.D, (cuuint64_t)p.B};
+    cuuint64_t gstr[4] = {swap ? str_h : str_w, swap ? str_w : str_h, (cuuint64_t)d->Hin * d->Win * d->in_ldc * 4,
+                          (cuuint64_t)p.D * d->Hin * d->Win * d->in_ldc * 4};
     cuuint32_t box[5] = {32, HL_HW, HL_HH, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim, gstr, box,
                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_halo: tensor map A"); return 1; }
     const int cp = d->cout_packed;
+    const long long tiles = (long long)p.B * p.D * nTH * nTW;
+    // column tile: the one that minimises (waves of CTAs on 148 SMs) x (work per CTA ~ BN)
+    auto cost = [&](int bn) { const long long ctas = tiles * ((cp + bn - 1) / bn); return (double)((ctas + 147) / 148) * bn; };
     if (cp <= 64) *rc = launch_halo<64>(p, tmA, w_kmajor, encode, st);
     else if (cp <= 128) *rc = launch_halo<128>(p, tmA, w_kmajor, encode, st);
-    else if (cp <= 192) *rc = launch_halo<192>(p, tmA, w_kmajor, encode, st);
+    else if (cp <= 192 && cp != 160) *rc = launch_halo<192>(p, tmA, w_kmajor, encode, st);
     else {
-        // 256-column tiles halve the A traffic per FLOP but leave SMs idle on small grids
-        const long long ctas256 = (long long)p.B * p.D * nTH * nTW * ((cp + 255) / 256);
-        if (cp % 128 == 0 && (cp % 256 != 0 || ctas256 < 2 * 148)) *rc = launch_halo<128>(p, tmA, w_kmajor, encode, st);
+        int best = 256;
+        double bc = cost(256) * 0.9;                                // 256-column tiles halve the A traffic per FLOP
+        if (cp % 128 == 0 && cost(128) < bc) { best = 128; bc = cost(128); }
+        if (cp % 160 == 0 && cost(160) < bc) { best = 160; bc = cost(160); }
+        if (best == 128) *rc = launch_halo<128>(p, tmA, w_kmajor, encode, st);
+        else if (best == 160) *rc = launch_halo<160>(p, tmA, w_kmajor, encode, st);
         else *rc = launch_halo<256>(p, tmA, w_kmajor, encode, st);
     }
     return 1;

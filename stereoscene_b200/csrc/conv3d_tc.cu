@@ -170,7 +170,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES = BN >= 256 ? 4 : BN >= 192 ? 5 : BN >= 128 ? 6 : 4;
+    static constexpr int STAGES = BN >= 256 ? 4 : BN >= 160 ? 5 : BN >= 128 ? 6 : 4;
     static constexpr int MIN_CTAS = BN <= 64 ? 2 : 1;
     static constexpr int A_BYTES = TC_BM * 128;
     static constexpr int B_BYTES = BN * 128;
@@ -577,13 +577,20 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     if (cp <= 32) return launch_tc<32>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
     if (cp <= 64) return launch_tc<64>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
     if (cp <= 128) return launch_tc<128>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
-    if (cp <= 192) return launch_tc<192>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
-    {   // wide layers on small grids: 256-column tiles leave most SMs idle, 128-column tiles double the CTA count
+    if (cp <= 192 && cp != 160) return launch_tc<192>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+    {   // wide layers: the column tile that minimises (waves of CTAs on 148 SMs) x (work per CTA ~ BN); 256-column tiles
+        // leave SMs idle on small grids, 160 columns turn the 300-CTA grid of the 640-channel 2-D layers into 240
         const int ncls = p.cls_d * p.cls_h * p.cls_w;
         const long long rows = ((long long)(p.Dout + p.cls_d - 1) / p.cls_d) * ((p.Hout + p.cls_h - 1) / p.cls_h) *
                                ((p.Wout + p.cls_w - 1) / p.cls_w);
-        const long long ctas256 = ((rows + TC_BM - 1) / TC_BM) * ((cp + 255) / 256) * p.B * ncls;
-        if (ctas256 < 2 * 148 && cp % 128 == 0) return launch_tc<128>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+        const long long mt = ((rows + TC_BM - 1) / TC_BM) * p.B * ncls;
+        auto cost = [&](int bn) { const long long ctas = mt * ((cp + bn - 1) / bn); return (double)((ctas + 147) / 148) * bn; };
+        int best = 256;
+        double bc = cost(256) * 0.9;
+        if (cp % 128 == 0 && cost(128) <= bc * 1.0001 / 0.9) { best = 128; bc = cost(128); }
+        if (cp % 160 == 0 && cost(160) < bc) { best = 160; bc = cost(160); }
+        if (best == 128) return launch_tc<128>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+        if (best == 160) return launch_tc<160>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
     }
     return launch_tc<256>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
 }

@@ -99,5 +99,154 @@ int try_conv_cout1(const ss_conv3d_desc* d, const float* x, const float* in_scal
     return 1;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Few-input-channel 3x3x3 convolution (Cin <= 2 -> Cout <= 32, stride 1, pad 1): the MIE redir1 layer
+// (Conv3d 2 -> 32 + bias + ReLU on the two BRI outputs, ViewTransformerLSSVoxel.py:239, 259).  K = 27*Cin = 54
+// is far too short for the generic implicit-GEMM tiles (one K step of 32 per tap, mostly padding): here a
+// CTA stages the (3 x 10 x 34 x Cin) halo of an 8 x 32 voxel tile in shared memory once (TF32-rounded) and
+// every warp runs mma.sync m16n8k8 over K = 56 with the whole weight matrix held in registers as B
+// fragments; A fragments are shared-memory reads at per-lane precomputed tap offsets.  The layer is then
+// bound by writing its 110 MB output.
+// ------------------------------------------------------------------------------------------------
+constexpr int CS_TH = 8, CS_TW = 32, CS_THREADS = 256;
+
+struct CsParams {
+    int B, D, H, W, Cout, CoutP, in_ldc, out_ldc, out_act, nTH, nTW;
+    const float* x; const float* w; const float* bias; float* y; double* stats;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(CS_THREADS)
+conv_cin_small_kernel(const CsParams p) {
+    constexpr int K = 27 * CIN, KSTEPS = (K + 7) / 8;
+    constexpr int HH = CS_TH + 2, HW = CS_TW + 2;
+    constexpr int TILE = 3 * HH * HW * CIN;
+    __shared__ float xs[TILE];
+    __shared__ float sst[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int bi = blockIdx.x;
+    const int tw = bi % p.nTW; bi /= p.nTW;
+    const int th = bi % p.nTH; bi /= p.nTH;
+    const int d = bi % p.D;
+    const int b = bi / p.D;
+    const int h0 = th * CS_TH, w0 = tw * CS_TW;
+
+    if (tid < 64) sst[tid] = 0.f;
+    for (int idx = tid; idx < TILE; idx += CS_THREADS) {
+        const int c = idx % CIN, ww = (idx / CIN) % HW, hh = (idx / (CIN * HW)) % HH, kd = idx / (CIN * HW * HH);
+        const int gd = d + kd - 1, gh = h0 + hh - 1, gw = w0 + ww - 1;
+        float v = 0.f;
+        if ((unsigned)gd < (unsigned)p.D && (unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.W)
+            v = __ldg(p.x + ((((size_t)b * p.D + gd) * p.H + gh) * p.W + gw) * p.in_ldc + c);
+        xs[idx] = __uint_as_float(f2tf32(v));
+    }
+    // B fragments of the whole [K x 32] weight matrix and the tap offsets of this lane's two K columns
+    uint32_t breg[KSTEPS][4][2];
+    int koff[KSTEPS][2];
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = ks * 8 + t + 4 * e;
+            int off = 0;
+            if (k < K) {
+                const int tap = k / CIN, c = k % CIN;
+                off = (((tap / 9) * HH + (tap / 3) % 3) * HW + tap % 3) * CIN + c;
+            }
+            koff[ks][e] = off;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int n = nt * 8 + g;
+                breg[ks][nt][e] = (k < K) ? f2tf32(__ldg(p.w + (size_t)k * p.CoutP + n)) : 0u;
+            }
+        }
+    float bias_r[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int n = nt * 8 + 2 * t + e;
+            bias_r[nt][e] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+        }
+    __syncthreads();
+
+    const int hl = warp;                                   // one tile row per warp, two 16-voxel M tiles along w
+    const int oh = h0 + hl;
+    const bool pair_ok = ((p.out_ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 7) == 0);
+    float ss[4][2], sq[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { ss[nt][0] = ss[nt][1] = sq[nt][0] = sq[nt][1] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int rb0 = (hl * HW + j * 16 + g) * CIN, rb1 = rb0 + 8 * CIN;
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            const uint32_t a[4] = {__float_as_uint(xs[rb0 + koff[ks][0]]), __float_as_uint(xs[rb1 + koff[ks][0]]),
+                                   __float_as_uint(xs[rb0 + koff[ks][1]]), __float_as_uint(xs[rb1 + koff[ks][1]])};
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], a, breg[ks][nt]);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int ow = w0 + j * 16 + g + 8 * r;
+            if (oh < p.H && ow < p.W) {
+                float* dst = p.y + ((((size_t)b * p.D + d) * p.H + oh) * p.W + ow) * p.out_ldc;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int n = nt * 8 + 2 * t;
+                    const float v0 = apply_act(acc[nt][2 * r + 0] + bias_r[nt][0], p.out_act);
+                    const float v1 = apply_act(acc[nt][2 * r + 1] + bias_r[nt][1], p.out_act);
+                    if (pair_ok && n + 1 < p.Cout) *reinterpret_cast<float2*>(dst + n) = make_float2(v0, v1);
+                    else {
+                        if (n < p.Cout) dst[n] = v0;
+                        if (n + 1 < p.Cout) dst[n + 1] = v1;
+                    }
+                    ss[nt][0] += v0; sq[nt][0] = fmaf(v0, v0, sq[nt][0]);
+                    ss[nt][1] += v1; sq[nt][1] = fmaf(v1, v1, sq[nt][1]);
+                }
+            }
+        }
+    }
+    if (p.stats) {                                          // reduce over the 8 row groups of the warp, then over warps
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float s = ss[nt][e], q = sq[nt][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+                if (g == 0) { atomicAdd(&sst[2 * (nt * 8 + 2 * t + e)], s); atomicAdd(&sst[2 * (nt * 8 + 2 * t + e) + 1], q); }
+            }
+        __syncthreads();
+        if (tid < 32 && tid < p.Cout) {
+            atomicAdd(p.stats + ((size_t)b * p.Cout + tid) * 2 + 0, (double)sst[2 * tid]);
+            atomicAdd(p.stats + ((size_t)b * p.Cout + tid) * 2 + 1, (double)sst[2 * tid + 1]);
+        }
+    }
+}
+
+// used by ss_conv3d_fwd for eligible layers; returns 1 if the layer was handled here
+int try_conv_cin_small(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                       const float* w_packed, const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
+    if (d->transposed || d->Cin > 2 || d->cout_packed != 32 || d->math != SS_MATH_TF32 || in_scale || d->in_act != SS_ACT_NONE) return 0;
+    if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 1 || d->sh != 1 || d->sw != 1 || d->pd != 1 || d->ph != 1 || d->pw != 1) return 0;
+    if (d->dd != 1 || d->dh != 1 || d->dw != 1 || d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
+    CsParams p;
+    p.B = d->B; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cout = d->Cout; p.CoutP = d->cout_packed; p.in_ldc = d->in_ldc;
+    p.out_ldc = d->out_ldc; p.out_act = d->out_act; p.nTH = (p.H + CS_TH - 1) / CS_TH; p.nTW = (p.W + CS_TW - 1) / CS_TW;
+    p.x = x; p.w = w_packed; p.bias = bias; p.y = y; p.stats = stats;
+    const long long blocks = (long long)p.B * p.D * p.nTH * p.nTW;
+    if (blocks > 0x7fffffffLL) return 0;
+    if (d->Cin == 1) conv_cin_small_kernel<1><<<(unsigned)blocks, CS_THREADS, 0, st>>>(p);
+    else conv_cin_small_kernel<2><<<(unsigned)blocks, CS_THREADS, 0, st>>>(p);
+    *rc = check_launch("conv_cin_small_kernel");
+    return 1;
+}
+
 }  // namespace ss
 

@@ -222,9 +222,10 @@ class ASPP(nn.Module):
 
 class DCN(nn.Module):
     """mmcv DeformConv2dPack semantics (no bias; offsets from a zero-initialised 3x3 conv),
-    ViewTransformerLSSBEVDepth.py:490-498.  Offsets come from the conv kernel in split-TF32 (they are
-    sampling positions), sampling runs in ss_deform_sample_fwd, the grouped GEMM on the tcgen05 conv
-    kernel (one 1x1 conv per group over the sampled rows)."""
+    ViewTransformerLSSBEVDepth.py:490-498.  Offsets come from the conv kernel in the selected math mode
+    (TF32 is also what the reference's own GPU run uses for this conv: cuDNN allows TF32 by default),
+    sampling runs in ss_deform_sample_fwd, the grouped GEMM on the tcgen05 conv kernel (one 1x1 conv
+    per group over the sampled rows)."""
 
     def __init__(self, cin, cout, k=3, padding=1, groups=4):
         super().__init__()
@@ -252,7 +253,7 @@ class DCN(nn.Module):
     def forward_vol(self, x: Vol) -> torch.Tensor:
         """x: pending [B,1,H,W,C] volume -> plain [B,1,H,W,Cout]."""
         B, _, H, W, _ = x.data.shape
-        off, _ = ops.conv(x, self.conv_offset, math_mode=ops.SS_MATH_3XTF32)             # [B,1,H,W,2*k*k]
+        off, _ = ops.conv(x, self.conv_offset)                                          # [B,1,H,W,2*k*k]
         off = ops.to_channels_first(off.squeeze(1))                                     # [B,2*k*k,H,W]
         S = ops.deform_sample(x.plain().squeeze(1), off, self.groups, self.k, 1, self.padding, 1)  # [B,H,W,G,k*k,C/G]
         G = self.groups

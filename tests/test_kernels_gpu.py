@@ -145,6 +145,19 @@ def test_few_input_channel_conv(ops):
     wide[..., 1:3] = _cl(x)                                   # input as a channel slice (ldc = 4)
     y, _ = ops.conv(ops.Vol(wide[..., 1:3]), mg, out_act=ops.SS_ACT_RELU, math_mode=ops.SS_MATH_TF32)
     assert rel_err(_ncdhw(y), want) < 1e-3
+    yp, _ = ops.conv(ops.Vol(wide[..., 1:3]), mg, out_act=ops.SS_ACT_RELU, math_mode=ops.SS_MATH_3XTF32)
+    assert rel_err(_ncdhw(yp), want) < 2e-4
+    # one input channel, 20 output channels (odd row pitch), map wider than one 32-voxel tile, GroupNorm sums
+    m1 = nn.Conv3d(1, 20, 3, 1, 1, bias=True)
+    x1 = torch.randn(1, 1, 4, 11, 45)
+    want1 = F.gelu(m1(x1)).detach()
+    mg1 = nn.Conv3d(1, 20, 3, 1, 1, bias=True).cuda()
+    mg1.load_state_dict(m1.state_dict())
+    ops.arena(torch.device("cuda", 0)).reset()
+    y1, st1 = ops.conv(ops.Vol(_cl(x1)), mg1, out_act=ops.SS_ACT_GELU, want_stats=True)
+    assert rel_err(_ncdhw(y1), want1) < 1e-3
+    wd = want1.double()
+    assert rel_err(st1[..., 0], wd.sum(dim=(2, 3, 4))) < 1e-3 and rel_err(st1[..., 1], (wd * wd).sum(dim=(2, 3, 4))) < 1e-3
 
 
 @pytest.mark.parametrize("mode", ["precise", "tf32"])
@@ -182,6 +195,29 @@ def test_conv2d_3x3_wide_halo_kernel(ops, pending):
     assert rel_err(got, want) < TOL["tf32"]
     wd = want.double()
     assert rel_err(st[..., 0], wd.sum(dim=(2, 3))) < 1e-3 and rel_err(st[..., 1], (wd * wd).sum(dim=(2, 3))) < 1e-3
+
+
+@pytest.mark.parametrize("dims", [(1, 16, 62), (3, 8, 70)])
+def test_conv_halo_swapped_axes_and_160_column_tile(ops, dims):
+    """Maps that are short in h and long in w run the halo kernel with its 32x8 tile laid along (w,h)
+    (tensor-map axes permuted, weight taps transposed); Cout = 160 exercises the 160-column tile.
+    2-D (kd = 1) and 3-D, pending affine + ReLU on the input, GroupNorm sums out."""
+    D, H, W = dims
+    torch.manual_seed(41)
+    m = nn.Conv3d(64, 160, (3 if D > 1 else 1, 3, 3), 1, (1 if D > 1 else 0, 1, 1), bias=False)
+    x = torch.randn(2, 64, D, H, W)
+    sc, sh = torch.rand(2, 64) + 0.5, torch.randn(2, 64) * 0.3
+    xin = F.relu(x * sc[:, :, None, None, None] + sh[:, :, None, None, None])
+    want = m(xin).detach()
+    mg = nn.Conv3d(64, 160, m.kernel_size, 1, m.padding, bias=False).cuda()
+    mg.load_state_dict(m.state_dict())
+    ops.arena(torch.device("cuda", 0)).reset()
+    y, st = ops.conv(ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU), mg, want_stats=True)
+    assert rel_err(_ncdhw(y), want) < TOL["tf32"]
+    wd = want.double()
+    assert rel_err(st[..., 0], wd.sum(dim=(2, 3, 4))) < 1e-3 and rel_err(st[..., 1], (wd * wd).sum(dim=(2, 3, 4))) < 1e-3
+    ref, _ = ops.conv(ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU), mg, math_mode=ops.SS_MATH_3XTF32)
+    assert rel_err(y, ref) < TOL["tf32"]
 
 
 @pytest.mark.parametrize("mode", ["precise", "tf32"])
@@ -383,7 +419,10 @@ def test_deformable_conv(ops, mode):
     finally:
         ops.set_default_math(ops.SS_MATH_TF32)
     assert got.shape == want.shape
-    assert rel_err(got, want) < TOL[mode]
+    # tf32: the offsets themselves are a TF32 conv output (as in the reference's own GPU run, cuDNN allow_tf32), and
+    # this case exaggerates them (|offset| ~ 2.5 px): a ~1e-3 px sampling error times the feature gradient adds to
+    # the GEMM's own rounding
+    assert rel_err(got, want) < (TOL[mode] if mode == "precise" else 3e-3)
 
 
 def test_channel_sums(ops):
