@@ -117,7 +117,7 @@ struct CsParams {
 };
 
 template <int CIN>
-__global__ void __launch_bounds__(CS_THREADS)
+__global__ void __launch_bounds__(CS_THREADS, 2)
 conv_cin_small_kernel(const CsParams p) {
     constexpr int K = 27 * CIN, KSTEPS = (K + 7) / 8;
     constexpr int HH = CS_TH + 2, HW = CS_TW + 2;

@@ -400,6 +400,20 @@ def disparity_taps(calib: torch.Tensor, n_bins: int, down: int = 1):
     return i0.contiguous(), w0.contiguous(), w1.contiguous()
 
 
+_taps_cache = {}
+
+
+def _cached_taps(calib: torch.Tensor, n_bins: int):
+    """disparity_taps keyed on the calibration tensor (calibration-only, like the splat index: constant
+    per sequence, so the handful of tiny host-side ops leaves the steady-state step)."""
+    key = (calib.data_ptr(), calib._version, tuple(calib.shape), calib.device, n_bins)
+    hit = _taps_cache.get("last")
+    if hit is None or hit[0] != key:
+        hit = (key, disparity_taps(calib, n_bins))
+        _taps_cache["last"] = hit
+    return hit[1]
+
+
 def gwc_warp(fea: torch.Tensor, calib: torch.Tensor, maxdisp: int, groups: int) -> torch.Tensor:
     """fea [2B,1,H,W,C] channels-last stereo features (left then right) -> cost volume
     [B,K=maxdisp,H,W,G]."""
@@ -409,7 +423,7 @@ def gwc_warp(fea: torch.Tensor, calib: torch.Tensor, maxdisp: int, groups: int) 
         raise RuntimeError("gwc_warp: features must be contiguous channels-last")
     B2, _, H, W, Cc = fea.shape
     B = B2 // 2
-    i0, w0, w1 = disparity_taps(calib.to(fea.device), maxdisp)
+    i0, w0, w1 = _cached_taps(calib if calib.device == fea.device else calib.to(fea.device), maxdisp)
     out = torch.empty((B, maxdisp, H, W, groups), dtype=torch.float32, device=fea.device)
     rc = lib.ss_gwc_warp_fwd(fea.data_ptr(), i0.data_ptr(), w0.data_ptr(), w1.data_ptr(), out.data_ptr(),
                              B, Cc, groups, H, W, maxdisp, maxdisp, _stream())
