@@ -44,7 +44,7 @@ extern "C" {
 #define SS_MATH_3XTF32 1               /* error-compensated split (hi/lo) TF32: ~fp32 accuracy */
 
 /* ABI version of this header; ss_abi_version() of the library must match. */
-#define SS_ABI_VERSION 2
+#define SS_ABI_VERSION 3
 int ss_abi_version(void);
 /* Text of the last CUDA error seen by the calling thread (host pointer, never NULL). */
 const char* ss_last_error_string(void);
@@ -197,6 +197,22 @@ int ss_bev_pool_fwd(const float* feats, const int64_t* coords, long long N, int 
  * ------------------------------------------------------------------------------------------- */
 int ss_trilinear_fwd(const float* x, float* y, uint8_t* labels, int B, int C, int Di, int Hi, int Wi,
                      int Do, int Ho, int Wo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Semantic-scene-completion scores (the step after the path: utils/ssc_metric.py:62-85, 109-168; call site
+ * occupancy/apis/test.py:113-115).  One pass over a predicted label volume and its ground truth:
+ *   counts[t*C + p]   += number of voxels selected by `nonempty` (NULL = all) whose remapped target / prediction
+ *                        are (t, p); where target == ignore_label both are remapped to 0, as the reference does
+ *                        in place (ssc_metric.py:147-148)
+ *   counts[C*C + 0..2] += completion tp, fp, fn over voxels with target != ignore_label (and nonempty, nonsurface),
+ *                        occupied = label > 0
+ * Per-class tp = counts[j*C+j], fp = column sum - tp, fn = row sum - tp.  counts: int64[C*C + 3], the caller
+ * zeroes it (or keeps accumulating across samples).  pred: uint8[n]; target: uint8[n] or int64[n]
+ * (target_elem_bytes = 1 / 8); nonempty / nonsurface: uint8[n] or NULL.  C <= 32.
+ * ------------------------------------------------------------------------------------------- */
+int ss_ssc_confusion_fwd(const uint8_t* pred, const void* target, int target_elem_bytes, const uint8_t* nonempty,
+                         const uint8_t* nonsurface, long long n, int C, int ignore_label, long long* counts,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Deformable-convolution sampling (mmcv DeformConv2dPack / torchvision deform_conv2d semantics,

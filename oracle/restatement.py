@@ -436,3 +436,44 @@ def volumetric_forward(sd, xl, xr, left, right, calib, grid_config, input_size, 
     if stages is not None:
         stages.update(enc0=levels[0], enc1=levels[1], enc2=levels[2], neck=neck, logits=logits, logits_up=up)
     return up
+
+
+# ------------------------------------------------------------------------------------------
+# next row N4: semantic-scene-completion scores of a label volume
+# ------------------------------------------------------------------------------------------
+def ssc_scores(y_pred, y_true, nonempty=None, nonsurface=None, n_classes=20, ignore=255):
+    """``SSCMetrics.update`` arithmetic (utils/ssc_metric.py:62-85 with ``get_score_completion``
+    :109-141 and ``get_score_semantic_and_completion`` :143-168), as int64 counts.
+
+    The reference edits ``y_pred`` / ``y_true`` in place inside the first score function
+    (``predict[target == 255] = 0; target[target == 255] = 0``), so by the time ``update`` builds
+    the mask of the semantic scores (``y_true != 255``) no ignored voxel is left: ignored voxels are
+    counted as (target 0, prediction 0) there, while the completion scores exclude them.
+    Returns dict(completion=int64[3] (tp, fp, fn), tps, fps, fns = int64[n_classes])."""
+    yp, yt = y_pred.clone().long(), y_true.clone().long()
+    sel_c = yt != ignore
+    if nonempty is not None:
+        sel_c = sel_c & nonempty.bool()
+    if nonsurface is not None:
+        sel_c = sel_c & nonsurface.bool()
+    ign = yt == ignore
+    yp[ign] = 0
+    yt[ign] = 0
+    bp, bt = yp > 0, yt > 0
+    completion = torch.stack([(bt & bp & sel_c).sum(), (~bt & bp & sel_c).sum(), (bt & ~bp & sel_c).sum()]).long()
+    sel_s = torch.ones_like(yt, dtype=torch.bool) if nonempty is None else nonempty.bool()
+    tps = torch.zeros(n_classes, dtype=torch.long)
+    fps, fns = tps.clone(), tps.clone()
+    for j in range(n_classes):
+        tps[j] = ((yt == j) & (yp == j) & sel_s).sum()
+        fps[j] = ((yt != j) & (yp == j) & sel_s).sum()
+        fns[j] = ((yt == j) & (yp != j) & sel_s).sum()
+    return dict(completion=completion, tps=tps, fps=fps, fns=fns)
+
+
+def ssc_compute(completion, tps, fps, fns):
+    """``SSCMetrics.compute`` (utils/ssc_metric.py:87-107)."""
+    ctp, cfp, cfn = [completion[i].double() for i in range(3)]
+    iou_ssc = tps.double() / (tps.double() + fps.double() + fns.double() + 1e-5)
+    return dict(precision=float(ctp / (ctp + cfp)), recall=float(ctp / (ctp + cfn)), iou=float(ctp / (ctp + cfp + cfn)),
+                iou_ssc=iou_ssc, iou_ssc_mean=float(iou_ssc[1:].mean()))

@@ -10,7 +10,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU = 0, 1, 2
 SS_MATH_TF32, SS_MATH_3XTF32 = 0, 1
@@ -50,6 +50,7 @@ SIGNATURES = {
     "ss_bev_pool_workspace_bytes": (_sz, [_ll, _ll]),
     "ss_bev_pool_fwd": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ss_trilinear_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ss_ssc_confusion_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _ll, _i, _i, _vp, _vp]),
     "ss_deform_sample_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ss_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
     "ss_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),

@@ -530,6 +530,39 @@ def bev_pool(feats: torch.Tensor, coords: torch.Tensor, B, D, H, W) -> torch.Ten
     return out
 
 
+def ssc_confusion(pred: torch.Tensor, target: torch.Tensor, n_classes: int, nonempty: Optional[torch.Tensor] = None,
+                  nonsurface: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+                  ignore_label: int = 255) -> torch.Tensor:
+    """int64[C*C+3]: confusion matrix [target][prediction] of the remapped labels + completion (tp, fp, fn);
+    ``counts`` (zeroed by the caller) lets several samples accumulate into one tensor."""
+    lib = cabi.load()
+    if not pred.is_cuda or not target.is_cuda:
+        raise RuntimeError("ssc_confusion: expected CUDA tensors (the hot path has no CPU fallback)")
+    if pred.shape != target.shape:
+        raise RuntimeError(f"ssc_confusion: shapes differ {tuple(pred.shape)} vs {tuple(target.shape)}")
+    if pred.dtype != torch.uint8:
+        pred = pred.to(torch.uint8)
+    if target.dtype not in (torch.uint8, torch.int64):
+        target = target.to(torch.int64)
+    pred, target = pred.contiguous(), target.contiguous()
+
+    def mask(m, name):
+        if m is None:
+            return None
+        if m.shape != target.shape:
+            raise RuntimeError(f"ssc_confusion: {name} has shape {tuple(m.shape)}, expected {tuple(target.shape)}")
+        m = m.contiguous()
+        return m.view(torch.uint8) if m.dtype == torch.bool else (m != 0).view(torch.uint8)
+
+    ne, ns = mask(nonempty, "nonempty"), mask(nonsurface, "nonsurface")
+    if counts is None:
+        counts = torch.zeros(n_classes * n_classes + 3, dtype=torch.int64, device=pred.device)
+    rc = lib.ss_ssc_confusion_fwd(pred.data_ptr(), target.data_ptr(), target.element_size(), _ptr(ne), _ptr(ns), pred.numel(),
+                                  n_classes, ignore_label, counts.data_ptr(), _stream())
+    cabi.check(rc, "ss_ssc_confusion_fwd")
+    return counts
+
+
 def deform_sample(x: torch.Tensor, offsets: torch.Tensor, groups: int, k: int, stride: int, pad: int, dil: int):
     """x [B,H,W,C] channels-last, offsets [B,2*k*k,Ho,Wo] NCHW -> S [B,Ho,Wo,groups,k*k,C/groups]."""
     lib = cabi.load()

@@ -13,17 +13,7 @@ from .. import ops
 from ..ops import SS_ACT_RELU, Vol
 from ..registry import HEADS
 from .layers import as_channels_last
-
-
-class SSCMetricState(nn.Module):
-    """Buffers of the reference's SSCMetrics (utils/ssc_metric.py:14-38) so state_dict keys match."""
-
-    def __init__(self, n_classes=20):
-        super().__init__()
-        for name in ("tps", "fps", "fns"):
-            self.register_buffer(name, torch.zeros(n_classes))
-        for name in ("completion_tp", "completion_fp", "completion_fn"):
-            self.register_buffer(name, torch.zeros(1))
+from .metrics import SSCMetrics
 
 
 @HEADS.register_module()
@@ -57,7 +47,7 @@ class OccHead(nn.Module):
                 nn.GroupNorm(norm_cfg["num_groups"], mid), nn.ReLU(inplace=True),
                 nn.Conv3d(mid, out_channel, 1, 1, 0, bias=bias)))
         if semantic_kitti:
-            self.ssc_metric = SSCMetricState(out_channel)
+            self.ssc_metric = SSCMetrics() if out_channel == 20 else SSCMetrics([str(i) for i in range(out_channel)])
 
     def forward_voxel_vol(self, voxel_feats):
         """voxel_feats: list[Vol] -> list of plain channels-last logits [B,X,Y,Z,classes]."""

@@ -490,6 +490,43 @@ def test_layout_round_trip(ops):
     assert torch.equal(ops.to_channels_first(y), x)
 
 
+def test_ssc_metrics_kernel_matches_reference(ops):
+    """ss_ssc_confusion_fwd through the SSCMetrics module (reference class name / methods): exact
+    integer agreement with the reference's own results (golden) and with the oracle on a full-size
+    256x256x32 label volume; uint8 and int64 targets, masks, accumulation over samples."""
+    import os
+    from stereoscene_b200.plugin.metrics import SSCMetrics
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ssc.npz"))
+    metric = SSCMetrics().cuda()
+    for name in ("c0", "c1", "c2"):
+        pred, true = torch.from_numpy(g[name + "_pred"]).cuda(), torch.from_numpy(g[name + "_true"]).cuda()
+        ne = torch.from_numpy(g[name + "_nonempty"]).cuda() if name + "_nonempty" in g else None
+        ns = torch.from_numpy(g[name + "_nonsurface"]).cuda() if name + "_nonsurface" in g else None
+        for tgt in (true, true.long()):                                         # uint8 and int64 ground truth
+            tp, fp, fn, tps, fps, fns = SSCMetrics().cuda().compute_single(pred.long(), tgt, ne, ns)
+            assert np.array_equal(np.array([tp, fp, fn], dtype=np.float64), g[name + "_completion"])
+            assert np.array_equal(tps, g[name + "_tps"]) and np.array_equal(fps, g[name + "_fps"]) and np.array_equal(fns, g[name + "_fns"])
+        metric.update(pred, true, ne, ns)
+    res = metric.compute()
+    assert np.allclose(res["iou_ssc"].cpu().numpy(), g["all_iou_ssc"], rtol=1e-6)
+    assert np.allclose([float(res["precision"]), float(res["recall"]), res["iou"], res["iou_ssc_mean"]], g["all_scalars"], rtol=1e-6)
+    assert set(metric.state_dict()) == {"tps", "fps", "fns", "completion_tp", "completion_fp", "completion_fn"}
+    # full-size volume against the oracle
+    gen = torch.Generator().manual_seed(3)
+    shape = (1, 256, 256, 32)
+    pred = torch.randint(0, 20, shape, generator=gen, dtype=torch.uint8)
+    true = torch.randint(0, 20, shape, generator=gen, dtype=torch.uint8)
+    true[torch.rand(shape, generator=gen) < 0.1] = 255
+    pred[torch.rand(shape, generator=gen) < 0.5] = 0
+    want = O.ssc_scores(pred, true)
+    comp, tps, fps, fns = SSCMetrics().cuda().scores(pred.cuda(), true.cuda())
+    assert torch.equal(comp.cpu(), want["completion"]) and torch.equal(tps.cpu(), want["tps"])
+    assert torch.equal(fps.cpu(), want["fps"]) and torch.equal(fns.cpu(), want["fns"])
+    # empty input is a no-op
+    z = ops.ssc_confusion(pred.cuda()[:0], true.cuda()[:0], 20)
+    assert int(z.sum()) == 0
+
+
 def test_errors_are_loud(ops):
     with pytest.raises(RuntimeError):
         ops.conv(ops.Vol(torch.randn(1, 2, 2, 2, 32)), nn.Conv3d(32, 32, 3, 1, 1))           # CPU tensor

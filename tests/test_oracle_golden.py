@@ -91,3 +91,25 @@ def test_restatement_matches_reference_live():
                              tuple(cfg["input_size"]), cfg["occ_size"], stages=st)
     for k in STAGES:
         assert rel_err(st[k], want[k]) < 2e-5, k
+
+
+def test_ssc_scores_restatement_matches_reference_golden():
+    """oracle.ssc_scores / ssc_compute against the reference's own SSCMetrics.update / compute
+    (tests/golden/golden_ssc.npz, written by oracle/make_golden_ssc.py)."""
+    import numpy as np
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ssc.npz"))
+    tot = dict(completion=torch.zeros(3, dtype=torch.long), tps=torch.zeros(20, dtype=torch.long),
+               fps=torch.zeros(20, dtype=torch.long), fns=torch.zeros(20, dtype=torch.long))
+    for name in ("c0", "c1", "c2"):
+        ne = torch.from_numpy(g[name + "_nonempty"]) if name + "_nonempty" in g else None
+        ns = torch.from_numpy(g[name + "_nonsurface"]) if name + "_nonsurface" in g else None
+        r = O.ssc_scores(torch.from_numpy(g[name + "_pred"]), torch.from_numpy(g[name + "_true"]), ne, ns)
+        assert np.array_equal(r["completion"].numpy(), g[name + "_completion"].astype(np.int64))
+        for k in ("tps", "fps", "fns"):
+            assert np.array_equal(r[k].numpy(), g[name + "_" + k].astype(np.int64)), (name, k)
+            tot[k] += r[k]
+        tot["completion"] += r["completion"]
+    res = O.ssc_compute(tot["completion"], tot["tps"], tot["fps"], tot["fns"])
+    assert np.allclose(res["iou_ssc"].numpy(), g["all_iou_ssc"], rtol=1e-6)
+    assert np.allclose([res["precision"], res["recall"], res["iou"], res["iou_ssc_mean"]], g["all_scalars"], rtol=1e-6)
