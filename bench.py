@@ -316,6 +316,7 @@ def run_ours(args):
     f0.record()
     if eng is not None:                      # make the engine's streams start after the start event
         eng.copy_stream.wait_event(f0)
+        eng.d2h_stream.wait_event(f0)
         eng.compute_stream.wait_event(f0)
     run_e2e(args.steps)
     f1.record()
@@ -489,6 +490,22 @@ def dominant_kernel_roofline(model, mc, dev, pk):
     byts = (lg.numel() + occ[0] * occ[1] * occ[2] * 20) * 4.0 + occ[0] * occ[1] * occ[2]
     kernels.append({"name": "trilinear_x2+argmax", "bound": "hbm", "ms": t * 1e3, "gbs": byts / t / 1e9,
                     "frac": byts / t / 1e9 / pk["hbm_gbs"]})
+    # (6) BRI attention (tensor-bound: 2 x 13.2 GFLOP of QK^T (two passes) + 13.2 GFLOP PV per call)
+    q = torch.softmax(torch.randn((1, D, H, W), device=dev) * 2, 1)
+    kvv = torch.softmax(torch.randn((1, D, H, W), device=dev) * 2, 1)
+    both = torch.empty((1, D, H, W, 2), device=dev)
+    prm = vt.volume_interaction.lss2stereo.packed()
+    t = _time_launches(lambda: ops.bri_attention(q, kvv, prm, both[..., 0], 2))
+    fl = 2.0 * (H * W) * (H * W) * D * 2
+    kernels.append({"name": "bri_attention 7680 tokens x 112 (prep + tcgen05 kernel + split combine)", "bound": "tensor", "ms": t * 1e3,
+                    "tflops": fl / t / 1e12, "frac": fl / t / 1e12 / pk["tflops"]})
+    # (7) DepthNet 2-D conv 640->640 k3 on the 48x160 map (tensor-bound, 56.6 GFLOP, one wave of 120 CTAs)
+    dc = vt.depth_net.depth_conv[0].conv1
+    xd = torch.randn((1, 1, H, W, dc.in_channels), device=dev)
+    t = _time_launches(lambda: ops.conv(Vol(xd), dc))
+    fl = 2.0 * H * W * 9 * dc.in_channels * dc.out_channels
+    kernels.append({"name": "depth_net conv2d 640->640 k3 (48x160)", "bound": "tensor", "ms": t * 1e3, "tflops": fl / t / 1e12,
+                    "frac": fl / t / 1e12 / pk["tflops"]})
     return roof, kernels
 
 

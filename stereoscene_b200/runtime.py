@@ -1,6 +1,6 @@
 """Serving-style runtime around the volumetric forward: static device buffers, the whole forward
 captured in ONE CUDA graph (~300 kernel launches per stereo pair collapse into a single graph launch),
-pinned host staging and a copy stream so the host->device transfer of pair i+1 and the device->host
+pinned host staging and two copy streams so the host->device transfer of pair i+1 and the device->host
 read of pair i-1 overlap the compute of pair i.
 
     eng = VolumetricEngine(model, left_calib, right_calib, calib, occ_size)
@@ -32,7 +32,10 @@ class VolumetricEngine:
         self.xl = [torch.empty(feature_shape, dtype=torch.float32, device=dev) for _ in range(2)]
         self.xr = [torch.empty(feature_shape, dtype=torch.float32, device=dev) for _ in range(2)]
         self.labels_host = [torch.empty((B, *self.occ_size), dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self.copy_stream = torch.cuda.Stream(device=dev)
+        # separate streams for the two copy directions: a download waits for ITS compute, and on a shared stream
+        # that wait would also hold back the next pair's upload (which only needs the slot's previous compute)
+        self.copy_stream = torch.cuda.Stream(device=dev)          # host -> device
+        self.d2h_stream = torch.cuda.Stream(device=dev)           # device -> host
         self.compute_stream = torch.cuda.Stream(device=dev)
         self.h2d_done = [torch.cuda.Event() for _ in range(2)]
         self.compute_done = [torch.cuda.Event() for _ in range(2)]
@@ -74,10 +77,10 @@ class VolumetricEngine:
             self.compute_done[slot].record(self.compute_stream)
 
     def _download(self, slot: int):
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.compute_done[slot])
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(self.compute_done[slot])
             self.labels_host[slot].copy_(self.outs[slot]["labels"], non_blocking=True)
-            self.d2h_done[slot].record(self.copy_stream)
+            self.d2h_done[slot].record(self.d2h_stream)
 
     # ---- public API --------------------------------------------------------------------------------------
     def infer(self, xl_host: torch.Tensor, xr_host: torch.Tensor) -> torch.Tensor:
