@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-HEAD_CONV_DRAM_BYTES = 630678016   # ncu --set full of conv_halo_kernel<192> (profiles/r01_head_conv_halo_ncu_full_raw.csv): 456.5 MB read + 174.1 MB written per launch
+HEAD_CONV_DRAM_BYTES = 633585152   # ncu --set full of conv_halo_kernel<192> (profiles/r01s2_head_conv_ncu_full_raw.csv): 459.2 MB read + 174.4 MB written per launch
 
 VOXELS = {"config1": 128 * 128 * 16, "config2": 256 * 256 * 32, "config0": 64 * 64 * 8, "tiny": 32 * 32 * 8,
           "config4": 512 * 512 * 64}
@@ -445,7 +445,7 @@ def dominant_kernel_roofline(model, mc, dev, pk):
     roof = {"bound": "tensor", "kernel": "conv_halo_kernel<192> (OccHead conv 384->192 k3 on the 128x128x16 grid; "
                                          "TMA halo planes + tcgen05.mma kind::tf32, TMEM accumulators)",
             "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-            "traffic": HEAD_CONV_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01_head_conv_halo_ncu_full_raw.csv "
+            "traffic": HEAD_CONV_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01s2_head_conv_ncu_full_raw.csv "
                                                                 "(dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
             "launch_ms": t * 1e3, "algorithmic_flops": flops,
             "algorithmic_bytes": (x.numel() + y.numel()) * 4.0,
