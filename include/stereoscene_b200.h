@@ -44,7 +44,7 @@ extern "C" {
 #define SS_MATH_3XTF32 1               /* error-compensated split (hi/lo) TF32: ~fp32 accuracy */
 
 /* ABI version of this header; ss_abi_version() of the library must match. */
-#define SS_ABI_VERSION 3
+#define SS_ABI_VERSION 4
 int ss_abi_version(void);
 /* Text of the last CUDA error seen by the calling thread (host pointer, never NULL). */
 const char* ss_last_error_string(void);
@@ -93,6 +93,26 @@ int ss_conv3d_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_sc
  *   ConvTranspose: w_kmajor[t][co][ci] = tf32(weight[ci][co][kd][kh][kw])     (rows >= Cout are zero) */
 int ss_conv3d_tc_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_scale, const float* in_shift,
                      const float* w_kmajor, const float* bias, float* y, double* stats, void* stream);
+
+/* Convolution with the residual join fused into its epilogue:
+ *   y = out_act( (conv(x) + bias) * out_scale + out_shift + res_act(res * res_scale + res_shift) )
+ * out_scale / out_shift: float[B*Cout] (eval BatchNorm of the convolution result) or NULL; res: channels-last volume of
+ * the output shape with voxel stride res_ldc, or NULL; res_scale / res_shift: its pending affine, float[B*Cout] or NULL.
+ * Replaces conv5 / conv6 + the two joins of every hourglass (ViewTransformerLSSVoxel.py:92-95), i.e. saves writing and
+ * re-reading the up-convolved tensor.  Served by the stride-2 transposed k3 kernel only: ask
+ * ss_conv3d_tc_join_supported(desc) first (1 = yes); otherwise use ss_conv3d_tc_fwd + ss_affine_join_fwd. */
+typedef struct ss_conv3d_join {
+    const float* out_scale;
+    const float* out_shift;
+    const float* res;
+    const float* res_scale;
+    const float* res_shift;
+    int32_t res_ldc;
+    int32_t res_act;                  /* SS_ACT_NONE | SS_ACT_RELU, applied to the residual after its affine */
+} ss_conv3d_join;
+int ss_conv3d_tc_join_supported(const ss_conv3d_desc* desc);
+int ss_conv3d_tc_join_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_scale, const float* in_shift,
+                          const float* w_kmajor, const float* bias, const ss_conv3d_join* join, float* y, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Normalisation bookkeeping on [B,C] vectors (the volume itself is never touched).

@@ -10,7 +10,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU = 0, 1, 2
 SS_MATH_TF32, SS_MATH_3XTF32 = 0, 1
@@ -21,6 +21,11 @@ class ConvDesc(C.Structure):
         "B", "Din", "Hin", "Win", "Cin", "Dout", "Hout", "Wout", "Cout",
         "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw", "dd", "dh", "dw",
         "transposed", "in_ldc", "out_ldc", "in_act", "out_act", "math", "cout_packed")]
+
+
+class ConvJoin(C.Structure):
+    _fields_ = [("out_scale", C.c_void_p), ("out_shift", C.c_void_p), ("res", C.c_void_p), ("res_scale", C.c_void_p),
+                ("res_shift", C.c_void_p), ("res_ldc", C.c_int32), ("res_act", C.c_int32)]
 
 
 class NativeLibraryError(RuntimeError):
@@ -36,6 +41,8 @@ SIGNATURES = {
     "ss_launch_count": (_ll, []),
     "ss_conv3d_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_conv3d_tc_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ss_conv3d_tc_join_supported": (_i, [C.POINTER(ConvDesc)]),
+    "ss_conv3d_tc_join_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvJoin), _vp, _vp]),
     "ss_gn_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _f, _vp, _vp, _i, _vp]),
     "ss_ca3d_gate": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ss_affine_join_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _i, _vp, _vp]),

@@ -530,7 +530,8 @@ namespace ss {
 int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                      const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
 int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
-                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
+                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join);
+int conv_tpose_join_supported(const ss_conv3d_desc* d);
 int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
 }
@@ -570,7 +571,7 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
         // wide 3x3x3 stride-1 layers: halo-resident kernel (planes loaded once per chunk, two M tiles per weight tile)
         if (try_conv_halo(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
         // stride-2 transposed 3x3x3 layers: one CTA per input tile computes all 8 output parity classes
-        if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
+        if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, nullptr)) return rcm;
     }
     const int cp = d->cout_packed;
     const int ntaps_total = d->kd * d->kh * d->kw;
@@ -593,4 +594,32 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
         if (best == 160) return launch_tc<160>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
     }
     return launch_tc<256>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+}
+
+
+// Convolution with the residual join fused into its epilogue (hourglass conv5 / conv6 + their joins,
+// ViewTransformerLSSVoxel.py:92-95).  Served by the stride-2 transposed kernel; ss_conv3d_tc_join_supported tells the caller
+// whether a layer qualifies (otherwise: ss_conv3d_tc_fwd followed by ss_affine_join_fwd).
+extern "C" int ss_conv3d_tc_join_supported(const ss_conv3d_desc* d) {
+    if (!d || d->Cin % 32 != 0 || d->in_ldc % 4 != 0) return 0;
+    return ss::conv_tpose_join_supported(d);
+}
+
+extern "C" int ss_conv3d_tc_join_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                                     const float* w_kmajor, const float* bias, const ss_conv3d_join* join, float* y, void* stream) {
+    using namespace ss;
+    SS_REQUIRE(d && x && w_kmajor && y && join, "ss_conv3d_tc_join_fwd: null pointer");
+    SS_REQUIRE(d->Cin % TC_BK == 0 && d->in_ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(w_kmajor) & 15) == 0, "ss_conv3d_tc_join_fwd: alignment / Cin % 32");
+    SS_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "ss_conv3d_tc_join_fwd: scale/shift must come together");
+    SS_REQUIRE((join->out_scale == nullptr) == (join->out_shift == nullptr) && (join->res_scale == nullptr) == (join->res_shift == nullptr),
+               "ss_conv3d_tc_join_fwd: join scale/shift must come together");
+    SS_REQUIRE(!join->res || join->res_ldc >= d->Cout, "ss_conv3d_tc_join_fwd: res_ldc");
+    SS_REQUIRE(join->res_act == SS_ACT_NONE || join->res_act == SS_ACT_RELU, "ss_conv3d_tc_join_fwd: res_act");
+    SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_tc_join_fwd: in_act");
+    SS_REQUIRE(d->out_ldc >= d->Cout && d->cout_packed >= d->Cout, "ss_conv3d_tc_join_fwd: ldc");
+    SS_REQUIRE(conv_tpose_join_supported(d), "ss_conv3d_tc_join_fwd: layer not supported by the fused kernel (query ss_conv3d_tc_join_supported)");
+    int rc = 0;
+    if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, nullptr, reinterpret_cast<cudaStream_t>(stream), &rc, join)) return rc;
+    return set_arg_error("ss_conv3d_tc_join_fwd: layer not supported by the fused kernel");
 }

@@ -31,6 +31,13 @@ struct TposeParams {
     const float* bias;
     float* y;
     double* stats;
+    // fused join (ss_conv3d_tc_join_fwd): y = out_act((conv + bias) * o_scale + o_shift + res_act(res * r_scale + r_shift))
+    const float* o_scale;
+    const float* o_shift;
+    const float* res;
+    const float* r_scale;
+    const float* r_shift;
+    int res_ldc, res_act, has_join;
 };
 
 __device__ __forceinline__ uint32_t t_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,6 +136,7 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TP_NPL + 2 * TP_SB + 1);
     int* tab = reinterpret_cast<int*>(tmem_slot + 4);                        // [27]
     float* ssc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tab + 32) + 15) & ~(uintptr_t)15);
+    float* jsc = ssc + 2 * p.Cin;                                            // [4][BN]: o_scale, o_shift, r_scale, r_shift of batch b
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = uniform_warp_index();
@@ -162,6 +170,14 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
     for (int i = tid; i < 2 * BN; i += TP_THREADS) sstat[i] = 0.0;
+    if (p.has_join)
+        for (int i = tid; i < BN; i += TP_THREADS) {
+            const bool in = i < p.Cout;
+            jsc[i] = (in && p.o_scale) ? __ldg(p.o_scale + (size_t)b * p.Cout + i) : 1.f;
+            jsc[BN + i] = (in && p.o_shift) ? __ldg(p.o_shift + (size_t)b * p.Cout + i) : 0.f;
+            jsc[2 * BN + i] = (in && p.r_scale) ? __ldg(p.r_scale + (size_t)b * p.Cout + i) : 1.f;
+            jsc[3 * BN + i] = (in && p.r_shift) ? __ldg(p.r_shift + (size_t)b * p.Cout + i) : 0.f;
+        }
     if (has_aff)
         for (int i = tid; i < p.Cin; i += TP_THREADS) {
             ssc[i] = __ldg(p.in_scale + (size_t)b * p.Cin + i);
@@ -290,12 +306,42 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                 t_tmem_ld32(tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(cls * BN + ci * 32), r);
                 const int cbase = ci * 32;
                 float v[32];
+                if (p.has_join) {
+                    // residual-fused epilogue: the join that would re-read this tensor and the residual runs here
+                    const bool rvec = valid && p.res && ((p.res_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) &&
+                                      cbase + 32 <= p.Cout;
+                    const float* rsrc = p.res ? p.res + ov * p.res_ldc + cbase : nullptr;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    float f = __uint_as_float(r[k]);
-                    const int c = cbase + k;
-                    if (p.bias && c < p.Cout) f += __ldg(p.bias + c);
-                    v[k] = apply_act(f, p.out_act);
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        float rr[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (rvec) {
+                            const float4 t4 = ldg_f4(rsrc + 4 * k4);
+                            rr[0] = t4.x; rr[1] = t4.y; rr[2] = t4.z; rr[3] = t4.w;
+                        } else if (valid && p.res) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (cbase + 4 * k4 + e < p.Cout) rr[e] = __ldg(rsrc + 4 * k4 + e);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = 4 * k4 + e, c = cbase + k;
+                            float f = __uint_as_float(r[k]);
+                            if (p.bias && c < p.Cout) f += __ldg(p.bias + c);
+                            f = fmaf(f, jsc[c], jsc[BN + c]);
+                            float rv = fmaf(rr[e], jsc[2 * BN + c], jsc[3 * BN + c]);
+                            if (p.res_act == SS_ACT_RELU) rv = fmaxf(rv, 0.f);
+                            if (p.res) f += rv;
+                            v[k] = apply_act(f, p.out_act);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        float f = __uint_as_float(r[k]);
+                        const int c = cbase + k;
+                        if (p.bias && c < p.Cout) f += __ldg(p.bias + c);
+                        v[k] = apply_act(f, p.out_act);
+                    }
                 }
                 if (valid) {
                     float* dst = p.y + ov * p.out_ldc + cbase;
@@ -360,7 +406,7 @@ static int launch_tpose(const TposeParams& p, const CUtensorMap& tmA, const floa
         return set_arg_error("conv_tpose: tensor map B");
     constexpr int TP_SB = TP_SB_BYTES / (BN * 128);
     const size_t smem = 1024 + (size_t)TP_NPL * TP_PLANE_BYTES + (size_t)TP_SB * BN * 128 + 2 * BN * sizeof(double) +
-                        (3 * TP_NPL + 2 * TP_SB + 1) * sizeof(uint64_t) + 16 + 32 * sizeof(int) + 32 + 2 * (size_t)p.Cin * sizeof(float);
+                        (3 * TP_NPL + 2 * TP_SB + 1) * sizeof(uint64_t) + 16 + 32 * sizeof(int) + 32 + (2 * (size_t)p.Cin + 4 * BN) * sizeof(float);
     static thread_local size_t configured = 0;
     if (smem > configured) {
         SS_CUDA(cudaFuncSetAttribute(conv_tpose_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -372,8 +418,19 @@ static int launch_tpose(const TposeParams& p, const CUtensorMap& tmA, const floa
 }
 
 // returns 1 if the layer was handled here
+static bool tpose_eligible(const ss_conv3d_desc* d) {
+    if (!d->transposed || d->Cin % 32 != 0 || d->kd != 3 || d->kh != 3 || d->kw != 3) return false;
+    if (d->sd != 2 || d->sh != 2 || d->sw != 2 || d->pd != 1 || d->ph != 1 || d->pw != 1) return false;
+    if (d->math != SS_MATH_TF32 || (d->cout_packed != 32 && d->cout_packed != 64)) return false;
+    if (d->Dout > 2 * d->Din || d->Hout > 2 * d->Hin || d->Wout > 2 * d->Win) return false;
+    const int nTH = (d->Hin + TP_TH - 1) / TP_TH, nTW = (d->Win + TP_TW - 1) / TP_TW;
+    return (double)d->Hin * d->Win / ((double)nTH * TP_TH * nTW * TP_TW) >= 0.6;
+}
+
+int conv_tpose_join_supported(const ss_conv3d_desc* d) { return tpose_eligible(d) ? 1 : 0; }
+
 int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
-                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
+                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join) {
     if (!d->transposed || d->Cin % 32 != 0 || d->kd != 3 || d->kh != 3 || d->kw != 3) return 0;
     if (d->sd != 2 || d->sh != 2 || d->sw != 2 || d->pd != 1 || d->ph != 1 || d->pw != 1) return 0;
     if (d->math != SS_MATH_TF32 || (d->cout_packed != 32 && d->cout_packed != 64)) return 0;
@@ -394,6 +451,10 @@ int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scal
     p.Cout = d->Cout; p.CoutP = d->cout_packed; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
     p.nTH = nTH; p.nTW = nTW;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
+    p.has_join = join ? 1 : 0;
+    p.o_scale = join ? join->out_scale : nullptr; p.o_shift = join ? join->out_shift : nullptr;
+    p.res = join ? join->res : nullptr; p.r_scale = join ? join->res_scale : nullptr; p.r_shift = join ? join->res_shift : nullptr;
+    p.res_ldc = join ? join->res_ldc : 0; p.res_act = join ? join->res_act : 0;
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
     alignas(64) CUtensorMap tmA;
     cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.Din, (cuuint64_t)p.B};

@@ -27,6 +27,7 @@ from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH
 
 _DEFAULT_MATH = SS_MATH_TF32
 _USE_TCGEN05 = os.environ.get("STEREOSCENE_B200_NO_TCGEN05", "0") != "1"
+_FUSE_JOIN = os.environ.get("STEREOSCENE_B200_NO_FUSED_JOIN", "0") != "1"      # A/B switch for ops.conv_join
 
 
 def use_tcgen05(flag: bool):
@@ -236,6 +237,25 @@ def packed(module: torch.nn.Module) -> PackedConv:
     return pc
 
 
+def _halo_or_march_layer(pc: "PackedConv", Din: int, Hin: int, Win: int, Cin: int) -> bool:
+    """Mirror of the dispatch in ss_conv3d_tc_fwd (conv3d_halo.cu:try_conv_halo, conv3d_march.cu:try_conv_march32): does
+    this stride-1 3x3(x3) layer run on a kernel that applies a pending affine once per landed plane?  (Only used to
+    decide whether materialising a small pending input pays; a mismatch costs time, never correctness.)"""
+    if pc.transposed or pc.s != (1, 1, 1) or pc.d != (1, 1, 1) or pc.k[1:] != (3, 3) or pc.p[1:] != (1, 1):
+        return False
+    if not ((pc.k[0] == 3 and pc.p[0] == 1) or (pc.k[0] == 1 and pc.p[0] == 0)):
+        return False
+    if Cin == 32 and pc.CoutP == 32 and pc.k[0] == 3:
+        return Win >= 8 and Hin >= 8 and Din >= 3
+    if pc.CoutP < 64:
+        return False
+    tiles = lambda h, w: ((h + 31) // 32) * ((w + 7) // 8)        # noqa: E731
+    return Hin * Win / (256.0 * min(tiles(Hin, Win), tiles(Win, Hin))) >= 0.7
+
+
+_MATERIALIZE_BYTES = 16 << 20
+
+
 def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, out_act: int = SS_ACT_NONE,
          want_stats: bool = False, math_mode: Optional[int] = None, use_bias: bool = True):
     """y = act_out(conv(act_in(x*scale+shift)) + bias); returns (y [B,D',H',W',Cout], stats or None).
@@ -264,6 +284,15 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     # single-output-channel layers ride the tensor-core kernel too (N padded to 32): it is faster than the FMA kernel
     tc = (_USE_TCGEN05 and mm == SS_MATH_TF32 and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
           and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
+    if (tc and not x.is_plain and math.prod(pc.k) >= 27 and Cin >= 256 and xin.numel() * 4 <= _MATERIALIZE_BYTES
+            and not _halo_or_march_layer(pc, Din, Hin, Win, Cin)):
+        # the per-tap box kernel re-applies a pending affine for every tap (27 x the work of the plane kernels): for a
+        # small volume one elementwise pass first is cheaper (512-channel 32x32x4 layers: 0.18 -> 0.11 ms + 0.005)
+        x = Vol(x.plain())
+        xin = x.data
+        in_ldc = _vol_ldc(xin, "conv input")
+        d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
+                          1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
     if tc:
         rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights_kmajor().data_ptr(),
                                   _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
@@ -273,6 +302,47 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
                                _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
         cabi.check(rc, "ss_conv3d_fwd")
     return out, stats
+
+
+def conv_join(x: Vol, module: torch.nn.Module, out_affine: Optional[Vol], res: Optional[Vol], out_act: int = SS_ACT_NONE,
+              use_bias: bool = True) -> torch.Tensor:
+    """out_act( A_out(conv(x)) + A_res(res) ) as ONE kernel where the layer qualifies (stride-2 transposed k3 convs: the
+    hourglass up-convolutions), else conv followed by the join kernel.  ``out_affine`` carries only scale / shift / act of
+    the convolution result (e.g. ``bn_pending(None-like)``): its ``data`` is ignored.  Returns the plain joined tensor."""
+    lib = cabi.load()
+    pc = packed(module)
+    xin = x.data
+    B, Din, Hin, Win, Cin = xin.shape
+    Do, Ho, Wo = pc.out_size((Din, Hin, Win))
+    mm = _DEFAULT_MATH
+    fused_ok = (_USE_TCGEN05 and _FUSE_JOIN and mm == SS_MATH_TF32 and Cin % 32 == 0 and xin.data_ptr() % 16 == 0 and
+                (out_affine is None or out_affine.act == SS_ACT_NONE))
+    if fused_ok:
+        in_ldc = _vol_ldc(xin, "conv_join input")
+        out = torch.empty((B, Do, Ho, Wo, pc.Cout), dtype=torch.float32, device=xin.device)
+        d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d, 1 if pc.transposed else 0,
+                          in_ldc, pc.Cout, x.act, out_act, mm, pc.CoutP)
+        fused_ok = in_ldc % 4 == 0 and bool(lib.ss_conv3d_tc_join_supported(C.byref(d)))
+    if not fused_ok:
+        y, _ = conv(x, module, use_bias=use_bias)
+        yv = Vol(y) if out_affine is None else Vol(y, out_affine.scale, out_affine.shift, out_affine.act)
+        return join(yv, res, out_act=out_act)
+    if res is not None and tuple(res.data.shape) != tuple(out.shape):
+        raise RuntimeError(f"conv_join: residual has shape {tuple(res.data.shape)}, expected {tuple(out.shape)}")
+    for v in (out_affine, res):
+        if v is not None and v.scale is not None and (tuple(v.scale.shape) != (B, pc.Cout) or not v.scale.is_contiguous()
+                                                      or not v.shift.is_contiguous()):
+            raise RuntimeError("conv_join: affines must be contiguous [B,Cout]")
+    j = cabi.ConvJoin(_ptr(out_affine.scale) if out_affine is not None else None,
+                      _ptr(out_affine.shift) if out_affine is not None else None,
+                      _ptr(res.data) if res is not None else None, _ptr(res.scale) if res is not None else None,
+                      _ptr(res.shift) if res is not None else None,
+                      _vol_ldc(res.data, "conv_join residual") if res is not None else 0, res.act if res is not None else 0)
+    bias = module.bias if (use_bias and module.bias is not None) else None
+    rc = lib.ss_conv3d_tc_join_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights_kmajor().data_ptr(),
+                                   _ptr(bias.detach() if bias is not None else None), C.byref(j), out.data_ptr(), _stream())
+    cabi.check(rc, "ss_conv3d_tc_join_fwd")
+    return out
 
 
 def voxels_per_channel(t: torch.Tensor) -> int:

@@ -81,17 +81,16 @@ def conv_gn(x: Vol, seq: nn.Sequential, act: int, out=None, scale_out=None, shif
 
 
 def hourglass(hg: HourglassParams, x: Vol) -> torch.Tensor:
-    """ViewTransformerLSSVoxel.py:89-96.  11 convolutions, 2 joins, no normalisation pass."""
+    """ViewTransformerLSSVoxel.py:89-96.  11 convolutions, no normalisation pass; the two residual joins run in the
+    epilogues of the up-convolutions where the layer shapes qualify (ops.conv_join), else as join kernels."""
     c1 = conv_gn(x, hg.conv1[0], SS_ACT_RELU)
     c2 = conv_gn(c1, hg.conv2[0], SS_ACT_RELU)
     c3 = conv_gn(c2, hg.conv3[0], SS_ACT_RELU)
     c4 = conv_gn(c3, hg.conv4[0], SS_ACT_RELU)
-    u5, _ = ops.conv(c4, hg.conv5[0])
     r2 = conv_gn(c2, hg.redir2, SS_ACT_NONE)
-    c5 = ops.join(ops.bn_pending(u5, hg.conv5[1]), r2, out_act=SS_ACT_RELU)
-    u6, _ = ops.conv(Vol(c5), hg.conv6[0])
+    c5 = ops.conv_join(c4, hg.conv5[0], ops.bn_pending(c4.data, hg.conv5[1]), r2, out_act=SS_ACT_RELU)
     r1 = conv_gn(x, hg.redir1, SS_ACT_NONE)
-    return ops.join(ops.bn_pending(u6, hg.conv6[1]), r1, out_act=SS_ACT_RELU)
+    return ops.conv_join(Vol(c5), hg.conv6[0], ops.bn_pending(c5, hg.conv6[1]), r1, out_act=SS_ACT_RELU)
 
 
 def as_channels_last(x: torch.Tensor) -> torch.Tensor:

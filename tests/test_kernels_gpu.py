@@ -247,6 +247,41 @@ def test_conv_pending_affine_relu_and_gn_chain(ops, mode):
     assert float(wide[..., :8].min()) == 7.0 and float(wide[..., 40:].max()) == 7.0      # neighbours untouched
 
 
+@pytest.mark.parametrize("chans", [(64, 32), (128, 64)])
+def test_conv_join_fused_in_transposed_epilogue(ops, chans):
+    """Hourglass up-convolution + eval-BatchNorm + residual (with its own pending GroupNorm affine) + ReLU as ONE
+    kernel (ss_conv3d_tc_join_fwd) against the PyTorch composition, and against the unfused conv + join path."""
+    from stereoscene_b200 import cabi
+    cin, cout = chans
+    torch.manual_seed(51)
+    m = nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1, stride=2, bias=False)
+    bn = nn.BatchNorm3d(cout).eval()
+    nn.init.uniform_(bn.weight, 0.5, 1.5); nn.init.normal_(bn.bias, 0, 0.2)
+    bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(2, cin, 3, 16, 15)
+    sc, sh = torch.rand(2, cin) + 0.5, torch.randn(2, cin) * 0.3
+    r = torch.randn(2, cout, 6, 32, 30)
+    rs, rh = torch.rand(2, cout) + 0.5, torch.randn(2, cout) * 0.3
+    xin = F.relu(x * sc[:, :, None, None, None] + sh[:, :, None, None, None])
+    want = F.relu(bn(m(xin)) + (r * rs[:, :, None, None, None] + rh[:, :, None, None, None])).detach()
+    mg = nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1, stride=2, bias=False).cuda()
+    mg.load_state_dict(m.state_dict())
+    xv = ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU)
+    rv = ops.Vol(_cl(r), rs.cuda(), rh.cuda(), ops.SS_ACT_NONE)
+    d = cabi.ConvDesc(2, 3, 16, 15, cin, 6, 32, 30, cout, 3, 3, 3, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, cin, cout, 1, 1, 0, max(32, cout))
+    assert cabi.load().ss_conv3d_tc_join_supported(d) == 1                      # this shape takes the fused kernel
+    got = ops.conv_join(xv, mg, ops.bn_pending(_cl(x), bn.cuda()), rv, out_act=ops.SS_ACT_RELU)
+    assert rel_err(_ncdhw(got), want) < TOL["tf32"]
+    y, _ = ops.conv(xv, mg)
+    unfused = ops.join(ops.bn_pending(y, bn), rv, out_act=ops.SS_ACT_RELU)
+    assert rel_err(got, unfused) < 1e-5
+    # a layer the fused kernel does not take falls back to conv + join
+    m2 = nn.ConvTranspose3d(64, 32, 2, 2, bias=False).cuda()
+    x2 = torch.randn(1, 64, 2, 4, 4)
+    got2 = ops.conv_join(ops.Vol(_cl(x2)), m2, None, None, out_act=ops.SS_ACT_RELU)
+    assert rel_err(_ncdhw(got2), F.relu(m2.cpu()(x2)).detach()) < TOL["tf32"]
+
+
 def test_bn_pending_join_and_alpha(ops):
     torch.manual_seed(6)
     bn = nn.BatchNorm3d(16).eval()

@@ -22,7 +22,7 @@ from stereoscene_b200.ops import Vol  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat", "redir1x1", "depth_conv", "aspp_dil", "mie_redir1", "frustum_conv_pending"])
+    ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat", "redir1x1", "depth_conv", "aspp_dil", "mie_redir1", "frustum_conv_pending", "stage2_conv", "tpose32", "hg_conv1", "neck_k4", "hg_redir2", "stage2_conv_plain", "hg_conv4", "hg_conv4_plain", "hg_conv3", "hg_conv3_plain", "hourglass"])
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--math", default="tf32")
     ap.add_argument("--reps", type=int, default=1)
@@ -65,6 +65,48 @@ def main():
         c = vt.stereo_volume_net.dres0[0][0]
         x = torch.randn((1, D, H, W, 32), device=dev)
         sc, sh = torch.rand((1, 32), device=dev) + 0.5, torch.randn((1, 32), device=dev) * 0.1
+        fn = lambda: ops.conv(Vol(x, sc, sh, ops.SS_ACT_RELU), c, want_stats=True)     # noqa: E731
+    elif a.what == "stage2_conv":
+        c = model.img_bev_encoder_backbone.layers[2][1].conv1
+        x = torch.randn((1, nx[0] // 4, nx[1] // 4, nx[2] // 4, 512), device=dev)
+        sc, sh = torch.rand((1, 512), device=dev) + 0.5, torch.randn((1, 512), device=dev) * 0.1
+        fn = lambda: ops.conv(Vol(x, sc, sh, ops.SS_ACT_RELU), c, want_stats=True)     # noqa: E731
+    elif a.what == "stage2_conv_plain":
+        c = model.img_bev_encoder_backbone.layers[2][1].conv1
+        x = torch.randn((1, nx[0] // 4, nx[1] // 4, nx[2] // 4, 512), device=dev)
+        fn = lambda: ops.conv(Vol(x), c, want_stats=True)     # noqa: E731
+    elif a.what in ("hg_conv4", "hg_conv4_plain"):
+        c = vt.stereo_volume_net.dres2.conv4[0][0]
+        x = torch.randn((1, D // 4, H // 4, W // 4, 128), device=dev)
+        sc, sh = torch.rand((1, 128), device=dev) + 0.5, torch.randn((1, 128), device=dev) * 0.1
+        v = Vol(x) if a.what.endswith("plain") else Vol(x, sc, sh, ops.SS_ACT_RELU)
+        fn = lambda: ops.conv(v, c, want_stats=True)     # noqa: E731
+    elif a.what in ("hg_conv3", "hg_conv3_plain"):
+        c = vt.stereo_volume_net.dres2.conv3[0][0]
+        x = torch.randn((1, D // 2, H // 2, W // 2, 64), device=dev)
+        sc, sh = torch.rand((1, 64), device=dev) + 0.5, torch.randn((1, 64), device=dev) * 0.1
+        v = Vol(x) if a.what.endswith("plain") else Vol(x, sc, sh, ops.SS_ACT_RELU)
+        fn = lambda: ops.conv(v, c, want_stats=True)     # noqa: E731
+    elif a.what == "hourglass":
+        from stereoscene_b200.plugin.layers import hourglass
+        x = torch.randn((1, D, H, W, 32), device=dev)
+        fn = lambda: hourglass(vt.stereo_volume_net.dres2, Vol(x))     # noqa: E731
+    elif a.what == "neck_k4":
+        c = model.img_bev_encoder_neck.deblocks[2][0]
+        x = torch.randn((1, nx[0] // 4, nx[1] // 4, nx[2] // 4, 512), device=dev)
+        fn = lambda: ops.conv(Vol(x), c, want_stats=True)     # noqa: E731
+    elif a.what == "tpose32":
+        c = vt.stereo_volume_net.dres2.conv6[0]
+        x = torch.randn((1, D // 2, H // 2, W // 2, 64), device=dev)
+        fn = lambda: ops.conv(Vol(x), c)     # noqa: E731
+    elif a.what == "hg_conv1":
+        c = vt.stereo_volume_net.dres2.conv1[0][0]
+        x = torch.randn((1, D, H, W, 32), device=dev)
+        fn = lambda: ops.conv(Vol(x), c, want_stats=True)     # noqa: E731
+    elif a.what == "hg_redir2":
+        c = vt.stereo_volume_net.dres2.redir2[0]
+        x = torch.randn((1, D // 2, H // 2, W // 2, 64), device=dev)
+        sc, sh = torch.rand((1, 64), device=dev) + 0.5, torch.randn((1, 64), device=dev) * 0.1
         fn = lambda: ops.conv(Vol(x, sc, sh, ops.SS_ACT_RELU), c, want_stats=True)     # noqa: E731
     elif a.what == "redir1x1":
         c = vt.stereo_volume_net.dres2.redir1[0]
