@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the forward in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
+    ap.add_argument("--pairs-per-step", type=int, default=1, help="stereo pairs per GPU per step (batch of one forward)")
     return ap.parse_args()
 
 
@@ -200,7 +201,7 @@ def run_ours(args):
     model, mc = presets.build(args.workload)
     synth.randomize_weights_(model, seed)
     model = model.to(dev).eval()
-    B = 1                                                   # stereo pairs per rank per step (weak scaling)
+    B = max(1, args.pairs_per_step)                         # stereo pairs per rank per step (weak scaling)
     xl_h, xr_h = synth.stereo_features(B, mc["input_size"], 8, seed=seed + rank, pin=True)
     left, right, calib = synth.kitti_calibration(B, mc["input_size"], device=dev)
     xl_d, xr_d = xl_h.to(dev), xr_h.to(dev)
