@@ -169,7 +169,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
 bri_attn_tc_kernel(const BriTcParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKVmn,
                    const __grid_constant__ CUtensorMap tmKV) {
     extern __shared__ unsigned char bt_smem[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(bt_smem) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET from the extern __shared__ array: pointers derived this way keep the shared state space
+    // (ld/st.shared); rounding a uintptr_t instead turns every access through them into a generic load / store
+    unsigned char* base = bt_smem + ((1024u - ((uint32_t)__cvta_generic_to_shared(bt_smem) & 1023u)) & 1023u);
     const int DP = p.DP;
     const uint32_t BOXB = (uint32_t)DP * 128u;                   // one [DP depth rows][32 tokens] box
     unsigned char* Qs = base;                                    // 4 boxes: 128 queries

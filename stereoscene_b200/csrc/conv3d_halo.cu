@@ -114,7 +114,9 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
     using Cfg = HaloCfg<BN>;
     constexpr int SB = Cfg::SB;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET from the extern __shared__ array: pointers derived this way keep the shared state space
+    // (ld/st.shared); rounding a uintptr_t instead turns every access through them into a generic load / store
+    unsigned char* base = smem_dyn + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     unsigned char* planes = base;                                            // HL_NPL plane slots
     unsigned char* bring = base + HL_NPL * HL_PLANE_BYTES;                   // SB weight tiles
     unsigned char* aux = bring + SB * Cfg::B_BYTES;

@@ -296,7 +296,9 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     constexpr int MR_HW = Cfg::HW, MR_PLANE_ROWS = Cfg::PLANE_ROWS, MR_PLANE_BYTES = Cfg::PLANE_BYTES, MR_W_BYTES = Cfg::W_BYTES;
     constexpr int PAD = Cfg::PAD;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET from the extern __shared__ array: pointers derived this way keep the shared state space
+    // (ld/st.shared); rounding a uintptr_t instead turns every access through them into a generic load / store
+    unsigned char* base = smem_dyn + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     unsigned char* wres = base;                                   // resident weights
     unsigned char* planes = base + MR_W_BYTES;                    // MR_NP plane slots (MR_W_BYTES is a multiple of 1024)
     unsigned char* aux = planes + MR_NP * MR_PLANE_BYTES;

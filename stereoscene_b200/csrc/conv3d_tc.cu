@@ -188,7 +188,9 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned stage ring (SWIZZLE_128B atoms are 1024 B)
-    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET from the extern __shared__ array: pointers derived this way keep the shared state space
+    // (ld/st.shared); rounding a uintptr_t instead turns every access through them into a generic load / store
+    unsigned char* ring = smem_dyn + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     unsigned char* aux = ring + STAGES * Cfg::STAGE_BYTES;
     int4* taps = reinterpret_cast<int4*>(aux);                             // [TC_MAX_TAPS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(taps + TC_MAX_TAPS) + 2 * BN);   // full[S], ready[S], empty[S], accum
@@ -532,6 +534,8 @@ int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_sc
 int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                    const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join);
 int conv_tpose_join_supported(const ss_conv3d_desc* d);
+int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
+                const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
 int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
 }
@@ -568,6 +572,8 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     {   // 32-channel 3x3x3 stride-1 layers: persistent marching kernel (halo planes + resident weights)
         int rcm = 0;
         if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
+        // pointwise layers with short K: persistent streaming GEMM with resident weights
+        if (try_conv_pw(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
         // wide 3x3x3 stride-1 layers: halo-resident kernel (planes loaded once per chunk, two M tiles per weight tile)
         if (try_conv_halo(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
         // stride-2 transposed 3x3x3 layers: one CTA per input tile computes all 8 output parity classes

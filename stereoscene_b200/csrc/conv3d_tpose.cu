@@ -127,7 +127,9 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
     constexpr int TP_SB = TP_SB_BYTES / B_BYTES;
     constexpr int TMEM_COLS = 8 * BN <= 256 ? 256 : 512;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET from the extern __shared__ array: pointers derived this way keep the shared state space
+    // (ld/st.shared); rounding a uintptr_t instead turns every access through them into a generic load / store
+    unsigned char* base = smem_dyn + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     unsigned char* planes = base;
     unsigned char* bring = base + TP_NPL * TP_PLANE_BYTES;
     unsigned char* aux = bring + TP_SB * B_BYTES;

@@ -1,0 +1,365 @@
+// Pointwise (1x1x1, stride 1) convolution as a persistent streaming GEMM on tcgen05: the layers whose K is one
+// or a few 32-channel chunks and whose cost is reading the input once and writing the output once --
+// hourglass redir2 (64 -> 64, ViewTransformerLSSVoxel.py:88), the encoder's input_proj (128 -> 128,
+// resnet3d.py:143-148), the neck's k = s = 1 "deconv" (128 -> 128, second_fpn_3d.py:53-59), the occupancy
+// head's classifier (192 -> 20, occhead.py:106).  The per-tap box kernel runs them as thousands of CTAs with
+// 2-6 K steps each, i.e. it measures CTA set-up, not memory.
+//
+// Design (one CTA per SM, like the marching kernel): the whole weight matrix [CoutP x Cin] stays RESIDENT in
+// shared memory (K-major SWIZZLE_128B, one TMA box per 32-channel chunk); the CTA walks a contiguous range of
+// 128-voxel row tiles of the flat [V x Cin] input (2-D TMA boxes {32 ch, 128 rows} into a ring of whole tiles),
+// issues Cin/8 MMAs (N = CoutP rounded to 32) per tile into a 4-slot TMEM ring, and the epilogue of tile t
+// (tcgen05.ld, bias, activation, stores, GroupNorm sums) overlaps the loads and MMAs of the following tiles.
+// Pending affine / ReLU of the producer: 4 fix-up warps rewrite each landed tile in place (TF32-rounded).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ss {
+
+constexpr int PW_ACC = 4;                            // TMEM accumulator ring
+constexpr int PW_THREADS = 8 * 32 + 64;              // 4 epilogue warps, 4 fix-up / epilogue warps, producer, MMA
+constexpr int PW_TILE = 128;                         // voxel rows per tile (UMMA M)
+
+struct PwParams {
+    long long V;                                     // B * D * H * W voxels
+    long long total_tiles;
+    int vox_per_batch;                               // D*H*W (a multiple of 128 when stats are requested)
+    int Cin, KC, Cout, NP, out_ldc, in_act, out_act, slots, scratch_floats;
+    const float* in_scale;
+    const float* in_shift;
+    const float* bias;
+    float* y;
+    double* stats;
+};
+
+__device__ __forceinline__ uint32_t pw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pw_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void pw_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void pw_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "PWWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PWWAIT_DONE;\n\t"
+        "bra PWWAIT_LOOP;\n\t"
+        "PWWAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void pw_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(PW_THREADS, 1)
+conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
+    extern __shared__ unsigned char pw_smem[];
+    // 1024-byte alignment as an OFFSET from the extern __shared__ array: pointers derived this way keep the shared state space
+    // (ld/st.shared); rounding a uintptr_t instead turns every access through them into a generic load / store
+    unsigned char* base = pw_smem + ((1024u - ((uint32_t)__cvta_generic_to_shared(pw_smem) & 1023u)) & 1023u);
+    const int KC = p.KC, NP = p.NP, S = p.slots;
+    const uint32_t W_BYTES = (uint32_t)KC * NP * 128, TILE_BYTES = (uint32_t)KC * PW_TILE * 128;
+    unsigned char* wres = base;                                   // KC chunks of [NP rows][128 B]
+    unsigned char* ring = base + W_BYTES;                         // S tiles of KC chunks of [128 rows][128 B]
+    unsigned char* aux = ring + (size_t)S * TILE_BYTES;
+    float* scratch = reinterpret_cast<float*>(aux);               // 8 warps x 32 x 32 floats, XOR-swizzled (GroupNorm column sums); 0 without stats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + p.scratch_floats);
+    // barriers: w_full, a_full[S], a_ready[S], a_empty[S], t_full[ACC], t_empty[ACC]   (S <= 4)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * 4 + 2 * PW_ACC);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = uniform_warp_index();
+    const uint32_t w_full = pw_smem_u32(bars), a_full0 = pw_smem_u32(bars + 1), a_ready0 = pw_smem_u32(bars + 5),
+                   a_empty0 = pw_smem_u32(bars + 9), t_full0 = pw_smem_u32(bars + 13), t_empty0 = pw_smem_u32(bars + 13 + PW_ACC);
+    const bool has_aff = (p.in_scale != nullptr);
+    const bool in_relu = (p.in_act == SS_ACT_RELU);
+    const bool fixup = has_aff || in_relu;
+    const int G = NP / 32;                                        // 32-column groups of the accumulator
+    const int wgroups = fixup ? 1 : (G >= 2 ? 2 : 1);             // epilogue warp groups (of 4 warps) that drain TMEM
+    const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
+    const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+
+    if (tid == 0) {
+        pw_mbar_init(w_full, 1);
+        for (int s = 0; s < 4; ++s) {
+            pw_mbar_init(a_full0 + 8 * s, 1);
+            pw_mbar_init(a_ready0 + 8 * s, 128);
+            pw_mbar_init(a_empty0 + 8 * s, 1);
+        }
+        for (int a = 0; a < PW_ACC; ++a) {
+            pw_mbar_init(t_full0 + 8 * a, 1);
+            pw_mbar_init(t_empty0 + 8 * a, 128 * wgroups);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(pw_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t ring_u32 = pw_smem_u32(ring), wres_u32 = pw_smem_u32(wres);
+
+    if (warp == 8) {
+        // ======================= TMA PRODUCER ======================================================
+        if (t_begin < t_end) {
+            mbar_expect_tx_elect(w_full, W_BYTES);
+            for (int kc = 0; kc < KC; ++kc) tma_2d_elect(wres_u32 + (uint32_t)kc * NP * 128, &tmW, w_full, kc * 32, 0);
+            uint32_t L = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++L) {
+                const uint32_t slot = L % (uint32_t)S;
+                pw_mbar_wait(a_empty0 + 8 * slot, ((L / (uint32_t)S) & 1u) ^ 1u);
+                const uint32_t bar = a_full0 + 8 * slot;
+                mbar_expect_tx_elect(bar, TILE_BYTES);
+                const int row0 = (int)(t * PW_TILE);
+                for (int kc = 0; kc < KC; ++kc)
+                    tma_2d_elect(ring_u32 + slot * TILE_BYTES + (uint32_t)kc * PW_TILE * 128, &tmA, bar, kc * 32, row0);
+                __syncwarp();
+            }
+        }
+    } else if (warp == 9) {
+        // ======================= MMA ISSUER (warp-uniform, elected issue) ==========================
+        if (t_begin < t_end) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t D_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+            pw_mbar_wait(w_full, 0);
+            const uint32_t rdy0 = fixup ? a_ready0 : a_full0;
+            uint32_t L = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++L) {
+                const uint32_t slot = L % (uint32_t)S, acc = L % PW_ACC;
+                pw_mbar_wait(rdy0 + 8 * slot, (L / (uint32_t)S) & 1u);
+                pw_mbar_wait(t_empty0 + 8 * acc, ((L / PW_ACC) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = umma_desc_lo(ring_u32 + slot * TILE_BYTES), b0 = umma_desc_lo(wres_u32);
+                const uint32_t dcol = tmem_base + acc * (uint32_t)NP;
+                for (int kc = 0; kc < KC; ++kc) {
+                    const uint32_t ak = a0 + (uint32_t)kc * (PW_TILE * 128 / 16), bk = b0 + (uint32_t)kc * ((uint32_t)NP * 128 / 16);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ss_tf32<D_HI, D_HI>(dcol, ak + 2 * k, bk + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                }
+                umma_commit_elect(t_full0 + 8 * acc);
+                umma_commit_elect(a_empty0 + 8 * slot);
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && fixup) {
+        // ======================= FIX-UP WARPS (4..7): pending affine / ReLU, once per landed tile, in place ===
+        if (t_begin < t_end) {
+            const int ft = tid - 128;                      // 0..127
+            const int chunk = ft & 7;                      // 16-byte chunk (4 channels) of a 128-byte row
+            uint32_t L = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++L) {
+                const uint32_t slot = L % (uint32_t)S;
+                pw_mbar_wait(a_full0 + 8 * slot, (L / (uint32_t)S) & 1u);
+                const long long row0 = t * PW_TILE;
+                unsigned char* tile = ring + (size_t)slot * TILE_BYTES;
+                for (int kc = 0; kc < KC; ++kc) {
+                    unsigned char* ch = tile + (size_t)kc * PW_TILE * 128;
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_aff) {                                              // a tile never straddles two samples
+                        const size_t bo = (size_t)(row0 / p.vox_per_batch) * p.Cin + kc * 32 + chunk * 4;
+                        sc = ldg_f4(p.in_scale + bo);
+                        sh = ldg_f4(p.in_shift + bo);
+                    }
+                    for (int r = ft >> 3; r < PW_TILE; r += 16) {
+                        const long long v = row0 + r;
+                        if (v < p.V) {                                          // rows past the end stay zero
+                            float4* ptr = reinterpret_cast<float4*>(ch + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            float4 x = *ptr;
+                            if (has_aff) {
+                                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+                            }
+                            if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                            uint4 o;
+                            o.x = f2tf32(x.x); o.y = f2tf32(x.y); o.z = f2tf32(x.z); o.w = f2tf32(x.w);
+                            *reinterpret_cast<uint4*>(ptr) = o;
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                pw_mbar_arrive(a_ready0 + 8 * slot);
+            }
+        }
+    }
+    if (warp < 8 && !(warp >= 4 && fixup) && (warp >> 2) < wgroups && t_begin < t_end) {
+        // ======================= EPILOGUE WARPS: lane quarter q, column groups wg, wg + wgroups, ... ============
+        const int q = warp & 3, wg = warp >> 2;
+        const int row = q * 32 + lane;
+        const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        const bool want_stats = p.stats != nullptr;
+        const int act = p.out_act;
+        float* sc = scratch + warp * (32 * 32);
+        float run_s[4] = {0.f, 0.f, 0.f, 0.f}, run_q[4] = {0.f, 0.f, 0.f, 0.f};     // lane = column: running sums per owned group
+        int run_b = (int)((t_begin * PW_TILE) / p.vox_per_batch);
+        auto flush = [&]() {
+            if (want_stats) {
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    const int c = (wg + gi * wgroups) * 32 + lane;
+                    if (wg + gi * wgroups < G && c < p.Cout) {
+                        atomicAdd(p.stats + ((size_t)run_b * p.Cout + c) * 2 + 0, (double)run_s[gi]);
+                        atomicAdd(p.stats + ((size_t)run_b * p.Cout + c) * 2 + 1, (double)run_q[gi]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { run_s[i] = 0.f; run_q[i] = 0.f; }
+        };
+        uint32_t L = 0;
+        for (long long t = t_begin; t < t_end; ++t, ++L) {
+            const uint32_t acc = L % PW_ACC;
+            const long long v = t * PW_TILE + row;
+            const int tb = (int)((t * PW_TILE) / p.vox_per_batch);              // tiles never straddle samples when stats are on
+            if (tb != run_b) { flush(); run_b = tb; }
+            pw_mbar_wait(t_full0 + 8 * acc, (L / PW_ACC) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool valid = v < p.V;
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+                const int g = wg + gi * wgroups;
+                if (g >= G) break;
+                uint32_t r[32];
+                pw_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)NP + (uint32_t)(g * 32), r);
+                const int cbase = g * 32;
+                float x[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(r[k]);
+                if (p.bias) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cbase + k < p.Cout) x[k] += __ldg(p.bias + cbase + k);
+                }
+                if (act == SS_ACT_RELU) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) x[k] = fmaxf(x[k], 0.f);
+                } else if (act == SS_ACT_GELU) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) x[k] = gelu_erf(x[k]);
+                }
+                if (valid) {
+                    float* dst = p.y + (size_t)v * p.out_ldc + cbase;
+                    if (vec_ok && cbase + 32 <= p.Cout) {
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            if (cbase + k < p.Cout) dst[k] = x[k];
+                    }
+                }
+                if (want_stats) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) sc[lane * 32 + (k ^ lane)] = valid ? x[k] : 0.f;      // bank = k ^ lane: conflict-free
+                    __syncwarp();
+                    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};      // four independent chains
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const float e = sc[rr * 32 + (lane ^ rr)];
+                        cs[rr & 3] += e;
+                        cq[rr & 3] = fmaf(e, e, cq[rr & 3]);
+                    }
+                    __syncwarp();
+                    run_s[gi] += (cs[0] + cs[1]) + (cs[2] + cs[3]);
+                    run_q[gi] += (cq[0] + cq[1]) + (cq[2] + cq[3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            pw_mbar_arrive(t_empty0 + 8 * acc);                     // accumulator may be overwritten
+        }
+        flush();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+typedef CUresult (*PwEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// returns 1 if the layer was handled here
+int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
+                const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
+    if (d->kd != 1 || d->kh != 1 || d->kw != 1 || d->sd != 1 || d->sh != 1 || d->sw != 1) return 0;      // also ConvTranspose k = s = 1
+    if (d->pd != 0 || d->ph != 0 || d->pw != 0 || d->math != SS_MATH_TF32) return 0;
+    if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
+    if (d->Cin % 32 != 0 || d->Cin > 256 || d->cout_packed > 128) return 0;
+    const long long vpb = (long long)d->Din * d->Hin * d->Win, V = vpb * d->B;
+    if (vpb % PW_TILE != 0 || vpb > 0x7fffffffLL || V < 148LL * PW_TILE * 2) return 0;       // small volumes: the box kernel is fine
+    const bool pending = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
+    if (pending && d->Cin > 64) return 0;            // 4 fix-up warps cannot keep up with wide pending inputs: the box kernel's TMEM fix-up path wins
+    const int KC = d->Cin / 32, NP = (d->cout_packed + 31) / 32 * 32;
+    const size_t w_bytes = (size_t)KC * NP * 128, tile_bytes = (size_t)KC * PW_TILE * 128;
+    const int scratch_floats = stats ? 8 * 32 * 32 : 0;
+    const size_t fixed = 1024 + w_bytes + (size_t)scratch_floats * sizeof(float) + (1 + 12 + 2 * PW_ACC) * sizeof(uint64_t) + 64;
+    if (fixed + 2 * tile_bytes > 227 * 1024) return 0;
+    int slots = (int)((227 * 1024 - fixed) / tile_bytes);
+    if (slots > 4) slots = 4;
+    if (slots < 2) return 0;
+    static PwEncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) return 0;
+        encode = reinterpret_cast<PwEncodeTiledFn>(ptr);
+    }
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
+    alignas(64) CUtensorMap tmA, tmW;
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)d->Cin, (cuuint64_t)V};
+        cuuint64_t gstr[1] = {(cuuint64_t)d->in_ldc * 4};
+        cuuint32_t box[2] = {32, PW_TILE};
+        cuuint32_t estr[2] = {1, 1};
+        if (encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(x), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_pw: tensor map A"); return 1; }
+    }
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->cout_packed};
+        cuuint64_t gstr[1] = {(cuuint64_t)d->Cin * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)NP};
+        cuuint32_t estr[2] = {1, 1};
+        if (encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_kmajor), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_pw: tensor map W"); return 1; }
+    }
+    PwParams p;
+    p.V = V; p.total_tiles = (V + PW_TILE - 1) / PW_TILE; p.vox_per_batch = (int)vpb;
+    p.Cin = d->Cin; p.KC = KC; p.Cout = d->Cout; p.NP = NP; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
+    p.slots = slots; p.scratch_floats = scratch_floats;
+    p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
+    const size_t smem = fixed + (size_t)slots * tile_bytes;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { *rc = set_cuda_error(e, "conv_pw: smem attribute"); return 1; }
+        configured = smem;
+    }
+    const unsigned grid = (unsigned)(p.total_tiles < 148 ? p.total_tiles : 148);
+    conv_pw_kernel<<<grid, PW_THREADS, smem, st>>>(p, tmA, tmW);
+    *rc = check_launch("conv_pw_kernel");
+    return 1;
+}
+
+}  // namespace ss

@@ -220,6 +220,44 @@ def test_conv_halo_swapped_axes_and_160_column_tile(ops, dims):
     assert rel_err(y, ref) < TOL["tf32"]
 
 
+@pytest.mark.parametrize("case", ["hg_redir2", "head_classifier", "neck_k1_slice", "input_proj"])
+def test_pointwise_streaming_kernel(ops, case):
+    """1x1x1 layers with short K on the persistent resident-weight kernel (conv_pw.cu): pending GroupNorm + ReLU
+    input, bias, odd Cout (20), ConvTranspose3d k = s = 1 into a channel slice of a wider buffer, GroupNorm sums,
+    batch 2 (sums per sample).  Volumes are large enough (>= 2 tiles per SM) to take that kernel."""
+    torch.manual_seed(61)
+    if case == "hg_redir2":
+        m, shape, pending, stats = nn.Conv3d(64, 64, 1, bias=False), (1, 64, 40, 32, 32), True, True
+    elif case == "head_classifier":
+        m, shape, pending, stats = nn.Conv3d(192, 20, 1, bias=True), (2, 192, 20, 32, 32), True, False
+    elif case == "neck_k1_slice":
+        m, shape, pending, stats = nn.ConvTranspose3d(128, 128, 1, 1, bias=False), (2, 128, 24, 32, 32), False, True
+    else:
+        m, shape, pending, stats = nn.Conv3d(128, 128, 1, bias=False), (1, 128, 40, 32, 32), False, True
+    B, Cin = shape[0], shape[1]
+    x = torch.randn(shape)
+    sc, sh = torch.rand(B, Cin) + 0.5, torch.randn(B, Cin) * 0.3
+    xin = F.relu(x * sc[:, :, None, None, None] + sh[:, :, None, None, None]) if pending else x
+    want = m(xin).detach()
+    mg = type(m)(m.in_channels, m.out_channels, 1, 1, bias=m.bias is not None).cuda()
+    mg.load_state_dict(m.state_dict())
+    v = ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU) if pending else ops.Vol(_cl(x))
+    ops.arena(torch.device("cuda", 0)).reset()
+    out = None
+    if case == "neck_k1_slice":
+        wide = torch.full(shape[:1] + shape[2:] + (384,), 7.0, device="cuda")
+        out = wide[..., 128:256]
+    y, st = ops.conv(v, mg, out=out, want_stats=stats)
+    assert rel_err(_ncdhw(y), want) < TOL["tf32"]
+    if stats:
+        wd = want.double()
+        assert rel_err(st[..., 0], wd.sum(dim=(2, 3, 4))) < 1e-3 and rel_err(st[..., 1], (wd * wd).sum(dim=(2, 3, 4))) < 1e-3
+    if out is not None:
+        assert float(wide[..., :128].min()) == 7.0 and float(wide[..., 256:].max()) == 7.0
+    ref, _ = ops.conv(v, mg, math_mode=ops.SS_MATH_3XTF32)
+    assert rel_err(y, ref) < TOL["tf32"]
+
+
 @pytest.mark.parametrize("mode", ["precise", "tf32"])
 def test_conv_pending_affine_relu_and_gn_chain(ops, mode):
     """conv -> GroupNorm -> ReLU -> conv -> GroupNorm, with both norms applied as pending affines,

@@ -22,7 +22,7 @@ from stereoscene_b200.ops import Vol  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat", "redir1x1", "depth_conv", "aspp_dil", "mie_redir1", "frustum_conv_pending", "stage2_conv", "tpose32", "hg_conv1", "neck_k4", "hg_redir2", "stage2_conv_plain", "hg_conv4", "hg_conv4_plain", "hg_conv3", "hg_conv3_plain", "hourglass"])
+    ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat", "redir1x1", "depth_conv", "aspp_dil", "mie_redir1", "frustum_conv_pending", "stage2_conv", "tpose32", "hg_conv1", "neck_k4", "hg_redir2", "stage2_conv_plain", "hg_conv4", "hg_conv4_plain", "hg_conv3", "hg_conv3_plain", "hourglass", "pw_proj"])
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--math", default="tf32")
     ap.add_argument("--reps", type=int, default=1)
@@ -91,6 +91,10 @@ def main():
         from stereoscene_b200.plugin.layers import hourglass
         x = torch.randn((1, D, H, W, 32), device=dev)
         fn = lambda: hourglass(vt.stereo_volume_net.dres2, Vol(x))     # noqa: E731
+    elif a.what == "pw_proj":
+        c = model.img_bev_encoder_backbone.input_proj[0]
+        x = torch.randn((1, nx[0], nx[1], nx[2], 128), device=dev)
+        fn = lambda: ops.conv(Vol(x), c, want_stats=True)     # noqa: E731
     elif a.what == "neck_k4":
         c = model.img_bev_encoder_neck.deblocks[2][0]
         x = torch.randn((1, nx[0] // 4, nx[1] // 4, nx[2] // 4, 512), device=dev)
