@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-HEAD_CONV_DRAM_BYTES = 633585152   # ncu --set full of conv_halo_kernel<192> (profiles/r01s2_head_conv_ncu_full_raw.csv): 459.2 MB read + 174.4 MB written per launch
+HEAD_CONV_DRAM_BYTES = 638642176   # ncu --set full of conv_halo_kernel<192> (profiles/r01s2_head_conv_ncu_full_raw.csv): 461.8 MB read + 176.9 MB written per launch
 
 VOXELS = {"config1": 128 * 128 * 16, "config2": 256 * 256 * 32, "config0": 64 * 64 * 8, "tiny": 32 * 32 * 8,
           "config4": 512 * 512 * 64}
