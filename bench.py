@@ -378,16 +378,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def stage_breakdown(model, xl, xr, left, right, calib, occ, iters=5):
-    """Eager per-stage device times (CUDA events), reference stage names."""
+def stage_breakdown(model, xl, xr, left, right, calib, occ, iters=7):
+    """Eager per-stage device times (CUDA events, median over `iters` runs after one warm-up), reference stage names."""
     from stereoscene_b200 import ops
     vt = model.img_view_transformer
     keys = ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    acc = [0.0] * 4
+    samples = [[] for _ in range(4)]
     with torch.no_grad():
         for it in range(iters + 1):
             ml = vt.get_mlp_input(*[left[k] for k in keys]); mr = vt.get_mlp_input(*[right[k] for k in keys])
+            torch.cuda.synchronize()
             ev[0].record()
             bev, _ = vt([xl] + [left[k] for k in keys] + [ml] + [xr] + [right[k] for k in keys] + [mr] + [calib, None, None])
             ev[1].record()
@@ -401,9 +402,9 @@ def stage_breakdown(model, xl, xr, left, right, calib, occ, iters=5):
             torch.cuda.synchronize()
             if it:
                 for i in range(4):
-                    acc[i] += ev[i].elapsed_time(ev[i + 1])
+                    samples[i].append(ev[i].elapsed_time(ev[i + 1]))
     names = ("view_transformer", "bev_encoder", "bev_neck", "occ_head+upsample")
-    return {n: a / iters for n, a in zip(names, acc)}
+    return {n: statistics.median(a) for n, a in zip(names, samples)}
 
 
 def _time_launches(fn, iters=10, warm=3):

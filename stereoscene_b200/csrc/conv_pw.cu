@@ -1,16 +1,18 @@
-// Pointwise (1x1x1, stride 1) convolution as a persistent streaming GEMM on tcgen05: the layers whose K is one
-// or a few 32-channel chunks and whose cost is reading the input once and writing the output once --
+// Pointwise convolution as a persistent streaming GEMM on tcgen05: 1x1x1 stride-1 layers and "k = s" transposed
+// convolutions (every input voxel produces s^3 output voxels, one weight matrix per output parity class) --
+// the layers whose K is a few 32-channel chunks and whose cost is reading the input and writing the output once:
 // hourglass redir2 (64 -> 64, ViewTransformerLSSVoxel.py:88), the encoder's input_proj (128 -> 128,
-// resnet3d.py:143-148), the neck's k = s = 1 "deconv" (128 -> 128, second_fpn_3d.py:53-59), the occupancy
-// head's classifier (192 -> 20, occhead.py:106).  The per-tap box kernel runs them as thousands of CTAs with
-// 2-6 K steps each, i.e. it measures CTA set-up, not memory.
+// resnet3d.py:143-148), the neck's deblocks (ConvTranspose3d k = s = 1 / 2 / 4, second_fpn_3d.py:53-59).
+// The per-tap box kernel runs them as thousands of CTAs with 4-16 K steps each, i.e. it measures CTA set-up.
 //
-// Design (one CTA per SM, like the marching kernel): the whole weight matrix [CoutP x Cin] stays RESIDENT in
-// shared memory (K-major SWIZZLE_128B, one TMA box per 32-channel chunk); the CTA walks a contiguous range of
-// 128-voxel row tiles of the flat [V x Cin] input (2-D TMA boxes {32 ch, 128 rows} into a ring of whole tiles),
-// issues Cin/8 MMAs (N = CoutP rounded to 32) per tile into a 4-slot TMEM ring, and the epilogue of tile t
-// (tcgen05.ld, bias, activation, stores, GroupNorm sums) overlaps the loads and MMAs of the following tiles.
-// Pending affine / ReLU of the producer: 4 fix-up warps rewrite each landed tile in place (TF32-rounded).
+// Design (one CTA per SM): the weight matrix of the current (class, column half) GROUP stays RESIDENT in shared
+// memory (K-major SWIZZLE_128B, one TMA box per 32-channel chunk, re-loaded only when the CTA's contiguous range of
+// work items crosses into the next group); the CTA walks 128-voxel row tiles of the flat [V x Cin] input, whose
+// 32-channel chunks ({32 ch, 128 rows} 2-D TMA boxes, 16 KB) stream through a chunk-granular ring -- a slot is
+// released as soon as its 4 MMAs retire, so the ring always holds the next chunks whatever the tile size;
+// accumulators live in a 4-slot TMEM ring and the epilogue of item t (tcgen05.ld, bias, activation, scatter to the
+// class's output voxels, GroupNorm sums) overlaps the loads and MMAs of the following items.
+// Pending affine / ReLU of the producer: 4 fix-up warps rewrite each landed chunk in place (TF32-rounded).
 #include <cuda.h>
 #include "common.cuh"
 
@@ -19,12 +21,17 @@ namespace ss {
 constexpr int PW_ACC = 4;                            // TMEM accumulator ring
 constexpr int PW_THREADS = 8 * 32 + 64;              // 4 epilogue warps, 4 fix-up / epilogue warps, producer, MMA
 constexpr int PW_TILE = 128;                         // voxel rows per tile (UMMA M)
+constexpr int PW_MAXRS = 12;                         // chunk ring slots (16 KB each)
 
 struct PwParams {
-    long long V;                                     // B * D * H * W voxels
-    long long total_tiles;
-    int vox_per_batch;                               // D*H*W (a multiple of 128 when stats are requested)
-    int Cin, KC, Cout, NP, out_ldc, in_act, out_act, slots, scratch_floats;
+    long long V;                                     // B * D * H * W input voxels
+    long long T;                                     // row tiles = ceil(V / 128)
+    long long total_items;                           // groups * T
+    int vox_per_batch;                               // D*H*W (a multiple of 128)
+    int D, H, W;                                     // input grid (class scatter)
+    int s;                                           // 1, or the stride of a k = s transposed conv
+    int NH;                                          // column halves per class (1 or 2)
+    int Cin, KC, Cout, CoutP, NP, out_ldc, in_act, out_act, RS, scratch_floats;
     const float* in_scale;
     const float* in_shift;
     const float* bias;
@@ -68,36 +75,39 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
 conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
     extern __shared__ unsigned char pw_smem[];
     // 1024-byte alignment as an OFFSET from the extern __shared__ array: pointers derived this way keep the shared state space
-    // (ld/st.shared); rounding a uintptr_t instead turns every access through them into a generic load / store
     unsigned char* base = pw_smem + ((1024u - ((uint32_t)__cvta_generic_to_shared(pw_smem) & 1023u)) & 1023u);
-    const int KC = p.KC, NP = p.NP, S = p.slots;
-    const uint32_t W_BYTES = (uint32_t)KC * NP * 128, TILE_BYTES = (uint32_t)KC * PW_TILE * 128;
+    const int KC = p.KC, NP = p.NP, RS = p.RS;
+    const uint32_t W_BYTES = (uint32_t)KC * NP * 128;
+    constexpr uint32_t CH_BYTES = PW_TILE * 128;
     unsigned char* wres = base;                                   // KC chunks of [NP rows][128 B]
-    unsigned char* ring = base + W_BYTES;                         // S tiles of KC chunks of [128 rows][128 B]
-    unsigned char* aux = ring + (size_t)S * TILE_BYTES;
+    unsigned char* ring = base + W_BYTES;                         // RS chunks of [128 rows][128 B]
+    unsigned char* aux = ring + (size_t)RS * CH_BYTES;
     float* scratch = reinterpret_cast<float*>(aux);               // 8 warps x 32 x 32 floats, XOR-swizzled (GroupNorm column sums); 0 without stats
     uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + p.scratch_floats);
-    // barriers: w_full, a_full[S], a_ready[S], a_empty[S], t_full[ACC], t_empty[ACC]   (S <= 4)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * 4 + 2 * PW_ACC);
+    // barriers: w_full, w_empty, c_full[MAXRS], c_ready[MAXRS], c_empty[MAXRS], t_full[ACC], t_empty[ACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 3 * PW_MAXRS + 2 * PW_ACC);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = uniform_warp_index();
-    const uint32_t w_full = pw_smem_u32(bars), a_full0 = pw_smem_u32(bars + 1), a_ready0 = pw_smem_u32(bars + 5),
-                   a_empty0 = pw_smem_u32(bars + 9), t_full0 = pw_smem_u32(bars + 13), t_empty0 = pw_smem_u32(bars + 13 + PW_ACC);
+    const uint32_t w_full = pw_smem_u32(bars), w_empty = pw_smem_u32(bars + 1), c_full0 = pw_smem_u32(bars + 2),
+                   c_ready0 = pw_smem_u32(bars + 2 + PW_MAXRS), c_empty0 = pw_smem_u32(bars + 2 + 2 * PW_MAXRS),
+                   t_full0 = pw_smem_u32(bars + 2 + 3 * PW_MAXRS), t_empty0 = pw_smem_u32(bars + 2 + 3 * PW_MAXRS + PW_ACC);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
     const bool fixup = has_aff || in_relu;
     const int G = NP / 32;                                        // 32-column groups of the accumulator
     const int wgroups = fixup ? 1 : (G >= 2 ? 2 : 1);             // epilogue warp groups (of 4 warps) that drain TMEM
-    const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
-    const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+    // this CTA's contiguous range of work items; item = group * T + tile, group = class * NH + column half
+    const long long it_begin = p.total_items * blockIdx.x / gridDim.x;
+    const long long it_end = p.total_items * (blockIdx.x + 1) / gridDim.x;
 
     if (tid == 0) {
         pw_mbar_init(w_full, 1);
-        for (int s = 0; s < 4; ++s) {
-            pw_mbar_init(a_full0 + 8 * s, 1);
-            pw_mbar_init(a_ready0 + 8 * s, 128);
-            pw_mbar_init(a_empty0 + 8 * s, 1);
+        pw_mbar_init(w_empty, 1);
+        for (int s = 0; s < PW_MAXRS; ++s) {
+            pw_mbar_init(c_full0 + 8 * s, 1);
+            pw_mbar_init(c_ready0 + 8 * s, 128);
+            pw_mbar_init(c_empty0 + 8 * s, 1);
         }
         for (int a = 0; a < PW_ACC; ++a) {
             pw_mbar_init(t_full0 + 8 * a, 1);
@@ -119,100 +129,112 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
 
     if (warp == 8) {
         // ======================= TMA PRODUCER ======================================================
-        if (t_begin < t_end) {
-            mbar_expect_tx_elect(w_full, W_BYTES);
-            for (int kc = 0; kc < KC; ++kc) tma_2d_elect(wres_u32 + (uint32_t)kc * NP * 128, &tmW, w_full, kc * 32, 0);
-            uint32_t L = 0;
-            for (long long t = t_begin; t < t_end; ++t, ++L) {
-                const uint32_t slot = L % (uint32_t)S;
-                pw_mbar_wait(a_empty0 + 8 * slot, ((L / (uint32_t)S) & 1u) ^ 1u);
-                const uint32_t bar = a_full0 + 8 * slot;
-                mbar_expect_tx_elect(bar, TILE_BYTES);
-                const int row0 = (int)(t * PW_TILE);
-                for (int kc = 0; kc < KC; ++kc)
-                    tma_2d_elect(ring_u32 + slot * TILE_BYTES + (uint32_t)kc * PW_TILE * 128, &tmA, bar, kc * 32, row0);
+        uint32_t Lc = 0, nload = 0;
+        long long cur_group = -1;
+        for (long long it = it_begin; it < it_end; ++it) {
+            const long long group = it / p.T, t = it - group * p.T;
+            if (group != cur_group) {                                  // weights of the next (class, column half)
+                cur_group = group;
+                if (nload > 0) pw_mbar_wait(w_empty, (nload - 1) & 1u);     // every MMA of the previous group has retired
+                const int wrow0 = (int)(group / p.NH) * p.CoutP + (int)(group % p.NH) * NP;
+                mbar_expect_tx_elect(w_full, W_BYTES);
+                for (int kc = 0; kc < KC; ++kc) tma_2d_elect(wres_u32 + (uint32_t)kc * NP * 128, &tmW, w_full, kc * 32, wrow0);
+                ++nload;
+                __syncwarp();
+            }
+            const int row0 = (int)(t * PW_TILE);
+            for (int kc = 0; kc < KC; ++kc, ++Lc) {
+                const uint32_t slot = Lc % (uint32_t)RS;
+                pw_mbar_wait(c_empty0 + 8 * slot, ((Lc / (uint32_t)RS) & 1u) ^ 1u);
+                const uint32_t bar = c_full0 + 8 * slot;
+                mbar_expect_tx_elect(bar, CH_BYTES);
+                tma_2d_elect(ring_u32 + slot * CH_BYTES, &tmA, bar, kc * 32, row0);
                 __syncwarp();
             }
         }
     } else if (warp == 9) {
         // ======================= MMA ISSUER (warp-uniform, elected issue) ==========================
-        if (t_begin < t_end) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            constexpr uint32_t D_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-            pw_mbar_wait(w_full, 0);
-            const uint32_t rdy0 = fixup ? a_ready0 : a_full0;
-            uint32_t L = 0;
-            for (long long t = t_begin; t < t_end; ++t, ++L) {
-                const uint32_t slot = L % (uint32_t)S, acc = L % PW_ACC;
-                pw_mbar_wait(rdy0 + 8 * slot, (L / (uint32_t)S) & 1u);
-                pw_mbar_wait(t_empty0 + 8 * acc, ((L / PW_ACC) & 1u) ^ 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = umma_desc_lo(ring_u32 + slot * TILE_BYTES), b0 = umma_desc_lo(wres_u32);
-                const uint32_t dcol = tmem_base + acc * (uint32_t)NP;
-                for (int kc = 0; kc < KC; ++kc) {
-                    const uint32_t ak = a0 + (uint32_t)kc * (PW_TILE * 128 / 16), bk = b0 + (uint32_t)kc * ((uint32_t)NP * 128 / 16);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ss_tf32<D_HI, D_HI>(dcol, ak + 2 * k, bk + 2 * k, idesc, (kc | k) ? 1u : 0u);
-                }
-                umma_commit_elect(t_full0 + 8 * acc);
-                umma_commit_elect(a_empty0 + 8 * slot);
-                __syncwarp();
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t D_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t rdy0 = fixup ? c_ready0 : c_full0;
+        const uint32_t b0 = umma_desc_lo(wres_u32);
+        uint32_t Lc = 0, L = 0, nload = 0;
+        long long cur_group = -1;
+        for (long long it = it_begin; it < it_end; ++it, ++L) {
+            const long long group = it / p.T;
+            if (group != cur_group) {
+                if (cur_group >= 0) umma_commit_elect(w_empty);      // fires when the previous group's MMAs are done with the weights
+                cur_group = group;
+                pw_mbar_wait(w_full, nload & 1u);
+                ++nload;
             }
+            const uint32_t acc = L % PW_ACC;
+            pw_mbar_wait(t_empty0 + 8 * acc, ((L / PW_ACC) & 1u) ^ 1u);
+            const uint32_t dcol = tmem_base + acc * (uint32_t)NP;
+            for (int kc = 0; kc < KC; ++kc, ++Lc) {
+                const uint32_t slot = Lc % (uint32_t)RS;
+                pw_mbar_wait(rdy0 + 8 * slot, (Lc / (uint32_t)RS) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ak = umma_desc_lo(ring_u32 + slot * CH_BYTES), bk = b0 + (uint32_t)kc * ((uint32_t)NP * 128 / 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss_tf32<D_HI, D_HI>(dcol, ak + 2 * k, bk + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                umma_commit_elect(c_empty0 + 8 * slot);
+            }
+            umma_commit_elect(t_full0 + 8 * acc);
+            __syncwarp();
         }
     } else if (warp >= 4 && fixup) {
-        // ======================= FIX-UP WARPS (4..7): pending affine / ReLU, once per landed tile, in place ===
-        if (t_begin < t_end) {
-            const int ft = tid - 128;                      // 0..127
-            const int chunk = ft & 7;                      // 16-byte chunk (4 channels) of a 128-byte row
-            uint32_t L = 0;
-            for (long long t = t_begin; t < t_end; ++t, ++L) {
-                const uint32_t slot = L % (uint32_t)S;
-                pw_mbar_wait(a_full0 + 8 * slot, (L / (uint32_t)S) & 1u);
-                const long long row0 = t * PW_TILE;
-                unsigned char* tile = ring + (size_t)slot * TILE_BYTES;
-                for (int kc = 0; kc < KC; ++kc) {
-                    unsigned char* ch = tile + (size_t)kc * PW_TILE * 128;
-                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_aff) {                                              // a tile never straddles two samples
-                        const size_t bo = (size_t)(row0 / p.vox_per_batch) * p.Cin + kc * 32 + chunk * 4;
-                        sc = ldg_f4(p.in_scale + bo);
-                        sh = ldg_f4(p.in_shift + bo);
-                    }
-                    for (int r = ft >> 3; r < PW_TILE; r += 16) {
-                        const long long v = row0 + r;
-                        if (v < p.V) {                                          // rows past the end stay zero
-                            float4* ptr = reinterpret_cast<float4*>(ch + r * 128 + ((chunk ^ (r & 7)) << 4));
-                            float4 x = *ptr;
-                            if (has_aff) {
-                                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
-                            }
-                            if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                            uint4 o;
-                            o.x = f2tf32(x.x); o.y = f2tf32(x.y); o.z = f2tf32(x.z); o.w = f2tf32(x.w);
-                            *reinterpret_cast<uint4*>(ptr) = o;
+        // ======================= FIX-UP WARPS (4..7): pending affine / ReLU, once per landed chunk, in place ===
+        const int ft = tid - 128;                      // 0..127
+        const int chunk = ft & 7;                      // 16-byte chunk (4 channels) of a 128-byte row
+        uint32_t Lc = 0;
+        for (long long it = it_begin; it < it_end; ++it) {
+            const long long t = it % p.T;
+            const long long row0 = t * PW_TILE;
+            for (int kc = 0; kc < KC; ++kc, ++Lc) {
+                const uint32_t slot = Lc % (uint32_t)RS;
+                pw_mbar_wait(c_full0 + 8 * slot, (Lc / (uint32_t)RS) & 1u);
+                unsigned char* ch = ring + (size_t)slot * CH_BYTES;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_aff) {                                              // a tile never straddles two samples
+                    const size_t bo = (size_t)(row0 / p.vox_per_batch) * p.Cin + kc * 32 + chunk * 4;
+                    sc = ldg_f4(p.in_scale + bo);
+                    sh = ldg_f4(p.in_shift + bo);
+                }
+                for (int r = ft >> 3; r < PW_TILE; r += 16) {
+                    if (row0 + r < p.V) {                                   // rows past the end stay zero
+                        float4* ptr = reinterpret_cast<float4*>(ch + r * 128 + ((chunk ^ (r & 7)) << 4));
+                        float4 x = *ptr;
+                        if (has_aff) {
+                            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
                         }
+                        if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        uint4 o;
+                        o.x = f2tf32(x.x); o.y = f2tf32(x.y); o.z = f2tf32(x.z); o.w = f2tf32(x.w);
+                        *reinterpret_cast<uint4*>(ptr) = o;
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                pw_mbar_arrive(a_ready0 + 8 * slot);
+                pw_mbar_arrive(c_ready0 + 8 * slot);
             }
         }
     }
-    if (warp < 8 && !(warp >= 4 && fixup) && (warp >> 2) < wgroups && t_begin < t_end) {
+    if (warp < 8 && !(warp >= 4 && fixup) && (warp >> 2) < wgroups && it_begin < it_end) {
         // ======================= EPILOGUE WARPS: lane quarter q, column groups wg, wg + wgroups, ... ============
         const int q = warp & 3, wg = warp >> 2;
         const int row = q * 32 + lane;
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         const bool want_stats = p.stats != nullptr;
         const int act = p.out_act;
+        const int s = p.s, Ho = p.H * s, Wo = p.W * s, Do = p.D * s;
         float* sc = scratch + warp * (32 * 32);
-        float run_s[4] = {0.f, 0.f, 0.f, 0.f}, run_q[4] = {0.f, 0.f, 0.f, 0.f};     // lane = column: running sums per owned group
-        int run_b = (int)((t_begin * PW_TILE) / p.vox_per_batch);
+        float run_s[4] = {0.f, 0.f, 0.f, 0.f}, run_q[4] = {0.f, 0.f, 0.f, 0.f};     // lane = column: running sums per owned column group
+        int run_b = -1, run_n0 = 0;
         auto flush = [&]() {
-            if (want_stats) {
+            if (want_stats && run_b >= 0) {
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
-                    const int c = (wg + gi * wgroups) * 32 + lane;
+                    const int c = run_n0 + (wg + gi * wgroups) * 32 + lane;
                     if (wg + gi * wgroups < G && c < p.Cout) {
                         atomicAdd(p.stats + ((size_t)run_b * p.Cout + c) * 2 + 0, (double)run_s[gi]);
                         atomicAdd(p.stats + ((size_t)run_b * p.Cout + c) * 2 + 1, (double)run_q[gi]);
@@ -223,21 +245,30 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
             for (int i = 0; i < 4; ++i) { run_s[i] = 0.f; run_q[i] = 0.f; }
         };
         uint32_t L = 0;
-        for (long long t = t_begin; t < t_end; ++t, ++L) {
+        for (long long it = it_begin; it < it_end; ++it, ++L) {
+            const long long group = it / p.T, t = it - group * p.T;
+            const int cls = (int)(group / p.NH), n0 = (int)(group % p.NH) * NP;          // output parity class, first output column
             const uint32_t acc = L % PW_ACC;
             const long long v = t * PW_TILE + row;
-            const int tb = (int)((t * PW_TILE) / p.vox_per_batch);              // tiles never straddle samples when stats are on
-            if (tb != run_b) { flush(); run_b = tb; }
+            const int tb = (int)((t * PW_TILE) / p.vox_per_batch);                      // tiles never straddle samples
+            if (tb != run_b || n0 != run_n0) { flush(); run_b = tb; run_n0 = n0; }
+            const bool valid = v < p.V;
+            size_t ov = (size_t)v;                                                       // s == 1: output voxel = input voxel
+            if (s > 1 && valid) {
+                const int vv = (int)(v - (long long)tb * p.vox_per_batch);
+                const int iw = vv % p.W, ih = (vv / p.W) % p.H, id = vv / (p.W * p.H);
+                const int a = cls / (s * s), bb = (cls / s) % s, c = cls % s;
+                ov = (((size_t)tb * Do + (id * s + a)) * Ho + (ih * s + bb)) * Wo + (iw * s + c);
+            }
             pw_mbar_wait(t_full0 + 8 * acc, (L / PW_ACC) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool valid = v < p.V;
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi) {
                 const int g = wg + gi * wgroups;
                 if (g >= G) break;
                 uint32_t r[32];
                 pw_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)NP + (uint32_t)(g * 32), r);
-                const int cbase = g * 32;
+                const int cbase = n0 + g * 32;
                 float x[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(r[k]);
@@ -254,7 +285,7 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
                     for (int k = 0; k < 32; ++k) x[k] = gelu_erf(x[k]);
                 }
                 if (valid) {
-                    float* dst = p.y + (size_t)v * p.out_ldc + cbase;
+                    float* dst = p.y + ov * p.out_ldc + cbase;
                     if (vec_ok && cbase + 32 <= p.Cout) {
 #pragma unroll
                         for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
@@ -300,22 +331,38 @@ typedef CUresult (*PwEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 // returns 1 if the layer was handled here
 int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                 const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
-    if (d->kd != 1 || d->kh != 1 || d->kw != 1 || d->sd != 1 || d->sh != 1 || d->sw != 1) return 0;      // also ConvTranspose k = s = 1
-    if (d->pd != 0 || d->ph != 0 || d->pw != 0 || d->math != SS_MATH_TF32) return 0;
-    if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
-    if (d->Cin % 32 != 0 || d->Cin > 256 || d->cout_packed > 128) return 0;
-    const long long vpb = (long long)d->Din * d->Hin * d->Win, V = vpb * d->B;
-    if (vpb % PW_TILE != 0 || vpb > 0x7fffffffLL || V < 148LL * PW_TILE * 2) return 0;       // small volumes: the box kernel is fine
+    if (d->math != SS_MATH_TF32 || d->pd != 0 || d->ph != 0 || d->pw != 0 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
+    int s = 1;
+    if (d->kd == 1 && d->kh == 1 && d->kw == 1 && d->sd == 1 && d->sh == 1 && d->sw == 1) {       // also ConvTranspose k = s = 1
+        if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
+    } else if (d->transposed && d->kd == d->sd && d->kh == d->sh && d->kw == d->sw && d->sd == d->sh && d->sh == d->sw &&
+               (d->sd == 2 || d->sd == 4)) {                                                        // non-overlapping up-convolution
+        s = d->sd;
+        if (d->Dout != d->Din * s || d->Hout != d->Hin * s || d->Wout != d->Win * s) return 0;
+    } else {
+        return 0;
+    }
+    if (d->Cin % 32 != 0 || d->Cin > 512 || d->cout_packed > 128) return 0;
     const bool pending = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
     if (pending && d->Cin > 64) return 0;            // 4 fix-up warps cannot keep up with wide pending inputs: the box kernel's TMEM fix-up path wins
-    const int KC = d->Cin / 32, NP = (d->cout_packed + 31) / 32 * 32;
-    const size_t w_bytes = (size_t)KC * NP * 128, tile_bytes = (size_t)KC * PW_TILE * 128;
+    const long long vpb = (long long)d->Din * d->Hin * d->Win, V = vpb * d->B;
+    const int ncls = s * s * s;
+    if (vpb % PW_TILE != 0 || V >= (1ll << 31) || V * ncls < 148LL * PW_TILE * 2) return 0;      // small volumes: the box kernel is fine
+    if (s > 1 && d->cout_packed % 32 != 0) return 0;
+    const int KC = d->Cin / 32;
+    int NP = (d->cout_packed + 31) / 32 * 32, NH = 1;
     const int scratch_floats = stats ? 8 * 32 * 32 : 0;
-    const size_t fixed = 1024 + w_bytes + (size_t)scratch_floats * sizeof(float) + (1 + 12 + 2 * PW_ACC) * sizeof(uint64_t) + 64;
-    if (fixed + 2 * tile_bytes > 227 * 1024) return 0;
-    int slots = (int)((227 * 1024 - fixed) / tile_bytes);
-    if (slots > 4) slots = 4;
-    if (slots < 2) return 0;
+    auto fixed_bytes = [&](int np) { return (size_t)1024 + (size_t)KC * np * 128 + (size_t)scratch_floats * sizeof(float) +
+                                            (2 + 3 * PW_MAXRS + 2 * PW_ACC) * sizeof(uint64_t) + 64; };
+    const size_t min_ring = (size_t)(KC < 4 ? 4 : (KC > 6 ? 4 : KC)) * PW_TILE * 128;              // at least 4 chunks in flight
+    if (fixed_bytes(NP) + min_ring > 227 * 1024) {                                                  // weights too big: two column halves
+        if (NP % 64 != 0) return 0;
+        NP /= 2; NH = 2;
+        if (fixed_bytes(NP) + min_ring > 227 * 1024) return 0;
+    }
+    int RS = (int)((227 * 1024 - fixed_bytes(NP)) / (PW_TILE * 128));
+    if (RS > PW_MAXRS) RS = PW_MAXRS;
+    if (RS < 2) return 0;
     static PwEncodeTiledFn encode = nullptr;
     if (!encode) {
         void* ptr = nullptr;
@@ -324,19 +371,18 @@ int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, 
             qres != cudaDriverEntryPointSuccess) return 0;
         encode = reinterpret_cast<PwEncodeTiledFn>(ptr);
     }
-    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
     alignas(64) CUtensorMap tmA, tmW;
     {
         cuuint64_t gdim[2] = {(cuuint64_t)d->Cin, (cuuint64_t)V};
         cuuint64_t gstr[1] = {(cuuint64_t)d->in_ldc * 4};
         cuuint32_t box[2] = {32, PW_TILE};
         cuuint32_t estr[2] = {1, 1};
-        if (encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(x), gdim, gstr,
+        if (encode(&tmA, pending ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(x), gdim, gstr,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_pw: tensor map A"); return 1; }
     }
-    {
-        cuuint64_t gdim[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->cout_packed};
+    {   // K-major weights [taps * CoutP rows][Cin]: class c of a k = s transposed conv is tap c
+        cuuint64_t gdim[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ncls * d->cout_packed};
         cuuint64_t gstr[1] = {(cuuint64_t)d->Cin * 4};
         cuuint32_t box[2] = {32, (cuuint32_t)NP};
         cuuint32_t estr[2] = {1, 1};
@@ -345,18 +391,19 @@ int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_pw: tensor map W"); return 1; }
     }
     PwParams p;
-    p.V = V; p.total_tiles = (V + PW_TILE - 1) / PW_TILE; p.vox_per_batch = (int)vpb;
-    p.Cin = d->Cin; p.KC = KC; p.Cout = d->Cout; p.NP = NP; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
-    p.slots = slots; p.scratch_floats = scratch_floats;
+    p.V = V; p.T = (V + PW_TILE - 1) / PW_TILE; p.total_items = p.T * ncls * NH; p.vox_per_batch = (int)vpb;
+    p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.s = s; p.NH = NH;
+    p.Cin = d->Cin; p.KC = KC; p.Cout = d->Cout; p.CoutP = d->cout_packed; p.NP = NP; p.out_ldc = d->out_ldc;
+    p.in_act = d->in_act; p.out_act = d->out_act; p.RS = RS; p.scratch_floats = scratch_floats;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    const size_t smem = fixed + (size_t)slots * tile_bytes;
+    const size_t smem = fixed_bytes(NP) + (size_t)RS * PW_TILE * 128;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { *rc = set_cuda_error(e, "conv_pw: smem attribute"); return 1; }
         configured = smem;
     }
-    const unsigned grid = (unsigned)(p.total_tiles < 148 ? p.total_tiles : 148);
+    const unsigned grid = (unsigned)(p.total_items < 148 ? p.total_items : 148);
     conv_pw_kernel<<<grid, PW_THREADS, smem, st>>>(p, tmA, tmW);
     *rc = check_launch("conv_pw_kernel");
     return 1;

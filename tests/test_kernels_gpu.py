@@ -220,7 +220,7 @@ def test_conv_halo_swapped_axes_and_160_column_tile(ops, dims):
     assert rel_err(y, ref) < TOL["tf32"]
 
 
-@pytest.mark.parametrize("case", ["hg_redir2", "head_classifier", "neck_k1_slice", "input_proj"])
+@pytest.mark.parametrize("case", ["hg_redir2", "head_classifier", "neck_k1_slice", "input_proj", "neck_k2s2", "neck_k4s4"])
 def test_pointwise_streaming_kernel(ops, case):
     """1x1x1 layers with short K on the persistent resident-weight kernel (conv_pw.cu): pending GroupNorm + ReLU
     input, bias, odd Cout (20), ConvTranspose3d k = s = 1 into a channel slice of a wider buffer, GroupNorm sums,
@@ -232,6 +232,10 @@ def test_pointwise_streaming_kernel(ops, case):
         m, shape, pending, stats = nn.Conv3d(192, 20, 1, bias=True), (2, 192, 20, 32, 32), True, False
     elif case == "neck_k1_slice":
         m, shape, pending, stats = nn.ConvTranspose3d(128, 128, 1, 1, bias=False), (2, 128, 24, 32, 32), False, True
+    elif case == "neck_k2s2":      # 8 output parity classes, weights resident per class
+        m, shape, pending, stats = nn.ConvTranspose3d(256, 128, 2, 2, bias=False), (2, 256, 8, 32, 32), False, True
+    elif case == "neck_k4s4":      # 64 classes x 2 column halves (K = 512 does not fit with 128 columns)
+        m, shape, pending, stats = nn.ConvTranspose3d(512, 128, 4, 4, bias=False), (1, 512, 8, 16, 16), False, True
     else:
         m, shape, pending, stats = nn.Conv3d(128, 128, 1, bias=False), (1, 128, 40, 32, 32), False, True
     B, Cin = shape[0], shape[1]
@@ -239,13 +243,13 @@ def test_pointwise_streaming_kernel(ops, case):
     sc, sh = torch.rand(B, Cin) + 0.5, torch.randn(B, Cin) * 0.3
     xin = F.relu(x * sc[:, :, None, None, None] + sh[:, :, None, None, None]) if pending else x
     want = m(xin).detach()
-    mg = type(m)(m.in_channels, m.out_channels, 1, 1, bias=m.bias is not None).cuda()
+    mg = type(m)(m.in_channels, m.out_channels, m.kernel_size, m.stride, bias=m.bias is not None).cuda()
     mg.load_state_dict(m.state_dict())
     v = ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU) if pending else ops.Vol(_cl(x))
     ops.arena(torch.device("cuda", 0)).reset()
     out = None
-    if case == "neck_k1_slice":
-        wide = torch.full(shape[:1] + shape[2:] + (384,), 7.0, device="cuda")
+    if case.startswith("neck"):
+        wide = torch.full((B,) + tuple(want.shape[2:]) + (384,), 7.0, device="cuda")
         out = wide[..., 128:256]
     y, st = ops.conv(v, mg, out=out, want_stats=stats)
     assert rel_err(_ncdhw(y), want) < TOL["tf32"]
