@@ -4,7 +4,7 @@
  * The reference has no native code and no FFI: its hot path is PyTorch module code that reaches
  * ATen / cuDNN / cuBLAS and ONE external compiled operator (mmdet3d.ops.bev_pool).  The drop-in
  * boundary is therefore (a) the mmdet3d registry names + module signatures, mirrored in Python by
- * stereoscene_b200/plugin/*, and (b) this C ABI, which is what those modules (or a maintainer's
+ * stereoscene_b200/plugin (every module there), and (b) this C ABI, which is what those modules (or a maintainer's
  * ctypes / pybind stub) bind.  Every entry point names the reference code it
  * replaces (paths relative to /root/reference/projects/mmdet3d_plugin/occupancy/).
  *

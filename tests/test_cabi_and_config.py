@@ -35,6 +35,35 @@ def test_header_symbols_are_exported_and_bound():
     assert loaded.ss_launch_count() >= 0
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors of ss_conv3d_desc / ss_conv3d_join have the C compiler's size and field offsets
+    (a plain-C translation unit including the public header is compiled with gcc: the header is C, not C++)."""
+    import shutil
+    import subprocess
+    from stereoscene_b200 import cabi
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    fields_desc = [n for n, _ in cabi.ConvDesc._fields_]
+    fields_join = [n for n, _ in cabi.ConvJoin._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "stereoscene_b200.h"', 'int main(void) {',
+           '  printf("%zu %zu %d\\n", sizeof(ss_conv3d_desc), sizeof(ss_conv3d_join), SS_ABI_VERSION);']
+    for f in fields_desc:
+        src.append(f'  printf("%zu\\n", offsetof(ss_conv3d_desc, {f}));')
+    for f in fields_join:
+        src.append(f'  printf("%zu\\n", offsetof(ss_conv3d_join, {f}));')
+    src.append('  return 0; }')
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(out[0]), int(out[1]), int(out[2])] == [ctypes.sizeof(cabi.ConvDesc), ctypes.sizeof(cabi.ConvJoin), cabi.ABI_VERSION]
+    offs = [int(x) for x in out[3:]]
+    want = [getattr(cabi.ConvDesc, f).offset for f in fields_desc] + [getattr(cabi.ConvJoin, f).offset for f in fields_join]
+    assert offs == want
+
+
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     from stereoscene_b200 import cabi
     monkeypatch.setattr(cabi, "_lib", None)
