@@ -370,6 +370,13 @@ def run_ours(args):
         "kernels": kernels,
         "peaks": pk,
     }
+    if args.workload == "config2":
+        # whole-step algorithmic totals of SURVEY.md section 8(a) (B=1, fp32 storage, incl. depth_net): 3,986 GFLOP and 9,139 MB
+        # of compulsory traffic per stereo pair -- the step is tensor-bound in TF32 (floor 3986/826 = 4.8 ms vs 1.4 ms of HBM)
+        sec = ms_dev / args.steps * 1e-3 / B
+        line["step_roofline"] = {"algorithmic_gflop": 3986.0, "algorithmic_mb": 9139.0, "tflops": 3986.0 / sec / 1e3,
+                                 "tflops_frac_of_bf16_peak": 3986.0 / sec / 1e3 / pk["tflops"], "hbm_gbs": 9139.0 / sec / 1e3,
+                                 "hbm_frac": 9139.0 / sec / 1e3 / pk["hbm_gbs"], "bound": "tensor (TF32 = half the bf16 peak)"}
     if world == 1 and not args.no_cpu_baseline:
         cb = time_cpu(args.workload, 1, 1, 90.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
