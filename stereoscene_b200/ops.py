@@ -479,7 +479,9 @@ def _cached_taps(calib: torch.Tensor, n_bins: int):
     key = (calib.data_ptr(), calib._version, tuple(calib.shape), calib.device, n_bins)
     hit = _taps_cache.get("last")
     if hit is None or hit[0] != key:
-        hit = (key, disparity_taps(calib, n_bins))
+        # the entry keeps `calib` alive, so its storage cannot be recycled for another tensor that would alias the key;
+        # an in-place update bumps _version
+        hit = (key, disparity_taps(calib, n_bins), calib)
         _taps_cache["last"] = hit
     return hit[1]
 

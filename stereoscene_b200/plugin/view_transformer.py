@@ -512,7 +512,7 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         idx = ops.splat_build_index(geom, self.dx.detach().cpu().tolist(), self.bx.detach().cpu().tolist(), nx,
                                     want_coords=self.stage_outputs is not None)
         if self.cache_splat_index:
-            self._index_cache = (key, idx)
+            self._index_cache = (key, idx, cal)      # holding the tensors keeps their storage from being recycled under the key
         return idx
 
     def voxel_pooling(self, geom_feats, x):
