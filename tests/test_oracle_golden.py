@@ -113,3 +113,27 @@ def test_ssc_scores_restatement_matches_reference_golden():
     res = O.ssc_compute(tot["completion"], tot["tps"], tot["fps"], tot["fns"])
     assert np.allclose(res["iou_ssc"].numpy(), g["all_iou_ssc"], rtol=1e-6)
     assert np.allclose([res["precision"], res["recall"], res["iou"], res["iou_ssc_mean"]], g["all_scalars"], rtol=1e-6)
+
+
+def test_semkitti_label_writer_matches_reference(tmp_path):
+    """stereoscene_b200.semkitti_io against the reference's own table (read from its semantickitti.yaml by the
+    reference's get_inv_map arithmetic, utils/semkitti_io.py:99-111) and file format (apis/test.py:49-64)."""
+    import numpy as np
+    import os
+    from stereoscene_b200 import semkitti_io as S
+    inv = S.get_inv_map()
+    assert inv.dtype == np.int32 and inv.tolist() == [0, 10, 11, 15, 18, 20, 30, 31, 32, 40, 44, 48, 49, 50, 51, 70, 71, 72, 80, 81]
+    ref_yaml = "/root/reference/semantickitti.yaml"
+    if os.path.exists(ref_yaml):                                   # build container: pin the table to the reference's file
+        import yaml
+        cfg = yaml.safe_load(open(ref_yaml))
+        want = np.zeros(20, dtype=np.int32)
+        want[list(cfg["learning_map_inv"].keys())] = list(cfg["learning_map_inv"].values())
+        assert np.array_equal(inv, want)
+    g = torch.Generator().manual_seed(2)
+    logits = torch.randn(20, 6, 5, 4, generator=g)
+    p1 = S.save_output_semantic_kitti(logits, str(tmp_path / "a"), "08", "000123")
+    p2 = S.save_output_semantic_kitti(logits.argmax(0).to(torch.uint8), str(tmp_path / "b"), "08", "000123")
+    assert p1.endswith("a/sequences/08/predictions/000123.label")
+    want_bytes = inv[logits.argmax(0).numpy().reshape(-1)].astype(np.uint16).tobytes()        # test.py:52-57
+    assert open(p1, "rb").read() == want_bytes == open(p2, "rb").read()
