@@ -131,3 +131,21 @@ def test_unsupported_options_raise():
         CustomResNet3D(depth=50)
     with pytest.raises(NotImplementedError):
         OccHead(in_channels=[384], out_channel=20, supervise_points=True)
+
+
+def test_plane_kernel_dispatch_mirror():
+    """ops._halo_or_march_layer mirrors the C dispatch (conv3d_halo.cu:try_conv_halo, conv3d_march.cu:try_conv_march32) for
+    the layers of stereoscene.py: it decides whether a small pending input is materialised before a per-tap layer."""
+    import torch.nn as nn
+    from stereoscene_b200 import ops
+    f = lambda m, d, h, w: ops._halo_or_march_layer(ops.PackedConv(m), d, h, w, m.in_channels)       # noqa: E731
+    assert f(nn.Conv3d(384, 192, 3, 1, 1, bias=False), 128, 128, 16)          # occupancy head: halo kernel
+    assert f(nn.Conv3d(128, 128, 3, 1, 1, bias=False), 128, 128, 16)          # encoder stage 0
+    assert f(nn.Conv2d(640, 640, 3, 1, 1, bias=False), 1, 48, 160)            # DepthNet 2-D layers (axes swapped)
+    assert f(nn.Conv3d(32, 32, 3, 1, 1, bias=False), 112, 48, 160)            # frustum layers: marching kernel
+    assert f(nn.Conv3d(64, 64, 3, 1, 1, bias=False), 56, 24, 80)              # hourglass conv2 (swapped: 83 % tile use)
+    assert not f(nn.Conv3d(512, 512, 3, 1, 1, bias=False), 32, 32, 4)         # stage 2: per-tap kernel -> materialise
+    assert not f(nn.Conv3d(128, 128, 3, 1, 1, bias=False), 28, 12, 40)        # hourglass conv4
+    assert not f(nn.Conv3d(128, 256, 3, 2, 1, bias=False), 128, 128, 16)      # strided
+    assert not f(nn.Conv2d(640, 640, 3, padding=6, dilation=6, bias=False), 1, 48, 160)   # dilated ASPP branch
+    assert not f(nn.ConvTranspose3d(128, 64, 3, 2, 1, 1, bias=False), 28, 12, 40)
