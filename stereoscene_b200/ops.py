@@ -48,6 +48,10 @@ def default_math() -> int:
     return _DEFAULT_MATH
 
 
+# name -> mode constant, for the tests / bench (--math)
+MATH_MODES = {"tf32": SS_MATH_TF32, "3xtf32": SS_MATH_3XTF32}
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

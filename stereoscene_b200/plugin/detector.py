@@ -81,7 +81,12 @@ class BEVDepthOccupancy(nn.Module):
     # ---- the volumetric path ---------------------------------------------------------------
     def bev_encoder_vol(self, bev: torch.Tensor) -> Vol:
         levels = self.img_bev_encoder_backbone.forward_vol(Vol(bev))
-        return self.img_bev_encoder_neck.forward_vol(levels)
+        neck = self.img_bev_encoder_neck.forward_vol(levels)
+        st = self.img_view_transformer.stage_outputs
+        if st is not None:          # per-stage capture for the parity tests (logical NCDHW views, neck materialised)
+            st.update(bev_feat=bev.permute(0, 4, 1, 2, 3), neck=neck.ncdhw(),
+                      **{f"enc{i}": t.permute(0, 4, 1, 2, 3) for i, t in enumerate(levels)})
+        return neck
 
     def forward_features(self, x_left, x_right, left, right, calib, occ_size=None, want_labels=False):
         """Volumetric forward from image-backbone features.

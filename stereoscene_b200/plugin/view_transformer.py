@@ -380,10 +380,16 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         return nn.Parameter(torch.stack((xs, ys, ds), -1), requires_grad=False)
 
     def get_geometry(self, rots, trans, intrins, post_rots, post_trans, bda):
-        """Frustum points in the ego frame, [B,N,D,fH,fW,3].  Small (3 floats per frustum point)
-        and calibration-only: kept in PyTorch so it is the reference's arithmetic."""
+        """Frustum points in the ego frame, [B,N,D,fH,fW,3] (reference-signature entry, evaluated on the device the
+        arguments live on; the product forward evaluates it on the host, see ``splat_index``)."""
+        return self._geometry(self.frustum, rots, trans, intrins, post_rots, post_trans, bda)
+
+    @staticmethod
+    def _geometry(frustum, rots, trans, intrins, post_rots, post_trans, bda):
+        """Small (3 floats per frustum point) and calibration-only: kept in PyTorch ops in the reference's order so
+        that it is the reference's arithmetic (VTB:123-156)."""
         B, N, _ = trans.shape
-        pts = self.frustum - post_trans.view(B, N, 1, 1, 1, 3)
+        pts = frustum - post_trans.view(B, N, 1, 1, 1, 3)
         pts = torch.inverse(post_rots).view(B, N, 1, 1, 1, 3, 3).matmul(pts.unsqueeze(-1))
         pts = torch.cat((pts[..., :2, :] * pts[..., 2:3, :], pts[..., 2:3, :]), 5)
         if intrins.shape[3] == 4:          # KITTI: 4x4 with the projection shift in column 3
@@ -404,7 +410,8 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         if bda is None:
             bda = torch.eye(3).to(rot).view(1, 3, 3).repeat(B, 1, 1)
         bda = bda.view(B, 1, *bda.shape[-2:]).repeat(1, N, 1, 1)
-        if intrin.shape[-1] == 4:
+        kitti = intrin.shape[-1] == 4
+        if kitti:
             items = [intrin[:, :, 0, 0], intrin[:, :, 1, 1], intrin[:, :, 0, 2], intrin[:, :, 1, 2],
                      intrin[:, :, 0, 3], intrin[:, :, 1, 3], intrin[:, :, 2, 3]]
         else:
@@ -413,7 +420,7 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
                   post_rot[:, :, 1, 1], post_tran[:, :, 1], bda[:, :, 0, 0], bda[:, :, 0, 1], bda[:, :, 1, 0],
                   bda[:, :, 1, 1], bda[:, :, 2, 2]]
         mlp_input = torch.stack(items, dim=-1)
-        if bda.shape[-1] == 4:
+        if kitti and bda.shape[-1] == 4:      # the reference appends the bda translation only in its KITTI branch (VTB:612-636)
             mlp_input = torch.cat((mlp_input, bda[:, :, :3, -1]), dim=2)
         sensor2ego = torch.cat([rot, tran.reshape(B, N, 3, 1)], dim=-1).reshape(B, N, -1)
         return torch.cat([mlp_input, sensor2ego], dim=-1)
@@ -505,7 +512,13 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in cal) + (self.frustum.data_ptr(),)
         if self.cache_splat_index and self._index_cache is not None and self._index_cache[0] == key:
             return self._index_cache[1]
-        geom = self.get_geometry(*cal)
+        # Geometry is calibration-only and feeds an INTEGER quantisation, so it is evaluated once per calibration on the
+        # host in fp32 -- the reference's own CPU arithmetic (torch.inverse = LAPACK getrf/getri, the same small matmuls),
+        # bit-identical to the oracle -- and uploaded; a device evaluation (cuSOLVER / cuBLAS rounding) could move points
+        # that sit on a voxel face.  The result is cached below, so the host round trip never recurs in steady state.
+        with torch.no_grad():
+            frustum = self.frustum.detach().cpu()
+            geom = self._geometry(frustum, *[t.detach().cpu() for t in cal]).to(self.frustum.device)
         if self.stage_outputs is not None:
             self.stage_outputs["geom"] = geom
         nx = [int(round(float(v))) for v in self.nx.detach().cpu()]

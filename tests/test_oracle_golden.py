@@ -137,3 +137,31 @@ def test_semkitti_label_writer_matches_reference(tmp_path):
     assert p1.endswith("a/sequences/08/predictions/000123.label")
     want_bytes = inv[logits.argmax(0).numpy().reshape(-1)].astype(np.uint16).tobytes()        # test.py:52-57
     assert open(p1, "rb").read() == want_bytes == open(p2, "rb").read()
+
+
+@pytest.mark.parametrize("workload", ["config1", "config2"])
+def test_restatement_matches_reference_golden_full_size(workload):
+    """BASELINE.json configs[1] / configs[2]: the oracle against the reference's own forward at full size (sampled
+    stage boundaries + the complete voxel index), fixtures from oracle/make_golden_full.py."""
+    from util import full_inputs, golden_full, sample_stage, stage_error
+    meta, gold = golden_full(workload)
+    model, mc = build_model(workload, meta["seed"])
+    assert mc["model"]["img_view_transformer"]["grid_config"] == meta["grid_config"] and mc["occ_size"] == meta["occ_size"]
+    sd = cpu_state_dict(model)
+    xl, xr, left, right, calib = full_inputs(meta)
+    st = {}
+    with torch.no_grad():
+        O.volumetric_forward(sd, xl, xr, left, right, calib, meta["grid_config"], tuple(meta["input_size"]),
+                             meta["occ_size"], stages=st)
+    for key in meta["samplers"]:
+        if key not in st:          # stages the restatement does not expose separately (BRI halves, MIE internals, neck alias)
+            continue
+        e = stage_error(sample_stage(st[key], meta, key), gold[key], meta["stats"][key])
+        assert e["max"] < 2e-5 and e["rms"] < 5e-5, (key, e)
+    gc = meta["grid_config"]
+    dx, bx, nx = O.gen_dx_bx(gc["xbound"], gc["ybound"], gc["zbound"])
+    idx, kept = O.voxel_indices(st["geom"], dx, bx, nx)
+    n = [int(v) for v in nx.tolist()]
+    lin = torch.where(kept, (idx[:, 0] * n[1] + idx[:, 1]) * n[2] + idx[:, 2], torch.full_like(idx[:, 0], -1))
+    assert np.array_equal(np.unpackbits(gold["kept_bits"])[: kept.numel()].astype(bool), kept.numpy())
+    assert np.array_equal(gold["voxel_lin"], lin.to(torch.int32).numpy()) and int(kept.sum()) == meta["kept_points"]

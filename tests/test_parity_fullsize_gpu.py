@@ -1,0 +1,142 @@
+"""Full-size parity of the product forward (BASELINE.json configs[1] = 128x128x16 grid, configs[2] = stereoscene.py as
+shipped, 256x256x32) in EVERY math mode the library offers, against
+
+  * the golden fixtures written by the reference's own unmodified forward (oracle/make_golden_full.py: strided samples
+    of every stage boundary + the complete integer voxel index), and
+  * the CPU oracle (oracle/restatement.py) run live on the same seeded inputs (complete tensors, label agreement).
+
+Two error figures per stage (tests/util.py:stage_error): ``max`` = max|d| / max|ref| and ``rms`` = rms(d) / rms(ref).
+The north star's bar is 1e-3 relative on the logits; the tolerances below are the bar for the compensated modes and
+the measured TF32 figures (with head-room) for the plain-TF32 mode -- the per-stage table of every run is written to
+gpurun_out/parity_<workload>_<mode>.json and the committed copy lives in profiles/r02_parity_*.md.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as O
+from util import build_model, cpu_state_dict, full_inputs, golden_full, sample_stage, stage_error
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# mode -> (max-norm tolerance, rms-norm tolerance) on the final logits (and every voxel-space stage before them)
+LOGIT_TOL = {"3xtf32": (1e-3, 1e-3), "tf32x3": (1e-3, 1e-3), "tf32": (2e-2, 2e-2)}
+
+
+def _modes():
+    from stereoscene_b200 import ops
+    return ops.MATH_MODES
+
+
+def _reference_layout(out, st):
+    """Our stage tensors in the reference's logical layouts (the layouts the fixtures were sampled in)."""
+    t = {
+        "stereo_fea": st["stereo_fea"].squeeze(1).permute(0, 3, 1, 2),
+        "gwc_warp": st["gwc_warp"].permute(0, 4, 1, 2, 3),
+        "stereo_prob": st["stereo_prob"], "lss_prob": st["lss_prob"], "depth_net": st["depth_net"],
+        "bri_lss2stereo": st["bri"][..., 0].unsqueeze(1), "bri_stereo2lss": st["bri"][..., 1].unsqueeze(1),
+        "mie_hourglass": st["mie_hourglass"].permute(0, 4, 1, 2, 3), "mie_ca3d": st["mie_ca3d"].permute(0, 4, 1, 2, 3),
+        "depth_prob": st["depth_prob"], "bev_feat": st["bev_feat"], "enc0": st["enc0"], "enc1": st["enc1"],
+        "enc2": st["enc2"], "neck": st["neck"], "logits": out["logits_lowres"], "logits_up": out["output_voxels"],
+    }
+    return t
+
+
+_oracle_cache = {}
+
+
+def _oracle_run(workload, meta):
+    """The CPU oracle at full size, once per workload (seconds on the GPU box's host cores)."""
+    if workload not in _oracle_cache:
+        model, mc = build_model(workload, meta["seed"])
+        sd = cpu_state_dict(model)
+        xl, xr, left, right, calib = full_inputs(meta)
+        st = {}
+        with torch.no_grad():
+            up = O.volumetric_forward(sd, xl, xr, left, right, calib, meta["grid_config"], tuple(meta["input_size"]),
+                                      meta["occ_size"], stages=st)
+        _oracle_cache[workload] = dict(logits_up=up, depth_prob=st["depth_prob"], geom=st["geom"], bev_feat=st["bev_feat"])
+    return _oracle_cache[workload]
+
+
+def _product_run(workload, meta, mode):
+    from stereoscene_b200 import ops
+    model, mc = build_model(workload, meta["seed"], device="cuda")
+    xl, xr, left, right, calib = full_inputs(meta, device="cuda")
+    vt = model.img_view_transformer
+    vt.stage_outputs = {}
+    ops.set_default_math(_modes()[mode])
+    try:
+        with torch.no_grad():
+            out = model.forward_features(xl, xr, left, right, calib, occ_size=meta["occ_size"], want_labels=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_default_math(ops.SS_MATH_TF32)
+    st = dict(vt.stage_outputs)
+    vt.stage_outputs = None
+    return out, st
+
+
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3", "3xtf32"])
+@pytest.mark.parametrize("workload", ["config1", "config2"])
+def test_forward_vs_reference_golden_and_oracle(workload, mode):
+    if mode not in _modes():
+        pytest.skip(f"math mode {mode} not offered by this build")
+    meta, gold = golden_full(workload)
+    out, st = _product_run(workload, meta, mode)
+    got = _reference_layout(out, st)
+
+    # ---- every stage boundary against the reference's own forward (sampled)
+    table = {}
+    for key in meta["samplers"]:
+        table[key] = stage_error(sample_stage(got[key], meta, key), gold[key], meta["stats"][key])
+
+    # ---- integer path: the product forward's kept mask and voxel ids == the reference's, exactly, at every point
+    idx = st["splat_index"]
+    c = idx.coords.cpu().long()
+    kept = c[:, 3] > 0
+    lin = torch.where(kept, (c[:, 0] * idx.ny + c[:, 1]) * idx.nz + c[:, 2], torch.full_like(c[:, 0], -1)).to(torch.int32)
+    want_kept = np.unpackbits(gold["kept_bits"])[: kept.numel()].astype(bool)
+    index_mismatch = int((kept.numpy() != want_kept).sum() + (lin.numpy() != gold["voxel_lin"]).sum())
+
+    # ---- complete tensors against the live CPU oracle
+    orc = _oracle_run(workload, meta)
+    up, want_up = out["output_voxels"].cpu(), orc["logits_up"]
+    d = (up - want_up).double()
+    live = dict(
+        logits_up_max=float(d.abs().max() / want_up.abs().max()),
+        logits_up_rms=float(d.pow(2).mean().sqrt() / want_up.double().pow(2).mean().sqrt()),
+        depth_prob_max=float((st["depth_prob"].cpu() - orc["depth_prob"]).abs().max() / orc["depth_prob"].abs().max()),
+        label_agreement=float((out["labels"].cpu().long() == want_up.argmax(1)).float().mean()),
+        geom_bit_exact=bool(torch.equal(st["geom"].cpu(), orc["geom"])),
+    )
+    # sample labels of the golden (reference's own argmax on its sample)
+    lab_s = sample_stage(out["output_voxels"], meta, "logits_up").argmax(1).cpu().numpy().astype(np.uint8)
+    live["label_agreement_golden_sample"] = float((lab_s == gold["labels_up_sample"]).mean())
+
+    report = dict(workload=workload, mode=mode, stages=table, index_mismatch=index_mismatch,
+                  kept_points=int(kept.sum()), points=int(kept.numel()), live_oracle=live)
+    outdir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(outdir, exist_ok=True)
+    with open(os.path.join(outdir, f"parity_{workload}_{mode}.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    print(f"\n[{workload} / {mode}] stage            max|d|/max|ref|   rms(d)/rms(ref)")
+    for k, v in table.items():
+        print(f"  {k:16s} {v['max']:.3e}        {v['rms']:.3e}")
+    print("  live oracle:", {k: (f"{v:.3e}" if isinstance(v, float) else v) for k, v in live.items()}, "index mismatch", index_mismatch)
+
+    # ---- assertions
+    assert index_mismatch == 0 and int(kept.sum()) == meta["kept_points"]
+    assert live["geom_bit_exact"]
+    tol_max, tol_rms = LOGIT_TOL[mode]
+    for key in ("depth_prob", "bev_feat", "enc0", "enc1", "enc2", "neck", "logits", "logits_up"):
+        assert table[key]["max"] < tol_max and table[key]["rms"] < tol_rms, (key, table[key])
+    for key in table:                      # the frustum stages are tighter than the end-to-end bound in every mode
+        assert table[key]["max"] < tol_max, (key, table[key])
+    assert live["logits_up_max"] < tol_max and live["logits_up_rms"] < tol_rms
+    assert live["label_agreement"] > (0.999 if mode != "tf32" else 0.98)

@@ -44,3 +44,36 @@ def tiny_inputs(cfg, device="cpu"):
 
 def cpu_state_dict(model):
     return {k: v.detach().cpu() for k, v in model.state_dict().items()}
+
+
+# ---- full-size fixtures (tests/golden/golden_config{1,2}.npz, written by oracle/make_golden_full.py) -------------
+def golden_full(workload: str):
+    with open(os.path.join(GOLDEN, f"golden_{workload}.json")) as f:
+        meta = json.load(f)
+    return meta, np.load(os.path.join(GOLDEN, f"golden_{workload}.npz"))
+
+
+def full_inputs(meta, device="cpu"):
+    """The seeded synthetic pair + KITTI calibration the fixture was generated from."""
+    B = meta["batch"]
+    xl, xr = synth.stereo_features(B, tuple(meta["input_size"]), 8, seed=meta["seed"])
+    left, right, calib = synth.kitti_calibration(B, tuple(meta["input_size"]))
+    mv = lambda d: {k: v.to(device) for k, v in d.items()}   # noqa: E731
+    return xl.to(device), xr.to(device), mv(left), mv(right), calib.to(device)
+
+
+def sample_stage(t, meta, key):
+    """Re-apply the fixture's strided sampler to a full stage tensor (logical reference layout)."""
+    sl = tuple(slice(*s) for s in meta["samplers"][key])
+    return t[sl]
+
+
+def stage_error(got_sample, want_sample, stat) -> dict:
+    """Errors of a sampled stage against the reference's sample, normalised by FULL-tensor statistics of the
+    reference (absmax, rms from the fixture's json): ``max`` = max|d| / absmax (the rel-to-max reading of the north
+    star's "1e-3 relative"), ``rms`` = rms(d) / rms(ref) (relative L2 error, the stricter reading)."""
+    a = got_sample.detach().cpu().double().numpy() if torch.is_tensor(got_sample) else np.asarray(got_sample, np.float64)
+    b = np.asarray(want_sample, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = a - b
+    return dict(max=float(np.abs(d).max() / stat["absmax"]), rms=float(np.sqrt((d * d).mean()) / stat["rms"]))
