@@ -34,10 +34,78 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-HEAD_CONV_DRAM_BYTES = 638642176   # ncu --set full of conv_halo_kernel<192> (profiles/r01s2_head_conv_ncu_full_raw.csv): 461.8 MB read + 176.9 MB written per launch
+# roofline.traffic of the dominant kernel comes from the ncu --set full capture committed this round; tools/prof_kernels.sh
+# writes the two DRAM counters of that capture into profiles/r02_head_conv_traffic.json next to the raw page
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_head_conv_traffic.json")
 
 VOXELS = {"config1": 128 * 128 * 16, "config2": 256 * 256 * 32, "config0": 64 * 64 * 8, "tiny": 32 * 32 * 8,
           "config4": 512 * 512 * 64}
+
+
+def workload_config(workload: str, B: int = 1) -> str:
+    """The ONE description of the workload both arms print (so the driver sees the same config on both lines)."""
+    from stereoscene_b200 import presets
+    occ = presets.WORKLOADS[workload][0]
+    return (f"{workload}: synthetic 1242x375 stereo -> 384x1280 -> 48x160x112 frustum -> {'x'.join(map(str, occ))} logits, "
+            f"20 classes, B={B} stereo pair per step per worker (features after the 2-D image backbone)")
+
+
+def policy_text(ops, name: str) -> str:
+    names = {ops.SS_MATH_TF32: "tf32", ops.SS_MATH_TF32X3: "tf32x3 (compensated, tcgen05)", ops.SS_MATH_3XTF32: "3xtf32 (compensated, mma.sync)"}
+    pol = ops.MATH_POLICIES[name]
+    return ", ".join(f"{g}={names[pol.get(g, ops.SS_MATH_TF32)]}" for g in ("stereo", "depthnet", "mie", "voxel"))
+
+
+def measure_tf32_peak(dev) -> float:
+    """cuBLAS TF32 GEMM throughput (TFLOP/s) on this GPU, measured here: the denominator of the tensor roofline of a
+    kernel that multiplies in TF32 (MEASURED_PEAKS.json only holds the bf16 figure)."""
+    n = 8192
+    a = torch.randn((n, n), device=dev)
+    b = torch.randn((n, n), device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(3):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 10 * 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return best
+
+
+def golden_parity(workload: str, out: dict, seed: int):
+    """Error of the benchmarked forward's logits against the committed fixture of the REFERENCE's own forward on the same
+    seeded inputs (tests/golden/golden_<workload>.npz, written by oracle/make_golden_full.py): max|d|/max|ref| and
+    rms(d)/rms(ref) on the fixture's strided sample, label agreement on the sample.  None if there is no fixture."""
+    import numpy as np
+    js = os.path.join(ROOT, "tests", "golden", f"golden_{workload}.json")
+    if not os.path.exists(js):
+        return None
+    with open(js) as f:
+        meta = json.load(f)
+    if meta["seed"] != seed:
+        return None
+    gold = np.load(os.path.join(ROOT, "tests", "golden", f"golden_{workload}.npz"))
+    res = {}
+    for key, t in (("logits_up", out["output_voxels"]), ("logits", out["logits_lowres"]), ("depth_prob", out["depth"])):
+        sl = tuple(slice(*x) for x in meta["samplers"][key])
+        d = t[:1][sl].detach().cpu().double().numpy() - gold[key].astype(np.float64)
+        res[key] = {"max_rel": float(np.abs(d).max() / meta["stats"][key]["absmax"]),
+                    "rms_rel": float(np.sqrt((d * d).mean()) / meta["stats"][key]["rms"])}
+    sl = tuple(slice(*x) for x in meta["samplers"]["logits_up"])
+    lab = out["output_voxels"][:1][sl].argmax(1).cpu().numpy().astype(np.uint8)
+    res["label_agreement"] = float((lab == gold["labels_up_sample"]).mean())
+    res["against"] = f"tests/golden/golden_{workload}.npz (reference's own forward, seed {seed})"
+    return res
 
 
 def parse():
@@ -47,7 +115,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(VOXELS))
-    ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"])
+    ap.add_argument("--math", default="mixed", choices=["mixed", "tf32", "tf32x3", "3xtf32"],
+                    help="per-stage math policy (stereoscene_b200.ops.MATH_POLICIES); 'mixed' = plain TF32 tensor-core math with "
+                         "the error-compensated TF32x3 mode on depth_net and the MIE block: the cheapest policy whose logits "
+                         "are within 1e-3 of the reference's forward")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the extra timing + error lines of the other math policies")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the forward in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
@@ -165,8 +237,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "voxels/sec", "value": cb["value"], "unit": "voxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_forward"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: synthetic 1242x375 stereo pair -> "
-                               f"{VOXELS[args.workload]} output voxels, 20 classes, B=1 per step",
+        "config": {"workload": workload_config(args.workload, 1),
                    "note": "reference has no native/GPU-independent build; its CPU path = PyTorch CPU fp32 "
                            "(oracle port pinned to the reference's own forward), all host threads"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -195,7 +266,7 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cabi.load()
-    ops.set_default_math(ops.SS_MATH_3XTF32 if args.math == "3xtf32" else ops.SS_MATH_TF32)
+    ops.set_math_policy(args.math)
 
     seed = 0
     model, mc = presets.build(args.workload)
@@ -347,16 +418,50 @@ def run_ours(args):
     e2e = sharding.whole_job_voxels_per_s(VOXELS[args.workload], B, world, args.steps, ms_e2e)
 
     # ---- roofline of the dominant kernel, timed alone (CUDA events on the launching stream) -------
+    pk["tf32_tflops_cublas"] = measure_tf32_peak(dev)
     roof, kernels = dominant_kernel_roofline(model, mc, dev, pk)
+
+    # ---- parity of the benchmarked mode (and, at N=1, time + parity of the other math policies) -------------------
+    parity = None
+    if B == 1:
+        with torch.no_grad():
+            parity = golden_parity(args.workload, forward(xl_d, xr_d), seed)
+    other_modes = {}
+    if world == 1 and not args.no_other_modes and args.workload in ("config1", "config2"):
+        for name in ("tf32", "mixed", "tf32x3"):
+            if name == args.math:
+                continue
+            ops.set_math_policy(name)
+            try:
+                with torch.no_grad():
+                    o = forward(xl_d, xr_d)
+                    torch.cuda.synchronize()
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        forward(xl_d, xr_d)
+                for _ in range(3):
+                    g2.replay()
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(10):
+                    g2.replay()
+                a1.record()
+                torch.cuda.synchronize()
+                msm = a0.elapsed_time(a1) / 10
+                other_modes[name] = {"ms_per_step": msm, "value": VOXELS[args.workload] * B / (msm * 1e-3),
+                                     "math_policy": policy_text(ops, name), "parity": golden_parity(args.workload, o, seed)}
+                del g2
+            finally:
+                ops.set_math_policy(args.math)
 
     line = {
         "metric": "voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32(3xtf32)", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: synthetic 1242x375 stereo -> 384x1280 -> 48x160x112 frustum -> "
-                               f"{'x'.join(map(str, occ))} logits, 20 classes, B={B} stereo pair per GPU per step "
-                               "(features after the 2-D image backbone)",
-                   "storage": "fp32 channels-last", "math": args.math, "cuda_graph": graph is not None,
+        "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+        "config": {"workload": workload_config(args.workload, B),
+                   "storage": "fp32 channels-last", "math": args.math, "math_policy": policy_text(ops, args.math),
+                   "cuda_graph": graph is not None,
                    "l2": "no flush: one step streams > 9 GB of activations, >> 126 MB L2",
                    "parallelism": f"sample-sharded x{world} (no data-path collective)"},
         "e2e": {"value": e2e, "unit": "voxels/s", "ms_per_step": ms_e2e / args.steps,
@@ -369,6 +474,8 @@ def run_ours(args):
         "roofline": roof,
         "kernels": kernels,
         "peaks": pk,
+        "parity": parity,
+        "other_math_policies": other_modes,
     }
     if args.workload == "config2":
         # whole-step algorithmic totals of SURVEY.md section 8(a) (B=1, fp32 storage, incl. depth_net): 3,986 GFLOP and 9,139 MB
@@ -446,20 +553,26 @@ def dominant_kernel_roofline(model, mc, dev, pk):
 
     def head_conv():
         ops.arena(dev).reset()
-        ops.conv(vin, head, out=y, want_stats=True)
+        ops.conv(vin, head, out=y, want_stats=True, math_mode=ops.SS_MATH_TF32)
     t = _time_launches(head_conv)
     V = nx[0] * nx[1] * nx[2]
     flops = 2.0 * V * 27 * head.in_channels * head.out_channels
     ach = flops / t / 1e12
+    traffic, traffic_src = None, "no ncu capture of this round found (profiles/r02_head_conv_traffic.json)"
+    if os.path.exists(TRAFFIC_JSON):
+        with open(TRAFFIC_JSON) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+    tf32_peak = pk.get("tf32_tflops_cublas") or pk["tflops"] / 2
     roof = {"bound": "tensor", "kernel": "conv_halo_kernel<192> (OccHead conv 384->192 k3 on the 128x128x16 grid; "
                                          "TMA halo planes + tcgen05.mma kind::tf32, TMEM accumulators)",
-            "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-            "traffic": HEAD_CONV_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01s2_head_conv_ncu_full_raw.csv "
-                                                                "(dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+            "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+            "peak_bf16": pk["tflops"], "frac_of_bf16_peak": ach / pk["tflops"],
+            "traffic": traffic, "traffic_source": traffic_src,
             "launch_ms": t * 1e3, "algorithmic_flops": flops,
             "algorithmic_bytes": (x.numel() + y.numel()) * 4.0,
-            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({pk['source']}); the kernel multiplies in TF32, whose "
-                           "nominal peak is half the bf16 peak, so frac 0.5 = TF32 speed of light"}
+            "peak_source": "peak = cuBLAS TF32 GEMM (8192^3) measured in this run on this GPU: the kernel multiplies in TF32; "
+                           f"peak_bf16 = MEASURED_PEAKS.json bf16 burst ({pk['source']}) for reference"}
     kernels.append({"name": "occ_head conv3d 384->192 k3", "bound": "tensor", "ms": t * 1e3, "tflops": ach,
                     "frac": ach / pk["tflops"]})
     # (2) full-res 32->32 k3 frustum conv (HBM-bound in the algorithmic accounting: in + out once)
@@ -470,10 +583,18 @@ def dominant_kernel_roofline(model, mc, dev, pk):
 
     def frustum_conv():
         ops.arena(dev).reset()
-        ops.conv(Vol(xv), c32, out=yv, want_stats=True)
+        ops.conv(Vol(xv), c32, out=yv, want_stats=True, math_mode=ops.SS_MATH_TF32)
     t = _time_launches(frustum_conv)
     byts = 2.0 * xv.numel() * 4
     kernels.append({"name": "frustum conv3d 32->32 k3 (112x48x160)", "bound": "hbm", "ms": t * 1e3,
+                    "gbs": byts / t / 1e9, "frac": byts / t / 1e9 / pk["hbm_gbs"],
+                    "tflops": 2.0 * D * H * W * 27 * 32 * 32 / t / 1e12})
+
+    def frustum_conv_x3():
+        ops.arena(dev).reset()
+        ops.conv(Vol(xv), c32, out=yv, want_stats=True, math_mode=ops.SS_MATH_TF32X3)
+    t = _time_launches(frustum_conv_x3)
+    kernels.append({"name": "frustum conv3d 32->32 k3, compensated TF32x3 (3 accumulating launches)", "bound": "hbm", "ms": t * 1e3,
                     "gbs": byts / t / 1e9, "frac": byts / t / 1e9 / pk["hbm_gbs"],
                     "tflops": 2.0 * D * H * W * 27 * 32 * 32 / t / 1e12})
     # (3) gwc + warp (write-bound)
@@ -511,10 +632,13 @@ def dominant_kernel_roofline(model, mc, dev, pk):
     # (7) DepthNet 2-D conv 640->640 k3 on the 48x160 map (tensor-bound, 56.6 GFLOP, one wave of 120 CTAs)
     dc = vt.depth_net.depth_conv[0].conv1
     xd = torch.randn((1, 1, H, W, dc.in_channels), device=dev)
-    t = _time_launches(lambda: ops.conv(Vol(xd), dc))
+    t = _time_launches(lambda: ops.conv(Vol(xd), dc, math_mode=ops.SS_MATH_TF32))
     fl = 2.0 * H * W * 9 * dc.in_channels * dc.out_channels
     kernels.append({"name": "depth_net conv2d 640->640 k3 (48x160)", "bound": "tensor", "ms": t * 1e3, "tflops": fl / t / 1e12,
                     "frac": fl / t / 1e12 / pk["tflops"]})
+    t = _time_launches(lambda: ops.conv(Vol(xd), dc, math_mode=ops.SS_MATH_TF32X3))
+    kernels.append({"name": "depth_net conv2d 640->640 k3, compensated TF32x3", "bound": "tensor", "ms": t * 1e3,
+                    "tflops": fl / t / 1e12, "frac": fl / t / 1e12 / pk["tflops"]})
     return roof, kernels
 
 

@@ -41,15 +41,20 @@ extern "C" {
 #define SS_ACT_GELU 2                  /* exact erf GELU (nn.GELU default) */
 
 #define SS_MATH_TF32 0                 /* tensor-core TF32 multiply, fp32 accumulate */
-#define SS_MATH_3XTF32 1               /* error-compensated split (hi/lo) TF32: ~fp32 accuracy */
+#define SS_MATH_3XTF32 1               /* error-compensated split (hi/lo) TF32 on the mma.sync kernels: ~fp32 accuracy */
+#define SS_MATH_TF32X3 2               /* the same compensation on the tcgen05 kernels (ss_conv3d_tc_fwd / _join_fwd): three TF32
+                                          launches lo(x)*hi(w) + hi(x)*lo(w) + hi(x)*hi(w) accumulated in fp32 */
 
 /* ABI version of this header; ss_abi_version() of the library must match. */
-#define SS_ABI_VERSION 4
+#define SS_ABI_VERSION 5
 int ss_abi_version(void);
 /* Text of the last CUDA error seen by the calling thread (host pointer, never NULL). */
 const char* ss_last_error_string(void);
 /* Number of kernel launches issued through this library by the calling process so far. */
 long long ss_launch_count(void);
+/* Per-kernel launch census of the calling process: writes "kernel_name=count\n" lines (one per kernel family that has
+ * launched at least once) into buf (HOST, NUL-terminated, truncated to cap bytes) and returns the number of families. */
+int ss_kernel_census(char* buf, size_t cap);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense 3-D / 2-D convolution family (implicit GEMM on tensor cores).
@@ -86,11 +91,14 @@ int ss_conv3d_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_sc
 
 /* Same contract on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM,
  * mbarrier-pipelined shared-memory staging with the pending affine applied by the producer warps).
- * Requirements: Cin % 32 == 0, in_ldc % 4 == 0, x 16-byte aligned, desc->math == SS_MATH_TF32.
+ * Requirements: Cin % 32 == 0, in_ldc % 4 == 0, x 16-byte aligned, desc->math == SS_MATH_TF32 or SS_MATH_TF32X3.
  * w_kmajor: float[taps][cout_packed][Cin] (K-major: the 32-channel chunk of one output channel is one
  * 128-byte shared-memory row), values pre-rounded to TF32 (round-to-nearest, ties away from zero):
  *   Conv:          w_kmajor[t][co][ci] = tf32(weight[co][ci][kd][kh][kw])
- *   ConvTranspose: w_kmajor[t][co][ci] = tf32(weight[ci][co][kd][kh][kw])     (rows >= Cout are zero) */
+ *   ConvTranspose: w_kmajor[t][co][ci] = tf32(weight[ci][co][kd][kh][kw])     (rows >= Cout are zero)
+ * SS_MATH_TF32X3: w_kmajor holds TWO such arrays back to back, hi = tf32(w) followed by lo = tf32(w - hi); the activations
+ * are split the same way on the fly and the three partial products are accumulated into y by three launches (y is read
+ * back by the second and third), so the result has ~fp32 accuracy at ~3x the tensor work. */
 int ss_conv3d_tc_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_scale, const float* in_shift,
                      const float* w_kmajor, const float* bias, float* y, double* stats, void* stream);
 

@@ -10,10 +10,10 @@ import os
 
 from . import _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU = 0, 1, 2
-SS_MATH_TF32, SS_MATH_3XTF32 = 0, 1
+SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3 = 0, 1, 2
 
 
 class ConvDesc(C.Structure):
@@ -39,6 +39,7 @@ SIGNATURES = {
     "ss_abi_version": (_i, []),
     "ss_last_error_string": (C.c_char_p, []),
     "ss_launch_count": (_ll, []),
+    "ss_kernel_census": (_i, [C.c_char_p, _sz]),
     "ss_conv3d_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_conv3d_tc_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_conv3d_tc_join_supported": (_i, [C.POINTER(ConvDesc)]),
@@ -98,3 +99,14 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().ss_launch_count())
+
+
+def kernel_census() -> dict:
+    """kernel name -> launches issued by this process so far (per kernel family of the library)."""
+    buf = C.create_string_buffer(8192)
+    load().ss_kernel_census(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        k, _, v = line.partition("=")
+        out[k] = int(v)
+    return out

@@ -11,10 +11,12 @@ extern thread_local char g_last_error[256];
 extern std::atomic<long long> g_launches;
 
 int set_cuda_error(cudaError_t e, const char* where);
+void count_kernel(const char* name);
 int set_arg_error(const char* msg);
 
 inline int check_launch(const char* where) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_kernel(where);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, where);
     return SS_OK;
@@ -38,6 +40,20 @@ __device__ __forceinline__ uint32_t f2tf32(float x) {
     uint32_t r;
     asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
+}
+
+// One pass of the error-compensated mode (SS_MATH_TF32X3) on the tcgen05 kernels.  x = hi + lo with hi = tf32(x),
+// lo = tf32(x - hi), likewise for the weights (split on the host); conv(x, w) ~= lo_x*hi_w + hi_x*lo_w + hi_x*hi_w, each
+// term one ordinary TF32 launch whose products are exact in fp32.  a_lo selects which part of the A operand the fix-up
+// warps write; accumulate makes the epilogue add the output already in memory (bias, activation, statistics and a
+// fused join belong to the last pass only).
+struct ConvPass {
+    int a_lo;
+    int accumulate;
+};
+__device__ __forceinline__ uint32_t f2tf32_part(float x, int a_lo) {
+    const uint32_t h = f2tf32(x);
+    return a_lo ? f2tf32(x - __uint_as_float(h)) : h;
 }
 
 // D(16x8,f32) += A(16x8,tf32,row) * B(8x8,tf32,col)

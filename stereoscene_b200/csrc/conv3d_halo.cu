@@ -31,6 +31,7 @@ struct HaloParams {
     int nTH, nTW;
     int sH, sW, swap;             // voxel strides of the kernel's h / w axes; swap = 1: the kernel's (h,w) are the tensor's (w,h)
     int KD;                       // depth taps: 3 (3x3x3, pad 1) or 1 (2-D 3x3 layers, D == 1 planes)
+    int a_lo, accumulate;         // ConvPass (common.cuh)
     const float* in_scale;
     const float* in_shift;
     const float* bias;
@@ -137,7 +138,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
                    accum_bar = h_smem_u32(bars + 3 * HL_NPL + 2 * SB);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu;
+    const bool fixup = has_aff || in_relu || p.a_lo;
     const int kchunks = p.Cin / 32;
     const int KD = p.KD;
 
@@ -248,7 +249,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
                         }
                         if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                         uint4 o;
-                        o.x = f2tf32(v.x); o.y = f2tf32(v.y); o.z = f2tf32(v.z); o.w = f2tf32(v.w);
+                        o.x = f2tf32_part(v.x, p.a_lo); o.y = f2tf32_part(v.y, p.a_lo); o.z = f2tf32_part(v.z, p.a_lo); o.w = f2tf32_part(v.w, p.a_lo);
                         *reinterpret_cast<uint4*>(ptr) = o;
                     }
                 }
@@ -283,6 +284,20 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
             float v[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+            if (p.accumulate && valid) {                       // later pass of the compensated mode: add the partial result
+                const float* src = p.y + ov * p.out_ldc + cbase;
+                if (vec_ok && cbase + 32 <= p.Cout) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(src + k);
+                        v[k] += t4.x; v[k + 1] += t4.y; v[k + 2] += t4.z; v[k + 3] += t4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cbase + k < p.Cout) v[k] += src[k];
+                }
+            }
             if (has_bias) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k)
@@ -373,7 +388,7 @@ static int launch_halo(const HaloParams& p, const CUtensorMap& tmA, const float*
 
 // returns 1 if the layer was handled here
 int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
-                  const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
+                  const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps) {
     if (d->transposed || d->Cin % 32 != 0 || d->cout_packed < 64 || d->kh != 3 || d->kw != 3) return 0;
     if (!((d->kd == 3 && d->pd == 1) || (d->kd == 1 && d->pd == 0))) return 0;     // 3x3x3, or 2-D 3x3 (one plane per chunk)
     if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
@@ -401,7 +416,8 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
     p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act; p.nTH = nTH; p.nTW = nTW; p.KD = d->kd;
     p.swap = swap; p.sH = swap ? 1 : d->Win; p.sW = swap ? d->Win : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
     alignas(64) CUtensorMap tmA;
     // tensor map dims in the kernel's order (C, w, h, D, B); the byte strides say which tensor axis each one walks
     const cuuint64_t str_w = (cuuint64_t)d->in_ldc * 4, str_h = (cuuint64_t)d->Win * d->in_ldc * 4;

@@ -53,6 +53,7 @@ struct MarchParams {
     int B, D, H, W, Cout, out_ldc, in_act, out_act;
     int nTH, nTW;
     long long total_tiles;                           // B * nTH * nTW * D
+    int a_lo, accumulate;                            // ConvPass (common.cuh)
     const float* in_scale;
     const float* in_shift;
     const float* bias;
@@ -255,6 +256,23 @@ __device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t
         float v[NCOL];
 #pragma unroll
         for (int k = 0; k < NCOL; ++k) v[k] = __uint_as_float(r[k]) + bias_r[k];
+        if (p.accumulate) {                                     // later pass of the compensated mode: add the partial result
+            const int ah = c.th * MR_TH + lh, aw = c.tw * MR_TW + lw;
+            if (ah < p.H && aw < p.W) {
+                const float* src = p.y + ((((size_t)c.b * p.D + c.d) * p.H + ah) * p.W + aw) * p.out_ldc + col0;
+                if (vec_ok) {
+#pragma unroll
+                    for (int k = 0; k < NCOL; k += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(src + k);
+                        v[k] += t4.x; v[k + 1] += t4.y; v[k + 2] += t4.z; v[k + 3] += t4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NCOL; ++k)
+                        if (col0 + k < p.Cout) v[k] += src[k];
+                }
+            }
+        }
         if (act == SS_ACT_RELU) {
 #pragma unroll
             for (int k = 0; k < NCOL; ++k) v[k] = fmaxf(v[k], 0.f);
@@ -314,7 +332,7 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                    t_empty0 = m_smem_u32(bars + 1 + 3 * MR_NP + MR_ACC);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu;
+    const bool fixup = has_aff || in_relu || p.a_lo;
 
     // this CTA's contiguous range of flat tiles
     const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
@@ -499,7 +517,7 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                                 }
                                 if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                                 uint4 o;
-                                o.x = f2tf32(v.x); o.y = f2tf32(v.y); o.z = f2tf32(v.z); o.w = f2tf32(v.w);
+                                o.x = f2tf32_part(v.x, p.a_lo); o.y = f2tf32_part(v.y, p.a_lo); o.z = f2tf32_part(v.z, p.a_lo); o.w = f2tf32_part(v.w, p.a_lo);
                                 *reinterpret_cast<uint4*>(ptr) = o;
                             }
                         }
@@ -568,7 +586,7 @@ static int launch_march(const MarchParams& p, const ss_conv3d_desc* d, const flo
 
 // returns 1 if the layer was handled by the marching kernel
 int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
-                     const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
+                     const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps) {
     if (d->transposed || d->Cin != 32 || d->cout_packed != 32) return 0;      // Cout < 32 layers arrive padded to 32 weight rows
     const bool k3 = d->kd == 3 && d->kh == 3 && d->kw == 3 && d->pd == 1 && d->ph == 1 && d->pw == 1;
     const bool k1 = d->kd == 1 && d->kh == 1 && d->kw == 1 && d->pd == 0 && d->ph == 0 && d->pw == 0;
@@ -590,7 +608,8 @@ int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_sc
     p.nTH = (p.H + MR_TH - 1) / MR_TH; p.nTW = (p.W + MR_TW - 1) / MR_TW;
     p.total_tiles = (long long)p.B * p.nTH * p.nTW * p.D;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
     *rc = k3 ? launch_march<3>(p, d, x, w_kmajor, fixup, encode, st) : launch_march<1>(p, d, x, w_kmajor, fixup, encode, st);
     return 1;
 }

@@ -45,6 +45,7 @@ struct TcParams {
     const float* bias;
     float* y;
     double* stats;
+    int a_lo, accumulate;      // ConvPass (common.cuh)
 };
 
 __host__ __device__ inline int tc_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -216,7 +217,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
                    accum_bar = smem_u32(bars + 3 * STAGES);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu;
+    const bool fixup = has_aff || in_relu || p.a_lo;
 
     // ---- per-CTA setup ------------------------------------------------------------------------
     if (tid == 0) {
@@ -346,8 +347,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
                         w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
                     }
                     if (in_relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
-                    o[4 * j + 0] = ok ? f2tf32(w.x) : 0u; o[4 * j + 1] = ok ? f2tf32(w.y) : 0u;
-                    o[4 * j + 2] = ok ? f2tf32(w.z) : 0u; o[4 * j + 3] = ok ? f2tf32(w.w) : 0u;
+                    o[4 * j + 0] = ok ? f2tf32_part(w.x, p.a_lo) : 0u; o[4 * j + 1] = ok ? f2tf32_part(w.y, p.a_lo) : 0u;
+                    o[4 * j + 2] = ok ? f2tf32_part(w.z, p.a_lo) : 0u; o[4 * j + 3] = ok ? f2tf32_part(w.w, p.a_lo) : 0u;
                 }
                 tmem_st16_nowait(t_row + (uint32_t)(slot * TC_BK + hh * 16), o);
             }
@@ -387,6 +388,20 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             float v[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+            if (p.accumulate && ov >= 0) {                     // later pass of the compensated mode: add the partial result
+                const float* src = p.y + (size_t)ov * p.out_ldc + cbase;
+                if (vec_ok && cbase + 32 <= p.Cout) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(src + k);
+                        v[k] += t4.x; v[k + 1] += t4.y; v[k + 2] += t4.z; v[k + 3] += t4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cbase + k < p.Cout) v[k] += src[k];
+                }
+            }
             if (has_bias) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k)
@@ -498,7 +513,7 @@ static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, i
         cuuint32_t estr[5] = {1, (cuuint32_t)isw, (cuuint32_t)ish, (cuuint32_t)isd, 1};
         // plain input: TFLOAT32 (the TMA unit rounds fp32 -> tf32); pending affine: raw FLOAT32, the fix-up
         // warps round once, after the affine
-        const bool fixup = (p.in_scale != nullptr) || (p.in_act == SS_ACT_RELU);
+        const bool fixup = (p.in_scale != nullptr) || (p.in_act == SS_ACT_RELU) || p.a_lo;
         CUresult r = encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -530,35 +545,18 @@ static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, i
 
 namespace ss {
 int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
-                     const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
+                     const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps);
 int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
-                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join);
+                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join, const ConvPass& ps);
 int conv_tpose_join_supported(const ss_conv3d_desc* d);
 int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
-                const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
+                const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps);
 int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
-                  const float* bias, float* y, double* stats, cudaStream_t st, int* rc);
-}
+                  const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps);
 
-// wk: float[taps][cout_packed][Cin], K-major, values already rounded to TF32.
-extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
-                                const float* w_kmajor, const float* bias, float* y, double* stats, void* stream) {
-    using namespace ss;
-    SS_REQUIRE(d && x && w_kmajor && y, "ss_conv3d_tc_fwd: null pointer");
-    SS_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0, "ss_conv3d_tc_fwd: empty shape");
-    SS_REQUIRE(d->Cin % TC_BK == 0 && d->in_ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
-               "ss_conv3d_tc_fwd: needs Cin % 32 == 0 and 16-byte aligned channels-last input");
-    SS_REQUIRE((reinterpret_cast<uintptr_t>(w_kmajor) & 15) == 0, "ss_conv3d_tc_fwd: weights must be 16-byte aligned");
-    SS_REQUIRE(d->kd >= 1 && d->kd <= 4 && d->kh >= 1 && d->kh <= 4 && d->kw >= 1 && d->kw <= 4, "ss_conv3d_tc_fwd: kernel extent");
-    SS_REQUIRE(d->sd >= 1 && d->sd <= 8 && d->sh >= 1 && d->sh <= 8 && d->sw >= 1 && d->sw <= 8, "ss_conv3d_tc_fwd: stride");
-    SS_REQUIRE(d->cout_packed >= d->Cout && d->cout_packed % 8 == 0, "ss_conv3d_tc_fwd: cout_packed");
-    SS_REQUIRE(d->in_ldc >= d->Cin && d->out_ldc >= d->Cout, "ss_conv3d_tc_fwd: ldc");
-    SS_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "ss_conv3d_tc_fwd: scale/shift must come together");
-    SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_tc_fwd: in_act");
-    SS_REQUIRE(d->Cin <= 4096, "ss_conv3d_tc_fwd: Cin limited to 4096");
-    SS_REQUIRE((long long)d->B * d->Dout * d->Hout * d->Wout < (1ll << 31), "ss_conv3d_tc_fwd: output too large");
-    SS_REQUIRE(d->math == SS_MATH_TF32, "ss_conv3d_tc_fwd: TF32 only (use ss_conv3d_fwd for 3xTF32)");
-    if (d->transposed) SS_REQUIRE(d->dd == 1 && d->dh == 1 && d->dw == 1, "ss_conv3d_tc_fwd: dilated transposed conv unsupported");
+// One TF32 launch of the convolution family: picks the kernel for the layer shape (d->math must be SS_MATH_TF32 here).
+static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
+                       const float* bias, float* y, double* stats, cudaStream_t st, const ConvPass& ps) {
     TcParams p;
     p.B = d->B; p.Din = d->Din; p.Hin = d->Hin; p.Win = d->Win; p.Cin = d->Cin;
     p.Dout = d->Dout; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout; p.CoutP = d->cout_packed;
@@ -567,17 +565,17 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     p.transposed = d->transposed; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
     p.cls_d = d->transposed ? d->sd : 1; p.cls_h = d->transposed ? d->sh : 1; p.cls_w = d->transposed ? d->sw : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     {   // 32-channel 3x3x3 stride-1 layers: persistent marching kernel (halo planes + resident weights)
         int rcm = 0;
-        if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
+        if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
         // pointwise layers with short K: persistent streaming GEMM with resident weights
-        if (try_conv_pw(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
+        if (try_conv_pw(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
         // wide 3x3x3 stride-1 layers: halo-resident kernel (planes loaded once per chunk, two M tiles per weight tile)
-        if (try_conv_halo(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm)) return rcm;
+        if (try_conv_halo(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
         // stride-2 transposed 3x3x3 layers: one CTA per input tile computes all 8 output parity classes
-        if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, nullptr)) return rcm;
+        if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, nullptr, ps)) return rcm;
     }
     const int cp = d->cout_packed;
     const int ntaps_total = d->kd * d->kh * d->kw;
@@ -602,13 +600,58 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     return launch_tc<256>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
 }
 
+// The compensated mode (SS_MATH_TF32X3): three TF32 launches that accumulate into y, smallest terms first.
+// w_kmajor holds the hi parts followed by the lo parts (2 x taps x cout_packed x Cin floats).
+template <typename F>
+static int tc_three_pass(const ss_conv3d_desc* d, const float* w_kmajor, F&& launch) {
+    ss_conv3d_desc t = *d;
+    t.math = SS_MATH_TF32;
+    const size_t wn = (size_t)d->kd * d->kh * d->kw * d->cout_packed * d->Cin;
+    if (d->math == SS_MATH_TF32) return launch(&t, w_kmajor, ConvPass{0, 0}, true);
+    ss_conv3d_desc part = t;
+    part.out_act = SS_ACT_NONE;
+    int rc = launch(&part, w_kmajor, ConvPass{1, 0}, false);                 // lo(x) * hi(w)
+    if (rc != SS_OK) return rc;
+    rc = launch(&part, w_kmajor + wn, ConvPass{0, 1}, false);                // hi(x) * lo(w)
+    if (rc != SS_OK) return rc;
+    return launch(&t, w_kmajor, ConvPass{0, 1}, true);                       // hi(x) * hi(w) + bias, activation, statistics, join
+}
+}  // namespace ss
+
+// wk: float[taps][cout_packed][Cin], K-major, values already rounded to TF32.
+extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                                const float* w_kmajor, const float* bias, float* y, double* stats, void* stream) {
+    using namespace ss;
+    SS_REQUIRE(d && x && w_kmajor && y, "ss_conv3d_tc_fwd: null pointer");
+    SS_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0, "ss_conv3d_tc_fwd: empty shape");
+    SS_REQUIRE(d->Cin % TC_BK == 0 && d->in_ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+               "ss_conv3d_tc_fwd: needs Cin % 32 == 0 and 16-byte aligned channels-last input");
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(w_kmajor) & 15) == 0, "ss_conv3d_tc_fwd: weights must be 16-byte aligned");
+    SS_REQUIRE(d->kd >= 1 && d->kd <= 4 && d->kh >= 1 && d->kh <= 4 && d->kw >= 1 && d->kw <= 4, "ss_conv3d_tc_fwd: kernel extent");
+    SS_REQUIRE(d->sd >= 1 && d->sd <= 8 && d->sh >= 1 && d->sh <= 8 && d->sw >= 1 && d->sw <= 8, "ss_conv3d_tc_fwd: stride");
+    SS_REQUIRE(d->cout_packed >= d->Cout && d->cout_packed % 8 == 0, "ss_conv3d_tc_fwd: cout_packed");
+    SS_REQUIRE(d->in_ldc >= d->Cin && d->out_ldc >= d->Cout, "ss_conv3d_tc_fwd: ldc");
+    SS_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "ss_conv3d_tc_fwd: scale/shift must come together");
+    SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_tc_fwd: in_act");
+    SS_REQUIRE(d->Cin <= 4096, "ss_conv3d_tc_fwd: Cin limited to 4096");
+    SS_REQUIRE((long long)d->B * d->Dout * d->Hout * d->Wout < (1ll << 31), "ss_conv3d_tc_fwd: output too large");
+    SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3, "ss_conv3d_tc_fwd: TF32 / TF32X3 only (use ss_conv3d_fwd for 3xTF32 on mma.sync)");
+    if (d->transposed) SS_REQUIRE(d->dd == 1 && d->dh == 1 && d->dw == 1, "ss_conv3d_tc_fwd: dilated transposed conv unsupported");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return tc_three_pass(d, w_kmajor, [&](const ss_conv3d_desc* dd, const float* w, const ConvPass& ps, bool last) {
+        return tc_dispatch(dd, x, in_scale, in_shift, w, last ? bias : nullptr, y, last ? stats : nullptr, st, ps);
+    });
+}
+
 
 // Convolution with the residual join fused into its epilogue (hourglass conv5 / conv6 + their joins,
 // ViewTransformerLSSVoxel.py:92-95).  Served by the stride-2 transposed kernel; ss_conv3d_tc_join_supported tells the caller
 // whether a layer qualifies (otherwise: ss_conv3d_tc_fwd followed by ss_affine_join_fwd).
 extern "C" int ss_conv3d_tc_join_supported(const ss_conv3d_desc* d) {
     if (!d || d->Cin % 32 != 0 || d->in_ldc % 4 != 0) return 0;
-    return ss::conv_tpose_join_supported(d);
+    ss_conv3d_desc t = *d;
+    if (t.math == SS_MATH_TF32X3) t.math = SS_MATH_TF32;        // the compensated mode runs the same kernel three times
+    return ss::conv_tpose_join_supported(&t);
 }
 
 extern "C" int ss_conv3d_tc_join_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
@@ -624,8 +667,12 @@ extern "C" int ss_conv3d_tc_join_fwd(const ss_conv3d_desc* d, const float* x, co
     SS_REQUIRE(join->res_act == SS_ACT_NONE || join->res_act == SS_ACT_RELU, "ss_conv3d_tc_join_fwd: res_act");
     SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_tc_join_fwd: in_act");
     SS_REQUIRE(d->out_ldc >= d->Cout && d->cout_packed >= d->Cout, "ss_conv3d_tc_join_fwd: ldc");
-    SS_REQUIRE(conv_tpose_join_supported(d), "ss_conv3d_tc_join_fwd: layer not supported by the fused kernel (query ss_conv3d_tc_join_supported)");
-    int rc = 0;
-    if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, nullptr, reinterpret_cast<cudaStream_t>(stream), &rc, join)) return rc;
-    return set_arg_error("ss_conv3d_tc_join_fwd: layer not supported by the fused kernel");
+    SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3, "ss_conv3d_tc_join_fwd: math mode");
+    SS_REQUIRE(ss_conv3d_tc_join_supported(d), "ss_conv3d_tc_join_fwd: layer not supported by the fused kernel (query ss_conv3d_tc_join_supported)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return tc_three_pass(d, w_kmajor, [&](const ss_conv3d_desc* dd, const float* w, const ConvPass& ps, bool last) {
+        int rc = 0;
+        if (try_conv_tpose(dd, x, in_scale, in_shift, w, last ? bias : nullptr, y, nullptr, st, &rc, last ? join : nullptr, ps)) return rc;
+        return set_arg_error("ss_conv3d_tc_join_fwd: layer not supported by the fused kernel");
+    });
 }

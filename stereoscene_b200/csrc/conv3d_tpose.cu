@@ -38,6 +38,7 @@ struct TposeParams {
     const float* r_scale;
     const float* r_shift;
     int res_ldc, res_act, has_join;
+    int a_lo, accumulate;            // ConvPass (common.cuh)
 };
 
 __device__ __forceinline__ uint32_t t_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -152,7 +153,7 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                    accum_bar = t_smem_u32(bars + 3 * TP_NPL + 2 * TP_SB);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu;
+    const bool fixup = has_aff || in_relu || p.a_lo;
     const int kchunks = p.Cin / 32;
 
     if (tid == 0) {
@@ -279,7 +280,7 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                         }
                         if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                         uint4 o;
-                        o.x = f2tf32(v.x); o.y = f2tf32(v.y); o.z = f2tf32(v.z); o.w = f2tf32(v.w);
+                        o.x = f2tf32_part(v.x, p.a_lo); o.y = f2tf32_part(v.y, p.a_lo); o.z = f2tf32_part(v.z, p.a_lo); o.w = f2tf32_part(v.w, p.a_lo);
                         *reinterpret_cast<uint4*>(ptr) = o;
                     }
                 }
@@ -308,6 +309,12 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                 t_tmem_ld32(tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(cls * BN + ci * 32), r);
                 const int cbase = ci * 32;
                 float v[32];
+                if (p.accumulate) {                            // later pass of the compensated mode: add the partial result
+                    const float* src = p.y + ov * p.out_ldc + cbase;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (valid && cbase + k < p.Cout) r[k] = __float_as_uint(__uint_as_float(r[k]) + src[k]);
+                }
                 if (p.has_join) {
                     // residual-fused epilogue: the join that would re-read this tensor and the residual runs here
                     const bool rvec = valid && p.res && ((p.res_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) &&
@@ -432,7 +439,7 @@ static bool tpose_eligible(const ss_conv3d_desc* d) {
 int conv_tpose_join_supported(const ss_conv3d_desc* d) { return tpose_eligible(d) ? 1 : 0; }
 
 int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
-                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join) {
+                   const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join, const ConvPass& ps) {
     if (!d->transposed || d->Cin % 32 != 0 || d->kd != 3 || d->kh != 3 || d->kw != 3) return 0;
     if (d->sd != 2 || d->sh != 2 || d->sw != 2 || d->pd != 1 || d->ph != 1 || d->pw != 1) return 0;
     if (d->math != SS_MATH_TF32 || (d->cout_packed != 32 && d->cout_packed != 64)) return 0;
@@ -457,7 +464,8 @@ int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scal
     p.o_scale = join ? join->out_scale : nullptr; p.o_shift = join ? join->out_shift : nullptr;
     p.res = join ? join->res : nullptr; p.r_scale = join ? join->res_scale : nullptr; p.r_shift = join ? join->res_shift : nullptr;
     p.res_ldc = join ? join->res_ldc : 0; p.res_act = join ? join->res_act : 0;
-    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
     alignas(64) CUtensorMap tmA;
     cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.Din, (cuuint64_t)p.B};
     cuuint64_t gstr[4] = {(cuuint64_t)d->in_ldc * 4, (cuuint64_t)p.Win * d->in_ldc * 4, (cuuint64_t)p.Hin * p.Win * d->in_ldc * 4,

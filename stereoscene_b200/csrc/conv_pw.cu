@@ -37,6 +37,7 @@ struct PwParams {
     const float* bias;
     float* y;
     double* stats;
+    int a_lo, accumulate;                            // ConvPass (common.cuh)
 };
 
 __device__ __forceinline__ uint32_t pw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,7 +95,7 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
                    t_full0 = pw_smem_u32(bars + 2 + 3 * PW_MAXRS), t_empty0 = pw_smem_u32(bars + 2 + 3 * PW_MAXRS + PW_ACC);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu;
+    const bool fixup = has_aff || in_relu || p.a_lo;
     const int G = NP / 32;                                        // 32-column groups of the accumulator
     const int wgroups = fixup ? 1 : (G >= 2 ? 2 : 1);             // epilogue warp groups (of 4 warps) that drain TMEM
     // this CTA's contiguous range of work items; item = group * T + tile, group = class * NH + column half
@@ -210,7 +211,7 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
                         }
                         if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                         uint4 o;
-                        o.x = f2tf32(x.x); o.y = f2tf32(x.y); o.z = f2tf32(x.z); o.w = f2tf32(x.w);
+                        o.x = f2tf32_part(x.x, p.a_lo); o.y = f2tf32_part(x.y, p.a_lo); o.z = f2tf32_part(x.z, p.a_lo); o.w = f2tf32_part(x.w, p.a_lo);
                         *reinterpret_cast<uint4*>(ptr) = o;
                     }
                 }
@@ -272,6 +273,20 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
                 float x[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(r[k]);
+                if (p.accumulate && valid) {                   // later pass of the compensated mode: add the partial result
+                    const float* src = p.y + ov * p.out_ldc + cbase;
+                    if (vec_ok && cbase + 32 <= p.Cout) {
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(src + k);
+                            x[k] += t4.x; x[k + 1] += t4.y; x[k + 2] += t4.z; x[k + 3] += t4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            if (cbase + k < p.Cout) x[k] += src[k];
+                    }
+                }
                 if (p.bias) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k)
@@ -330,7 +345,7 @@ typedef CUresult (*PwEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 // returns 1 if the layer was handled here
 int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
-                const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
+                const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps) {
     if (d->math != SS_MATH_TF32 || d->pd != 0 || d->ph != 0 || d->pw != 0 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
     int s = 1;
     if (d->kd == 1 && d->kh == 1 && d->kw == 1 && d->sd == 1 && d->sh == 1 && d->sw == 1) {       // also ConvTranspose k = s = 1
@@ -343,7 +358,7 @@ int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, 
         return 0;
     }
     if (d->Cin % 32 != 0 || d->Cin > 512 || d->cout_packed > 128) return 0;
-    const bool pending = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU);
+    const bool pending = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
     if (pending && d->Cin > 64) return 0;            // 4 fix-up warps cannot keep up with wide pending inputs: the box kernel's TMEM fix-up path wins
     const long long vpb = (long long)d->Din * d->Hin * d->Win, V = vpb * d->B;
     const int ncls = s * s * s;
@@ -396,6 +411,7 @@ int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, 
     p.Cin = d->Cin; p.KC = KC; p.Cout = d->Cout; p.CoutP = d->cout_packed; p.NP = NP; p.out_ldc = d->out_ldc;
     p.in_act = d->in_act; p.out_act = d->out_act; p.RS = RS; p.scratch_floats = scratch_floats;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
     const size_t smem = fixed_bytes(NP) + (size_t)RS * PW_TILE * 128;
     static thread_local size_t configured = 0;
     if (smem > configured) {

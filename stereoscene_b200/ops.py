@@ -23,7 +23,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import cabi
-from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_TF32  # noqa: F401
+from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_TF32, SS_MATH_TF32X3  # noqa: F401
 
 _DEFAULT_MATH = SS_MATH_TF32
 _USE_TCGEN05 = os.environ.get("STEREOSCENE_B200_NO_TCGEN05", "0") != "1"
@@ -38,18 +38,72 @@ def use_tcgen05(flag: bool):
 
 
 def set_default_math(mode: int):
-    """SS_MATH_TF32 (fast) or SS_MATH_3XTF32 (split-TF32, ~fp32 accuracy) for conv / BRI energy."""
-    global _DEFAULT_MATH
-    assert mode in (SS_MATH_TF32, SS_MATH_3XTF32)
+    """Uniform math mode for every stage (switches the per-stage policy off): SS_MATH_TF32 (fast), SS_MATH_TF32X3 (error-compensated split TF32 on the tcgen05 kernels, ~fp32 accuracy at ~3x the
+    tensor work) or SS_MATH_3XTF32 (the same compensation on the mma.sync kernels) for conv / BRI energy."""
+    global _DEFAULT_MATH, _POLICY
+    assert mode in (SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3)
     _DEFAULT_MATH = mode
+    _POLICY = None                      # a uniform mode replaces the per-stage policy
 
 
 def default_math() -> int:
     return _DEFAULT_MATH
 
 
+# ---- per-stage math policy -----------------------------------------------------------------------------------------
+# The path has four stage groups: "stereo" (stereofeature_net, cost volume, cost aggregation), "depthnet", "mie"
+# (BRI + DVE) -- the frustum-space stages, each ending in a softmax over depth that amplifies an absolute error of the
+# depth logits into a relative error of the probabilities -- and "voxel" (3-D encoder, neck, head).  Measured at
+# configs[2] against the reference's own forward (profiles/r02_parity_*.md): with the frustum stages compensated the
+# voxel stages stay within 1e-3 of the reference in plain TF32, while compensating the voxel stages alone changes
+# nothing.  A policy maps group -> math mode; the modules enter ``math_scope(group)`` around their stage.
+MATH_POLICIES = {
+    "tf32": {},                                                                          # every stage plain TF32
+    "mixed": {"stereo": SS_MATH_TF32X3, "depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3},   # the parity-green product mode
+    "tf32x3": {g: SS_MATH_TF32X3 for g in ("stereo", "depthnet", "mie", "voxel")},
+    "3xtf32": {g: SS_MATH_3XTF32 for g in ("stereo", "depthnet", "mie", "voxel")},
+}
+DEFAULT_POLICY = "mixed"
+_POLICY: Optional[dict] = dict(MATH_POLICIES[DEFAULT_POLICY])
+
+
+def set_math_policy(policy):
+    """``policy``: a name from MATH_POLICIES, a dict group -> SS_MATH_*, or None = the product default ("mixed":
+    the cheapest policy whose logits are within 1e-3 of the reference at configs[1] and configs[2])."""
+    global _POLICY, _DEFAULT_MATH
+    if policy is None:
+        policy = DEFAULT_POLICY
+    if isinstance(policy, str):
+        policy = MATH_POLICIES[policy]
+    _POLICY = dict(policy)
+    _DEFAULT_MATH = SS_MATH_TF32
+
+
+def math_policy():
+    return _POLICY
+
+
+class math_scope:
+    """Context manager: run a stage group in the math mode the active policy assigns to it (no policy: unchanged)."""
+
+    def __init__(self, group: str):
+        self.group = group
+
+    def __enter__(self):
+        global _DEFAULT_MATH
+        self.saved = _DEFAULT_MATH
+        if _POLICY is not None:
+            _DEFAULT_MATH = _POLICY.get(self.group, SS_MATH_TF32)
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFAULT_MATH
+        _DEFAULT_MATH = self.saved
+        return False
+
+
 # name -> mode constant, for the tests / bench (--math)
-MATH_MODES = {"tf32": SS_MATH_TF32, "3xtf32": SS_MATH_3XTF32}
+MATH_MODES = {"tf32": SS_MATH_TF32, "tf32x3": SS_MATH_TF32X3, "3xtf32": SS_MATH_3XTF32}
 
 
 def _stream() -> int:
@@ -182,6 +236,8 @@ class PackedConv:
         self._w = None
         self._kkey = None
         self._wk = None
+        self._skey = None
+        self._ws = None
 
     def weights(self) -> torch.Tensor:
         w = self.module.weight
@@ -220,6 +276,31 @@ class PackedConv:
                 self._wk = bits.view(torch.float32).contiguous()
             self._kkey = key
         return self._wk
+
+    def weights_kmajor_split(self) -> torch.Tensor:
+        """float[2][taps][Cout_padded][Cin]: hi = tf32(w) followed by lo = tf32(w - hi) -- the B operands of the
+        compensated tcgen05 mode (SS_MATH_TF32X3)."""
+        w = self.module.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self._skey:
+            with torch.no_grad():
+                wd = w.detach()
+                if wd.dim() == 4:
+                    wd = wd.unsqueeze(2)
+                pk = wd.permute(2, 3, 4, 1, 0) if self.transposed else wd.permute(2, 3, 4, 0, 1)   # [k,k,k,Cout,Cin]
+                pk = pk.reshape(-1, self.Cout, self.Cin).float()
+                if self.CoutP != self.Cout:
+                    pk = torch.nn.functional.pad(pk, (0, 0, 0, self.CoutP - self.Cout))
+                pk = pk.contiguous()
+
+                def rna(t):
+                    return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+                hi = rna(pk)
+                lo = rna((pk - hi).contiguous())
+                self._ws = torch.stack([hi, lo]).contiguous()
+            self._skey = key
+        return self._ws
 
     def out_size(self, din: Sequence[int]) -> Tuple[int, int, int]:
         out = []
@@ -286,8 +367,11 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
                       1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
     # single-output-channel layers ride the tensor-core kernel too (N padded to 32): it is faster than the FMA kernel
-    tc = (_USE_TCGEN05 and mm == SS_MATH_TF32 and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
+    tc = (_USE_TCGEN05 and mm in (SS_MATH_TF32, SS_MATH_TF32X3) and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
           and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
+    if mm == SS_MATH_TF32X3 and not tc:        # layers the tcgen05 kernels do not take (Cin = 2, odd strides): mma.sync split TF32
+        mm = SS_MATH_3XTF32
+        d.math = mm
     if (tc and not x.is_plain and math.prod(pc.k) >= 27 and Cin >= 256 and xin.numel() * 4 <= _MATERIALIZE_BYTES
             and not _halo_or_march_layer(pc, Din, Hin, Win, Cin)):
         # the per-tap box kernel re-applies a pending affine for every tap (27 x the work of the plane kernels): for a
@@ -298,7 +382,8 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
         d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
                           1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
     if tc:
-        rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights_kmajor().data_ptr(),
+        wk = pc.weights_kmajor_split() if mm == SS_MATH_TF32X3 else pc.weights_kmajor()
+        rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), wk.data_ptr(),
                                   _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
         cabi.check(rc, "ss_conv3d_tc_fwd")
     else:
@@ -319,7 +404,7 @@ def conv_join(x: Vol, module: torch.nn.Module, out_affine: Optional[Vol], res: O
     B, Din, Hin, Win, Cin = xin.shape
     Do, Ho, Wo = pc.out_size((Din, Hin, Win))
     mm = _DEFAULT_MATH
-    fused_ok = (_USE_TCGEN05 and _FUSE_JOIN and mm == SS_MATH_TF32 and Cin % 32 == 0 and xin.data_ptr() % 16 == 0 and
+    fused_ok = (_USE_TCGEN05 and _FUSE_JOIN and mm in (SS_MATH_TF32, SS_MATH_TF32X3) and Cin % 32 == 0 and xin.data_ptr() % 16 == 0 and
                 (out_affine is None or out_affine.act == SS_ACT_NONE))
     if fused_ok:
         in_ldc = _vol_ldc(xin, "conv_join input")
@@ -343,7 +428,8 @@ def conv_join(x: Vol, module: torch.nn.Module, out_affine: Optional[Vol], res: O
                       _ptr(res.shift) if res is not None else None,
                       _vol_ldc(res.data, "conv_join residual") if res is not None else 0, res.act if res is not None else 0)
     bias = module.bias if (use_bias and module.bias is not None) else None
-    rc = lib.ss_conv3d_tc_join_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), pc.weights_kmajor().data_ptr(),
+    wk = pc.weights_kmajor_split() if mm == SS_MATH_TF32X3 else pc.weights_kmajor()
+    rc = lib.ss_conv3d_tc_join_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), wk.data_ptr(),
                                    _ptr(bias.detach() if bias is not None else None), C.byref(j), out.data_ptr(), _stream())
     cabi.check(rc, "ss_conv3d_tc_join_fwd")
     return out
@@ -376,15 +462,16 @@ def bn_pending(y: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, act: 
     """Eval-mode BatchNorm as a pending affine from the running statistics (host-side, cached:
     it depends on parameters only)."""
     B = y.shape[0]
-    key = (id(bn), B, bn.weight.data_ptr(), bn.weight._version, bn.bias._version, bn.running_mean._version,
+    key = (bn.weight.data_ptr(), bn.weight._version, bn.bias._version, bn.running_mean._version,
            bn.running_var._version, bn.weight.device)
-    hit = _bn_cache.get(id(bn))
-    if hit is None or hit[0] != key:
+    slot = (id(bn), B)                                  # one entry per (module, batch size): alternating batch sizes do not thrash
+    hit = _bn_cache.get(slot)
+    if hit is None or hit[0] != key or hit[3] is not bn:
         with torch.no_grad():
             sc = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
             sh = bn.bias.detach().float() - bn.running_mean.float() * sc
-            hit = (key, sc.unsqueeze(0).repeat(B, 1).contiguous(), sh.unsqueeze(0).repeat(B, 1).contiguous())
-        _bn_cache[id(bn)] = hit
+            hit = (key, sc.unsqueeze(0).repeat(B, 1).contiguous(), sh.unsqueeze(0).repeat(B, 1).contiguous(), bn)
+        _bn_cache[slot] = hit
     return Vol(y, hit[1], hit[2], act)
 
 
@@ -475,19 +562,54 @@ def disparity_taps(calib: torch.Tensor, n_bins: int, down: int = 1):
 
 
 _taps_cache = {}
+_TAPS_CACHE_ENTRIES = 8
 
 
 def _cached_taps(calib: torch.Tensor, n_bins: int):
     """disparity_taps keyed on the calibration tensor (calibration-only, like the splat index: constant
     per sequence, so the handful of tiny host-side ops leaves the steady-state step)."""
     key = (calib.data_ptr(), calib._version, tuple(calib.shape), calib.device, n_bins)
-    hit = _taps_cache.get("last")
-    if hit is None or hit[0] != key:
+    hit = _taps_cache.get(key)
+    if hit is None:
         # the entry keeps `calib` alive, so its storage cannot be recycled for another tensor that would alias the key;
-        # an in-place update bumps _version
+        # an in-place update bumps _version.  Small LRU: sequences / models alternating in one process do not thrash.
         hit = (key, disparity_taps(calib, n_bins), calib)
-        _taps_cache["last"] = hit
+        _taps_cache[key] = hit
+        while len(_taps_cache) > _TAPS_CACHE_ENTRIES:
+            _taps_cache.pop(next(iter(_taps_cache)))
+    else:
+        _taps_cache[key] = _taps_cache.pop(key)          # most recently used last
     return hit[1]
+
+
+_taps_dev_cache = {}
+
+
+def _taps_on(device, calib, n_bins, taps):
+    """Device copy of host-side taps, cached under the same calibration identity."""
+    key = (calib.data_ptr(), calib._version, tuple(calib.shape), calib.device, n_bins, device)
+    hit = _taps_dev_cache.get(key)
+    if hit is None:
+        hit = (tuple(t.to(device) for t in taps), calib)
+        _taps_dev_cache[key] = hit
+        while len(_taps_dev_cache) > _TAPS_CACHE_ENTRIES:
+            _taps_dev_cache.pop(next(iter(_taps_dev_cache)))
+    return hit[0]
+
+
+def cached_state():
+    """Every tensor the op wrappers keep in their caches right now (packed weights, BatchNorm affines, disparity taps).
+    A CUDA graph bakes their device addresses in, so whoever captures one must hold these references for the life of
+    the graph: a cache eviction then cannot hand the memory to another tensor under the graph's feet
+    (stereoscene_b200.runtime.VolumetricEngine does)."""
+    keep = []
+    for pc in _packed_cache.values():
+        keep += [pc._w, pc._wk, pc._ws]
+    for hit in _bn_cache.values():
+        keep += [hit[1], hit[2]]
+    for hit in list(_taps_cache.values()) + list(_taps_dev_cache.values()):
+        keep.append(hit[1] if isinstance(hit[1], tuple) else hit[0])
+    return [t for t in keep if t is not None]
 
 
 def gwc_warp(fea: torch.Tensor, calib: torch.Tensor, maxdisp: int, groups: int) -> torch.Tensor:
@@ -499,7 +621,9 @@ def gwc_warp(fea: torch.Tensor, calib: torch.Tensor, maxdisp: int, groups: int) 
         raise RuntimeError("gwc_warp: features must be contiguous channels-last")
     B2, _, H, W, Cc = fea.shape
     B = B2 // 2
-    i0, w0, w1 = _cached_taps(calib if calib.device == fea.device else calib.to(fea.device), maxdisp)
+    i0, w0, w1 = _cached_taps(calib, maxdisp)            # keyed on the caller's tensor, wherever it lives
+    if i0.device != fea.device:
+        i0, w0, w1 = _taps_on(fea.device, calib, maxdisp, (i0, w0, w1))
     out = torch.empty((B, maxdisp, H, W, groups), dtype=torch.float32, device=fea.device)
     rc = lib.ss_gwc_warp_fwd(fea.data_ptr(), i0.data_ptr(), w0.data_ptr(), w1.data_ptr(), out.data_ptr(),
                              B, Cc, groups, H, W, maxdisp, maxdisp, _stream())
@@ -522,8 +646,11 @@ def bri_attention(q: torch.Tensor, kv: torch.Tensor, params: torch.Tensor, out: 
     N = int(math.prod(q.shape[2:]))
     wsb = int(lib.ss_bri_workspace_bytes(B, D, N))
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=q.device)
+    mm = _DEFAULT_MATH if math_mode is None else math_mode
+    if mm == SS_MATH_TF32X3:          # BRI on tcgen05 is within 2e-5 of an fp64 evaluation in plain TF32 (softmax algebra in fp32)
+        mm = SS_MATH_TF32
     rc = lib.ss_bri_attn_fwd(q.data_ptr(), kv.data_ptr(), params.data_ptr(), ws.data_ptr(), wsb, out.data_ptr(), out_ld,
-                             B, D, N, _DEFAULT_MATH if math_mode is None else math_mode, _stream())
+                             B, D, N, mm, _stream())
     cabi.check(rc, "ss_bri_attn_fwd")
     return out
 

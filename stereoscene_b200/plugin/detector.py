@@ -80,8 +80,9 @@ class BEVDepthOccupancy(nn.Module):
 
     # ---- the volumetric path ---------------------------------------------------------------
     def bev_encoder_vol(self, bev: torch.Tensor) -> Vol:
-        levels = self.img_bev_encoder_backbone.forward_vol(Vol(bev))
-        neck = self.img_bev_encoder_neck.forward_vol(levels)
+        with ops.math_scope("voxel"):
+            levels = self.img_bev_encoder_backbone.forward_vol(Vol(bev))
+            neck = self.img_bev_encoder_neck.forward_vol(levels)
         st = self.img_view_transformer.stage_outputs
         if st is not None:          # per-stage capture for the parity tests (logical NCDHW views, neck materialised)
             st.update(bev_feat=bev.permute(0, 4, 1, 2, 3), neck=neck.ncdhw(),
@@ -101,7 +102,8 @@ class BEVDepthOccupancy(nn.Module):
         geo_r = [right[k] for k in keys] + [mr]
         bev, depth = vt([x_left] + geo_l + [x_right] + geo_r + [calib, None, None])
         neck = self.bev_encoder_vol(bev.permute(0, 2, 3, 4, 1))
-        logits = self.pts_bbox_head.forward_voxel_vol([neck])[0]            # [B,X,Y,Z,classes]
+        with ops.math_scope("voxel"):
+            logits = self.pts_bbox_head.forward_voxel_vol([neck])[0]        # [B,X,Y,Z,classes]
         labels = None
         if occ_size is not None:
             up, labels = ops.trilinear(logits, occ_size, want_labels=want_labels)
@@ -127,7 +129,8 @@ class BEVDepthOccupancy(nn.Module):
     def simple_test(self, img_metas, img=None, rescale=False, points_occ=None, gt_occ=None, points_uv=None):
         """bevdepth_occupancy.py:275-297."""
         voxel_feats, depth, img_feats = self.extract_img_feat(img, img_metas)
-        logits = self.pts_bbox_head.forward_voxel_vol(voxel_feats)[0]
+        with ops.math_scope("voxel"):
+            logits = self.pts_bbox_head.forward_voxel_vol(voxel_feats)[0]
         up, _ = ops.trilinear(logits, tuple(gt_occ.shape[1:]))
         return {"output_voxels": up.permute(0, 4, 1, 2, 3), "output_points": None, "evaluation_semantic": 0,
                 "target_voxels": gt_occ}

@@ -510,8 +510,12 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
     def splat_index(self, rots, trans, intrins, post_rots, post_trans, bda) -> ops.SplatIndex:
         cal = (rots, trans, intrins, post_rots, post_trans, bda)
         key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in cal) + (self.frustum.data_ptr(),)
-        if self.cache_splat_index and self._index_cache is not None and self._index_cache[0] == key:
-            return self._index_cache[1]
+        if self._index_cache is None:
+            self._index_cache = {}
+        hit = self._index_cache.get(key) if self.cache_splat_index else None
+        if hit is not None:
+            self._index_cache[key] = self._index_cache.pop(key)          # most recently used last
+            return hit[0]
         # Geometry is calibration-only and feeds an INTEGER quantisation, so it is evaluated once per calibration on the
         # host in fp32 -- the reference's own CPU arithmetic (torch.inverse = LAPACK getrf/getri, the same small matmuls),
         # bit-identical to the oracle -- and uploaded; a device evaluation (cuSOLVER / cuBLAS rounding) could move points
@@ -525,8 +529,19 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         idx = ops.splat_build_index(geom, self.dx.detach().cpu().tolist(), self.bx.detach().cpu().tolist(), nx,
                                     want_coords=self.stage_outputs is not None)
         if self.cache_splat_index:
-            self._index_cache = (key, idx, cal)      # holding the tensors keeps their storage from being recycled under the key
+            # holding the calibration tensors keeps their storage from being recycled under the key; a few entries so that
+            # sequences (KITTI calibration differs per sequence) / engines alternating on one model do not thrash
+            self._index_cache[key] = (idx, cal)
+            while len(self._index_cache) > 8:
+                self._index_cache.pop(next(iter(self._index_cache)))
         return idx
+
+    def cached_state(self):
+        """Tensors of the calibration caches (see ops.cached_state)."""
+        keep = []
+        for idx, _ in (self._index_cache or {}).values():
+            keep += [idx.order, idx.voxel_start, idx.coords]
+        return [t for t in keep if t is not None]
 
     def voxel_pooling(self, geom_feats, x):
         """Reference-signature entry (ViewTransformerLSSVoxel.py:432-476): geom [B,N,D,H,W,3], lifted
@@ -555,14 +570,17 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
             raise NotImplementedError("the stereo path is defined for one camera per side (N=1)")
         # one channels-last copy of the feature pair serves the stereo branch (both maps) and depth_net (left)
         pair_cl = ops.to_channels_last(torch.cat([feat_left, feat_right], 0)).unsqueeze(1)      # [2B,1,H,W,Cin]
-        stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
+        with ops.math_scope("stereo"):
+            stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
 
-        depth_cl, ctx_cl = self.depth_net.forward_vol(pair_cl[:B], mlp_input)
+        with ops.math_scope("depthnet"):
+            depth_cl, ctx_cl = self.depth_net.forward_vol(pair_cl[:B], mlp_input)
         depth_logits = ops.to_channels_first(depth_cl.squeeze(1))                 # [B,D,H,W]
         lss = ops.softmax_d(depth_logits)
         img_feat = ctx_cl.squeeze(1)                                              # [B,H,W,C] channels-last
 
-        depth_prob = self.mutual_interactive_ensemble(stereo, lss)
+        with ops.math_scope("mie"):
+            depth_prob = self.mutual_interactive_ensemble(stereo, lss)
 
         index = self.splat_index(rots, trans, intrins, post_rots, post_trans, bda)
         bev = ops.lift_splat(depth_prob, img_feat, index)                         # [B,X,Y,Z,C]

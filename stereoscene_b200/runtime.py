@@ -55,6 +55,13 @@ class VolumetricEngine:
                     out = self._forward(s)
                 self.graphs.append(g)
                 self.outs.append(out)
+            # The graphs bake in the device addresses of everything the forward read from the op / calibration caches
+            # (packed weights, BatchNorm affines, disparity taps, the splat index).  Those caches are shared by every
+            # engine / eager call on the process and evict; the engine therefore OWNS references to what its graphs
+            # read, so an eviction can never hand that memory to another tensor while a graph still points at it.
+            from . import ops
+            self._graph_reads = ops.cached_state() + model.img_view_transformer.cached_state() + \
+                [getattr(m, a) for m in model.modules() for a in ("_split", "_affine", "_gconvs") if getattr(m, a, None) is not None]
         torch.cuda.synchronize(dev)
 
     def _forward(self, slot: int):
@@ -96,8 +103,9 @@ class VolumetricEngine:
         return self.outs[slot]["output_voxels"]
 
     def stream(self, pairs: Iterable[Tuple[torch.Tensor, torch.Tensor]]) -> Iterator[torch.Tensor]:
-        """Pipelined inference: yields the host label volume of every pair, in order.  The yielded tensor is a
-        reused pinned buffer: consume (or copy) it before advancing the iterator twice."""
+        """Pipelined inference: yields the host label volume of every pair, in order.  The yielded tensor is one of two
+        reused pinned buffers and is valid only until the NEXT ``next()`` on the iterator (advancing enqueues the download
+        of pair i+2 into the slot of pair i): consume or copy it before advancing."""
         pending = []
         for i, (xl_host, xr_host) in enumerate(pairs):
             slot = i & 1

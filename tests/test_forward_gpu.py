@@ -174,3 +174,32 @@ def test_volumetric_engine_matches_eager_and_keeps_order():
         assert (gg != w).float().mean().item() < 1e-3, i
     # different pairs really give different volumes, so an ordering mix-up would be seen
     assert (want[0] != want[4]).any()
+
+
+def test_engine_graphs_survive_cache_eviction_by_another_calibration():
+    """Two engines with different calibrations on one model (KITTI calibration differs per sequence): the second one
+    evicts / replaces the shared cache entries (disparity taps, splat index) the first engine's CUDA graphs point at.
+    The first engine must keep replaying the same labels -- it owns references to everything its graphs read."""
+    from stereoscene_b200 import ops
+    from stereoscene_b200.runtime import VolumetricEngine
+    cfg, _ = golden_tiny()
+    model, mc = build_model("tiny", cfg["seed"], device="cuda")
+    xl, xr, left, right, calib = tiny_inputs(cfg, device="cuda")
+    ops.set_default_math(ops.SS_MATH_TF32)
+    a, b = xl.cpu().pin_memory(), xr.cpu().pin_memory()
+    eng1 = VolumetricEngine(model, left, right, calib, cfg["occ_size"], tuple(xl.shape))
+    want = eng1.infer(a, b).clone()
+    for i in range(10):                                     # more calibrations than any cache holds entries
+        left2 = {k: v.clone() for k, v in left.items()}
+        right2 = {k: v.clone() for k, v in right.items()}
+        left2["trans"] = left2["trans"] + 0.37 * (i + 1)
+        right2["trans"] = right2["trans"] + 0.37 * (i + 1)
+        eng2 = VolumetricEngine(model, left2, right2, calib * (0.5 + 0.05 * i), cfg["occ_size"], tuple(xl.shape), warmup=1)
+        other = eng2.infer(a, b).clone()
+        del eng2
+    assert (other != want).any()                            # the other calibration really gives another volume
+    torch.cuda.empty_cache()
+    junk = [torch.full((1 << 20,), float("nan"), device="cuda") for _ in range(64)]      # recycle freed blocks with garbage
+    del junk
+    again = eng1.infer(a, b)
+    assert (again != want).float().mean().item() < 1e-3

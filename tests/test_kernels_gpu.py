@@ -20,7 +20,7 @@ from util import rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"precise": 2e-4, "tf32": 1e-3}
+TOL = {"precise": 2e-4, "tf32": 1e-3, "tf32x3": 2e-4}
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +31,7 @@ def ops():
 
 
 def _mode(ops, name):
-    return ops.SS_MATH_3XTF32 if name == "precise" else ops.SS_MATH_TF32
+    return {"precise": ops.SS_MATH_3XTF32, "tf32": ops.SS_MATH_TF32, "tf32x3": ops.SS_MATH_TF32X3}[name]
 
 
 def _cl(x):  # NCDHW cpu -> channels-last cuda [B,D,H,W,C]
@@ -71,7 +71,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["precise", "tf32"])
+@pytest.mark.parametrize("mode", ["precise", "tf32", "tf32x3"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv3d_family(ops, case, mode):
     name, make, shape = case
@@ -114,6 +114,31 @@ def test_tcgen05_conv_agrees_with_mma_sync(ops, case):
         ops.use_tcgen05(True)
     assert rel_err(y1, y0) < 1e-3
     assert rel_err(st1[..., 1], st0[..., 1]) < 2e-3
+
+
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[0] not in ("k3_2_32_bias",)],
+                         ids=[c[0] for c in CONV_CASES if c[0] not in ("k3_2_32_bias",)])
+def test_compensated_tcgen05_conv_matches_fp32(ops, case):
+    """SS_MATH_TF32X3 (three accumulating TF32 launches of the tcgen05 kernels: lo*hi + hi*lo + hi*hi) with a pending
+    affine + ReLU on the input, an output activation and the epilogue sums, against an fp64 evaluation of the layer."""
+    name, make, shape = case
+    torch.manual_seed(zlib.crc32(name.encode()) % 1000 + 2)
+    m = make()
+    x = torch.randn(shape)
+    B, Cin = shape[0], shape[1]
+    sc, sh = torch.rand(B, Cin) + 0.5, torch.randn(B, Cin) * 0.3
+    xin = torch.relu(x * sc.view(B, Cin, 1, 1, 1) + sh.view(B, Cin, 1, 1, 1))
+    want = torch.relu(m.double()(xin.double())).float()
+    mg = make().cuda()
+    mg.load_state_dict(m.float().state_dict())
+    v = ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU)
+    n0 = ops.cabi.kernel_census().get("conv_igemm_kernel", 0)
+    y, st = ops.conv(v, mg, want_stats=True, out_act=ops.SS_ACT_RELU, math_mode=ops.SS_MATH_TF32X3)
+    torch.cuda.synchronize()
+    assert ops.cabi.kernel_census().get("conv_igemm_kernel", 0) == n0, "compensated mode fell back to the mma.sync kernel"
+    assert rel_err(_ncdhw(y), want) < 5e-5
+    assert rel_err(st[..., 0], want.double().sum(dim=(2, 3, 4))) < 1e-4
+    assert rel_err(st[..., 1], (want.double() ** 2).sum(dim=(2, 3, 4))) < 1e-4
 
 
 def test_single_output_channel_conv(ops):
@@ -308,6 +333,8 @@ def test_conv_join_fused_in_transposed_epilogue(ops, chans):
     want = F.relu(bn(m(xin)) + (r * rs[:, :, None, None, None] + rh[:, :, None, None, None])).detach()
     mg = nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1, stride=2, bias=False).cuda()
     mg.load_state_dict(m.state_dict())
+    want64 = F.relu(bn.double()(m.double()(xin.double())) + (r * rs[:, :, None, None, None] + rh[:, :, None, None, None]).double()).float().detach()
+    bn.float(); m.float()
     xv = ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU)
     rv = ops.Vol(_cl(r), rs.cuda(), rh.cuda(), ops.SS_ACT_NONE)
     d = cabi.ConvDesc(2, 3, 16, 15, cin, 6, 32, 30, cout, 3, 3, 3, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, cin, cout, 1, 1, 0, max(32, cout))
@@ -317,6 +344,16 @@ def test_conv_join_fused_in_transposed_epilogue(ops, chans):
     y, _ = ops.conv(xv, mg)
     unfused = ops.join(ops.bn_pending(y, bn), rv, out_act=ops.SS_ACT_RELU)
     assert rel_err(got, unfused) < 1e-5
+    # the compensated mode runs the same fused kernel three times (the join belongs to the last pass)
+    ops.set_default_math(ops.SS_MATH_TF32X3)
+    try:
+        n0 = cabi.kernel_census().get("conv_tpose_kernel", 0)
+        got3 = ops.conv_join(xv, mg, ops.bn_pending(_cl(x), bn.cuda()), rv, out_act=ops.SS_ACT_RELU)
+        torch.cuda.synchronize()
+        assert cabi.kernel_census()["conv_tpose_kernel"] == n0 + 3
+    finally:
+        ops.set_default_math(ops.SS_MATH_TF32)
+    assert rel_err(_ncdhw(got3), want64) < 5e-5
     # a layer the fused kernel does not take falls back to conv + join
     m2 = nn.ConvTranspose3d(64, 32, 2, 2, bias=False).cuda()
     x2 = torch.randn(1, 64, 2, 4, 4)

@@ -25,12 +25,12 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # mode -> (max-norm tolerance, rms-norm tolerance) on the final logits (and every voxel-space stage before them)
-LOGIT_TOL = {"3xtf32": (1e-3, 1e-3), "tf32x3": (1e-3, 1e-3), "tf32": (2e-2, 2e-2)}
+LOGIT_TOL = {"3xtf32": (1e-3, 1e-3), "tf32x3": (1e-3, 1e-3), "mixed": (1e-3, 1e-3), "tf32": (2e-2, 2e-2)}
 
 
 def _modes():
     from stereoscene_b200 import ops
-    return ops.MATH_MODES
+    return ops.MATH_POLICIES
 
 
 def _reference_layout(out, st):
@@ -70,19 +70,19 @@ def _product_run(workload, meta, mode):
     xl, xr, left, right, calib = full_inputs(meta, device="cuda")
     vt = model.img_view_transformer
     vt.stage_outputs = {}
-    ops.set_default_math(_modes()[mode])
+    ops.set_math_policy(mode)
     try:
         with torch.no_grad():
             out = model.forward_features(xl, xr, left, right, calib, occ_size=meta["occ_size"], want_labels=True)
         torch.cuda.synchronize()
     finally:
-        ops.set_default_math(ops.SS_MATH_TF32)
+        ops.set_math_policy(None)
     st = dict(vt.stage_outputs)
     vt.stage_outputs = None
     return out, st
 
 
-@pytest.mark.parametrize("mode", ["tf32", "tf32x3", "3xtf32"])
+@pytest.mark.parametrize("mode", ["tf32", "mixed", "tf32x3", "3xtf32"])
 @pytest.mark.parametrize("workload", ["config1", "config2"])
 def test_forward_vs_reference_golden_and_oracle(workload, mode):
     if mode not in _modes():
