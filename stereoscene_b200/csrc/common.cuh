@@ -51,10 +51,17 @@ struct ConvPass {
     int a_lo;
     int accumulate;
 };
-__device__ __forceinline__ uint32_t f2tf32_part(float x, int a_lo) {
+template <bool LO>
+__device__ __forceinline__ uint32_t f2tf32_part(float x) {
     const uint32_t h = f2tf32(x);
-    return a_lo ? f2tf32(x - __uint_as_float(h)) : h;
+    if constexpr (LO) return f2tf32(x - __uint_as_float(h));
+    else return h;
 }
+// The fix-up loops are unswitched on the (kernel-uniform) a_lo flag: `SS_UNSWITCH_LO(p.a_lo, body)` runs `body(tag)` with
+// decltype(tag)::value == a_lo as a compile-time constant, so the plain-TF32 path carries no extra instructions.
+struct LoTrue { static constexpr bool value = true; };
+struct LoFalse { static constexpr bool value = false; };
+#define SS_UNSWITCH_LO(flag, body) do { if (flag) body(ss::LoTrue{}); else body(ss::LoFalse{}); } while (0)
 
 // D(16x8,f32) += A(16x8,tf32,row) * B(8x8,tf32,col)
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

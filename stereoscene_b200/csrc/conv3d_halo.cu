@@ -236,23 +236,27 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
             const int dpl = d - KD / 2 + (L % KD), c0 = (L / KD) * 32;
             if ((unsigned)dpl < (unsigned)p.D) {
                 unsigned char* pl = planes + slot * HL_PLANE_BYTES;
-                for (int idx = tid; idx < HL_PLANE_ROWS * 8; idx += HL_WORKERS) {
-                    const int r = idx >> 3, chunk = idx & 7;
-                    const int hh = h0 - 1 + r / HL_HW, ww = w0 - 1 + r % HL_HW;
-                    if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
-                        float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
-                        float4 v = *ptr;
-                        if (has_aff) {
-                            const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
-                            const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
-                            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                auto fix = [&](auto lo_tag) {
+                    constexpr bool LO = decltype(lo_tag)::value;
+                    for (int idx = tid; idx < HL_PLANE_ROWS * 8; idx += HL_WORKERS) {
+                        const int r = idx >> 3, chunk = idx & 7;
+                        const int hh = h0 - 1 + r / HL_HW, ww = w0 - 1 + r % HL_HW;
+                        if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
+                            float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            float4 v = *ptr;
+                            if (has_aff) {
+                                const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
+                                const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
+                                v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                            }
+                            if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            uint4 o;
+                            o.x = f2tf32_part<LO>(v.x); o.y = f2tf32_part<LO>(v.y); o.z = f2tf32_part<LO>(v.z); o.w = f2tf32_part<LO>(v.w);
+                            *reinterpret_cast<uint4*>(ptr) = o;
                         }
-                        if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        uint4 o;
-                        o.x = f2tf32_part(v.x, p.a_lo); o.y = f2tf32_part(v.y, p.a_lo); o.z = f2tf32_part(v.z, p.a_lo); o.w = f2tf32_part(v.w, p.a_lo);
-                        *reinterpret_cast<uint4*>(ptr) = o;
                     }
-                }
+                };
+                SS_UNSWITCH_LO(p.a_lo, fix);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             h_mbar_arrive(pa_ready0 + 8 * slot);

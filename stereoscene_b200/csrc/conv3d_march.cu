@@ -506,21 +506,25 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                     const int dpl = c.d - PAD + s;
                     if ((unsigned)dpl < (unsigned)p.D) {           // planes outside the volume are all padding
                         unsigned char* pl = planes + slot * MR_PLANE_BYTES;
-                        for (int r = ft >> 3; r < MR_PLANE_ROWS; r += 16) {
-                            const int hh = c.th * MR_TH - PAD + r / MR_HW, ww = c.tw * MR_TW - PAD + r % MR_HW;
-                            if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
-                                float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
-                                float4 v = *ptr;
-                                if (has_aff) {
-                                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                                    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        auto fix = [&](auto lo_tag) {
+                            constexpr bool LO = decltype(lo_tag)::value;
+                            for (int r = ft >> 3; r < MR_PLANE_ROWS; r += 16) {
+                                const int hh = c.th * MR_TH - PAD + r / MR_HW, ww = c.tw * MR_TW - PAD + r % MR_HW;
+                                if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
+                                    float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
+                                    float4 v = *ptr;
+                                    if (has_aff) {
+                                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                                    }
+                                    if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                                    uint4 o;
+                                    o.x = f2tf32_part<LO>(v.x); o.y = f2tf32_part<LO>(v.y); o.z = f2tf32_part<LO>(v.z); o.w = f2tf32_part<LO>(v.w);
+                                    *reinterpret_cast<uint4*>(ptr) = o;
                                 }
-                                if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                                uint4 o;
-                                o.x = f2tf32_part(v.x, p.a_lo); o.y = f2tf32_part(v.y, p.a_lo); o.z = f2tf32_part(v.z, p.a_lo); o.w = f2tf32_part(v.w, p.a_lo);
-                                *reinterpret_cast<uint4*>(ptr) = o;
                             }
-                        }
+                        };
+                        SS_UNSWITCH_LO(p.a_lo, fix);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     m_mbar_arrive(p_ready0 + 8 * slot);

@@ -325,37 +325,41 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
         for (int j = 0; j < 8; ++j) roff[j] = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::A_COL0;
-        for (int step = grp; step < nsteps; step += 2) {
-            const int slot = step % STAGES;
-            const uint32_t use = (uint32_t)(step / STAGES);
-            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
-            mbar_wait(full0 + 8 * slot, use & 1u);
-            const unsigned char* a_src = ring + slot * Cfg::STAGE_BYTES;
-            const bool ok = (vmask >> tap) & 1ull;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {       // two halves of 16 channels: 4 loads in flight, one tcgen05.st each
-                float4 v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(a_src + roff[hh * 4 + j]);
-                uint32_t o[16];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float4 w = v[j];
-                    if (has_aff) {
-                        const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + hh * 16 + 4 * j);     // warp-uniform: broadcast
-                        const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + hh * 16 + 4 * j);
-                        w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+        auto fix = [&](auto lo_tag) {
+            constexpr bool LO = decltype(lo_tag)::value;
+            for (int step = grp; step < nsteps; step += 2) {
+                const int slot = step % STAGES;
+                const uint32_t use = (uint32_t)(step / STAGES);
+                const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
+                mbar_wait(full0 + 8 * slot, use & 1u);
+                const unsigned char* a_src = ring + slot * Cfg::STAGE_BYTES;
+                const bool ok = (vmask >> tap) & 1ull;
+    #pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {       // two halves of 16 channels: 4 loads in flight, one tcgen05.st each
+                    float4 v[4];
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(a_src + roff[hh * 4 + j]);
+                    uint32_t o[16];
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 w = v[j];
+                        if (has_aff) {
+                            const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + hh * 16 + 4 * j);     // warp-uniform: broadcast
+                            const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + hh * 16 + 4 * j);
+                            w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+                        }
+                        if (in_relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+                        o[4 * j + 0] = ok ? f2tf32_part<LO>(w.x) : 0u; o[4 * j + 1] = ok ? f2tf32_part<LO>(w.y) : 0u;
+                        o[4 * j + 2] = ok ? f2tf32_part<LO>(w.z) : 0u; o[4 * j + 3] = ok ? f2tf32_part<LO>(w.w) : 0u;
                     }
-                    if (in_relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
-                    o[4 * j + 0] = ok ? f2tf32_part(w.x, p.a_lo) : 0u; o[4 * j + 1] = ok ? f2tf32_part(w.y, p.a_lo) : 0u;
-                    o[4 * j + 2] = ok ? f2tf32_part(w.z, p.a_lo) : 0u; o[4 * j + 3] = ok ? f2tf32_part(w.w, p.a_lo) : 0u;
+                    tmem_st16_nowait(t_row + (uint32_t)(slot * TC_BK + hh * 16), o);
                 }
-                tmem_st16_nowait(t_row + (uint32_t)(slot * TC_BK + hh * 16), o);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(ready0 + 8 * slot);
             }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(ready0 + 8 * slot);
-        }
+        };
+        SS_UNSWITCH_LO(p.a_lo, fix);
     }
 
     // ======================= EPILOGUE: 8 warps drain TMEM ========================================

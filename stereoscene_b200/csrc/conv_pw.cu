@@ -202,19 +202,23 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
                     sc = ldg_f4(p.in_scale + bo);
                     sh = ldg_f4(p.in_shift + bo);
                 }
-                for (int r = ft >> 3; r < PW_TILE; r += 16) {
-                    if (row0 + r < p.V) {                                   // rows past the end stay zero
-                        float4* ptr = reinterpret_cast<float4*>(ch + r * 128 + ((chunk ^ (r & 7)) << 4));
-                        float4 x = *ptr;
-                        if (has_aff) {
-                            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+                auto fix = [&](auto lo_tag) {
+                    constexpr bool LO = decltype(lo_tag)::value;
+                    for (int r = ft >> 3; r < PW_TILE; r += 16) {
+                        if (row0 + r < p.V) {                                   // rows past the end stay zero
+                            float4* ptr = reinterpret_cast<float4*>(ch + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            float4 x = *ptr;
+                            if (has_aff) {
+                                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+                            }
+                            if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                            uint4 o;
+                            o.x = f2tf32_part<LO>(x.x); o.y = f2tf32_part<LO>(x.y); o.z = f2tf32_part<LO>(x.z); o.w = f2tf32_part<LO>(x.w);
+                            *reinterpret_cast<uint4*>(ptr) = o;
                         }
-                        if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                        uint4 o;
-                        o.x = f2tf32_part(x.x, p.a_lo); o.y = f2tf32_part(x.y, p.a_lo); o.z = f2tf32_part(x.z, p.a_lo); o.w = f2tf32_part(x.w, p.a_lo);
-                        *reinterpret_cast<uint4*>(ptr) = o;
                     }
-                }
+                };
+                SS_UNSWITCH_LO(p.a_lo, fix);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 pw_mbar_arrive(c_ready0 + 8 * slot);
             }

@@ -116,8 +116,10 @@ struct CsParams {
     const float* x; const float* w; const float* bias; float* y; double* stats;
 };
 
-template <int CIN>
-__global__ void __launch_bounds__(CS_THREADS, 2)
+// PRECISE: error-compensated split TF32 (SS_MATH_3XTF32 / the Cin <= 2 layer of an SS_MATH_TF32X3 forward): the halo tile is
+// kept in fp32, A and B fragments are split hi/lo in registers and every k-step issues lo*hi + hi*lo + hi*hi.
+template <int CIN, bool PRECISE>
+__global__ void __launch_bounds__(CS_THREADS, PRECISE ? 1 : 2)
 conv_cin_small_kernel(const CsParams p) {
     constexpr int K = 27 * CIN, KSTEPS = (K + 7) / 8;
     constexpr int HH = CS_TH + 2, HW = CS_TW + 2;
@@ -140,10 +142,11 @@ conv_cin_small_kernel(const CsParams p) {
         float v = 0.f;
         if ((unsigned)gd < (unsigned)p.D && (unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.W)
             v = __ldg(p.x + ((((size_t)b * p.D + gd) * p.H + gh) * p.W + gw) * p.in_ldc + c);
-        xs[idx] = __uint_as_float(f2tf32(v));
+        xs[idx] = PRECISE ? v : __uint_as_float(f2tf32(v));
     }
     // B fragments of the whole [K x 32] weight matrix and the tap offsets of this lane's two K columns
     uint32_t breg[KSTEPS][4][2];
+    uint32_t blo[PRECISE ? KSTEPS : 1][4][2];
     int koff[KSTEPS][2];
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks)
@@ -159,7 +162,9 @@ conv_cin_small_kernel(const CsParams p) {
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int n = nt * 8 + g;
-                breg[ks][nt][e] = (k < K) ? f2tf32(__ldg(p.w + (size_t)k * p.CoutP + n)) : 0u;
+                const float wv = (k < K) ? __ldg(p.w + (size_t)k * p.CoutP + n) : 0.f;
+                breg[ks][nt][e] = f2tf32(wv);
+                if constexpr (PRECISE) blo[ks][nt][e] = f2tf32(wv - __uint_as_float(breg[ks][nt][e]));
             }
         }
     float bias_r[4][2];
@@ -186,10 +191,23 @@ conv_cin_small_kernel(const CsParams p) {
         for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
-            const uint32_t a[4] = {__float_as_uint(xs[rb0 + koff[ks][0]]), __float_as_uint(xs[rb1 + koff[ks][0]]),
-                                   __float_as_uint(xs[rb0 + koff[ks][1]]), __float_as_uint(xs[rb1 + koff[ks][1]])};
+            if constexpr (PRECISE) {
+                const float af[4] = {xs[rb0 + koff[ks][0]], xs[rb1 + koff[ks][0]], xs[rb0 + koff[ks][1]], xs[rb1 + koff[ks][1]]};
+                uint32_t a[4], al[4];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], a, breg[ks][nt]);
+                for (int i = 0; i < 4; ++i) { a[i] = f2tf32(af[i]); al[i] = f2tf32(af[i] - __uint_as_float(a[i])); }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    mma_tf32(acc[nt], al, breg[ks][nt]);
+                    mma_tf32(acc[nt], a, blo[ks][nt]);
+                    mma_tf32(acc[nt], a, breg[ks][nt]);
+                }
+            } else {
+                const uint32_t a[4] = {__float_as_uint(xs[rb0 + koff[ks][0]]), __float_as_uint(xs[rb1 + koff[ks][0]]),
+                                       __float_as_uint(xs[rb0 + koff[ks][1]]), __float_as_uint(xs[rb1 + koff[ks][1]])};
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], a, breg[ks][nt]);
+            }
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -233,7 +251,9 @@ conv_cin_small_kernel(const CsParams p) {
 // used by ss_conv3d_fwd for eligible layers; returns 1 if the layer was handled here
 int try_conv_cin_small(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                        const float* w_packed, const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
-    if (d->transposed || d->Cin > 2 || d->cout_packed != 32 || d->math != SS_MATH_TF32 || in_scale || d->in_act != SS_ACT_NONE) return 0;
+    if (d->transposed || d->Cin > 2 || d->cout_packed != 32 || in_scale || d->in_act != SS_ACT_NONE) return 0;
+    if (d->math != SS_MATH_TF32 && d->math != SS_MATH_3XTF32) return 0;
+    const bool precise = d->math == SS_MATH_3XTF32;
     if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 1 || d->sh != 1 || d->sw != 1 || d->pd != 1 || d->ph != 1 || d->pw != 1) return 0;
     if (d->dd != 1 || d->dh != 1 || d->dw != 1 || d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
     CsParams p;
@@ -242,8 +262,13 @@ int try_conv_cin_small(const ss_conv3d_desc* d, const float* x, const float* in_
     p.x = x; p.w = w_packed; p.bias = bias; p.y = y; p.stats = stats;
     const long long blocks = (long long)p.B * p.D * p.nTH * p.nTW;
     if (blocks > 0x7fffffffLL) return 0;
-    if (d->Cin == 1) conv_cin_small_kernel<1><<<(unsigned)blocks, CS_THREADS, 0, st>>>(p);
-    else conv_cin_small_kernel<2><<<(unsigned)blocks, CS_THREADS, 0, st>>>(p);
+    if (d->Cin == 1) {
+        if (precise) conv_cin_small_kernel<1, true><<<(unsigned)blocks, CS_THREADS, 0, st>>>(p);
+        else conv_cin_small_kernel<1, false><<<(unsigned)blocks, CS_THREADS, 0, st>>>(p);
+    } else {
+        if (precise) conv_cin_small_kernel<2, true><<<(unsigned)blocks, CS_THREADS, 0, st>>>(p);
+        else conv_cin_small_kernel<2, false><<<(unsigned)blocks, CS_THREADS, 0, st>>>(p);
+    }
     *rc = check_launch("conv_cin_small_kernel");
     return 1;
 }

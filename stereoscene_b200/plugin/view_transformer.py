@@ -291,18 +291,22 @@ class DepthNet(nn.Module):
         """x: channels-last [B,1,H,W,Cin] -> (depth logits [B,1,H,W,D], context [B,1,H,W,ctx]), both
         channels-last."""
         m = self.bn(mlp_input.reshape(-1, mlp_input.shape[-1]))          # GroupNorm on the [B,cam] calibration vector
-        v = conv_gn(Vol(x), self.reduce_conv, SS_ACT_RELU)
-        # SE gates are > 0: relu(gn(y)) * g == relu(gn(y) * g), so each gate is a rescaled pending affine
-        gc = self.context_se.gate(self.context_mlp(m))
-        gd = self.depth_se.gate(self.depth_mlp(m))
-        context, _ = ops.conv(Vol(v.data, (v.scale * gc).contiguous(), (v.shift * gc).contiguous(), SS_ACT_RELU),
-                              self.context_conv)
+        with ops.math_scope("depthnet.trunk"):
+            v = conv_gn(Vol(x), self.reduce_conv, SS_ACT_RELU)
+            # SE gates are > 0: relu(gn(y)) * g == relu(gn(y) * g), so each gate is a rescaled pending affine
+            gc = self.context_se.gate(self.context_mlp(m))
+            gd = self.depth_se.gate(self.depth_mlp(m))
+            context, _ = ops.conv(Vol(v.data, (v.scale * gc).contiguous(), (v.shift * gc).contiguous(), SS_ACT_RELU),
+                                  self.context_conv)
         d = Vol(v.data, (v.scale * gd).contiguous(), (v.shift * gd).contiguous(), SS_ACT_RELU)
-        for i in range(3):
-            d = self.depth_conv[i].forward_vol(d)
-        d = self.depth_conv[3].forward_vol(d)
-        d = self.depth_conv[4].forward_vol(d)
-        depth, _ = ops.conv(Vol(d), self.depth_conv[5])
+        with ops.math_scope("depthnet.blocks"):
+            for i in range(3):
+                d = self.depth_conv[i].forward_vol(d)
+        with ops.math_scope("depthnet.aspp"):
+            d = self.depth_conv[3].forward_vol(d)
+        with ops.math_scope("depthnet.dcn"):
+            d = self.depth_conv[4].forward_vol(d)
+            depth, _ = ops.conv(Vol(d), self.depth_conv[5])
         return depth, context
 
     def forward(self, x, mlp_input):
@@ -494,14 +498,18 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         both = torch.empty((B, D, H, W, 2), dtype=torch.float32, device=stereo.device)
         ops.bri_attention(stereo, lss, vi.lss2stereo.packed(), both[..., 0], 2)      # q = stereo, kv = lss
         ops.bri_attention(lss, stereo, vi.stereo2lss.packed(), both[..., 1], 2)      # q = lss, kv = stereo
-        x, _ = ops.conv(Vol(both), vi.redir1, out_act=SS_ACT_RELU)
-        x = hourglass(vi.dres1, Vol(x))
+        with ops.math_scope("mie.redir1"):
+            x, _ = ops.conv(Vol(both), vi.redir1, out_act=SS_ACT_RELU)
+        with ops.math_scope("mie.hourglass"):
+            x = hourglass(vi.dres1, Vol(x))
         fn = vi.CA3D.fn
-        d, st = ops.conv(Vol(x), fn.conv1[0], out_act=SS_ACT_GELU, want_stats=True)
-        dv = ops.ca3d_gate(ops.gn_pending(d, st, fn.conv1[2]), st, fn.conv2[0], fn.conv2[2])
-        o, st2 = ops.conv(dv, fn.conv[0], out_act=SS_ACT_GELU, want_stats=True)
-        x2 = ops.join(ops.gn_pending(o, st2, fn.conv[2]), Vol(x), alpha=vi.CA3D.alpha)
-        z, _ = ops.conv(Vol(x2), vi.redir2, out_act=SS_ACT_RELU)
+        with ops.math_scope("mie.ca3d"):
+            d, st = ops.conv(Vol(x), fn.conv1[0], out_act=SS_ACT_GELU, want_stats=True)
+            dv = ops.ca3d_gate(ops.gn_pending(d, st, fn.conv1[2]), st, fn.conv2[0], fn.conv2[2])
+            o, st2 = ops.conv(dv, fn.conv[0], out_act=SS_ACT_GELU, want_stats=True)
+            x2 = ops.join(ops.gn_pending(o, st2, fn.conv[2]), Vol(x), alpha=vi.CA3D.alpha)
+        with ops.math_scope("mie.redir2"):
+            z, _ = ops.conv(Vol(x2), vi.redir2, out_act=SS_ACT_RELU)
         if self.stage_outputs is not None:
             self.stage_outputs.update(bri=both, mie_hourglass=x, mie_ca3d=x2)
         return ops.softmax_d(z.view(B, D, H, W))

@@ -36,11 +36,21 @@ def run(workload, policy):
         f"{stage_error(sample_stage(v, meta, k), gold[k], meta['stats'][k])['rms']:.2e}" for k, v in got.items()), flush=True)
 
 
+SUB = ("depthnet.trunk", "depthnet.blocks", "depthnet.aspp", "depthnet.dcn", "mie.redir1", "mie.hourglass", "mie.ca3d", "mie.redir2")
+
 if __name__ == "__main__":
     import itertools
     wl = sys.argv[1] if len(sys.argv) > 1 else "config2"
-    X3 = ops.SS_MATH_TF32X3
-    groups = ("stereo", "depthnet", "mie")
-    for mask in itertools.product((0, 1), repeat=3):
-        run(wl, {g: (X3 if m else ops.SS_MATH_TF32) for g, m in zip(groups, mask)})
-    run(wl, {g: X3 for g in groups + ("voxel",)})
+    what = sys.argv[2] if len(sys.argv) > 2 else "groups"
+    X3, T = ops.SS_MATH_TF32X3, ops.SS_MATH_TF32
+    if what == "groups":
+        groups = ("stereo", "depthnet", "mie")
+        for mask in itertools.product((0, 1), repeat=3):
+            run(wl, {g: (X3 if m else T) for g, m in zip(groups, mask)})
+        run(wl, {g: X3 for g in groups + ("voxel",)})
+    elif what == "leave-one-out":          # depth_net + MIE compensated except one sub-stage (printed names = what IS compensated)
+        for drop in SUB:
+            run(wl, {g: (T if g == drop else X3) for g in SUB})
+    else:                                   # explicit list of compensated sub-stages: a,b,c
+        keep = what.split(",")
+        run(wl, {g: (X3 if g in keep else T) for g in SUB})

@@ -24,7 +24,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat", "redir1x1", "depth_conv", "aspp_dil", "mie_redir1", "frustum_conv_pending", "stage2_conv", "tpose32", "hg_conv1", "neck_k4", "hg_redir2", "stage2_conv_plain", "hg_conv4", "hg_conv4_plain", "hg_conv3", "hg_conv3_plain", "hourglass", "pw_proj"])
     ap.add_argument("--workload", default="config2")
-    ap.add_argument("--math", default="tf32")
+    ap.add_argument("--math", default="mixed", help="math policy (ops.MATH_POLICIES); single-kernel cases run plain TF32 unless --kernel-math says otherwise")
+    ap.add_argument("--kernel-math", default="tf32", choices=["tf32", "tf32x3", "3xtf32"])
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--time-one", action="store_true")
     ap.add_argument("--time", action="store_true", help="time every kernel case with CUDA events instead of profiling one")
@@ -35,7 +36,10 @@ def main():
             subprocess.run([sys.executable, __file__, "--what", w, "--time-one", "--workload", a.workload])
         return
     dev = torch.device("cuda", 0)
-    ops.set_default_math(ops.SS_MATH_3XTF32 if a.math == "3xtf32" else ops.SS_MATH_TF32)
+    if a.what == "step":
+        ops.set_math_policy(a.math)
+    else:
+        ops.set_default_math(ops.MATH_MODES[a.kernel_math])
     model, mc = presets.build(a.workload)
     synth.randomize_weights_(model, 0)
     model = model.to(dev).eval()
