@@ -45,6 +45,9 @@ extern "C" {
 #define SS_MATH_TF32X3 2               /* the same compensation on the tcgen05 kernels (ss_conv3d_tc_fwd / _join_fwd): three TF32
                                           launches lo(x)*hi(w) + hi(x)*lo(w) + hi(x)*hi(w) accumulated in fp32 */
 
+#define SS_MATH_F16X3 3                /* single-launch compensated mode of ss_conv3d_tc_fwd: both operands split into fp16 hi/lo halves
+                                          (22 significand bits), six kind::f16 MMAs per 32-channel chunk = 1.5x the TF32 tensor work */
+
 /* ABI version of this header; ss_abi_version() of the library must match. */
 #define SS_ABI_VERSION 5
 int ss_abi_version(void);
@@ -78,6 +81,8 @@ typedef struct ss_conv3d_desc {
     int32_t out_act;                  /* SS_ACT_*, applied after bias, before the statistics and the store */
     int32_t math;                     /* SS_MATH_* */
     int32_t cout_packed;              /* Cout rounded up to a multiple of 8: row length of w_packed */
+    float acc_scale;                  /* SS_MATH_F16X3 only: power of two the accumulator is multiplied by (the packed weights were
+                                         multiplied by its inverse so that their lo halves stay out of the fp16 subnormals) */
 } ss_conv3d_desc;
 
 /* w_packed: float[taps][Cin][cout_packed], taps = kd*kh*kw in (kd,kh,kw) row-major order, i.e.
@@ -98,7 +103,11 @@ int ss_conv3d_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_sc
  *   ConvTranspose: w_kmajor[t][co][ci] = tf32(weight[ci][co][kd][kh][kw])     (rows >= Cout are zero)
  * SS_MATH_TF32X3: w_kmajor holds TWO such arrays back to back, hi = tf32(w) followed by lo = tf32(w - hi); the activations
  * are split the same way on the fly and the three partial products are accumulated into y by three launches (y is read
- * back by the second and third), so the result has ~fp32 accuracy at ~3x the tensor work. */
+ * back by the second and third), so the result has ~fp32 accuracy at ~3x the tensor work.
+ * SS_MATH_F16X3 (only where ss_conv3d_tc_f16x3_supported(desc) == 1: the halo-resident and per-tap box kernels): every
+ * 128-byte row of w_kmajor, i.e. one output channel's 32-channel chunk, holds 64 fp16 values instead of 32 floats:
+ * hi = fp16(w / acc_scale) of the 32 channels followed by lo = fp16(w / acc_scale - hi); same array extent as in TF32 mode. */
+int ss_conv3d_tc_f16x3_supported(const ss_conv3d_desc* desc);
 int ss_conv3d_tc_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_scale, const float* in_shift,
                      const float* w_kmajor, const float* bias, float* y, double* stats, void* stream);
 

@@ -13,14 +13,14 @@ from . import _build
 ABI_VERSION = 5
 
 SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU = 0, 1, 2
-SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3 = 0, 1, 2
+SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3, SS_MATH_F16X3 = 0, 1, 2, 3
 
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "B", "Din", "Hin", "Win", "Cin", "Dout", "Hout", "Wout", "Cout",
         "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw", "dd", "dh", "dw",
-        "transposed", "in_ldc", "out_ldc", "in_act", "out_act", "math", "cout_packed")]
+        "transposed", "in_ldc", "out_ldc", "in_act", "out_act", "math", "cout_packed")] + [("acc_scale", C.c_float)]
 
 
 class ConvJoin(C.Structure):
@@ -43,6 +43,7 @@ SIGNATURES = {
     "ss_conv3d_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_conv3d_tc_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_conv3d_tc_join_supported": (_i, [C.POINTER(ConvDesc)]),
+    "ss_conv3d_tc_f16x3_supported": (_i, [C.POINTER(ConvDesc)]),
     "ss_conv3d_tc_join_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvJoin), _vp, _vp]),
     "ss_gn_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _f, _vp, _vp, _i, _vp]),
     "ss_ca3d_gate": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -1,5 +1,6 @@
 // Shared device/host helpers for the stereoscene_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
@@ -50,7 +51,29 @@ __device__ __forceinline__ uint32_t f2tf32(float x) {
 struct ConvPass {
     int a_lo;
     int accumulate;
+    int f16 = 0;              // SS_MATH_F16X3: single launch, fp16 hi/lo split of both operands (see split_f16x4)
+    float acc_scale = 1.0f;   //   the accumulator is multiplied by this power of two (the weights were pre-scaled by its inverse)
 };
+// SS_MATH_F16X3: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 significand bits); one 128-byte shared-memory row
+// that held 32 fp32 channels holds [hi(32 ch) | lo(32 ch)] as 64 fp16 K elements, the weight rows hold [hi(w) | lo(w)] the
+// same way, and every 32-channel chunk issues six kind::f16 MMAs (K = 16): hi*hi, lo*hi, hi*lo -- 1.5x the MMA count of a
+// plain TF32 pass (four K = 8 MMAs), in ONE launch with the accumulator staying in TMEM.
+__device__ __forceinline__ void split_f16x4(float4 v, uint2& hi, uint2& lo) {
+    v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
+    v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+    hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+// cute::UMMA::InstrDescriptor for kind::f16 with fp16 operands: c_format F32 (1) at [4,6), a/b format F16 (0), K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// descriptor-word offsets (16-byte units inside the 128-byte row) of the six MMAs of one chunk: A part, B part
+__device__ constexpr int kF16A[6] = {0, 2, 4, 6, 0, 2};
+__device__ constexpr int kF16B[6] = {0, 2, 0, 2, 4, 6};
 template <bool LO>
 __device__ __forceinline__ uint32_t f2tf32_part(float x) {
     const uint32_t h = f2tf32(x);
@@ -134,6 +157,31 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "elect.sync _|q, 0xffffffff;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(B_HI) : "memory");
+}
+template <uint32_t A_HI, uint32_t B_HI>
+__device__ __forceinline__ void umma_ss_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(A_HI), "n"(B_HI) : "memory");
+}
+template <uint32_t B_HI>
+__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(B_HI) : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {

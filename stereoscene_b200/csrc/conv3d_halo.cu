@@ -32,6 +32,7 @@ struct HaloParams {
     int sH, sW, swap;             // voxel strides of the kernel's h / w axes; swap = 1: the kernel's (h,w) are the tensor's (w,h)
     int KD;                       // depth taps: 3 (3x3x3, pad 1) or 1 (2-D 3x3 layers, D == 1 planes)
     int a_lo, accumulate;         // ConvPass (common.cuh)
+    float acc_scale;              // F16 variant: accumulator scale (power of two)
     const float* in_scale;
     const float* in_shift;
     const float* bias;
@@ -109,7 +110,9 @@ struct HaloCfg {
     static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
 
-template <int BN>
+// F16 = the single-launch fp16-split compensated variant (SS_MATH_F16X3, see common.cuh:split_f16x4): the workers rewrite
+// every landed fp32 plane row in place as [hi | lo] fp16 halves and each (chunk, tap) issues six kind::f16 MMAs.
+template <int BN, bool F16>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     using Cfg = HaloCfg<BN>;
@@ -138,7 +141,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
                    accum_bar = h_smem_u32(bars + 3 * HL_NPL + 2 * SB);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu || p.a_lo;
+    const bool fixup = F16 || has_aff || in_relu || p.a_lo;
     const int kchunks = p.Cin / 32;
     const int KD = p.KD;
 
@@ -217,9 +220,16 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint32_t ao = (uint32_t)(((mt * 16 + ce / 3) * HL_HW + (ce % 3)) * 128) >> 4;
+                    if constexpr (F16) {
+                        constexpr uint32_t idesc16 = make_idesc_f16(128, BN);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_ss_tf32<A_HI, B_HI>(tmem_base + (uint32_t)(mt * BN), a_lo + ao + 2 * k, b_lo + 2 * k, idesc, (Lp | ce | k) ? 1u : 0u);
+                        for (int i = 0; i < 6; ++i)
+                            umma_ss_f16<A_HI, B_HI>(tmem_base + (uint32_t)(mt * BN), a_lo + ao + kF16A[i], b_lo + kF16B[i], idesc16, (Lp | ce | i) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_ss_tf32<A_HI, B_HI>(tmem_base + (uint32_t)(mt * BN), a_lo + ao + 2 * k, b_lo + 2 * k, idesc, (Lp | ce | k) ? 1u : 0u);
+                    }
                 }
                 umma_commit_elect(pb_empty0 + 8 * bslot);
                 if (ce == 8) umma_commit_elect(pa_empty0 + 8 * pslot);
@@ -234,7 +244,38 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
             const int slot = L % HL_NPL;
             h_mbar_wait(pa_full0 + 8 * slot, (uint32_t)(L / HL_NPL) & 1u);
             const int dpl = d - KD / 2 + (L % KD), c0 = (L / KD) * 32;
-            if ((unsigned)dpl < (unsigned)p.D) {
+            if constexpr (F16) {
+                if ((unsigned)dpl < (unsigned)p.D) {
+                    unsigned char* pl = planes + slot * HL_PLANE_BYTES;
+                    // the 8 lanes that share a row read their fp32 chunks, then (after a warp sync) overwrite the row
+                    // with its fp16 halves: chunk j (channels 4j..4j+3) -> 8 bytes of hi at 8j, 8 bytes of lo at 64 + 8j
+                    constexpr int ITERS = (HL_PLANE_ROWS * 8 + HL_WORKERS - 1) / HL_WORKERS;
+                    for (int it = 0; it < ITERS; ++it) {
+                        const int idx = tid + it * HL_WORKERS;
+                        const int r = idx >> 3, chunk = idx & 7;
+                        const int hh = h0 - 1 + r / HL_HW, ww = w0 - 1 + r % HL_HW;
+                        const bool act = idx < HL_PLANE_ROWS * 8 && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
+                        unsigned char* row = pl + r * 128;
+                        uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+                        if (act) {
+                            float4 v = *reinterpret_cast<const float4*>(row + ((chunk ^ (r & 7)) << 4));
+                            if (has_aff) {
+                                const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
+                                const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
+                                v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                            }
+                            if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            split_f16x4(v, hi, lo);
+                        }
+                        __syncwarp();
+                        if (act) {
+                            *reinterpret_cast<uint2*>(row + ((((chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = hi;
+                            *reinterpret_cast<uint2*>(row + (((4 + (chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = lo;
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else if ((unsigned)dpl < (unsigned)p.D) {
                 unsigned char* pl = planes + slot * HL_PLANE_BYTES;
                 auto fix = [&](auto lo_tag) {
                     constexpr bool LO = decltype(lo_tag)::value;
@@ -288,6 +329,10 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
             float v[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+            if constexpr (F16) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] *= p.acc_scale;
+            }
             if (p.accumulate && valid) {                       // later pass of the compensated mode: add the partial result
                 const float* src = p.y + ov * p.out_ldc + cbase;
                 if (vec_ok && cbase + 32 <= p.Cout) {
@@ -367,7 +412,7 @@ typedef CUresult (*HEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int BN>
+template <int BN, bool F16>
 static int launch_halo(const HaloParams& p, const CUtensorMap& tmA, const float* wk, HEncodeTiledFn encode, cudaStream_t st) {
     using Cfg = HaloCfg<BN>;
     alignas(64) CUtensorMap tmB;
@@ -382,12 +427,12 @@ static int launch_halo(const HaloParams& p, const CUtensorMap& tmA, const float*
                         (3 * HL_NPL + 2 * Cfg::SB + 1) * sizeof(uint64_t) + 16 + 32 + 2 * (size_t)p.Cin * sizeof(float);
     static thread_local size_t configured = 0;
     if (smem > configured) {
-        SS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid((unsigned)((long long)p.B * p.D * p.nTH * p.nTW), (unsigned)((p.CoutP + BN - 1) / BN), 1);
-    conv_halo_kernel<BN><<<grid, HL_THREADS, smem, st>>>(p, tmA, tmB);
-    return check_launch("conv_halo_kernel");
+    conv_halo_kernel<BN, F16><<<grid, HL_THREADS, smem, st>>>(p, tmA, tmB);
+    return check_launch(F16 ? "conv_halo_f16x3_kernel" : "conv_halo_kernel");
 }
 
 // returns 1 if the layer was handled here
@@ -420,8 +465,8 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
     p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act; p.nTH = nTH; p.nTW = nTW; p.KD = d->kd;
     p.swap = swap; p.sH = swap ? 1 : d->Win; p.sW = swap ? d->Win : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
-    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale;
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo || ps.f16;
     alignas(64) CUtensorMap tmA;
     // tensor map dims in the kernel's order (C, w, h, D, B); the byte strides say which tensor axis each one walks
     const cuuint64_t str_w = (cuuint64_t)d->in_ldc * 4, str_h = (cuuint64_t)d->Win * d->in_ldc * 4;
@@ -437,18 +482,23 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
     const long long tiles = (long long)p.B * p.D * nTH * nTW;
     // column tile: the one that minimises (waves of CTAs on 148 SMs) x (work per CTA ~ BN)
     auto cost = [&](int bn) { const long long ctas = tiles * ((cp + bn - 1) / bn); return (double)((ctas + 147) / 148) * bn; };
-    if (cp <= 64) *rc = launch_halo<64>(p, tmA, w_kmajor, encode, st);
-    else if (cp <= 128) *rc = launch_halo<128>(p, tmA, w_kmajor, encode, st);
-    else if (cp <= 192 && cp != 160) *rc = launch_halo<192>(p, tmA, w_kmajor, encode, st);
+    int best = 256;
+    if (cp <= 64) best = 64;
+    else if (cp <= 128) best = 128;
+    else if (cp <= 192 && cp != 160) best = 192;
     else {
-        int best = 256;
         double bc = cost(256) * 0.9;                                // 256-column tiles halve the A traffic per FLOP
         if (cp % 128 == 0 && cost(128) < bc) { best = 128; bc = cost(128); }
         if (cp % 160 == 0 && cost(160) < bc) { best = 160; bc = cost(160); }
-        if (best == 128) *rc = launch_halo<128>(p, tmA, w_kmajor, encode, st);
-        else if (best == 160) *rc = launch_halo<160>(p, tmA, w_kmajor, encode, st);
-        else *rc = launch_halo<256>(p, tmA, w_kmajor, encode, st);
     }
+#define SS_HALO_LAUNCH(BN_)                                                                        \
+    *rc = ps.f16 ? launch_halo<BN_, true>(p, tmA, w_kmajor, encode, st) : launch_halo<BN_, false>(p, tmA, w_kmajor, encode, st)
+    if (best == 64) SS_HALO_LAUNCH(64);
+    else if (best == 128) SS_HALO_LAUNCH(128);
+    else if (best == 160) SS_HALO_LAUNCH(160);
+    else if (best == 192) SS_HALO_LAUNCH(192);
+    else SS_HALO_LAUNCH(256);
+#undef SS_HALO_LAUNCH
     return 1;
 }
 

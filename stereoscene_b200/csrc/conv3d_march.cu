@@ -588,6 +588,17 @@ static int launch_march(const MarchParams& p, const ss_conv3d_desc* d, const flo
     return check_launch("conv_march32_kernel");
 }
 
+int conv_march32_eligible(const ss_conv3d_desc* d) {
+    if (d->transposed || d->Cin != 32 || d->cout_packed != 32) return 0;
+    const bool k3 = d->kd == 3 && d->kh == 3 && d->kw == 3 && d->pd == 1 && d->ph == 1 && d->pw == 1;
+    const bool k1 = d->kd == 1 && d->kh == 1 && d->kw == 1 && d->pd == 0 && d->ph == 0 && d->pw == 0;
+    if (!k3 && !k1) return 0;
+    if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
+    if (d->Win < 8 || d->Hin < 8 || d->Din < 3) return 0;
+    if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win || d->math != SS_MATH_TF32) return 0;
+    return 1;
+}
+
 // returns 1 if the layer was handled by the marching kernel
 int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                      const float* w_kmajor, const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps) {

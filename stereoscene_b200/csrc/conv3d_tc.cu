@@ -46,6 +46,7 @@ struct TcParams {
     float* y;
     double* stats;
     int a_lo, accumulate;      // ConvPass (common.cuh)
+    float acc_scale;           // F16 variant: accumulator scale (power of two)
 };
 
 __host__ __device__ inline int tc_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -129,6 +130,10 @@ __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t 
           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st8_nowait(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -182,7 +187,10 @@ struct TcCfg {
     static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;   // power of two >= need (2 CTAs/SM at 256)
 };
 
-template <int BN>
+// F16 = the single-launch fp16-split compensated variant (SS_MATH_F16X3, common.cuh:split_f16x4): the fix-up warps write the
+// A operand into the TMEM ring as packed fp16 pairs [hi(32 ch) | lo(32 ch)] (32 columns, as in TF32 mode) and every K step
+// issues six TS-mode kind::f16 MMAs against weight rows packed the same way.
+template <int BN, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::MIN_CTAS)
 conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     using Cfg = TcCfg<BN>;
@@ -217,7 +225,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
                    accum_bar = smem_u32(bars + 3 * STAGES);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu || p.a_lo;
+    const bool fixup = F16 || has_aff || in_relu || p.a_lo;
 
     // ---- per-CTA setup ------------------------------------------------------------------------
     if (tid == 0) {
@@ -288,7 +296,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             tc_fence_after();
             const uint32_t a_addr = ring_u32 + slot * Cfg::STAGE_BYTES;
             const uint32_t a_lo = umma_desc_lo(a_addr), b_lo = umma_desc_lo(a_addr + Cfg::A_BYTES);
-            if (fixup) {                              // A from the TMEM ring written by the fix-up warps
+            if constexpr (F16) {
+                constexpr uint32_t idesc16 = make_idesc_f16(TC_BM, BN);
+                const uint32_t a_tmem = tmem_base + (uint32_t)(Cfg::A_COL0 + slot * TC_BK);
+#pragma unroll
+                for (int i = 0; i < 6; ++i)      // TMEM columns: 8 per K = 16 fp16 (two per 32-bit cell) -> 4 x the 16-byte descriptor units
+                    umma_ts_f16<D_HI>(tmem_base, a_tmem + (uint32_t)(4 * kF16A[i]), b_lo + kF16B[i], idesc16, (step | i) ? 1u : 0u);
+            } else if (fixup) {                       // A from the TMEM ring written by the fix-up warps
                 const uint32_t a_tmem = tmem_base + (uint32_t)(Cfg::A_COL0 + slot * TC_BK);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k)
@@ -325,6 +339,42 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
         for (int j = 0; j < 8; ++j) roff[j] = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::A_COL0;
+        if constexpr (F16) {
+            for (int step = grp; step < nsteps; step += 2) {
+                const int slot = step % STAGES;
+                const uint32_t use = (uint32_t)(step / STAGES);
+                const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
+                mbar_wait(full0 + 8 * slot, use & 1u);
+                const unsigned char* a_src = ring + slot * Cfg::STAGE_BYTES;
+                const bool ok = (vmask >> tap) & 1ull;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {       // 16 channels -> 8 packed hi words + 8 packed lo words
+                    float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(a_src + roff[hh * 4 + j]);
+                    uint32_t oh[8], ol[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 w = v[j];
+                        if (has_aff) {
+                            const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + hh * 16 + 4 * j);
+                            const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + hh * 16 + 4 * j);
+                            w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+                        }
+                        if (in_relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+                        uint2 hi, lo;
+                        split_f16x4(w, hi, lo);
+                        oh[2 * j] = ok ? hi.x : 0u; oh[2 * j + 1] = ok ? hi.y : 0u;
+                        ol[2 * j] = ok ? lo.x : 0u; ol[2 * j + 1] = ok ? lo.y : 0u;
+                    }
+                    tmem_st8_nowait(t_row + (uint32_t)(slot * TC_BK + hh * 8), oh);
+                    tmem_st8_nowait(t_row + (uint32_t)(slot * TC_BK + 16 + hh * 8), ol);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(ready0 + 8 * slot);
+            }
+        } else {
         auto fix = [&](auto lo_tag) {
             constexpr bool LO = decltype(lo_tag)::value;
             for (int step = grp; step < nsteps; step += 2) {
@@ -360,6 +410,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             }
         };
         SS_UNSWITCH_LO(p.a_lo, fix);
+        }
     }
 
     // ======================= EPILOGUE: 8 warps drain TMEM ========================================
@@ -392,6 +443,10 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             float v[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+            if constexpr (F16) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] *= p.acc_scale;
+            }
             if (p.accumulate && ov >= 0) {                     // later pass of the compensated mode: add the partial result
                 const float* src = p.y + (size_t)ov * p.out_ldc + cbase;
                 if (vec_ok && cbase + 32 <= p.Cout) {
@@ -497,7 +552,7 @@ static void choose_box(int Dc, int Hc, int Wc, int sd, int sh, int sw, int& TD, 
         }
 }
 
-template <int BN>
+template <int BN, bool F16 = false>
 static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, int ntaps_total, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
     EncodeTiledFn encode = get_encode_fn();
@@ -517,7 +572,7 @@ static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, i
         cuuint32_t estr[5] = {1, (cuuint32_t)isw, (cuuint32_t)ish, (cuuint32_t)isd, 1};
         // plain input: TFLOAT32 (the TMA unit rounds fp32 -> tf32); pending affine: raw FLOAT32, the fix-up
         // warps round once, after the affine
-        const bool fixup = (p.in_scale != nullptr) || (p.in_act == SS_ACT_RELU) || p.a_lo;
+        const bool fixup = F16 || (p.in_scale != nullptr) || (p.in_act == SS_ACT_RELU) || p.a_lo;
         CUresult r = encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -537,12 +592,12 @@ static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, i
                   (3 * Cfg::STAGES + 1) * sizeof(uint64_t) + 16 + 2 * (size_t)p.Cin * sizeof(float) + 32;
     static thread_local size_t configured = 0;
     if (smem > configured) {
-        SS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid((unsigned)(p.nTD * p.nTH * p.nTW), (unsigned)((p.CoutP + BN - 1) / BN), (unsigned)(p.B * ncls));
-    conv_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(p, tmA, tmB);
-    return check_launch("conv_tc_kernel");
+    conv_tc_kernel<BN, F16><<<grid, TC_THREADS, smem, st>>>(p, tmA, tmB);
+    return check_launch(F16 ? "conv_tc_f16x3_kernel" : "conv_tc_kernel");
 }
 
 }  // namespace ss
@@ -553,6 +608,8 @@ int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_sc
 int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                    const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join, const ConvPass& ps);
 int conv_tpose_join_supported(const ss_conv3d_desc* d);
+int conv_march32_eligible(const ss_conv3d_desc* d);
+int conv_pw_eligible(const ss_conv3d_desc* d);
 int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                 const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps);
 int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
@@ -569,39 +626,48 @@ static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_
     p.transposed = d->transposed; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
     p.cls_d = d->transposed ? d->sd : 1; p.cls_h = d->transposed ? d->sh : 1; p.cls_w = d->transposed ? d->sw : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale;
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
-    {   // 32-channel 3x3x3 stride-1 layers: persistent marching kernel (halo planes + resident weights)
+    {
         int rcm = 0;
-        if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
-        // pointwise layers with short K: persistent streaming GEMM with resident weights
-        if (try_conv_pw(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
+        if (!ps.f16) {
+            // 32-channel 3x3x3 stride-1 layers: persistent marching kernel (halo planes + resident weights)
+            if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
+            // pointwise layers with short K: persistent streaming GEMM with resident weights
+            if (try_conv_pw(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
+        }
         // wide 3x3x3 stride-1 layers: halo-resident kernel (planes loaded once per chunk, two M tiles per weight tile)
         if (try_conv_halo(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
         // stride-2 transposed 3x3x3 layers: one CTA per input tile computes all 8 output parity classes
-        if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, nullptr, ps)) return rcm;
+        if (!ps.f16 && try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, nullptr, ps)) return rcm;
     }
     const int cp = d->cout_packed;
     const int ntaps_total = d->kd * d->kh * d->kw;
-    if (cp <= 32) return launch_tc<32>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
-    if (cp <= 64) return launch_tc<64>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
-    if (cp <= 128) return launch_tc<128>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
-    if (cp <= 192 && cp != 160) return launch_tc<192>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
-    {   // wide layers: the column tile that minimises (waves of CTAs on 148 SMs) x (work per CTA ~ BN); 256-column tiles
+    int best = 256;
+    if (cp <= 32) best = 32;
+    else if (cp <= 64) best = 64;
+    else if (cp <= 128) best = 128;
+    else if (cp <= 192 && cp != 160) best = 192;
+    else {  // wide layers: the column tile that minimises (waves of CTAs on 148 SMs) x (work per CTA ~ BN); 256-column tiles
         // leave SMs idle on small grids, 160 columns turn the 300-CTA grid of the 640-channel 2-D layers into 240
         const int ncls = p.cls_d * p.cls_h * p.cls_w;
         const long long rows = ((long long)(p.Dout + p.cls_d - 1) / p.cls_d) * ((p.Hout + p.cls_h - 1) / p.cls_h) *
                                ((p.Wout + p.cls_w - 1) / p.cls_w);
         const long long mt = ((rows + TC_BM - 1) / TC_BM) * p.B * ncls;
         auto cost = [&](int bn) { const long long ctas = mt * ((cp + bn - 1) / bn); return (double)((ctas + 147) / 148) * bn; };
-        int best = 256;
         double bc = cost(256) * 0.9;
         if (cp % 128 == 0 && cost(128) <= bc * 1.0001 / 0.9) { best = 128; bc = cost(128); }
         if (cp % 160 == 0 && cost(160) < bc) { best = 160; bc = cost(160); }
-        if (best == 128) return launch_tc<128>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
-        if (best == 160) return launch_tc<160>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
     }
-    return launch_tc<256>(p, x, d->in_ldc, w_kmajor, ntaps_total, st);
+#define SS_TC_LAUNCH(BN_)                                                                                          \
+    return ps.f16 ? launch_tc<BN_, true>(p, x, d->in_ldc, w_kmajor, ntaps_total, st) : launch_tc<BN_, false>(p, x, d->in_ldc, w_kmajor, ntaps_total, st)
+    if (best == 32) SS_TC_LAUNCH(32);
+    if (best == 64) SS_TC_LAUNCH(64);
+    if (best == 128) SS_TC_LAUNCH(128);
+    if (best == 160) SS_TC_LAUNCH(160);
+    if (best == 192) SS_TC_LAUNCH(192);
+    SS_TC_LAUNCH(256);
+#undef SS_TC_LAUNCH
 }
 
 // The compensated mode (SS_MATH_TF32X3): three TF32 launches that accumulate into y, smallest terms first.
@@ -612,6 +678,12 @@ static int tc_three_pass(const ss_conv3d_desc* d, const float* w_kmajor, F&& lau
     t.math = SS_MATH_TF32;
     const size_t wn = (size_t)d->kd * d->kh * d->kw * d->cout_packed * d->Cin;
     if (d->math == SS_MATH_TF32) return launch(&t, w_kmajor, ConvPass{0, 0}, true);
+    if (d->math == SS_MATH_F16X3) {            // single launch: fp16 hi/lo split of both operands inside the kernel
+        ConvPass ps{0, 0};
+        ps.f16 = 1;
+        ps.acc_scale = d->acc_scale;
+        return launch(&t, w_kmajor, ps, true);
+    }
     ss_conv3d_desc part = t;
     part.out_act = SS_ACT_NONE;
     int rc = launch(&part, w_kmajor, ConvPass{1, 0}, false);                 // lo(x) * hi(w)
@@ -621,6 +693,16 @@ static int tc_three_pass(const ss_conv3d_desc* d, const float* w_kmajor, F&& lau
     return launch(&t, w_kmajor, ConvPass{0, 1}, true);                       // hi(x) * hi(w) + bias, activation, statistics, join
 }
 }  // namespace ss
+
+// 1 if the layer runs as ONE launch in the fp16-split compensated mode (halo-resident or per-tap box kernel); layers that the
+// marching / pointwise / transposed kernels serve keep the three-launch SS_MATH_TF32X3 path on those kernels.
+extern "C" int ss_conv3d_tc_f16x3_supported(const ss_conv3d_desc* d) {
+    if (!d || d->Cin % 32 != 0 || d->in_ldc % 4 != 0) return 0;
+    ss_conv3d_desc t = *d;
+    t.math = SS_MATH_TF32;
+    if (ss::conv_march32_eligible(&t) || ss::conv_pw_eligible(&t) || ss::conv_tpose_join_supported(&t)) return 0;
+    return 1;
+}
 
 // wk: float[taps][cout_packed][Cin], K-major, values already rounded to TF32.
 extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
@@ -639,7 +721,9 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_tc_fwd: in_act");
     SS_REQUIRE(d->Cin <= 4096, "ss_conv3d_tc_fwd: Cin limited to 4096");
     SS_REQUIRE((long long)d->B * d->Dout * d->Hout * d->Wout < (1ll << 31), "ss_conv3d_tc_fwd: output too large");
-    SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3, "ss_conv3d_tc_fwd: TF32 / TF32X3 only (use ss_conv3d_fwd for 3xTF32 on mma.sync)");
+    SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3 || d->math == SS_MATH_F16X3,
+               "ss_conv3d_tc_fwd: TF32 / TF32X3 / F16X3 only (use ss_conv3d_fwd for 3xTF32 on mma.sync)");
+    if (d->math == SS_MATH_F16X3) SS_REQUIRE(ss_conv3d_tc_f16x3_supported(d) == 1 && d->acc_scale > 0.f, "ss_conv3d_tc_fwd: F16X3 not offered for this layer (ask ss_conv3d_tc_f16x3_supported)");
     if (d->transposed) SS_REQUIRE(d->dd == 1 && d->dh == 1 && d->dw == 1, "ss_conv3d_tc_fwd: dilated transposed conv unsupported");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return tc_three_pass(d, w_kmajor, [&](const ss_conv3d_desc* dd, const float* w, const ConvPass& ps, bool last) {

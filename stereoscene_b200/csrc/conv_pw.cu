@@ -347,6 +347,26 @@ typedef CUresult (*PwEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// shape test of try_conv_pw (without the pending-input / shared-memory refinements): used to route the compensated modes
+int conv_pw_eligible(const ss_conv3d_desc* d) {
+    if (d->math != SS_MATH_TF32 || d->pd != 0 || d->ph != 0 || d->pw != 0 || d->dd != 1 || d->dh != 1 || d->dw != 1) return 0;
+    int s = 1;
+    if (d->kd == 1 && d->kh == 1 && d->kw == 1 && d->sd == 1 && d->sh == 1 && d->sw == 1) {
+        if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
+    } else if (d->transposed && d->kd == d->sd && d->kh == d->sh && d->kw == d->sw && d->sd == d->sh && d->sh == d->sw &&
+               (d->sd == 2 || d->sd == 4)) {
+        s = d->sd;
+        if (d->Dout != d->Din * s || d->Hout != d->Hin * s || d->Wout != d->Win * s) return 0;
+    } else {
+        return 0;
+    }
+    if (d->Cin % 32 != 0 || d->Cin > 64 || d->cout_packed > 128) return 0;      // Cin > 64 with a forced fix-up goes to the box kernel
+    const long long vpb = (long long)d->Din * d->Hin * d->Win, V = vpb * d->B;
+    if (vpb % PW_TILE != 0 || V >= (1ll << 31) || V * s * s * s < 148LL * PW_TILE * 2) return 0;
+    if (s > 1 && d->cout_packed % 32 != 0) return 0;
+    return 1;
+}
+
 // returns 1 if the layer was handled here
 int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                 const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ConvPass& ps) {

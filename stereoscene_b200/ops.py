@@ -23,11 +23,19 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import cabi
-from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_TF32, SS_MATH_TF32X3  # noqa: F401
+from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_F16X3, SS_MATH_TF32, SS_MATH_TF32X3  # noqa: F401
 
 _DEFAULT_MATH = SS_MATH_TF32
 _USE_TCGEN05 = os.environ.get("STEREOSCENE_B200_NO_TCGEN05", "0") != "1"
 _FUSE_JOIN = os.environ.get("STEREOSCENE_B200_NO_FUSED_JOIN", "0") != "1"      # A/B switch for ops.conv_join
+_USE_F16X3 = os.environ.get("STEREOSCENE_B200_NO_F16X3", "0") != "1"           # A/B switch: single-launch fp16-split compensation
+
+
+def use_f16x3(flag: bool):
+    """Serve SS_MATH_TF32X3 layers of the halo-resident / box kernels with the single-launch fp16-split variant
+    (default) or with three accumulating TF32 launches like every other kernel family."""
+    global _USE_F16X3
+    _USE_F16X3 = bool(flag)
 
 
 def use_tcgen05(flag: bool):
@@ -244,6 +252,8 @@ class PackedConv:
         self._wk = None
         self._skey = None
         self._ws = None
+        self._hkey = None
+        self._wh = None
 
     def weights(self) -> torch.Tensor:
         w = self.module.weight
@@ -307,6 +317,34 @@ class PackedConv:
                 self._ws = torch.stack([hi, lo]).contiguous()
             self._skey = key
         return self._ws
+
+    def weights_kmajor_f16(self):
+        """(packed, acc_scale) for SS_MATH_F16X3: the K-major array of ``weights_kmajor`` in which every 128-byte row (one
+        output channel's 32-channel chunk) holds 64 fp16 values, hi = fp16(w / acc_scale) of the 32 channels followed by
+        lo = fp16(w / acc_scale - hi); acc_scale is the power of two that brings max|w| to ~2^10, so that the lo halves
+        of all but negligible weights are normal fp16 numbers."""
+        w = self.module.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self._hkey:
+            with torch.no_grad():
+                wd = w.detach()
+                if wd.dim() == 4:
+                    wd = wd.unsqueeze(2)
+                pk = wd.permute(2, 3, 4, 1, 0) if self.transposed else wd.permute(2, 3, 4, 0, 1)   # [k,k,k,Cout,Cin]
+                pk = pk.reshape(-1, self.Cout, self.Cin).float()
+                if self.CoutP != self.Cout:
+                    pk = torch.nn.functional.pad(pk, (0, 0, 0, self.CoutP - self.Cout))
+                amax = float(pk.abs().max())
+                e = math.floor(math.log2(amax)) if amax > 0.0 else 0
+                acc_scale = 2.0 ** (e - 10)
+                ws = pk * (1.0 / acc_scale)
+                hi = ws.half()
+                lo = (ws - hi.float()).half()
+                T, Cp, Ci = ws.shape
+                both = torch.cat([hi.view(T, Cp, Ci // 32, 32), lo.view(T, Cp, Ci // 32, 32)], dim=-1).contiguous()
+                self._wh = (both.view(T, Cp, Ci * 2).view(torch.float32).contiguous(), acc_scale)
+            self._hkey = key
+        return self._wh
 
     def out_size(self, din: Sequence[int]) -> Tuple[int, int, int]:
         out = []
@@ -375,6 +413,7 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     # single-output-channel layers ride the tensor-core kernel too (N padded to 32): it is faster than the FMA kernel
     tc = (_USE_TCGEN05 and mm in (SS_MATH_TF32, SS_MATH_TF32X3) and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
           and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
+    d.acc_scale = 1.0
     if mm == SS_MATH_TF32X3 and not tc:        # layers the tcgen05 kernels do not take (Cin = 2, odd strides): mma.sync split TF32
         mm = SS_MATH_3XTF32
         d.math = mm
@@ -387,6 +426,15 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
         in_ldc = _vol_ldc(xin, "conv input")
         d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
                           1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
+        d.acc_scale = 1.0
+    if tc and mm == SS_MATH_TF32X3 and _USE_F16X3 and lib.ss_conv3d_tc_f16x3_supported(C.byref(d)) == 1:
+        # the halo-resident / box kernels offer the compensation in ONE launch (fp16 hi/lo split, 1.5x the TF32 tensor work)
+        wk, d.acc_scale = pc.weights_kmajor_f16()
+        d.math = SS_MATH_F16X3
+        rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), wk.data_ptr(),
+                                  _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
+        cabi.check(rc, "ss_conv3d_tc_fwd")
+        return out, stats
     if tc:
         wk = pc.weights_kmajor_split() if mm == SS_MATH_TF32X3 else pc.weights_kmajor()
         rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), wk.data_ptr(),
@@ -610,7 +658,7 @@ def cached_state():
     (stereoscene_b200.runtime.VolumetricEngine does)."""
     keep = []
     for pc in _packed_cache.values():
-        keep += [pc._w, pc._wk, pc._ws]
+        keep += [pc._w, pc._wk, pc._ws, pc._wh[0] if pc._wh is not None else None]
     for hit in _bn_cache.values():
         keep += [hit[1], hit[2]]
     for hit in list(_taps_cache.values()) + list(_taps_dev_cache.values()):

@@ -116,12 +116,16 @@ def test_tcgen05_conv_agrees_with_mma_sync(ops, case):
     assert rel_err(st1[..., 1], st0[..., 1]) < 2e-3
 
 
+@pytest.mark.parametrize("single_launch", [True, False], ids=["f16x3", "3launch"])
 @pytest.mark.parametrize("case", [c for c in CONV_CASES if c[0] not in ("k3_2_32_bias",)],
                          ids=[c[0] for c in CONV_CASES if c[0] not in ("k3_2_32_bias",)])
-def test_compensated_tcgen05_conv_matches_fp32(ops, case):
-    """SS_MATH_TF32X3 (three accumulating TF32 launches of the tcgen05 kernels: lo*hi + hi*lo + hi*hi) with a pending
-    affine + ReLU on the input, an output activation and the epilogue sums, against an fp64 evaluation of the layer."""
+def test_compensated_tcgen05_conv_matches_fp32(ops, case, single_launch):
+    """SS_MATH_TF32X3 with a pending affine + ReLU on the input, an output activation and the epilogue sums, against an
+    fp64 evaluation of the layer.  Two implementations: three accumulating TF32 launches (lo*hi + hi*lo + hi*hi; every
+    tcgen05 kernel family) and, on the halo-resident / box kernels, ONE launch with both operands split into fp16 halves
+    (SS_MATH_F16X3, six kind::f16 MMAs per chunk)."""
     name, make, shape = case
+    ops.use_f16x3(single_launch)
     torch.manual_seed(zlib.crc32(name.encode()) % 1000 + 2)
     m = make()
     x = torch.randn(shape)
@@ -132,10 +136,20 @@ def test_compensated_tcgen05_conv_matches_fp32(ops, case):
     mg = make().cuda()
     mg.load_state_dict(m.float().state_dict())
     v = ops.Vol(_cl(x), sc.cuda(), sh.cuda(), ops.SS_ACT_RELU)
-    n0 = ops.cabi.kernel_census().get("conv_igemm_kernel", 0)
-    y, st = ops.conv(v, mg, want_stats=True, out_act=ops.SS_ACT_RELU, math_mode=ops.SS_MATH_TF32X3)
-    torch.cuda.synchronize()
-    assert ops.cabi.kernel_census().get("conv_igemm_kernel", 0) == n0, "compensated mode fell back to the mma.sync kernel"
+    c0 = ops.cabi.kernel_census()
+    try:
+        y, st = ops.conv(v, mg, want_stats=True, out_act=ops.SS_ACT_RELU, math_mode=ops.SS_MATH_TF32X3)
+        torch.cuda.synchronize()
+    finally:
+        ops.use_f16x3(True)
+    c1 = ops.cabi.kernel_census()
+    ran = {k: c1[k] - c0.get(k, 0) for k in c1 if k.startswith("conv_") and c1[k] - c0.get(k, 0) > 0}
+    assert "conv_igemm_kernel" not in ran, "compensated mode fell back to the mma.sync kernel"
+    f16 = [k for k in ran if "f16x3" in k]
+    if single_launch and f16:
+        assert sum(ran.values()) == 1, ran                      # ONE launch
+    elif not single_launch:
+        assert not f16 and sum(ran.values()) == 3, ran          # three accumulating launches
     assert rel_err(_ncdhw(y), want) < 5e-5
     assert rel_err(st[..., 0], want.double().sum(dim=(2, 3, 4))) < 1e-4
     assert rel_err(st[..., 1], (want.double() ** 2).sum(dim=(2, 3, 4))) < 1e-4
