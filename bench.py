@@ -123,7 +123,11 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the forward in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
-    ap.add_argument("--pairs-per-step", type=int, default=1, help="stereo pairs per GPU per step (batch of one forward)")
+    ap.add_argument("--pairs-per-step", type=int, default=1, help="stereo pairs per GPU per step (batch of one forward); with --shard x: pairs per step of the whole job")
+    ap.add_argument("--shard", default="sample", choices=["sample", "x"],
+                    help="sample: one stereo pair per rank, no data-path collective (throughput mode, default); x: the X-slab sharded "
+                         "latency mode of BASELINE.json configs[3] (stereoscene_b200/xshard.py): one all-gather of depth_prob||img_feat at "
+                         "the MIE boundary, halo exchange + GroupNorm all-reduce in the voxel stack; total work fixed -> strong scaling")
     return ap.parse_args()
 
 
@@ -244,13 +248,90 @@ def run_reference_arm(args):
         "e2e": {"value": cb["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_run": cb["steps_run"], "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def run_xshard(args):
+    """--shard x: latency of a FIXED job (args.pairs_per_step stereo pairs per step, default 1) on N ranks."""
+    import torch.distributed as dist
+    from stereoscene_b200 import cabi, ops, presets, sharding, synth, xshard
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    cabi.load()
+    ops.set_math_policy(args.math)
+    model, mc = presets.build(args.workload)
+    synth.randomize_weights_(model, 0)
+    model = model.to(dev).eval()
+    P = max(1, args.pairs_per_step)
+    counts = [len(range(r, P, world)) for r in range(world)]
+    b = max(counts)
+    xl, xr = synth.stereo_features(max(b, 1), mc["input_size"], 8, seed=rank, device=dev)
+    left, right, calib = synth.kitti_calibration(max(b, 1), mc["input_size"], device=dev)
+    occ = mc["occ_size"]
+    pipe = xshard.XShardedPipeline(model, world, rank)
+
+    def step():
+        with torch.no_grad():
+            return pipe.forward(xl, xr, left, right, calib, occ, counts)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n0 = cabi.launch_count()
+    outs = step()
+    torch.cuda.synchronize()
+    launches = cabi.launch_count() - n0
+    coll = dict(pipe.path.collectives)
+    gathered = pipe.gathered_bytes
+    for _ in range(max(2, args.warmup - 1)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = float(sharding.max_over_ranks(torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev))[0])
+    if rank == 0:
+        line = {
+            "metric": "voxels/sec", "value": VOXELS[args.workload] * P * args.steps / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": workload_config(args.workload, P), "math": args.math, "math_policy": policy_text(ops, args.math),
+                       "cuda_graph": False, "parallelism": f"x-slab x{world}: frustum stages of pair s on rank s % {world}, ONE all-gather of "
+                       "depth_prob||img_feat at the MIE boundary, halo send/recv + GroupNorm all-reduce in the voxel stack",
+                       "l2": "no flush: one step streams > 9 GB of activations, >> 126 MB L2"},
+            "shard": {"mode": "x-slab", "pairs_per_step": P, "slab_planes": pipe.plan.xs, "per_sample": coll,
+                      "allgather_bytes_per_step": gathered, "output": f"rank r holds planes [{2 * pipe.plan.xs} r, {2 * pipe.plan.xs} (r+1)) of every label volume"},
+            "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches), "clocks": clocks,
+            "latency_ms": ms / args.steps,
+        }
+        if xshard._TIMING:
+            line["shard"]["serialised_ms_per_step"] = {k: v / (args.steps + max(2, args.warmup - 1) + 1) for k, v in xshard.TIMES.items()}
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
+    if args.shard == "x":
+        return run_xshard(args)
     import torch.distributed as dist
     from stereoscene_b200 import cabi, ops, presets, synth
 
@@ -493,7 +574,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cb = time_cpu(args.workload, 1, 1, 90.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -648,8 +729,28 @@ def dominant_kernel_roofline(model, mc, dev, pk):
     return roof, kernels
 
 
+def _json_only_stdout():
+    """Keep stdout = the ONE JSON line: libraries (NCCL prints its version banner with printf) write to fd 1 behind Python's
+    back, so fd 1 is pointed at stderr for the life of the process and the line goes to a private copy of the real stdout."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    _REAL_STDOUT = _json_only_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -81,6 +81,9 @@ typedef struct ss_conv3d_desc {
     int32_t out_act;                  /* SS_ACT_*, applied after bias, before the statistics and the store */
     int32_t math;                     /* SS_MATH_* */
     int32_t cout_packed;              /* Cout rounded up to a multiple of 8: row length of w_packed */
+    int32_t stats_d0, stats_d1;       /* only output planes d in [stats_d0, stats_d1) contribute to `stats` (stats_d1 <= stats_d0: all
+                                         planes).  Lets a rank of the X-slab sharded mode run a layer on its slab + halo planes while the
+                                         GroupNorm sums cover the slab only (the halo outputs are overwritten by the next exchange). */
     float acc_scale;                  /* SS_MATH_F16X3 only: power of two the accumulator is multiplied by (the packed weights were
                                          multiplied by its inverse so that their lo halves stay out of the fp16 subnormals) */
 } ss_conv3d_desc;

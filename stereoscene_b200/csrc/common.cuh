@@ -43,6 +43,16 @@ __device__ __forceinline__ uint32_t f2tf32(float x) {
     return r;
 }
 
+// output planes that contribute to the GroupNorm sums (ss_conv3d_desc.stats_d0 / stats_d1; empty range = all planes)
+struct StatsRange {
+    int d0, d1;
+    __host__ __device__ bool has(int d) const { return d >= d0 && d < d1; }
+};
+inline StatsRange stats_range_of(const ss_conv3d_desc* d) {
+    if (d->stats_d1 <= d->stats_d0) return StatsRange{0, 0x7fffffff};
+    return StatsRange{d->stats_d0, d->stats_d1};
+}
+
 // One pass of the error-compensated mode (SS_MATH_TF32X3) on the tcgen05 kernels.  x = hi + lo with hi = tf32(x),
 // lo = tf32(x - hi), likewise for the weights (split on the host); conv(x, w) ~= lo_x*hi_w + hi_x*lo_w + hi_x*hi_w, each
 // term one ordinary TF32 launch whose products are exact in fp32.  a_lo selects which part of the A operand the fix-up

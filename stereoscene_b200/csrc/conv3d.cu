@@ -423,6 +423,8 @@ extern "C" int ss_conv3d_fwd(const ss_conv3d_desc* d, const float* x, const floa
     SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_fwd: in_act");
     SS_REQUIRE(!(in_scale && d->Cin > 4096), "ss_conv3d_fwd: pending affine limited to 4096 channels");
     SS_REQUIRE((long long)d->B * d->Dout * d->Hout * d->Wout < (1ll << 31), "ss_conv3d_fwd: output too large");
+    SS_REQUIRE(!stats || d->stats_d1 <= d->stats_d0 || (d->stats_d0 <= 0 && d->stats_d1 >= d->Dout),
+               "ss_conv3d_fwd: a restricted statistics plane range is only offered by ss_conv3d_tc_fwd");
     if (d->transposed) {
         SS_REQUIRE(d->dd == 1 && d->dh == 1 && d->dw == 1, "ss_conv3d_fwd: dilated transposed conv unsupported");
         SS_REQUIRE(d->Dout <= (d->Din - 1) * d->sd - 2 * d->pd + d->kd + d->sd - 1, "ss_conv3d_fwd: Dout");

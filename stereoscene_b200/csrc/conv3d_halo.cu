@@ -33,6 +33,7 @@ struct HaloParams {
     int KD;                       // depth taps: 3 (3x3x3, pad 1) or 1 (2-D 3x3 layers, D == 1 planes)
     int a_lo, accumulate;         // ConvPass (common.cuh)
     float acc_scale;              // F16 variant: accumulator scale (power of two)
+    StatsRange sr;                // output planes that contribute to stats
     const float* in_scale;
     const float* in_shift;
     const float* bias;
@@ -320,7 +321,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         float* part = reinterpret_cast<float*>(planes) + 8 * 32 * 33 + warp * (2 * BN);      // per-warp column sums (no atomics: fixed summation order)
         const int act = p.out_act;
         const bool has_bias = p.bias != nullptr;
-        const bool want_stats = p.stats != nullptr;
+        const bool want_stats = p.stats != nullptr && p.sr.has(d);
 #pragma unroll 1
         for (int ci = 0; ci < BN / 32; ++ci) {
             uint32_t r[32];
@@ -389,7 +390,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
-    if (p.stats) {
+    if (p.stats && p.sr.has(d)) {
         for (int i = tid; i < BN; i += HL_THREADS) {
             const int c = n0 + i;
             if (c < p.Cout) {
@@ -465,7 +466,7 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
     p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act; p.nTH = nTH; p.nTW = nTW; p.KD = d->kd;
     p.swap = swap; p.sH = swap ? 1 : d->Win; p.sW = swap ? d->Win : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale; p.sr = stats_range_of(d);
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo || ps.f16;
     alignas(64) CUtensorMap tmA;
     // tensor map dims in the kernel's order (C, w, h, D, B); the byte strides say which tensor axis each one walks

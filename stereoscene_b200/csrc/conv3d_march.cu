@@ -54,6 +54,7 @@ struct MarchParams {
     int nTH, nTW;
     long long total_tiles;                           // B * nTH * nTW * D
     int a_lo, accumulate;                            // ConvPass (common.cuh)
+    StatsRange sr;                                   // output planes that contribute to stats
     const float* in_scale;
     const float* in_shift;
     const float* bias;
@@ -291,7 +292,7 @@ __device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t
                 for (int k = 0; k < NCOL; ++k)
                     if (col0 + k < p.Cout) dst[k] = v[k];
             }
-            if (want_stats) {
+            if (want_stats && p.sr.has(c.d)) {
 #pragma unroll
                 for (int k = 0; k < NCOL; ++k) { acc_s[k] += v[k]; acc_q[k] = fmaf(v[k], v[k], acc_q[k]); }
             }
@@ -623,7 +624,7 @@ int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_sc
     p.nTH = (p.H + MR_TH - 1) / MR_TH; p.nTW = (p.W + MR_TW - 1) / MR_TW;
     p.total_tiles = (long long)p.B * p.nTH * p.nTW * p.D;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.sr = stats_range_of(d);
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
     *rc = k3 ? launch_march<3>(p, d, x, w_kmajor, fixup, encode, st) : launch_march<1>(p, d, x, w_kmajor, fixup, encode, st);
     return 1;

@@ -47,6 +47,7 @@ struct TcParams {
     double* stats;
     int a_lo, accumulate;      // ConvPass (common.cuh)
     float acc_scale;           // F16 variant: accumulator scale (power of two)
+    StatsRange sr;             // output planes that contribute to stats
 };
 
 __host__ __device__ inline int tc_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -422,9 +423,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
         const int row = q * 32 + lane;
         const int qd = q0d + row / (p.TW * p.TH), qh = q0h + (row / p.TW) % p.TH, qw = q0w + row % p.TW;
         int ov = -1;
+        bool st_row = false;                           // this row's output plane contributes to the GroupNorm sums
         if (qd < Dc && qh < Hc && qw < Wc) {
             const int od = qd * p.cls_d + rd, oh = qh * p.cls_h + rh, ow = qw * p.cls_w + rw;
             ov = ((b * p.Dout + od) * p.Hout + oh) * p.Wout + ow;
+            st_row = p.sr.has(od);
         }
         constexpr int CHUNKS = BN / 32;
         constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
@@ -486,7 +489,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             }
             if (want_stats) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) scratch[lane * 33 + k] = (ov >= 0) ? v[k] : 0.f;
+                for (int k = 0; k < 32; ++k) scratch[lane * 33 + k] = st_row ? v[k] : 0.f;
                 __syncwarp();
                 float cs = 0.f, cq = 0.f;
 #pragma unroll
@@ -626,7 +629,7 @@ static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_
     p.transposed = d->transposed; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
     p.cls_d = d->transposed ? d->sd : 1; p.cls_h = d->transposed ? d->sh : 1; p.cls_w = d->transposed ? d->sw : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale; p.sr = stats_range_of(d);
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
     {
         int rcm = 0;

@@ -39,6 +39,7 @@ struct TposeParams {
     const float* r_shift;
     int res_ldc, res_act, has_join;
     int a_lo, accumulate;            // ConvPass (common.cuh)
+    StatsRange sr;                   // output planes that contribute to stats
 };
 
 __device__ __forceinline__ uint32_t t_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -370,7 +371,7 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                 if (p.stats) {
                     float s[32], sq[32];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) { s[k] = valid ? v[k] : 0.f; sq[k] = s[k] * s[k]; }
+                    for (int k = 0; k < 32; ++k) { s[k] = (valid && p.sr.has(od)) ? v[k] : 0.f; sq[k] = s[k] * s[k]; }
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
                         const bool up = (lane & off) != 0;
@@ -468,7 +469,7 @@ int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scal
     p.o_scale = join ? join->out_scale : nullptr; p.o_shift = join ? join->out_shift : nullptr;
     p.res = join ? join->res : nullptr; p.r_scale = join ? join->res_scale : nullptr; p.r_shift = join ? join->res_shift : nullptr;
     p.res_ldc = join ? join->res_ldc : 0; p.res_act = join ? join->res_act : 0;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.sr = stats_range_of(d);
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
     alignas(64) CUtensorMap tmA;
     cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.Din, (cuuint64_t)p.B};

@@ -38,6 +38,7 @@ struct PwParams {
     float* y;
     double* stats;
     int a_lo, accumulate;                            // ConvPass (common.cuh)
+    StatsRange sr;                                   // output planes that contribute to stats
 };
 
 __device__ __forceinline__ uint32_t pw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -259,11 +260,18 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
             if (tb != run_b || n0 != run_n0) { flush(); run_b = tb; run_n0 = n0; }
             const bool valid = v < p.V;
             size_t ov = (size_t)v;                                                       // s == 1: output voxel = input voxel
-            if (s > 1 && valid) {
+            bool st_row = valid;                                                         // row contributes to the GroupNorm sums
+            if (valid) {
                 const int vv = (int)(v - (long long)tb * p.vox_per_batch);
-                const int iw = vv % p.W, ih = (vv / p.W) % p.H, id = vv / (p.W * p.H);
-                const int a = cls / (s * s), bb = (cls / s) % s, c = cls % s;
-                ov = (((size_t)tb * Do + (id * s + a)) * Ho + (ih * s + bb)) * Wo + (iw * s + c);
+                const int id = vv / (p.W * p.H);
+                if (s > 1) {
+                    const int iw = vv % p.W, ih = (vv / p.W) % p.H;
+                    const int a = cls / (s * s), bb = (cls / s) % s, c = cls % s;
+                    ov = (((size_t)tb * Do + (id * s + a)) * Ho + (ih * s + bb)) * Wo + (iw * s + c);
+                    st_row = p.sr.has(id * s + a);
+                } else {
+                    st_row = p.sr.has(id);
+                }
             }
             pw_mbar_wait(t_full0 + 8 * acc, (L / PW_ACC) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -316,7 +324,7 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
                 }
                 if (want_stats) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) sc[lane * 32 + (k ^ lane)] = valid ? x[k] : 0.f;      // bank = k ^ lane: conflict-free
+                    for (int k = 0; k < 32; ++k) sc[lane * 32 + (k ^ lane)] = st_row ? x[k] : 0.f;     // bank = k ^ lane: conflict-free
                     __syncwarp();
                     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};      // four independent chains
 #pragma unroll
@@ -435,7 +443,7 @@ int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, 
     p.Cin = d->Cin; p.KC = KC; p.Cout = d->Cout; p.CoutP = d->cout_packed; p.NP = NP; p.out_ldc = d->out_ldc;
     p.in_act = d->in_act; p.out_act = d->out_act; p.RS = RS; p.scratch_floats = scratch_floats;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.sr = stats_range_of(d);
     const size_t smem = fixed_bytes(NP) + (size_t)RS * PW_TILE * 128;
     static thread_local size_t configured = 0;
     if (smem > configured) {

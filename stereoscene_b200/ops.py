@@ -346,13 +346,14 @@ class PackedConv:
             self._hkey = key
         return self._wh
 
-    def out_size(self, din: Sequence[int]) -> Tuple[int, int, int]:
+    def out_size(self, din: Sequence[int], pad: Optional[Sequence[int]] = None) -> Tuple[int, int, int]:
+        p = self.p if pad is None else pad
         out = []
         for i in range(3):
             if self.transposed:
-                out.append((din[i] - 1) * self.s[i] - 2 * self.p[i] + self.d[i] * (self.k[i] - 1) + self.outpad[i] + 1)
+                out.append((din[i] - 1) * self.s[i] - 2 * p[i] + self.d[i] * (self.k[i] - 1) + self.outpad[i] + 1)
             else:
-                out.append((din[i] + 2 * self.p[i] - self.d[i] * (self.k[i] - 1) - 1) // self.s[i] + 1)
+                out.append((din[i] + 2 * p[i] - self.d[i] * (self.k[i] - 1) - 1) // self.s[i] + 1)
         return tuple(out)
 
 
@@ -386,9 +387,12 @@ _MATERIALIZE_BYTES = 16 << 20
 
 
 def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, out_act: int = SS_ACT_NONE,
-         want_stats: bool = False, math_mode: Optional[int] = None, use_bias: bool = True):
+         want_stats: bool = False, math_mode: Optional[int] = None, use_bias: bool = True,
+         pad: Optional[Sequence[int]] = None, stats_planes: Optional[Tuple[int, int]] = None):
     """y = act_out(conv(act_in(x*scale+shift)) + bias); returns (y [B,D',H',W',Cout], stats or None).
-    ``out`` may be a channel slice of a concatenation buffer."""
+    ``out`` may be a channel slice of a concatenation buffer.  ``pad`` overrides the module's padding and
+    ``stats_planes`` = (d0, d1) restricts the GroupNorm sums to output planes d0 <= d < d1: both serve the X-slab
+    sharded mode (stereoscene_b200.xshard), where a rank convolves its slab plus halo planes."""
     lib = cabi.load()
     pc = packed(module)
     xin = x.data
@@ -396,7 +400,9 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     B, Din, Hin, Win, Cin = xin.shape
     if Cin != pc.Cin:
         raise RuntimeError(f"conv: input has {Cin} channels, layer expects {pc.Cin}")
-    Do, Ho, Wo = pc.out_size((Din, Hin, Win))
+    pad_eff = tuple(pc.p) if pad is None else tuple(int(v) for v in pad)
+    Do, Ho, Wo = pc.out_size((Din, Hin, Win), pad_eff)
+    sd0, sd1 = (0, 0) if stats_planes is None else (int(stats_planes[0]), int(stats_planes[1]))
     if out is None:
         out = torch.empty((B, Do, Ho, Wo, pc.Cout), dtype=torch.float32, device=xin.device)
     elif tuple(out.shape) != (B, Do, Ho, Wo, pc.Cout):
@@ -408,8 +414,8 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
         if tuple(x.scale.shape) != (B, Cin) or not x.scale.is_contiguous() or not x.shift.is_contiguous():
             raise RuntimeError("conv: pending affine must be contiguous [B,Cin]")
     mm = _DEFAULT_MATH if math_mode is None else math_mode
-    d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
-                      1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
+    d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pad_eff, *pc.d,
+                      1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP, sd0, sd1)
     # single-output-channel layers ride the tensor-core kernel too (N padded to 32): it is faster than the FMA kernel
     tc = (_USE_TCGEN05 and mm in (SS_MATH_TF32, SS_MATH_TF32X3) and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
           and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
@@ -424,8 +430,8 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
         x = Vol(x.plain())
         xin = x.data
         in_ldc = _vol_ldc(xin, "conv input")
-        d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pc.p, *pc.d,
-                          1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP)
+        d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pad_eff, *pc.d,
+                          1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP, sd0, sd1)
         d.acc_scale = 1.0
     if tc and mm == SS_MATH_TF32X3 and _USE_F16X3 and lib.ss_conv3d_tc_f16x3_supported(C.byref(d)) == 1:
         # the halo-resident / box kernels offer the compensation in ONE launch (fp16 hi/lo split, 1.5x the TF32 tensor work)
@@ -494,8 +500,11 @@ def voxels_per_channel(t: torch.Tensor) -> int:
 
 
 def gn_pending(y: torch.Tensor, stats: torch.Tensor, gn: torch.nn.GroupNorm, act: int = SS_ACT_NONE,
-               scale_out: Optional[torch.Tensor] = None, shift_out: Optional[torch.Tensor] = None) -> Vol:
-    """Turn a producer's sums into the pending GroupNorm(+activation) of its raw output."""
+               scale_out: Optional[torch.Tensor] = None, shift_out: Optional[torch.Tensor] = None,
+               count: Optional[float] = None) -> Vol:
+    """Turn a producer's sums into the pending GroupNorm(+activation) of its raw output.  ``count`` = voxels per
+    (batch, channel) the sums cover (default: all of ``y``; the X-slab sharded mode passes the global count after
+    all-reducing the sums of the slabs)."""
     lib = cabi.load()
     B, Cc = stats.shape[0], stats.shape[1]
     if scale_out is None:
@@ -503,7 +512,7 @@ def gn_pending(y: torch.Tensor, stats: torch.Tensor, gn: torch.nn.GroupNorm, act
         scale_out, shift_out = ss[0], ss[1]
     ld = scale_out.stride(0) if B > 1 else max(Cc, scale_out.stride(0))
     rc = lib.ss_gn_finalize(stats.data_ptr(), gn.weight.data_ptr(), gn.bias.data_ptr(), B, Cc, gn.num_groups,
-                            float(voxels_per_channel(y)), float(gn.eps), scale_out.data_ptr(), shift_out.data_ptr(),
+                            float(voxels_per_channel(y) if count is None else count), float(gn.eps), scale_out.data_ptr(), shift_out.data_ptr(),
                             int(ld), _stream())
     cabi.check(rc, "ss_gn_finalize")
     return Vol(y, scale_out, shift_out, act)
@@ -747,8 +756,8 @@ def splat_build_index(geom: torch.Tensor, dx, bx, nx: Sequence[int], want_coords
     return SplatIndex(order, start, coords, n[0], n[1], n[2], B, P)
 
 
-def lift_splat(depth_prob: torch.Tensor, img_feat: torch.Tensor, index: SplatIndex) -> torch.Tensor:
-    """depth_prob [B,D,H,W], img_feat [B,H,W,C] (channels-last) -> bev [B,X,Y,Z,C]."""
+def lift_splat(depth_prob: torch.Tensor, img_feat: torch.Tensor, index: SplatIndex, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """depth_prob [B,D,H,W], img_feat [B,H,W,C] (channels-last) -> bev [B,X,Y,Z,C] (``out``: contiguous destination)."""
     lib = cabi.load()
     _need_cuda_f32(depth_prob, "lift depth_prob"); _need_cuda_f32(img_feat, "lift img_feat")
     if not (depth_prob.is_contiguous() and img_feat.is_contiguous()):
@@ -757,12 +766,24 @@ def lift_splat(depth_prob: torch.Tensor, img_feat: torch.Tensor, index: SplatInd
     Cc = img_feat.shape[-1]
     if index.B != B or index.P != D * H * W:
         raise RuntimeError("lift_splat: index was built for a different frustum")
-    out = torch.empty((B, index.nx, index.ny, index.nz, Cc), dtype=torch.float32, device=depth_prob.device)
+    if out is None:
+        out = torch.empty((B, index.nx, index.ny, index.nz, Cc), dtype=torch.float32, device=depth_prob.device)
+    elif tuple(out.shape) != (B, index.nx, index.ny, index.nz, Cc) or not out.is_contiguous():
+        raise RuntimeError("lift_splat: out must be a contiguous [B,X,Y,Z,C] tensor")
     rc = lib.ss_lift_splat_fwd(depth_prob.data_ptr(), img_feat.data_ptr(), index.order.data_ptr(),
                                index.voxel_start.data_ptr(), out.data_ptr(), B, D, H, W, Cc, index.nx, index.ny,
                                index.nz, _stream())
     cabi.check(rc, "ss_lift_splat_fwd")
     return out
+
+
+def splat_index_slab(index: SplatIndex, x0: int, x1: int) -> SplatIndex:
+    """The part of a (single-sample) splat index that fills voxels x0 <= x < x1: the index is sorted by voxel rank
+    (x slowest), so an X-slab is a contiguous range of the CSR offsets -- no re-sort, no communication."""
+    if index.B != 1:
+        raise RuntimeError("splat_index_slab: one sample per index (the sharded mode processes samples one by one)")
+    per_x = index.ny * index.nz
+    return SplatIndex(index.order, index.voxel_start[x0 * per_x: x1 * per_x + 1], None, x1 - x0, index.ny, index.nz, 1, index.P)
 
 
 def bev_pool(feats: torch.Tensor, coords: torch.Tensor, B, D, H, W) -> torch.Tensor:

@@ -566,7 +566,10 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         return out.permute(0, 1, 3, 4, 2)
 
     # ---- forward -------------------------------------------------------------------------------
-    def forward(self, input):
+    def frustum_forward(self, input):
+        """Stages (i), (N1), (iii) -- everything up to the MIE boundary: returns (depth_prob [B,D,fH,fW],
+        img_feat [B,fH,fW,C] channels-last, depth_logits, lss, stereo).  ``forward`` = this + lift (x) splat; the X-slab
+        sharded mode (stereoscene_b200.xshard) all-gathers the first two tensors here and splats slabs."""
         x, rots, trans, intrins, post_rots, post_trans, bda, mlp_input = input[:8]
         feat_left, mlp_left = input[0].squeeze(1), input[7]
         feat_right, mlp_right = input[8].squeeze(1), input[15]
@@ -589,7 +592,11 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
 
         with ops.math_scope("mie"):
             depth_prob = self.mutual_interactive_ensemble(stereo, lss)
+        return depth_prob, img_feat, depth_logits, lss, stereo
 
+    def forward(self, input):
+        rots, trans, intrins, post_rots, post_trans, bda = input[1:7]
+        depth_prob, img_feat, depth_logits, lss, stereo = self.frustum_forward(input)
         index = self.splat_index(rots, trans, intrins, post_rots, post_trans, bda)
         bev = ops.lift_splat(depth_prob, img_feat, index)                         # [B,X,Y,Z,C]
         if self.stage_outputs is not None:
