@@ -51,9 +51,10 @@ def workload_config(workload: str, B: int = 1) -> str:
 
 
 def policy_text(ops, name: str) -> str:
-    names = {ops.SS_MATH_TF32: "tf32", ops.SS_MATH_TF32X3: "tf32x3 (compensated, tcgen05)", ops.SS_MATH_3XTF32: "3xtf32 (compensated, mma.sync)"}
+    names = {ops.SS_MATH_TF32: "tf32", ops.SS_MATH_TF32X3: "tf32x3 (compensated, tcgen05)", ops.SS_MATH_3XTF32: "3xtf32 (compensated, mma.sync)",
+             ops.SS_MATH_F16: "f16 (fp16 operands = TF32's 11-bit significand, fp32 accumulate; TF32 where a kernel has no fp16 path)"}
     pol = ops.MATH_POLICIES[name]
-    return ", ".join(f"{g}={names[pol.get(g, ops.SS_MATH_TF32)]}" for g in ("stereo", "depthnet", "mie", "voxel"))
+    return ", ".join(f"{g}={names[m]}" for g, m in ((g, pol.get(g, ops.SS_MATH_TF32)) for g in ("stereo", "depthnet", "mie", "voxel")))
 
 
 def measure_tf32_peak(dev) -> float:
@@ -115,7 +116,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(VOXELS))
-    ap.add_argument("--math", default="mixed", choices=["mixed", "tf32", "tf32x3", "3xtf32"],
+    ap.add_argument("--math", default="mixed", choices=["mixed", "mixed16", "tf32", "f16", "tf32x3", "3xtf32"],
                     help="per-stage math policy (stereoscene_b200.ops.MATH_POLICIES); 'mixed' = plain TF32 tensor-core math with "
                          "the error-compensated TF32x3 mode on depth_net and the MIE block: the cheapest policy whose logits "
                          "are within 1e-3 of the reference's forward")

@@ -48,6 +48,10 @@ extern "C" {
 #define SS_MATH_F16X3 3                /* single-launch compensated mode of ss_conv3d_tc_fwd: both operands split into fp16 hi/lo halves
                                           (22 significand bits), six kind::f16 MMAs per 32-channel chunk = 1.5x the TF32 tensor work */
 
+#define SS_MATH_F16 4                  /* fp16 operands (the 11-bit significand of TF32 in fp16's range: activations saturate at 65504, the
+                                          weights are pre-scaled by a power of two), fp32 accumulate: kind::f16 runs at twice the TF32 MMA
+                                          rate.  Same packing and availability as SS_MATH_F16X3 (only the hi halves are multiplied) */
+
 /* ABI version of this header; ss_abi_version() of the library must match. */
 #define SS_ABI_VERSION 5
 int ss_abi_version(void);
@@ -107,7 +111,7 @@ int ss_conv3d_fwd(const ss_conv3d_desc* desc, const float* x, const float* in_sc
  * SS_MATH_TF32X3: w_kmajor holds TWO such arrays back to back, hi = tf32(w) followed by lo = tf32(w - hi); the activations
  * are split the same way on the fly and the three partial products are accumulated into y by three launches (y is read
  * back by the second and third), so the result has ~fp32 accuracy at ~3x the tensor work.
- * SS_MATH_F16X3 (only where ss_conv3d_tc_f16x3_supported(desc) == 1: the halo-resident and per-tap box kernels): every
+ * SS_MATH_F16X3 / SS_MATH_F16 (only where ss_conv3d_tc_f16x3_supported(desc) == 1: the halo-resident and per-tap box kernels): every
  * 128-byte row of w_kmajor, i.e. one output channel's 32-channel chunk, holds 64 fp16 values instead of 32 floats:
  * hi = fp16(w / acc_scale) of the 32 channels followed by lo = fp16(w / acc_scale - hi); same array extent as in TF32 mode. */
 int ss_conv3d_tc_f16x3_supported(const ss_conv3d_desc* desc);

@@ -13,7 +13,7 @@ from . import _build
 ABI_VERSION = 5
 
 SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU = 0, 1, 2
-SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3, SS_MATH_F16X3 = 0, 1, 2, 3
+SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3, SS_MATH_F16X3, SS_MATH_F16 = 0, 1, 2, 3, 4
 
 
 class ConvDesc(C.Structure):

@@ -61,7 +61,8 @@ inline StatsRange stats_range_of(const ss_conv3d_desc* d) {
 struct ConvPass {
     int a_lo;
     int accumulate;
-    int f16 = 0;              // SS_MATH_F16X3: single launch, fp16 hi/lo split of both operands (see split_f16x4)
+    int f16 = 0;              // SS_MATH_F16X3 / SS_MATH_F16: single launch on fp16 operands (see split_f16x4)
+    int f16_n = 6;            //   MMAs per 32-channel chunk: 6 = hi*hi + lo*hi + hi*lo (F16X3), 2 = hi*hi only (F16)
     float acc_scale = 1.0f;   //   the accumulator is multiplied by this power of two (the weights were pre-scaled by its inverse)
 };
 // SS_MATH_F16X3: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 significand bits); one 128-byte shared-memory row

@@ -33,6 +33,7 @@ struct HaloParams {
     int KD;                       // depth taps: 3 (3x3x3, pad 1) or 1 (2-D 3x3 layers, D == 1 planes)
     int a_lo, accumulate;         // ConvPass (common.cuh)
     float acc_scale;              // F16 variant: accumulator scale (power of two)
+    int f16_n;                    // F16 variant: MMAs per chunk (6 = compensated, 2 = fp16 single pass)
     StatsRange sr;                // output planes that contribute to stats
     const float* in_scale;
     const float* in_shift;
@@ -225,7 +226,8 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
                         constexpr uint32_t idesc16 = make_idesc_f16(128, BN);
 #pragma unroll
                         for (int i = 0; i < 6; ++i)
-                            umma_ss_f16<A_HI, B_HI>(tmem_base + (uint32_t)(mt * BN), a_lo + ao + kF16A[i], b_lo + kF16B[i], idesc16, (Lp | ce | i) ? 1u : 0u);
+                            if (i < p.f16_n)
+                                umma_ss_f16<A_HI, B_HI>(tmem_base + (uint32_t)(mt * BN), a_lo + ao + kF16A[i], b_lo + kF16B[i], idesc16, (Lp | ce | i) ? 1u : 0u);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -466,7 +468,7 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
     p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act; p.nTH = nTH; p.nTW = nTW; p.KD = d->kd;
     p.swap = swap; p.sH = swap ? 1 : d->Win; p.sW = swap ? d->Win : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale; p.sr = stats_range_of(d);
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale; p.sr = stats_range_of(d); p.f16_n = ps.f16_n;
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo || ps.f16;
     alignas(64) CUtensorMap tmA;
     // tensor map dims in the kernel's order (C, w, h, D, B); the byte strides say which tensor axis each one walks

@@ -47,6 +47,7 @@ struct TcParams {
     double* stats;
     int a_lo, accumulate;      // ConvPass (common.cuh)
     float acc_scale;           // F16 variant: accumulator scale (power of two)
+    int f16_n;                 // F16 variant: MMAs per K step (6 = compensated, 2 = fp16 single pass)
     StatsRange sr;             // output planes that contribute to stats
 };
 
@@ -302,7 +303,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
                 const uint32_t a_tmem = tmem_base + (uint32_t)(Cfg::A_COL0 + slot * TC_BK);
 #pragma unroll
                 for (int i = 0; i < 6; ++i)      // TMEM columns: 8 per K = 16 fp16 (two per 32-bit cell) -> 4 x the 16-byte descriptor units
-                    umma_ts_f16<D_HI>(tmem_base, a_tmem + (uint32_t)(4 * kF16A[i]), b_lo + kF16B[i], idesc16, (step | i) ? 1u : 0u);
+                    if (i < p.f16_n)
+                        umma_ts_f16<D_HI>(tmem_base, a_tmem + (uint32_t)(4 * kF16A[i]), b_lo + kF16B[i], idesc16, (step | i) ? 1u : 0u);
             } else if (fixup) {                       // A from the TMEM ring written by the fix-up warps
                 const uint32_t a_tmem = tmem_base + (uint32_t)(Cfg::A_COL0 + slot * TC_BK);
 #pragma unroll
@@ -629,7 +631,7 @@ static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_
     p.transposed = d->transposed; p.out_ldc = d->out_ldc; p.in_act = d->in_act; p.out_act = d->out_act;
     p.cls_d = d->transposed ? d->sd : 1; p.cls_h = d->transposed ? d->sh : 1; p.cls_w = d->transposed ? d->sw : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale; p.sr = stats_range_of(d);
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale; p.sr = stats_range_of(d); p.f16_n = ps.f16_n;
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
     {
         int rcm = 0;
@@ -681,9 +683,10 @@ static int tc_three_pass(const ss_conv3d_desc* d, const float* w_kmajor, F&& lau
     t.math = SS_MATH_TF32;
     const size_t wn = (size_t)d->kd * d->kh * d->kw * d->cout_packed * d->Cin;
     if (d->math == SS_MATH_TF32) return launch(&t, w_kmajor, ConvPass{0, 0}, true);
-    if (d->math == SS_MATH_F16X3) {            // single launch: fp16 hi/lo split of both operands inside the kernel
+    if (d->math == SS_MATH_F16X3 || d->math == SS_MATH_F16) {      // single launch on fp16 operands (split inside the kernel)
         ConvPass ps{0, 0};
         ps.f16 = 1;
+        ps.f16_n = d->math == SS_MATH_F16 ? 2 : 6;
         ps.acc_scale = d->acc_scale;
         return launch(&t, w_kmajor, ps, true);
     }
@@ -724,9 +727,9 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_tc_fwd: in_act");
     SS_REQUIRE(d->Cin <= 4096, "ss_conv3d_tc_fwd: Cin limited to 4096");
     SS_REQUIRE((long long)d->B * d->Dout * d->Hout * d->Wout < (1ll << 31), "ss_conv3d_tc_fwd: output too large");
-    SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3 || d->math == SS_MATH_F16X3,
-               "ss_conv3d_tc_fwd: TF32 / TF32X3 / F16X3 only (use ss_conv3d_fwd for 3xTF32 on mma.sync)");
-    if (d->math == SS_MATH_F16X3) SS_REQUIRE(ss_conv3d_tc_f16x3_supported(d) == 1 && d->acc_scale > 0.f, "ss_conv3d_tc_fwd: F16X3 not offered for this layer (ask ss_conv3d_tc_f16x3_supported)");
+    SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3 || d->math == SS_MATH_F16X3 || d->math == SS_MATH_F16,
+               "ss_conv3d_tc_fwd: TF32 / TF32X3 / F16X3 / F16 only (use ss_conv3d_fwd for 3xTF32 on mma.sync)");
+    if (d->math == SS_MATH_F16X3 || d->math == SS_MATH_F16) SS_REQUIRE(ss_conv3d_tc_f16x3_supported(d) == 1 && d->acc_scale > 0.f, "ss_conv3d_tc_fwd: F16X3 not offered for this layer (ask ss_conv3d_tc_f16x3_supported)");
     if (d->transposed) SS_REQUIRE(d->dd == 1 && d->dh == 1 && d->dw == 1, "ss_conv3d_tc_fwd: dilated transposed conv unsupported");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return tc_three_pass(d, w_kmajor, [&](const ss_conv3d_desc* dd, const float* w, const ConvPass& ps, bool last) {

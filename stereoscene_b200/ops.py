@@ -23,7 +23,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import cabi
-from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_F16X3, SS_MATH_TF32, SS_MATH_TF32X3  # noqa: F401
+from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_F16, SS_MATH_F16X3, SS_MATH_TF32, SS_MATH_TF32X3  # noqa: F401
 
 _DEFAULT_MATH = SS_MATH_TF32
 _USE_TCGEN05 = os.environ.get("STEREOSCENE_B200_NO_TCGEN05", "0") != "1"
@@ -49,7 +49,7 @@ def set_default_math(mode: int):
     """Uniform math mode for every stage (switches the per-stage policy off): SS_MATH_TF32 (fast), SS_MATH_TF32X3 (error-compensated split TF32 on the tcgen05 kernels, ~fp32 accuracy at ~3x the
     tensor work) or SS_MATH_3XTF32 (the same compensation on the mma.sync kernels) for conv / BRI energy."""
     global _DEFAULT_MATH, _POLICY
-    assert mode in (SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3)
+    assert mode in (SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3, SS_MATH_F16)
     _DEFAULT_MATH = mode
     _POLICY = None                      # a uniform mode replaces the per-stage policy
 
@@ -71,6 +71,12 @@ MATH_POLICIES = {
     "tf32": {},                                                                          # every stage plain TF32
     # the parity-green product mode (CA3D sits on a residual branch: leaving it in TF32 moves the logits error 6.8e-4 -> 7.4e-4)
     "mixed": {"depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_TF32},
+    # "mixed" / "tf32" with the uncompensated halo / box layers on fp16 operands (SS_MATH_F16: TF32's 11-bit significand, hence
+    # TF32's error -- measured -- at half the MMA count).  Measured NO faster (9.70 vs 9.83 ms): the fp32 planes still stream
+    # through a 2-slot ring and half of every weight row (the lo halves) is loaded unused, so the layers turn from tensor-bound
+    # into L2->SM bound; a real gain needs fp16 storage (64 channels per 128-byte row).  Kept for the tests and that follow-up.
+    "mixed16": {"stereo": SS_MATH_F16, "depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_F16, "voxel": SS_MATH_F16},
+    "f16": {g: SS_MATH_F16 for g in ("stereo", "depthnet", "mie", "voxel")},
     "tf32x3": {g: SS_MATH_TF32X3 for g in ("stereo", "depthnet", "mie", "voxel")},
     "3xtf32": {g: SS_MATH_3XTF32 for g in ("stereo", "depthnet", "mie", "voxel")},
 }
@@ -117,7 +123,7 @@ class math_scope:
 
 
 # name -> mode constant, for the tests / bench (--math)
-MATH_MODES = {"tf32": SS_MATH_TF32, "tf32x3": SS_MATH_TF32X3, "3xtf32": SS_MATH_3XTF32}
+MATH_MODES = {"tf32": SS_MATH_TF32, "f16": SS_MATH_F16, "tf32x3": SS_MATH_TF32X3, "3xtf32": SS_MATH_3XTF32}
 
 
 def _stream() -> int:
@@ -417,7 +423,7 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pad_eff, *pc.d,
                       1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP, sd0, sd1)
     # single-output-channel layers ride the tensor-core kernel too (N padded to 32): it is faster than the FMA kernel
-    tc = (_USE_TCGEN05 and mm in (SS_MATH_TF32, SS_MATH_TF32X3) and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
+    tc = (_USE_TCGEN05 and mm in (SS_MATH_TF32, SS_MATH_TF32X3, SS_MATH_F16) and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
           and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
     d.acc_scale = 1.0
     if mm == SS_MATH_TF32X3 and not tc:        # layers the tcgen05 kernels do not take (Cin = 2, odd strides): mma.sync split TF32
@@ -433,10 +439,14 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
         d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pad_eff, *pc.d,
                           1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP, sd0, sd1)
         d.acc_scale = 1.0
-    if tc and mm == SS_MATH_TF32X3 and _USE_F16X3 and lib.ss_conv3d_tc_f16x3_supported(C.byref(d)) == 1:
-        # the halo-resident / box kernels offer the compensation in ONE launch (fp16 hi/lo split, 1.5x the TF32 tensor work)
+    if mm == SS_MATH_F16 and not (tc and lib.ss_conv3d_tc_f16x3_supported(C.byref(d)) == 1):
+        mm = SS_MATH_TF32            # kernels without an fp16 operand path: TF32 has the same 11-bit significand
+        d.math = mm
+    if tc and ((mm == SS_MATH_TF32X3 and _USE_F16X3 and lib.ss_conv3d_tc_f16x3_supported(C.byref(d)) == 1) or mm == SS_MATH_F16):
+        # the halo-resident / box kernels take fp16 operands in ONE launch: the compensated hi/lo split (1.5x the TF32 tensor
+        # work) or the hi halves only (SS_MATH_F16: half the TF32 tensor work, same significand)
         wk, d.acc_scale = pc.weights_kmajor_f16()
-        d.math = SS_MATH_F16X3
+        d.math = SS_MATH_F16 if mm == SS_MATH_F16 else SS_MATH_F16X3
         rc = lib.ss_conv3d_tc_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), wk.data_ptr(),
                                   _ptr(bias.detach() if bias is not None else None), out.data_ptr(), _ptr(stats), _stream())
         cabi.check(rc, "ss_conv3d_tc_fwd")
@@ -463,7 +473,7 @@ def conv_join(x: Vol, module: torch.nn.Module, out_affine: Optional[Vol], res: O
     xin = x.data
     B, Din, Hin, Win, Cin = xin.shape
     Do, Ho, Wo = pc.out_size((Din, Hin, Win))
-    mm = _DEFAULT_MATH
+    mm = SS_MATH_TF32 if _DEFAULT_MATH == SS_MATH_F16 else _DEFAULT_MATH      # the transposed kernel has no fp16 operand path
     fused_ok = (_USE_TCGEN05 and _FUSE_JOIN and mm in (SS_MATH_TF32, SS_MATH_TF32X3) and Cin % 32 == 0 and xin.data_ptr() % 16 == 0 and
                 (out_affine is None or out_affine.act == SS_ACT_NONE))
     if fused_ok:
@@ -710,7 +720,7 @@ def bri_attention(q: torch.Tensor, kv: torch.Tensor, params: torch.Tensor, out: 
     wsb = int(lib.ss_bri_workspace_bytes(B, D, N))
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=q.device)
     mm = _DEFAULT_MATH if math_mode is None else math_mode
-    if mm == SS_MATH_TF32X3:          # BRI on tcgen05 is within 2e-5 of an fp64 evaluation in plain TF32 (softmax algebra in fp32)
+    if mm in (SS_MATH_TF32X3, SS_MATH_F16):          # BRI on tcgen05 is within 2e-5 of an fp64 evaluation in plain TF32 (softmax algebra in fp32)
         mm = SS_MATH_TF32
     rc = lib.ss_bri_attn_fwd(q.data_ptr(), kv.data_ptr(), params.data_ptr(), ws.data_ptr(), wsb, out.data_ptr(), out_ld,
                              B, D, N, mm, _stream())

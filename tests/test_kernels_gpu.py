@@ -20,7 +20,7 @@ from util import rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"precise": 2e-4, "tf32": 1e-3, "tf32x3": 2e-4}
+TOL = {"precise": 2e-4, "tf32": 1e-3, "tf32x3": 2e-4, "f16": 1e-3}
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +31,7 @@ def ops():
 
 
 def _mode(ops, name):
-    return {"precise": ops.SS_MATH_3XTF32, "tf32": ops.SS_MATH_TF32, "tf32x3": ops.SS_MATH_TF32X3}[name]
+    return {"precise": ops.SS_MATH_3XTF32, "tf32": ops.SS_MATH_TF32, "tf32x3": ops.SS_MATH_TF32X3, "f16": ops.SS_MATH_F16}[name]
 
 
 def _cl(x):  # NCDHW cpu -> channels-last cuda [B,D,H,W,C]
@@ -71,7 +71,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["precise", "tf32", "tf32x3"])
+@pytest.mark.parametrize("mode", ["precise", "tf32", "tf32x3", "f16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv3d_family(ops, case, mode):
     name, make, shape = case
