@@ -55,6 +55,8 @@ struct MarchParams {
     long long total_tiles;                           // B * nTH * nTW * D
     int a_lo, accumulate;                            // ConvPass (common.cuh)
     StatsRange sr;                                   // output planes that contribute to stats
+    float acc_scale;                                 // F16 variant: accumulator scale (power of two)
+    int f16_n;                                       // F16 variant: MMAs per chunk (6 = compensated, 2 = fp16 single pass)
     const float* in_scale;
     const float* in_shift;
     const float* bias;
@@ -155,6 +157,19 @@ __device__ __forceinline__ void m_umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(A_HI), "n"(B_HI) : "memory");
 }
+template <uint32_t A_HI, uint32_t B_HI>
+__device__ __forceinline__ void m_umma_lo_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(A_HI), "n"(B_HI) : "memory");
+}
 __device__ __forceinline__ void m_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -192,7 +207,7 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const MarchParams&
 // everything tile-invariant is hoisted: bias values live in registers, the tile coordinate is advanced
 // incrementally (no 64-bit divisions), the activation switch sits outside the element loops, and the
 // GroupNorm sums are per-thread running sums that are transposed / reduced once per (CTA, sample).
-template <int NCOL>
+template <int NCOL, bool F16>
 __device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t_begin, long long t_end, int q, int lane, int col0,
                                                uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0) {
     if (t_begin >= t_end) return;
@@ -256,7 +271,7 @@ __device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t
         m_mbar_arrive(t_empty0 + 8 * acc);                     // accumulator may be overwritten
         float v[NCOL];
 #pragma unroll
-        for (int k = 0; k < NCOL; ++k) v[k] = __uint_as_float(r[k]) + bias_r[k];
+        for (int k = 0; k < NCOL; ++k) v[k] = F16 ? fmaf(__uint_as_float(r[k]), p.acc_scale, bias_r[k]) : __uint_as_float(r[k]) + bias_r[k];
         if (p.accumulate) {                                     // later pass of the compensated mode: add the partial result
             const int ah = c.th * MR_TH + lh, aw = c.tw * MR_TW + lw;
             if (ah < p.H && aw < p.W) {
@@ -308,7 +323,9 @@ __device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t
     flush();
 }
 
-template <int KS>
+// F16 = the single-launch fp16-split variant (SS_MATH_F16X3 / SS_MATH_F16, common.cuh:split_f16x4): resident weight rows and
+// plane rows hold [hi | lo] fp16 halves, six kind::f16 MMAs per shift instead of four kind::tf32 ones.
+template <int KS, bool F16>
 __global__ void __launch_bounds__(MR_THREADS, 1)
 conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
     using Cfg = MarchCfg<KS>;
@@ -333,7 +350,7 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                    t_empty0 = m_smem_u32(bars + 1 + 3 * MR_NP + MR_ACC);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu || p.a_lo;
+    const bool fixup = F16 || has_aff || in_relu || p.a_lo;
 
     // this CTA's contiguous range of flat tiles
     const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
@@ -395,7 +412,9 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     } else if (warp == 9) {
         // ======================= MMA ISSUER ======================================================
         if (t_begin < t_end) {
-            constexpr uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t idesc0 = F16 ? ((1u << 4) | ((uint32_t)(128 >> 4) << 24))
+                                            : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24));
+            constexpr int NMMA = F16 ? 6 : 4;                // MMAs per (kh,kw) shift
             m_mbar_wait(w_full, 0);
             const uint32_t rdy0 = fixup ? p_ready0 : p_full0;
             uint32_t L = 0, tile_n = 0;
@@ -412,10 +431,20 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                         {
                             const uint64_t adesc = m_desc(planes_u32 + (uint32_t)slot * MR_PLANE_BYTES, MR_HW * 128);
                             const uint64_t bdesc = m_desc(wres_u32, 1024);
+                            if constexpr (F16) {
+                                constexpr uint32_t A1_HI = ((uint32_t)(MR_HW * 128) >> 4) | (1u << 14) | (2u << 29);
+                                constexpr uint32_t B1_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                m_umma_tf32(tmem_base + (uint32_t)(acc * MR_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                                            idesc0 | ((uint32_t)(MR_BN >> 3) << 17), k ? 1u : 0u, leader);
+                                for (int k = 0; k < 6; ++k)
+                                    if (k < p.f16_n)
+                                        m_umma_lo_f16<A1_HI, B1_HI>(tmem_base + (uint32_t)(acc * MR_BN), (uint32_t)adesc + kF16A[k], (uint32_t)bdesc + kF16B[k],
+                                                                    idesc0 | ((uint32_t)(MR_BN >> 3) << 17), k ? 1u : 0u);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    m_umma_tf32(tmem_base + (uint32_t)(acc * MR_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                                idesc0 | ((uint32_t)(MR_BN >> 3) << 17), k ? 1u : 0u, leader);
+                            }
                             m_umma_commit(t_full0 + 8 * acc, leader);
                             m_umma_commit(p_empty0 + 8 * slot, leader);
                         }
@@ -448,32 +477,29 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                         const uint32_t b0 = w_lo + (uint32_t)(2 - (s - jlo)) * 256u, b1 = b0 + (uint32_t)n0 * 256u;   // 32 rows = 256 x 16 B
                         const uint32_t id0 = idesc0 | ((uint32_t)(n0 * MR_BN >> 3) << 17), id1 = idesc0 | ((uint32_t)(n1 * MR_BN >> 3) << 17);
                         // first MMA of the plane: tile s (the last of the window) starts from zero, the others accumulate
+                        // one MMA of the plane: TF32 k-step or fp16 (A part, B part) pair number j of shift ce
+                        auto issue = [&](uint32_t dcol, uint32_t aw, uint32_t bw, uint32_t idw, uint32_t accum) {
+                            if constexpr (F16) m_umma_lo_f16<A_HI, B_HI>(dcol, aw, bw, idw, accum);
+                            else m_umma_lo<A_HI, B_HI>(dcol, aw, bw, idw, accum);
+                        };
                         if (fresh) {
                             const uint32_t rs = (tile_n + (uint32_t)jhi) & (MR_ACC - 1);
                             if (cnt > 1) {
                                 const int m0 = min(cnt - 1, MR_ACC - (int)r0), m1 = cnt - 1 - m0;
-                                m_umma_lo<A_HI, B_HI>(d0, a_lo, b0, idesc0 | ((uint32_t)(m0 * MR_BN >> 3) << 17), 1u);
-                                if (m1 > 0) m_umma_lo<A_HI, B_HI>(d1, a_lo, b0 + (uint32_t)m0 * 256u, idesc0 | ((uint32_t)(m1 * MR_BN >> 3) << 17), 1u);
+                                issue(d0, a_lo, b0, idesc0 | ((uint32_t)(m0 * MR_BN >> 3) << 17), 1u);
+                                if (m1 > 0) issue(d1, a_lo, b0 + (uint32_t)m0 * 256u, idesc0 | ((uint32_t)(m1 * MR_BN >> 3) << 17), 1u);
                             }
-                            m_umma_lo<A_HI, B_HI>(tmem_base + rs * MR_BN, a_lo, b0 + (uint32_t)(cnt - 1) * 256u, idesc0 | ((uint32_t)(MR_BN >> 3) << 17), 0u);
+                            issue(tmem_base + rs * MR_BN, a_lo, b0 + (uint32_t)(cnt - 1) * 256u, idesc0 | ((uint32_t)(MR_BN >> 3) << 17), 0u);
                         }
-                        if (n1 == 0) {
 #pragma unroll
-                            for (int i = 0; i < 36; ++i) {
-                                if (i == 0 && fresh) continue;
-                                const uint32_t ao = (uint32_t)((((i >> 2) / 3) * MR_HW + ((i >> 2) % 3)) * 128 + 32 * (i & 3)) >> 4;
-                                const uint32_t bo = (uint32_t)((i >> 2) * 96 * 128 + 32 * (i & 3)) >> 4;
-                                m_umma_lo<A_HI, B_HI>(d0, a_lo + ao, b0 + bo, id0, 1u);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 36; ++i) {
-                                if (i == 0 && fresh) continue;
-                                const uint32_t ao = (uint32_t)((((i >> 2) / 3) * MR_HW + ((i >> 2) % 3)) * 128 + 32 * (i & 3)) >> 4;
-                                const uint32_t bo = (uint32_t)((i >> 2) * 96 * 128 + 32 * (i & 3)) >> 4;
-                                m_umma_lo<A_HI, B_HI>(d0, a_lo + ao, b0 + bo, id0, 1u);
-                                m_umma_lo<A_HI, B_HI>(d1, a_lo + ao, b1 + bo, id1, 1u);
-                            }
+                        for (int i = 0; i < 9 * NMMA; ++i) {
+                            if (i == 0 && fresh) continue;
+                            const int ce = i / NMMA, j = i % NMMA;
+                            if (F16 && j >= p.f16_n) continue;
+                            const uint32_t ao = ((uint32_t)(((ce / 3) * MR_HW + (ce % 3)) * 128) >> 4) + (uint32_t)(F16 ? kF16A[j] : 2 * j);
+                            const uint32_t bo = ((uint32_t)(ce * 96 * 128) >> 4) + (uint32_t)(F16 ? kF16B[j] : 2 * j);
+                            issue(d0, a_lo + ao, b0 + bo, id0, 1u);
+                            if (n1 != 0) issue(d1, a_lo + ao, b1 + bo, id1, 1u);
                         }
                         if (s >= 2) m_umma_commit(t_full0 + 8 * ((tile_n + (uint32_t)s - 2u) & (MR_ACC - 1)), leader);   // tile s-2 is complete
                         m_umma_commit(p_empty0 + 8 * slot, leader);
@@ -505,7 +531,34 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                     const int slot = (int)(L % MR_NP);
                     m_mbar_wait(p_full0 + 8 * slot, (uint32_t)(L / MR_NP) & 1u);
                     const int dpl = c.d - PAD + s;
-                    if ((unsigned)dpl < (unsigned)p.D) {           // planes outside the volume are all padding
+                    if constexpr (F16) {
+                        if ((unsigned)dpl < (unsigned)p.D) {
+                            unsigned char* pl = planes + slot * MR_PLANE_BYTES;
+                            constexpr int ITERS = (MR_PLANE_ROWS + 15) / 16;
+                            for (int it = 0; it < ITERS; ++it) {       // the 8 lanes of a row read, sync, then overwrite it with [hi | lo]
+                                const int r = (ft >> 3) + 16 * it;
+                                const int hh = c.th * MR_TH - PAD + r / MR_HW, ww = c.tw * MR_TW - PAD + r % MR_HW;
+                                const bool actv = r < MR_PLANE_ROWS && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
+                                unsigned char* row = pl + r * 128;
+                                uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+                                if (actv) {
+                                    float4 v = *reinterpret_cast<const float4*>(row + ((chunk ^ (r & 7)) << 4));
+                                    if (has_aff) {
+                                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                                    }
+                                    if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                                    split_f16x4(v, hi, lo);
+                                }
+                                __syncwarp();
+                                if (actv) {
+                                    *reinterpret_cast<uint2*>(row + (((chunk >> 1) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = hi;
+                                    *reinterpret_cast<uint2*>(row + (((4 + (chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = lo;
+                                }
+                                __syncwarp();
+                            }
+                        }
+                    } else if ((unsigned)dpl < (unsigned)p.D) {    // planes outside the volume are all padding
                         unsigned char* pl = planes + slot * MR_PLANE_BYTES;
                         auto fix = [&](auto lo_tag) {
                             constexpr bool LO = decltype(lo_tag)::value;
@@ -536,8 +589,8 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     } else {
         // ======================= EPILOGUE WARPS (0..3, plus 4..7 when there is no fix-up work) =======
         // warps sharing a TMEM lane quarter split the 32 output columns when all 8 worker warps drain
-        if (fixup) march_epilogue<32>(p, t_begin, t_end, warp & 3, lane, 0, tmem_base, t_full0, t_empty0);
-        else march_epilogue<16>(p, t_begin, t_end, warp & 3, lane, (warp >> 2) * 16, tmem_base, t_full0, t_empty0);
+        if (fixup) march_epilogue<32, F16>(p, t_begin, t_end, warp & 3, lane, 0, tmem_base, t_full0, t_empty0);
+        else march_epilogue<16, F16>(p, t_begin, t_end, warp & 3, lane, (warp >> 2) * 16, tmem_base, t_full0, t_empty0);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -551,7 +604,7 @@ typedef CUresult (*MEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int KS>
+template <int KS, bool F16>
 static int launch_march(const MarchParams& p, const ss_conv3d_desc* d, const float* x, const float* w_kmajor, bool fixup,
                         MEncodeTiledFn encode, cudaStream_t st) {
     using Cfg = MarchCfg<KS>;
@@ -578,15 +631,15 @@ static int launch_march(const MarchParams& p, const ss_conv3d_desc* d, const flo
     const size_t smem = 1024 + Cfg::W_BYTES + MR_NP * Cfg::PLANE_BYTES + 32 * sizeof(uint64_t) + 64;
     static thread_local bool configured = false;
     if (!configured) {
-        SS_CUDA(cudaFuncSetAttribute(conv_march32_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SS_CUDA(cudaFuncSetAttribute(conv_march32_kernel<KS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)min((long long)sms, p.total_tiles);
-    conv_march32_kernel<KS><<<grid, MR_THREADS, smem, st>>>(p, tmA, tmW);
-    return check_launch("conv_march32_kernel");
+    conv_march32_kernel<KS, F16><<<grid, MR_THREADS, smem, st>>>(p, tmA, tmW);
+    return check_launch(F16 ? "conv_march32_f16x3_kernel" : "conv_march32_kernel");
 }
 
 int conv_march32_eligible(const ss_conv3d_desc* d) {
@@ -624,9 +677,10 @@ int try_conv_march32(const ss_conv3d_desc* d, const float* x, const float* in_sc
     p.nTH = (p.H + MR_TH - 1) / MR_TH; p.nTW = (p.W + MR_TW - 1) / MR_TW;
     p.total_tiles = (long long)p.B * p.nTH * p.nTW * p.D;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.sr = stats_range_of(d);
-    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
-    *rc = k3 ? launch_march<3>(p, d, x, w_kmajor, fixup, encode, st) : launch_march<1>(p, d, x, w_kmajor, fixup, encode, st);
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.sr = stats_range_of(d); p.acc_scale = ps.acc_scale; p.f16_n = ps.f16_n;
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo || ps.f16;
+    if (ps.f16) *rc = k3 ? launch_march<3, true>(p, d, x, w_kmajor, fixup, encode, st) : launch_march<1, true>(p, d, x, w_kmajor, fixup, encode, st);
+    else *rc = k3 ? launch_march<3, false>(p, d, x, w_kmajor, fixup, encode, st) : launch_march<1, false>(p, d, x, w_kmajor, fixup, encode, st);
     return 1;
 }
 

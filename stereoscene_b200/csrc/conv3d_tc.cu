@@ -635,16 +635,14 @@ static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
     {
         int rcm = 0;
-        if (!ps.f16) {
-            // 32-channel 3x3x3 stride-1 layers: persistent marching kernel (halo planes + resident weights)
-            if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
-            // pointwise layers with short K: persistent streaming GEMM with resident weights
-            if (try_conv_pw(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
-        }
+        // 32-channel 3x3x3 stride-1 layers: persistent marching kernel (halo planes + resident weights)
+        if (try_conv_march32(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
+        // pointwise layers with short K: persistent streaming GEMM with resident weights (no fp16 operand path)
+        if (!ps.f16 && try_conv_pw(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
         // wide 3x3x3 stride-1 layers: halo-resident kernel (planes loaded once per chunk, two M tiles per weight tile)
         if (try_conv_halo(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, ps)) return rcm;
         // stride-2 transposed 3x3x3 layers: one CTA per input tile computes all 8 output parity classes
-        if (!ps.f16 && try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, nullptr, ps)) return rcm;
+        if (try_conv_tpose(d, x, in_scale, in_shift, w_kmajor, bias, y, stats, st, &rcm, nullptr, ps)) return rcm;
     }
     const int cp = d->cout_packed;
     const int ntaps_total = d->kd * d->kh * d->kw;
@@ -700,13 +698,13 @@ static int tc_three_pass(const ss_conv3d_desc* d, const float* w_kmajor, F&& lau
 }
 }  // namespace ss
 
-// 1 if the layer runs as ONE launch in the fp16-split compensated mode (halo-resident or per-tap box kernel); layers that the
-// marching / pointwise / transposed kernels serve keep the three-launch SS_MATH_TF32X3 path on those kernels.
+// 1 if the layer runs as ONE launch in the fp16-split compensated mode (halo-resident, marching, transposed or per-tap box
+// kernel); layers that the pointwise streaming kernel serves keep the three-launch SS_MATH_TF32X3 path on that kernel.
 extern "C" int ss_conv3d_tc_f16x3_supported(const ss_conv3d_desc* d) {
     if (!d || d->Cin % 32 != 0 || d->in_ldc % 4 != 0) return 0;
     ss_conv3d_desc t = *d;
     t.math = SS_MATH_TF32;
-    if (ss::conv_march32_eligible(&t) || ss::conv_pw_eligible(&t) || ss::conv_tpose_join_supported(&t)) return 0;
+    if (ss::conv_pw_eligible(&t)) return 0;          // the pointwise streaming kernel has no fp16 operand path
     return 1;
 }
 
@@ -744,7 +742,7 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
 extern "C" int ss_conv3d_tc_join_supported(const ss_conv3d_desc* d) {
     if (!d || d->Cin % 32 != 0 || d->in_ldc % 4 != 0) return 0;
     ss_conv3d_desc t = *d;
-    if (t.math == SS_MATH_TF32X3) t.math = SS_MATH_TF32;        // the compensated mode runs the same kernel three times
+    t.math = SS_MATH_TF32;        // the compensated modes run the same kernel (three times, or once on fp16 halves)
     return ss::conv_tpose_join_supported(&t);
 }
 
@@ -761,7 +759,8 @@ extern "C" int ss_conv3d_tc_join_fwd(const ss_conv3d_desc* d, const float* x, co
     SS_REQUIRE(join->res_act == SS_ACT_NONE || join->res_act == SS_ACT_RELU, "ss_conv3d_tc_join_fwd: res_act");
     SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_tc_join_fwd: in_act");
     SS_REQUIRE(d->out_ldc >= d->Cout && d->cout_packed >= d->Cout, "ss_conv3d_tc_join_fwd: ldc");
-    SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3, "ss_conv3d_tc_join_fwd: math mode");
+    SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3 || d->math == SS_MATH_F16X3 || d->math == SS_MATH_F16,
+               "ss_conv3d_tc_join_fwd: math mode");
     SS_REQUIRE(ss_conv3d_tc_join_supported(d), "ss_conv3d_tc_join_fwd: layer not supported by the fused kernel (query ss_conv3d_tc_join_supported)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return tc_three_pass(d, w_kmajor, [&](const ss_conv3d_desc* dd, const float* w, const ConvPass& ps, bool last) {

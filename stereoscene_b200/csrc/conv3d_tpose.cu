@@ -40,6 +40,8 @@ struct TposeParams {
     int res_ldc, res_act, has_join;
     int a_lo, accumulate;            // ConvPass (common.cuh)
     StatsRange sr;                   // output planes that contribute to stats
+    float acc_scale;                 // F16 variant: accumulator scale (power of two)
+    int f16_n;                       // F16 variant: MMAs per chunk and tap (6 = compensated, 2 = fp16 single pass)
 };
 
 __device__ __forceinline__ uint32_t t_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,7 +124,8 @@ __host__ __device__ constexpr TposeTable tpose_table() {
     return t;   // 27 entries
 }
 
-template <int BN>
+// F16 = the single-launch fp16-split variant (SS_MATH_F16X3 / SS_MATH_F16, common.cuh:split_f16x4)
+template <int BN, bool F16>
 __global__ void __launch_bounds__(TP_THREADS, BN <= 32 ? 2 : 1)
 conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     constexpr int B_BYTES = BN * 128;
@@ -154,7 +157,7 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                    accum_bar = t_smem_u32(bars + 3 * TP_NPL + 2 * TP_SB);
     const bool has_aff = (p.in_scale != nullptr);
     const bool in_relu = (p.in_act == SS_ACT_RELU);
-    const bool fixup = has_aff || in_relu || p.a_lo;
+    const bool fixup = F16 || has_aff || in_relu || p.a_lo;
     const int kchunks = p.Cin / 32;
 
     if (tid == 0) {
@@ -246,10 +249,19 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                 const uint32_t b_lo = umma_desc_lo(bring_u32 + bslot * B_BYTES);
                 // first MMA into a class accumulator: its first tap of chunk 0 (taps of a class are consecutive)
                 const bool first_tap = (e == 0) || ((TAB.v[e > 0 ? e - 1 : 0] & 7) != cls);
+                if constexpr (F16) {
+                    constexpr uint32_t idesc16 = make_idesc_f16(128, BN);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_ss_tf32<A_HI, B_HI>(tmem_base + (uint32_t)(cls * BN), a_lo + 2 * k, b_lo + 2 * k, idesc,
-                                             (ch == 0 && first_tap && k == 0) ? 0u : 1u);
+                    for (int i = 0; i < 6; ++i)
+                        if (i < p.f16_n)
+                            umma_ss_f16<A_HI, B_HI>(tmem_base + (uint32_t)(cls * BN), a_lo + kF16A[i], b_lo + kF16B[i], idesc16,
+                                                    (ch == 0 && first_tap && i == 0) ? 0u : 1u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_ss_tf32<A_HI, B_HI>(tmem_base + (uint32_t)(cls * BN), a_lo + 2 * k, b_lo + 2 * k, idesc,
+                                                 (ch == 0 && first_tap && k == 0) ? 0u : 1u);
+                }
                 umma_commit_elect(pb_empty0 + 8 * bslot);
                 if (e == 26) {
                     umma_commit_elect(pa_empty0 + 8 * s0);
@@ -266,7 +278,36 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
             const int slot = L % TP_NPL;
             t_mbar_wait(pa_full0 + 8 * slot, (uint32_t)(L / TP_NPL) & 1u);
             const int dpl = q + (L & 1), c0 = (L / 2) * 32;
-            if (dpl < p.Din) {
+            if constexpr (F16) {
+                if (dpl < p.Din) {
+                    unsigned char* pl = planes + slot * TP_PLANE_BYTES;
+                    constexpr int ITERS = (TP_PLANE_ROWS * 8 + TP_WORKERS - 1) / TP_WORKERS;
+                    for (int it = 0; it < ITERS; ++it) {          // the 8 lanes of a row read, sync, then overwrite it with [hi | lo]
+                        const int idx = tid + it * TP_WORKERS;
+                        const int r = idx >> 3, chunk = idx & 7;
+                        const int hh = h0 + r / TP_HW, ww = w0 + r % TP_HW;
+                        const bool act = idx < TP_PLANE_ROWS * 8 && hh < p.Hin && ww < p.Win;
+                        unsigned char* row = pl + r * 128;
+                        uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+                        if (act) {
+                            float4 v = *reinterpret_cast<const float4*>(row + ((chunk ^ (r & 7)) << 4));
+                            if (has_aff) {
+                                const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
+                                const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
+                                v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                            }
+                            if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            split_f16x4(v, hi, lo);
+                        }
+                        __syncwarp();
+                        if (act) {
+                            *reinterpret_cast<uint2*>(row + (((chunk >> 1) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = hi;
+                            *reinterpret_cast<uint2*>(row + (((4 + (chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = lo;
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else if (dpl < p.Din) {
                 unsigned char* pl = planes + slot * TP_PLANE_BYTES;
                 auto fix = [&](auto lo_tag) {
                     constexpr bool LO = decltype(lo_tag)::value;
@@ -314,6 +355,10 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                 t_tmem_ld32(tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(cls * BN + ci * 32), r);
                 const int cbase = ci * 32;
                 float v[32];
+                if constexpr (F16) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * p.acc_scale);
+                }
                 if (p.accumulate) {                            // later pass of the compensated mode: add the partial result
                     const float* src = p.y + ov * p.out_ldc + cbase;
 #pragma unroll
@@ -408,7 +453,7 @@ typedef CUresult (*TEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int BN>
+template <int BN, bool F16>
 static int launch_tpose(const TposeParams& p, const CUtensorMap& tmA, const float* wk, TEncodeTiledFn encode, cudaStream_t st) {
     alignas(64) CUtensorMap tmB;
     cuuint64_t gdim[2] = {(cuuint64_t)p.Cin, (cuuint64_t)27 * p.CoutP};
@@ -423,12 +468,12 @@ static int launch_tpose(const TposeParams& p, const CUtensorMap& tmA, const floa
                         (3 * TP_NPL + 2 * TP_SB + 1) * sizeof(uint64_t) + 16 + 32 * sizeof(int) + 32 + (2 * (size_t)p.Cin + 4 * BN) * sizeof(float);
     static thread_local size_t configured = 0;
     if (smem > configured) {
-        SS_CUDA(cudaFuncSetAttribute(conv_tpose_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SS_CUDA(cudaFuncSetAttribute(conv_tpose_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid((unsigned)((long long)p.B * p.Din * p.nTH * p.nTW), 1, 1);
-    conv_tpose_kernel<BN><<<grid, TP_THREADS, smem, st>>>(p, tmA, tmB);
-    return check_launch("conv_tpose_kernel");
+    conv_tpose_kernel<BN, F16><<<grid, TP_THREADS, smem, st>>>(p, tmA, tmB);
+    return check_launch(F16 ? "conv_tpose_f16x3_kernel" : "conv_tpose_kernel");
 }
 
 // returns 1 if the layer was handled here
@@ -469,8 +514,8 @@ int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scal
     p.o_scale = join ? join->out_scale : nullptr; p.o_shift = join ? join->out_shift : nullptr;
     p.res = join ? join->res : nullptr; p.r_scale = join ? join->res_scale : nullptr; p.r_shift = join ? join->res_shift : nullptr;
     p.res_ldc = join ? join->res_ldc : 0; p.res_act = join ? join->res_act : 0;
-    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.sr = stats_range_of(d);
-    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo;
+    p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.sr = stats_range_of(d); p.acc_scale = ps.acc_scale; p.f16_n = ps.f16_n;
+    const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo || ps.f16;
     alignas(64) CUtensorMap tmA;
     cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.Din, (cuuint64_t)p.B};
     cuuint64_t gstr[4] = {(cuuint64_t)d->in_ldc * 4, (cuuint64_t)p.Win * d->in_ldc * 4, (cuuint64_t)p.Hin * p.Win * d->in_ldc * 4,
@@ -480,7 +525,8 @@ int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scal
     if (encode(&tmA, fixup ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float*>(x), gdim, gstr, box,
                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *rc = set_arg_error("conv_tpose: tensor map A"); return 1; }
-    *rc = (d->cout_packed == 32) ? launch_tpose<32>(p, tmA, w_kmajor, encode, st) : launch_tpose<64>(p, tmA, w_kmajor, encode, st);
+    if (ps.f16) *rc = (d->cout_packed == 32) ? launch_tpose<32, true>(p, tmA, w_kmajor, encode, st) : launch_tpose<64, true>(p, tmA, w_kmajor, encode, st);
+    else *rc = (d->cout_packed == 32) ? launch_tpose<32, false>(p, tmA, w_kmajor, encode, st) : launch_tpose<64, false>(p, tmA, w_kmajor, encode, st);
     return 1;
 }
 

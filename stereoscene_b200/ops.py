@@ -498,7 +498,12 @@ def conv_join(x: Vol, module: torch.nn.Module, out_affine: Optional[Vol], res: O
                       _ptr(res.shift) if res is not None else None,
                       _vol_ldc(res.data, "conv_join residual") if res is not None else 0, res.act if res is not None else 0)
     bias = module.bias if (use_bias and module.bias is not None) else None
-    wk = pc.weights_kmajor_split() if mm == SS_MATH_TF32X3 else pc.weights_kmajor()
+    d.acc_scale = 1.0
+    if mm == SS_MATH_TF32X3 and _USE_F16X3:
+        wk, d.acc_scale = pc.weights_kmajor_f16()
+        d.math = SS_MATH_F16X3
+    else:
+        wk = pc.weights_kmajor_split() if mm == SS_MATH_TF32X3 else pc.weights_kmajor()
     rc = lib.ss_conv3d_tc_join_fwd(C.byref(d), xin.data_ptr(), _ptr(x.scale), _ptr(x.shift), wk.data_ptr(),
                                    _ptr(bias.detach() if bias is not None else None), C.byref(j), out.data_ptr(), _stream())
     cabi.check(rc, "ss_conv3d_tc_join_fwd")

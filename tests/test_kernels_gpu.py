@@ -361,13 +361,16 @@ def test_conv_join_fused_in_transposed_epilogue(ops, chans):
     # the compensated mode runs the same fused kernel three times (the join belongs to the last pass)
     ops.set_default_math(ops.SS_MATH_TF32X3)
     try:
-        n0 = cabi.kernel_census().get("conv_tpose_kernel", 0)
-        got3 = ops.conv_join(xv, mg, ops.bn_pending(_cl(x), bn.cuda()), rv, out_act=ops.SS_ACT_RELU)
-        torch.cuda.synchronize()
-        assert cabi.kernel_census()["conv_tpose_kernel"] == n0 + 3
+        for single, kern, launches in ((False, "conv_tpose_kernel", 3), (True, "conv_tpose_f16x3_kernel", 1)):
+            ops.use_f16x3(single)
+            n0 = cabi.kernel_census().get(kern, 0)
+            got3 = ops.conv_join(xv, mg, ops.bn_pending(_cl(x), bn.cuda()), rv, out_act=ops.SS_ACT_RELU)
+            torch.cuda.synchronize()
+            assert cabi.kernel_census()[kern] == n0 + launches
+            assert rel_err(_ncdhw(got3), want64) < 5e-5, single
     finally:
+        ops.use_f16x3(True)
         ops.set_default_math(ops.SS_MATH_TF32)
-    assert rel_err(_ncdhw(got3), want64) < 5e-5
     # a layer the fused kernel does not take falls back to conv + join
     m2 = nn.ConvTranspose3d(64, 32, 2, 2, bias=False).cuda()
     x2 = torch.randn(1, 64, 2, 4, 4)
