@@ -125,6 +125,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     ap.add_argument("--pairs-per-step", type=int, default=1, help="stereo pairs per GPU per step (batch of one forward); with --shard x: pairs per step of the whole job")
+    ap.add_argument("--xshard-comm", default="peer", choices=["peer", "nccl"],
+                    help="--shard x: halo exchange / statistics all-reduce as NVLink peer-memory kernels (default) or torch.distributed calls")
     ap.add_argument("--shard", default="sample", choices=["sample", "x"],
                     help="sample: one stereo pair per rank, no data-path collective (throughput mode, default); x: the X-slab sharded "
                          "latency mode of BASELINE.json configs[3] (stereoscene_b200/xshard.py): one all-gather of depth_prob||img_feat at "
@@ -275,10 +277,11 @@ def run_xshard(args):
     P = max(1, args.pairs_per_step)
     counts = [len(range(r, P, world)) for r in range(world)]
     b = max(counts)
-    xl, xr = synth.stereo_features(max(b, 1), mc["input_size"], 8, seed=rank, device=dev)
+    xl, xr = synth.stereo_features(max(b, 1), mc["input_size"], 8, seed=rank, device=dev)      # only the owner's pair is used when P = 1
     left, right, calib = synth.kitti_calibration(max(b, 1), mc["input_size"], device=dev)
     occ = mc["occ_size"]
-    pipe = xshard.XShardedPipeline(model, world, rank)
+    pipe = xshard.XShardedPipeline(model, world, rank, peer_memory=(args.xshard_comm == "peer"))
+    pipe.use_graph = not args.no_graph and args.xshard_comm == "peer"
 
     def step():
         with torch.no_grad():
@@ -296,7 +299,7 @@ def run_xshard(args):
     launches = cabi.launch_count() - n0
     coll = dict(pipe.path.collectives)
     gathered = pipe.gathered_bytes
-    for _ in range(max(2, args.warmup - 1)):
+    for _ in range(max(4, args.warmup - 1)):          # >= 4: the voxel graph is captured on the third call
         step()
     sampler = ClockSampler(local)
     barrier()
@@ -315,10 +318,12 @@ def run_xshard(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": {"workload": workload_config(args.workload, P), "math": args.math, "math_policy": policy_text(ops, args.math),
-                       "cuda_graph": False, "parallelism": f"x-slab x{world}: frustum stages of pair s on rank s % {world}, ONE all-gather of "
+                       "cuda_graph": "voxel-space path (frustum stages eager)" if pipe.use_graph else False,
+                       "frustum_split": bool(pipe.split_frustum and world > 1 and P == 1),
+                       "parallelism": f"x-slab x{world}: frustum stages of pair s on rank s % {world}, ONE all-gather of "
                        "depth_prob||img_feat at the MIE boundary, halo send/recv + GroupNorm all-reduce in the voxel stack",
                        "l2": "no flush: one step streams > 9 GB of activations, >> 126 MB L2"},
-            "shard": {"mode": "x-slab", "pairs_per_step": P, "slab_planes": pipe.plan.xs, "per_sample": coll,
+            "shard": {"mode": "x-slab", "comm": "NVLink peer-memory kernels (csrc/peer.cu)" if args.xshard_comm == "peer" else "torch.distributed (NCCL)", "pairs_per_step": P, "slab_planes": pipe.plan.xs, "per_sample": coll,
                       "allgather_bytes_per_step": gathered, "output": f"rank r holds planes [{2 * pipe.plan.xs} r, {2 * pipe.plan.xs} (r+1)) of every label volume"},
             "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches), "clocks": clocks,
             "latency_ms": ms / args.steps,

@@ -268,6 +268,33 @@ int ss_ssc_confusion_fwd(const uint8_t* pred, const void* target, int target_ele
 int ss_deform_sample_fwd(const float* x, const float* offsets, float* out, int B, int H, int W, int C,
                          int groups, int kh, int kw, int stride, int pad, int dil, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * NVLink peer-memory collectives of the X-slab sharded mode (no reference counterpart: the reference only has DDP,
+ * occupancy/apis/mmdet_train.py:75-79).  Every rank allocates one pool, exports it through CUDA IPC and opens every peer's
+ * pool; exchanged tensors, flag words and slot areas live at the same offset in every pool.  `epoch` is a device counter
+ * bumped once per forward (flags are never reset: a call waits for flag >= *epoch).  All calls are stream-ordered kernels
+ * (capturable in a CUDA graph); they return 0 / SS_ERR_*.
+ *   ss_peer_halo_push: buf = [n + 2][plane_floats] of this rank.  Copies plane 1 into the lower neighbour's plane n + 1 and
+ *     plane n into the upper neighbour's plane 0 (peer_*_buf = the neighbour's buffer, NULL at the two ends of the grid, where
+ *     the outer halo plane is zeroed or, with edge_replicate, filled with a copy of the edge plane), raises the neighbours' flags
+ *     and waits until both neighbours have pushed theirs (a rank pushes only after the neighbour's stream has reached the same call, so
+ *     the neighbour's producer kernel can no longer overwrite the halo).  my_flags / peer_*_flags: int[4] at the same pool offset on every rank;
+ *     ticket: one zeroed unsigned int per call site.
+ *   ss_peer_stats_allreduce: stats[n] (double) += the same array of every other rank, summed in rank order on every rank.
+ *     slots[r] / flags[r]: rank r's slot area (world * n doubles) / flag array (world ints) for this call site, HOST arrays of
+ *     device pointers (own pool for r == rank, peer mappings otherwise).
+ * ------------------------------------------------------------------------------------------- */
+int ss_peer_pool_alloc(size_t bytes, void** ptr);
+int ss_peer_pool_free(void* ptr);
+int ss_peer_ipc_export(void* ptr, void* handle64);                          /* handle64: HOST buffer of 64 bytes */
+int ss_peer_ipc_open(const void* handle64, int peer_device, void** ptr);
+int ss_peer_ipc_close(void* ptr);
+int ss_peer_epoch_bump(int* epoch, void* stream);
+int ss_peer_halo_push(float* buf, float* peer_lo_buf, float* peer_hi_buf, long long plane_floats, int n, int edge_replicate,
+                      int* my_flags, int* peer_lo_flags, int* peer_hi_flags, unsigned int* ticket, const int* epoch, void* stream);
+int ss_peer_stats_allreduce(double* stats, int n, int world, int rank, double* const* slots, int* const* flags,
+                            const int* epoch, void* stream);
+
 /* Layout helpers: NCHW/NCDHW <-> channels-last copies ([B][C][V] <-> [B][V][C]). */
 int ss_nchw_to_nhwc(const float* x, float* y, int B, int C, long long V, int out_ldc, void* stream);
 int ss_nhwc_to_nchw(const float* x, float* y, int B, int C, long long V, int in_ldc, void* stream);

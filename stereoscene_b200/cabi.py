@@ -61,6 +61,14 @@ SIGNATURES = {
     "ss_trilinear_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ss_ssc_confusion_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _ll, _i, _i, _vp, _vp]),
     "ss_deform_sample_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ss_peer_pool_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "ss_peer_pool_free": (_i, [_vp]),
+    "ss_peer_ipc_export": (_i, [_vp, _vp]),
+    "ss_peer_ipc_open": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "ss_peer_ipc_close": (_i, [_vp]),
+    "ss_peer_epoch_bump": (_i, [_vp, _vp]),
+    "ss_peer_halo_push": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ss_peer_stats_allreduce": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp]),
     "ss_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
     "ss_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
 }

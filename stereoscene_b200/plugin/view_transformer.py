@@ -594,6 +594,23 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
             depth_prob = self.mutual_interactive_ensemble(stereo, lss)
         return depth_prob, img_feat, depth_logits, lss, stereo
 
+    # ---- the two independent halves of the frustum stage (the X-slab latency mode runs them on two ranks at once) -----
+    def stereo_branch(self, feat_left, feat_right, mlp_left, mlp_right, calib) -> torch.Tensor:
+        """(i) alone: stereo depth distribution [B,D,fH,fW] from the feature pair [B,Cin,fH,fW] x 2."""
+        with ops.math_scope("stereo"):
+            return self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib)
+
+    def depth_branch(self, feat_left, mlp_input):
+        """(N1) alone: (lss depth distribution [B,D,fH,fW], context features [B,fH,fW,C] channels-last)."""
+        left_cl = ops.to_channels_last(feat_left).unsqueeze(1)
+        with ops.math_scope("depthnet"):
+            depth_cl, ctx_cl = self.depth_net.forward_vol(left_cl, mlp_input)
+        return ops.softmax_d(ops.to_channels_first(depth_cl.squeeze(1))), ctx_cl.squeeze(1).contiguous()
+
+    def mie_branch(self, stereo, lss) -> torch.Tensor:
+        with ops.math_scope("mie"):
+            return self.mutual_interactive_ensemble(stereo, lss)
+
     def forward(self, input):
         rots, trans, intrins, post_rots, post_trans, bda = input[1:7]
         depth_prob, img_feat, depth_logits, lss, stereo = self.frustum_forward(input)

@@ -98,29 +98,42 @@ def exchange_halo(buf: torch.Tensor, n: int, plan: SlabPlan, group=None, edge: s
 class XShardedVoxelPath:
     """Lift (x) splat, CustomResNet3D, SECONDFPN3D, OccHead and the x2 resize of ONE sample on this rank's X-slab."""
 
-    def __init__(self, model, plan: SlabPlan, group=None, kernels=None):
+    def __init__(self, model, plan: SlabPlan, group=None, kernels=None, pool=None):
+        """``pool``: a stereoscene_b200.peer.PeerPool -> the halo exchange and the statistics all-reduce run as peer-memory
+        kernels over NVLink (no NCCL call per collective); None -> torch.distributed send/recv and all_reduce."""
         if kernels is None:
             from . import ops as kernels          # the CUDA library (fails loudly without it)
-        self.K, self.model, self.plan, self.group = kernels, model, plan, group
+        self.K, self.model, self.plan, self.group, self.pool = kernels, model, plan, group, pool
         self.collectives = {"halo_exchanges": 0, "halo_bytes": 0, "stat_allreduces": 0}
+        self._pool_off = {}
 
     # ---- communication ----------------------------------------------------------------------------------------------
     def exchange(self, buf, n, edge="zero"):
         self.collectives["halo_exchanges"] += 1
         self.collectives["halo_bytes"] += 2 * buf[:, 0].numel() * buf.element_size()
         with _timed("halo_ms"):
+            if self.pool is not None:
+                self.pool.halo_push(buf, self._pool_off[buf.data_ptr()], n, edge == "replicate")
+                return buf
             return exchange_halo(buf, n, self.plan, self.group, edge)
 
     def gn(self, y, stats, gnmod, act, count, scale_out=None, shift_out=None):
         """GroupNorm of a slab from GLOBAL statistics: sum the slab sums over the ranks, then finalise."""
         if self.plan.world > 1:
             with _timed("allreduce_ms"):
-                dist.all_reduce(stats, group=self.group)
+                if self.pool is not None:
+                    self.pool.allreduce(stats)
+                else:
+                    dist.all_reduce(stats, group=self.group)
             self.collectives["stat_allreduces"] += 1
         return self.K.gn_pending(y, stats, gnmod, act, scale_out, shift_out, count=count)
 
-    @staticmethod
-    def halo_buf(like: torch.Tensor, n: int, Y: int, Z: int, C: int) -> torch.Tensor:
+    def halo_buf(self, like: torch.Tensor, n: int, Y: int, Z: int, C: int) -> torch.Tensor:
+        """[1, n + 2, Y, Z, C] buffer; from the peer pool (same offset on every rank) when one is attached."""
+        if self.pool is not None:
+            t, off = self.pool.tensor((1, n + 2, Y, Z, C), like.dtype)
+            self._pool_off[t.data_ptr()] = off
+            return t
         return torch.empty((1, n + 2, Y, Z, C), dtype=like.dtype, device=like.device)
 
     # ---- 3x3x3 layers on a slab ---------------------------------------------------------------------------------------------
@@ -177,7 +190,8 @@ class XShardedVoxelPath:
             xin = K.Vol(x.data[:, 1:n + 1], x.scale, x.shift, x.act)          # 1x1x1 stride-s: interior planes only
             _, st = K.conv(xin, blk.downsample[0], out=rbuf[:, 1:m + 1], want_stats=True)
             res = self.gn(rbuf, st, blk.downsample[1], SS_ACT_NONE, count)
-        out = K.join(v2, res, out_act=SS_ACT_RELU)
+        out = self.halo_buf(y2, m, y2.shape[2], y2.shape[3], y2.shape[4])
+        K.join(v2, res, out_act=SS_ACT_RELU, out=out)
         self.exchange(out, m)
         return K.Vol(out), m, count
 
@@ -233,13 +247,26 @@ class XShardedPipeline:
     """The whole volumetric forward of a global batch in the sharded layout: frustum stages of sample s on rank s % R,
     one all-gather of ``depth_prob || img_feat`` at the MIE boundary, then every rank runs its X-slab of EVERY sample."""
 
-    def __init__(self, model, world: int, rank: int, group=None, kernels=None):
+    def __init__(self, model, world: int, rank: int, group=None, kernels=None, peer_memory: bool = False, pool_bytes: int = 0):
+        """``peer_memory``: run the voxel stack's collectives as NVLink peer-memory kernels (stereoscene_b200.peer) instead of
+        torch.distributed calls; ``pool_bytes``: size of the per-rank pool (default: sized for one sample's slab buffers)."""
         vt = model.img_view_transformer
         nx = [int(round(float(v))) for v in vt.nx.detach().cpu()]
         self.model, self.world, self.rank, self.group = model, world, rank, group
         self.plan = SlabPlan(nx[0], world, rank)
-        self.path = XShardedVoxelPath(model, self.plan, group, kernels)
+        pool = None
+        if peer_memory:
+            from .peer import PeerPool
+            if not pool_bytes:      # ~16 slab buffers of the widest level + the 384-channel neck buffer, with head-room
+                per_plane = nx[1] * nx[2] * 4
+                pool_bytes = int((self.plan.xs + 2) * per_plane * (16 * 128 + 384 + 64) * 1.25) + (64 << 20)
+            pool = PeerPool(pool_bytes, world, rank, vt.frustum.device, group)
+        self.pool = pool
+        self.path = XShardedVoxelPath(model, self.plan, group, kernels, pool)
         self.gathered_bytes = 0
+        self.split_frustum = True            # B = 1 on >= 2 ranks: stereo branch and depth_net on two ranks at once
+        self.use_graph = False               # peer pool only: replay the voxel-space path as one CUDA graph
+        self._graph = None
 
     def frustum(self, x_left, x_right, left, right, calib):
         """(depth_prob [b,D,H,W], img_feat [b,H,W,C]) of this rank's own samples."""
@@ -250,6 +277,41 @@ class XShardedPipeline:
         inp = [x_left] + [left[k] for k in keys] + [ml] + [x_right] + [right[k] for k in keys] + [mr] + [calib, None, None]
         dp, feat = vt.frustum_forward(inp)[:2]
         return dp, feat
+
+    def frustum_split(self, x_left, x_right, left, right, calib, owner: int, helper: int):
+        """B = 1 latency mode on >= 2 ranks: the stereo branch and depth_net are independent until the MIE block, so the
+        owner runs (i) while the helper runs (N1) on the left feature map it receives from the owner, and sends back the lss
+        distribution and the context features (7.4 MB).  Returns (depth_prob, img_feat) on the owner, None elsewhere."""
+        vt = self.model.img_view_transformer
+        keys = ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")
+        dev = vt.frustum.device
+        fH, fW = vt.frustum.shape[1], vt.frustum.shape[2]
+        if self.rank == owner:
+            ml = vt.get_mlp_input(*[left[k] for k in keys])
+            mr = vt.get_mlp_input(*[right[k] for k in keys])
+            fl = x_left.squeeze(1).contiguous()
+            send = dist.isend(fl, self._peer(helper), group=self.group)
+            self.path.K.arena(dev).reset()
+            stereo = vt.stereo_branch(fl, x_right.squeeze(1), ml, mr, calib)
+            lss = torch.empty((1, vt.D, fH, fW), dtype=torch.float32, device=dev)
+            feat = torch.empty((1, fH, fW, vt.numC_Trans), dtype=torch.float32, device=dev)
+            r1 = dist.irecv(lss, self._peer(helper), group=self.group)
+            r2 = dist.irecv(feat, self._peer(helper), group=self.group)
+            send.wait(); r1.wait(); r2.wait()
+            return vt.mie_branch(stereo, lss), feat
+        if self.rank == helper:
+            ml = vt.get_mlp_input(*[left[k] for k in keys])
+            fl = torch.empty((1, vt.numC_input, fH, fW), dtype=torch.float32, device=dev)
+            dist.recv(fl, self._peer(owner), group=self.group)
+            self.path.K.arena(dev).reset()
+            lss, feat = vt.depth_branch(fl, ml)
+            s1 = dist.isend(lss, self._peer(owner), group=self.group)
+            s2 = dist.isend(feat, self._peer(owner), group=self.group)
+            s1.wait(); s2.wait()
+        return None
+
+    def _peer(self, r: int) -> int:
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
 
     def gather(self, dp: torch.Tensor, feat: torch.Tensor):
         """The ONE data-path collective: all-gather of depth_prob || img_feat.  Every rank contributes the same number b of
@@ -279,9 +341,19 @@ class XShardedPipeline:
         fH, fW = vt.frustum.shape[1], vt.frustum.shape[2]
         dp = torch.zeros((b, vt.D, fH, fW), dtype=torch.float32, device=dev)
         feat = torch.zeros((b, fH, fW, vt.numC_Trans), dtype=torch.float32, device=dev)
-        if mine == 0 and hasattr(self.path.K, "arena"):
+        split = self.split_frustum and self.world > 1 and sum(counts) == 1
+        if split:
+            owner = counts.index(1)
+            got = self.frustum_split(x_left, x_right, {k: v[:1] for k, v in left.items()}, {k: v[:1] for k, v in right.items()},
+                                     calib[:1], owner, (owner + 1) % self.world)
+            if got is not None:
+                dp[:1].copy_(got[0])
+                feat[:1].copy_(got[1])
+            elif self.rank != (owner + 1) % self.world and hasattr(self.path.K, "arena"):
+                self.path.K.arena(dev).reset()
+        elif mine == 0 and hasattr(self.path.K, "arena"):
             self.path.K.arena(dev).reset()               # frustum_forward does this on the ranks that own a sample
-        if mine > 0:
+        if mine > 0 and not split:
             cut = lambda d: {k: v[:mine] for k, v in d.items()}      # noqa: E731
             with _timed("frustum_ms"):
                 d_, f_ = self.frustum(x_left[:mine], x_right[:mine], cut(left), cut(right), calib[:mine])
@@ -290,11 +362,41 @@ class XShardedPipeline:
         dps, fts = self.gather(dp, feat)
         one = {k: v[:1] for k, v in left.items()}
         index = vt.splat_index(*[one[k] for k in ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")])
-        K = self.path.K
         outs = []
-        with K.math_scope("voxel"):
-            for r in range(self.world if self.world > 1 else 1):
-                for i_ in range(counts[r]):
-                    g = r * b + i_
-                    outs.append(self.path.run(dps[g], fts[g], index, occ_size, want_labels))
+        for r in range(self.world if self.world > 1 else 1):
+            for i_ in range(counts[r]):
+                g = r * b + i_
+                outs.append(self._voxel(dps[g], fts[g], index, occ_size, want_labels))
         return outs
+
+    def _voxel_eager(self, dp, ft, index, occ_size, want_labels):
+        K = self.path.K
+        with K.math_scope("voxel"):
+            if self.pool is not None:
+                self.pool.begin()            # one pool generation per sample: rewind the bump allocators, advance the epoch
+                self.path._pool_off = {}
+            return self.path.run(dp, ft, index, occ_size, want_labels)
+
+    def _voxel(self, dp, ft, index, occ_size, want_labels):
+        """The voxel-space path of one sample: eager, or -- with the peer pool, whose collectives are plain kernels -- as ONE
+        CUDA graph replayed from static input buffers (every rank replays its own capture of the same sequence)."""
+        if not (self.use_graph and self.pool is not None):
+            return self._voxel_eager(dp, ft, index, occ_size, want_labels)
+        key = (tuple(occ_size), bool(want_labels))
+        if self._graph is None or self._graph[0] != key:
+            self._calls = getattr(self, "_calls", 0) + 1
+            out = self._voxel_eager(dp, ft, index, occ_size, want_labels)
+            if self._calls < 3:                       # warm the caches (packed weights, splat index) before capturing
+                return out
+            sdp, sft = dp.clone(), ft.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                gout = self._voxel_eager(sdp, sft, index, occ_size, want_labels)
+            self._graph = (key, g, sdp, sft, gout, index)
+            return out
+        _, g, sdp, sft, gout, _ = self._graph
+        sdp.copy_(dp)
+        sft.copy_(ft)
+        g.replay()
+        return gout

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _check_rank(rank, world, workload="tiny", policy="tf32"):
+def _check_rank(rank, world, workload="tiny", policy="tf32", peer=False):
     from stereoscene_b200 import ops, xshard
     cfg, _ = golden_tiny()
     model, mc = build_model(workload, cfg["seed"], device="cuda")
@@ -25,22 +25,28 @@ def _check_rank(rank, world, workload="tiny", policy="tf32"):
     ops.set_math_policy(policy)
     with torch.no_grad():
         ref = model.forward_features(xl, xr, left, right, calib, occ_size=cfg["occ_size"], want_labels=True)
-        pipe = xshard.XShardedPipeline(model, world, rank)
+        pipe = xshard.XShardedPipeline(model, world, rank, peer_memory=peer)
+        pipe.use_graph = peer                                 # peer pool: the voxel-space path is captured on the 3rd call, replayed after
         counts = [1] + [0] * (world - 1)                      # one sample in the job, owned by rank 0 (B = 1 latency mode)
-        outs = pipe.forward(xl if rank == 0 else None, xr if rank == 0 else None, left, right, calib, cfg["occ_size"], counts)
+        for _ in range(5 if peer else 1):                     # several generations of the peer pool (flags compare against a growing epoch)
+            outs = pipe.forward(xl if rank == 0 else None, xr if rank == 0 else None, left, right, calib, cfg["occ_size"], counts)
     torch.cuda.synchronize()
+    if pipe.pool is not None:
+        outs = [{k: (v.clone() if v is not None else None) for k, v in o.items()} for o in outs]
     ops.set_math_policy(None)
     assert len(outs) == 1
     plan = pipe.plan
     want = ref["output_voxels"].permute(0, 2, 3, 4, 1)[:, 2 * plan.x0: 2 * plan.x1]
     err = rel_err(outs[0]["logits"], want)
     lab = float((outs[0]["labels"] != ref["labels"][:, 2 * plan.x0: 2 * plan.x1]).float().mean())
-    return err, lab, dict(pipe.path.collectives), pipe.gathered_bytes
+    per_forward = {k: v // (4 if peer else 1) for k, v in pipe.path.collectives.items()}      # 3 eager calls + 1 capture
+    return err, lab, per_forward, pipe.gathered_bytes
 
 
+@pytest.mark.parametrize("peer", [False, True], ids=["dist", "peerpool"])
 @pytest.mark.parametrize("policy", ["tf32x3", "tf32"])
-def test_single_rank_slab_path_equals_ordinary_forward(policy):
-    err, lab, coll, _ = _check_rank(0, 1, policy=policy)
+def test_single_rank_slab_path_equals_ordinary_forward(policy, peer):
+    err, lab, coll, _ = _check_rank(0, 1, policy=policy, peer=peer)
     # the slab views take other kernels / tile shapes than the whole volume: in the compensated mode the two evaluations
     # agree to fp32 accumulation noise, in plain TF32 to the TF32 rounding noise the ~30-layer stack amplifies
     assert err < (2e-5 if policy == "tf32x3" else 1e-3), err
@@ -48,7 +54,7 @@ def test_single_rank_slab_path_equals_ordinary_forward(policy):
     assert coll["halo_exchanges"] == 15
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, peer=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -56,19 +62,20 @@ def _worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        q.put((rank,) + _check_rank(rank, world, policy="tf32x3"))
+        q.put((rank,) + _check_rank(rank, world, policy="tf32x3", peer=peer))
     finally:
         dist.barrier()
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_rank_sharded_forward_equals_unsharded():
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "nvlink-peer-memory"])
+def test_two_rank_sharded_forward_equals_unsharded(peer):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + (977 if peer else 0)) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, peer)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted(q.get(timeout=300) for _ in procs)
