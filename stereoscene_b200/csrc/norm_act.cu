@@ -188,6 +188,113 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restri
 
 using namespace ss;
 
+// GroupNorm finalize whose result is also multiplied by up to two per-(batch,channel) gates (> 0, e.g. SE gates:
+// relu(gn(y)) * g == relu(gn(y) * g)), one (scale, shift) pair per gate: out_k = (scale * gate_k, shift * gate_k).
+__global__ void gn_finalize_gated_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, int B, int C, int groups, double count, float eps,
+                                         const float* __restrict__ gate1, float* __restrict__ scale1, float* __restrict__ shift1,
+                                         const float* __restrict__ gate2, float* __restrict__ scale2, float* __restrict__ shift2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i % C;
+    const int cpg = C / groups, g0 = (c / cpg) * cpg;
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+        s += stats[((size_t)b * C + g0 + k) * 2 + 0];
+        q += stats[((size_t)b * C + g0 + k) * 2 + 1];
+    }
+    const double n = count * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = __ldg(gamma + c) * rstd;
+    const float sh = __ldg(beta + c) - (float)mean * sc;
+    const float g1 = __ldg(gate1 + i);
+    scale1[i] = sc * g1;
+    shift1[i] = sh * g1;
+    if (gate2) {
+        const float g2 = __ldg(gate2 + i);
+        scale2[i] = sc * g2;
+        shift2[i] = sh * g2;
+    }
+}
+
+// ASPP image-pooling branch folded into the pending shift of the fusing 1x1 conv's BatchNorm (ViewTransformerLSSBEVDepth.py:
+// 373-379, 394-406): the branch is constant over the map, so its share of conv1 is a per-(batch, channel) vector.
+//   pooled[c] = sum_x[b][c] / count;  t = W1 pooled;  g = relu(GroupNorm_groups(t));  u = Wp g;
+//   shift_out[b][j] = bn_shift[b][j] + bn_scale[b][j] * u[j]
+// One CTA per sample; W1: [mid][C], Wp: [mid][mid] (conv1's columns of the pooled branch), row-major.
+__global__ void __launch_bounds__(1024)
+aspp_pool_shift_kernel(const double* __restrict__ stats, double count, const float* __restrict__ w1, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, int groups, float eps, const float* __restrict__ wp,
+                       const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ shift_out,
+                       int C, int mid) {
+    extern __shared__ float sm[];
+    float* pooled = sm;                 // [C]
+    float* t = sm + C;                  // [mid]
+    float* red = t + mid;               // [2 * groups]
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int c = tid; c < C; c += blockDim.x) pooled[c] = (float)(stats[((size_t)b * C + c) * 2] / count);
+    __syncthreads();
+    for (int o = warp; o < mid; o += nwarp) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + (size_t)o * C + c), pooled[c], a);
+        a = warp_sum(a);
+        if (lane == 0) t[o] = a;
+    }
+    __syncthreads();
+    const int cpg = mid / groups;
+    if (warp < groups) {                // one warp per group: mean and variance over its channels
+        float s = 0.f, q = 0.f;
+        for (int k = lane; k < cpg; k += 32) { const float v = t[warp * cpg + k]; s += v; q = fmaf(v, v, q); }
+        s = warp_sum(s); q = warp_sum(q);
+        if (lane == 0) {
+            const float mean = s / cpg;
+            float var = q / cpg - mean * mean;
+            if (var < 0.f) var = 0.f;
+            red[2 * warp] = mean;
+            red[2 * warp + 1] = rsqrtf(var + eps);
+        }
+    }
+    __syncthreads();
+    for (int o = tid; o < mid; o += blockDim.x) {
+        const int g = o / cpg;
+        t[o] = fmaxf((t[o] - red[2 * g]) * red[2 * g + 1] * __ldg(gamma + o) + __ldg(beta + o), 0.f);
+    }
+    __syncthreads();
+    for (int j = warp; j < mid; j += nwarp) {
+        float a = 0.f;
+        for (int o = lane; o < mid; o += 32) a = fmaf(__ldg(wp + (size_t)j * mid + o), t[o], a);
+        a = warp_sum(a);
+        if (lane == 0) shift_out[(size_t)b * mid + j] = fmaf(__ldg(bn_scale + (size_t)b * mid + j), a, __ldg(bn_shift + (size_t)b * mid + j));
+    }
+}
+
+extern "C" int ss_gn_finalize_gated(const double* stats, const float* gamma, const float* beta, int B, int C, int groups,
+                                    double count, float eps, const float* gate1, float* scale1, float* shift1,
+                                    const float* gate2, float* scale2, float* shift2, void* stream) {
+    SS_REQUIRE(stats && gamma && beta && gate1 && scale1 && shift1, "ss_gn_finalize_gated: null pointer");
+    SS_REQUIRE(!gate2 || (scale2 && shift2), "ss_gn_finalize_gated: second gate needs its outputs");
+    SS_REQUIRE(B > 0 && C > 0 && groups > 0 && C % groups == 0 && count > 0, "ss_gn_finalize_gated: shape");
+    const int n = B * C;
+    gn_finalize_gated_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, gamma, beta, B, C, groups, count, eps, gate1,
+                                                                                scale1, shift1, gate2, scale2, shift2);
+    return check_launch("gn_finalize_gated_kernel");
+}
+
+extern "C" int ss_aspp_pool_shift(const double* stats, double count, const float* w1, const float* gamma, const float* beta, int groups,
+                                  float eps, const float* w_pool, const float* bn_scale, const float* bn_shift, float* shift_out,
+                                  int B, int C, int mid, void* stream) {
+    SS_REQUIRE(stats && w1 && gamma && beta && w_pool && bn_scale && bn_shift && shift_out, "ss_aspp_pool_shift: null pointer");
+    SS_REQUIRE(B > 0 && C > 0 && mid > 0 && groups > 0 && groups <= 32 && mid % groups == 0 && count > 0, "ss_aspp_pool_shift: shape");
+    const size_t smem = ((size_t)C + mid + 2 * groups) * sizeof(float);
+    SS_REQUIRE(smem <= 48 * 1024, "ss_aspp_pool_shift: channel counts too large");
+    aspp_pool_shift_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(stats, count, w1, gamma, beta, groups, eps, w_pool, bn_scale, bn_shift,
+                                                                     shift_out, C, mid);
+    return check_launch("aspp_pool_shift_kernel");
+}
+
 extern "C" int ss_gn_finalize(const double* stats, const float* gamma, const float* beta, int B, int C, int groups,
                               double count, float eps, float* scale, float* shift, int ld_out, void* stream) {
     SS_REQUIRE(stats && gamma && beta && scale && shift, "ss_gn_finalize: null pointer");

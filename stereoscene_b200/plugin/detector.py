@@ -96,8 +96,9 @@ class BEVDepthOccupancy(nn.Module):
         [B,classes,*occ_size], depth = depth_prob, labels = uint8 argmax or None)."""
         vt = self.img_view_transformer
         keys = ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")
-        ml = vt.get_mlp_input(*[left[k] for k in keys])
-        mr = vt.get_mlp_input(*[right[k] for k in keys])
+        # calibration-only vectors: cached per calibration like the splat index
+        ml = ops.cached_const("mlp_input", [left[k] for k in keys], lambda: vt.get_mlp_input(*[left[k] for k in keys]).contiguous())
+        mr = ops.cached_const("mlp_input", [right[k] for k in keys], lambda: vt.get_mlp_input(*[right[k] for k in keys]).contiguous())
         geo_l = [left[k] for k in keys] + [ml]
         geo_r = [right[k] for k in keys] + [mr]
         bev, depth = vt([x_left] + geo_l + [x_right] + geo_r + [calib, None, None])

@@ -86,10 +86,9 @@ class AttentionParams(nn.Module):
 
     def packed(self) -> torch.Tensor:
         """device float[7] = wq,bq,wk,bk,wv,bv,gamma for ss_bri_attn_fwd."""
-        return torch.cat([self.query_conv.weight.view(1), self.query_conv.bias.view(1),
-                          self.key_conv.weight.view(1), self.key_conv.bias.view(1),
-                          self.value_conv.weight.view(1), self.value_conv.bias.view(1),
-                          self.gamma.view(1)]).detach().float().contiguous()
+        ps = [self.query_conv.weight, self.query_conv.bias, self.key_conv.weight, self.key_conv.bias,
+              self.value_conv.weight, self.value_conv.bias, self.gamma]
+        return ops.cached_const("bri_params", ps, lambda: torch.cat([p.detach().view(1) for p in ps]).float().contiguous())
 
 
 class CA3DParams(nn.Module):
@@ -208,16 +207,14 @@ class ASPP(nn.Module):
         for i, br in enumerate((self.aspp1, self.aspp2, self.aspp3, self.aspp4)):
             ops.conv(x, br.atrous_conv, out=buf[..., i * mid:(i + 1) * mid])
         sc, sh = self._branch_affine(buf)
-        # pooled branch on [B,C] vectors: mean -> 1x1 conv -> GroupNorm -> ReLU (bilinear upsampling of a
-        # 1x1 map with align_corners=True is a broadcast)
-        pooled = (ops.channel_sums(x)[..., 0] / float(H * W)).float()
+        # pooled branch on [B,C] vectors: mean -> 1x1 conv -> GroupNorm -> ReLU -> its columns of conv1 (bilinear upsampling of
+        # a 1x1 map with align_corners=True is a broadcast), folded into bn1's pending shift by one small kernel
         gp = self.global_avg_pool
-        g = torch.relu(F.group_norm(pooled @ gp[1].weight.flatten(1).t(), gp[2].num_groups, gp[2].weight, gp[2].bias,
-                                    gp[2].eps))
         head, w_pool = self._conv1_split()
         y, _ = ops.conv(Vol(buf, sc, sh, SS_ACT_RELU), head)
         bn = ops.bn_pending(y, self.bn1, SS_ACT_RELU)
-        return Vol(y, bn.scale, torch.addcmul(bn.shift, bn.scale, g @ w_pool.t()).contiguous(), SS_ACT_RELU)
+        shift = ops.aspp_pool_shift(ops.channel_sums(x), H * W, gp[1].weight, gp[2], w_pool, bn.scale, bn.shift)
+        return Vol(y, bn.scale, shift, SS_ACT_RELU)
 
 
 class DCN(nn.Module):
@@ -290,15 +287,17 @@ class DepthNet(nn.Module):
     def forward_vol(self, x: torch.Tensor, mlp_input: torch.Tensor):
         """x: channels-last [B,1,H,W,Cin] -> (depth logits [B,1,H,W,D], context [B,1,H,W,ctx]), both
         channels-last."""
-        m = self.bn(mlp_input.reshape(-1, mlp_input.shape[-1]))          # GroupNorm on the [B,cam] calibration vector
+        # the SE gates depend on the calibration vector and the parameters only: cached per (calibration, checkpoint)
+        def gates():
+            m = self.bn(mlp_input.reshape(-1, mlp_input.shape[-1]))      # GroupNorm on the [B,cam] calibration vector
+            return (self.context_se.gate(self.context_mlp(m)).contiguous(), self.depth_se.gate(self.depth_mlp(m)).contiguous())
+        gc, gd = ops.cached_const("depthnet_gates", [mlp_input] + list(self.bn.parameters()) + list(self.context_mlp.parameters()) +
+                                  list(self.context_se.parameters()) + list(self.depth_mlp.parameters()) + list(self.depth_se.parameters()), gates)
         with ops.math_scope("depthnet.trunk"):
-            v = conv_gn(Vol(x), self.reduce_conv, SS_ACT_RELU)
+            y, st = ops.conv(Vol(x), self.reduce_conv[0], want_stats=True)
             # SE gates are > 0: relu(gn(y)) * g == relu(gn(y) * g), so each gate is a rescaled pending affine
-            gc = self.context_se.gate(self.context_mlp(m))
-            gd = self.depth_se.gate(self.depth_mlp(m))
-            context, _ = ops.conv(Vol(v.data, (v.scale * gc).contiguous(), (v.shift * gc).contiguous(), SS_ACT_RELU),
-                                  self.context_conv)
-        d = Vol(v.data, (v.scale * gd).contiguous(), (v.shift * gd).contiguous(), SS_ACT_RELU)
+            vc, d = ops.gn_pending_gated(y, st, self.reduce_conv[1], SS_ACT_RELU, gc, gd)
+            context, _ = ops.conv(vc, self.context_conv)
         with ops.math_scope("depthnet.blocks"):
             for i in range(3):
                 d = self.depth_conv[i].forward_vol(d)
@@ -455,15 +454,24 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         """stereofeature_net on the batched pair -> channels-last [2B,1,fH,fW,64].  ``pair_cl`` is the
         channels-last [2B,1,fH,fW,Cin] copy of cat(left, right) if the caller already made it."""
         net = self.stereo_volume_net.feature_withcam
-        x = pair_cl if pair_cl is not None else \
-            ops.to_channels_last(torch.cat([feat_left, feat_right], 0)).unsqueeze(1)     # [2B,1,H,W,Cin]
-        m = torch.cat([mlp_left, mlp_right], 0).reshape(-1, mlp_left.shape[-1])
-        v = conv_gn(Vol(x), net.reduce_conv, SS_ACT_RELU)
-        # SE gate > 0, so relu(gn(y)) * g == relu(gn(y) * g): fold it into the pending affine
-        gate = net.depth_se.gate(net.depth_mlp(m))
-        v = Vol(v.data, (v.scale * gate).contiguous(), (v.shift * gate).contiguous(), SS_ACT_RELU)
+        x = pair_cl if pair_cl is not None else self.pair_channels_last(feat_left, feat_right)      # [2B,1,H,W,Cin]
+        # SE gate > 0, so relu(gn(y)) * g == relu(gn(y) * g): fold it into the pending affine; it depends on the calibration
+        # and the parameters only, so it is cached per (calibration, checkpoint)
+        gate = ops.cached_const("stereo_gate", [mlp_left, mlp_right] + list(net.depth_mlp.parameters()) + list(net.depth_se.parameters()),
+                                lambda: net.depth_se.gate(net.depth_mlp(torch.cat([mlp_left, mlp_right], 0).reshape(-1, mlp_left.shape[-1]))).contiguous())
+        y, st = ops.conv(Vol(x), net.reduce_conv[0], want_stats=True)
+        v = ops.gn_pending_gated(y, st, net.reduce_conv[1], SS_ACT_RELU, gate)
         fea, _ = ops.conv(v, net.depth_conv[0])
         return fea
+
+    @staticmethod
+    def pair_channels_last(feat_left, feat_right) -> torch.Tensor:
+        """[B,Cin,H,W] x 2 -> channels-last [2B,1,H,W,Cin] (left then right) without the intermediate torch.cat copy."""
+        B, Cin, H, W = feat_left.shape
+        pair = torch.empty((2 * B, 1, H, W, Cin), dtype=torch.float32, device=feat_left.device)
+        ops.to_channels_last(feat_left, out=pair[:B])
+        ops.to_channels_last(feat_right, out=pair[B:])
+        return pair
 
     def cost_aggregation(self, volume: torch.Tensor) -> torch.Tensor:
         """ViewTransformerLSSVoxel.py:214-222 on a channels-last cost volume -> stereo depth
@@ -580,7 +588,7 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         if N != 1:
             raise NotImplementedError("the stereo path is defined for one camera per side (N=1)")
         # one channels-last copy of the feature pair serves the stereo branch (both maps) and depth_net (left)
-        pair_cl = ops.to_channels_last(torch.cat([feat_left, feat_right], 0)).unsqueeze(1)      # [2B,1,H,W,Cin]
+        pair_cl = self.pair_channels_last(feat_left, feat_right)                                # [2B,1,H,W,Cin]
         with ops.math_scope("stereo"):
             stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
 
