@@ -22,7 +22,8 @@ constexpr int HL_TH = 32, HL_TW = 8;
 constexpr int HL_HH = HL_TH + 2, HL_HW = HL_TW + 2;
 constexpr int HL_PLANE_ROWS = HL_HH * HL_HW;          // 340
 constexpr int HL_PLANE_BYTES = 43 * 1024;             // 340*128 = 43520 -> padded to a multiple of 1024
-constexpr int HL_NPL = 2;                             // plane ring (a plane lasts 9 taps x 8 MMAs: one slot of prefetch suffices)
+// plane ring: 2 slots (a plane lasts 9 taps x 8 MMAs: one slot of prefetch suffices); 3 in the fp16 single-pass mode, whose planes
+// are consumed twice as fast
 constexpr int HL_WORKERS = 256;
 constexpr int HL_THREADS = HL_WORKERS + 96;           // + A producer, MMA, B producer warps
 
@@ -103,22 +104,32 @@ __device__ __forceinline__ uint64_t h_desc(uint32_t saddr, uint32_t sbo_bytes) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-template <int BN>
+// MODE 0: TF32.  MODE 1: fp16 hi/lo split, six MMAs per chunk (SS_MATH_F16X3).  MODE 2: fp16 single pass (SS_MATH_F16): only the
+// hi halves are multiplied, so the weight tiles are the FIRST 64 bytes of every 128-byte row (TMA box of 16 floats, SWIZZLE_64B
+// in shared memory): half the L2->SM bytes and twice as many tiles in flight for the same shared memory, and a third plane slot.
+template <int BN, int MODE>
 struct HaloCfg {
+    static constexpr bool SINGLE = MODE == 2;
+    static constexpr int NPL = SINGLE ? 3 : 2;
     // weight-tile ring depth: a tile is consumed in 8 MMAs (~64 BN/128 x 8 cycles), far less than the TMA
     // round trip, so the ring has to hold several microseconds of tiles
-    static constexpr int SB = BN >= 256 ? 4 : BN >= 192 ? 5 : BN >= 160 ? 6 : BN >= 128 ? 8 : 12;
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int SB = SINGLE ? (BN >= 256 ? 5 : BN >= 192 ? 7 : BN >= 160 ? 8 : BN >= 128 ? 10 : 16)
+                                     : (BN >= 256 ? 4 : BN >= 192 ? 5 : BN >= 160 ? 6 : BN >= 128 ? 8 : 12);
+    static constexpr int B_BYTES = SINGLE ? BN * 64 : BN * 128;
+    static constexpr uint32_t B_HI = SINGLE ? ((512u >> 4) | (1u << 14) | (4u << 29))       // K-major SWIZZLE_64B, 8-row groups of 512 B
+                                            : ((1024u >> 4) | (1u << 14) | (2u << 29));
     static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
 
 // F16 = the single-launch fp16-split compensated variant (SS_MATH_F16X3, see common.cuh:split_f16x4): the workers rewrite
 // every landed fp32 plane row in place as [hi | lo] fp16 halves and each (chunk, tap) issues six kind::f16 MMAs.
-template <int BN, bool F16>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
-    using Cfg = HaloCfg<BN>;
+    using Cfg = HaloCfg<BN, MODE>;
+    constexpr bool F16 = MODE != 0;
     constexpr int SB = Cfg::SB;
+    constexpr int HL_NPL = Cfg::NPL;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment as an OFFSET from the extern __shared__ array: pointers derived this way keep the shared state space
     // (ld/st.shared); rounding a uintptr_t instead turns every access through them into a generic load / store
@@ -206,7 +217,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
     } else if (warp == 9) {
         // ======================= MMA ISSUER (warp-uniform; see common.cuh) ==========================
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t A_HI = umma_desc_hi(HL_HW * 128), B_HI = umma_desc_hi(1024);
+        constexpr uint32_t A_HI = umma_desc_hi(HL_HW * 128), B_HI = Cfg::B_HI;
         const uint32_t rdy0 = fixup ? pa_ready0 : pa_full0;
         int Lb = 0;
         for (int Lp = 0; Lp < kchunks * KD; ++Lp) {
@@ -225,9 +236,8 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
                     if constexpr (F16) {
                         constexpr uint32_t idesc16 = make_idesc_f16(128, BN);
 #pragma unroll
-                        for (int i = 0; i < 6; ++i)
-                            if (i < p.f16_n)
-                                umma_ss_f16<A_HI, B_HI>(tmem_base + (uint32_t)(mt * BN), a_lo + ao + kF16A[i], b_lo + kF16B[i], idesc16, (Lp | ce | i) ? 1u : 0u);
+                        for (int i = 0; i < (MODE == 2 ? 2 : 6); ++i)
+                            umma_ss_f16<A_HI, B_HI>(tmem_base + (uint32_t)(mt * BN), a_lo + ao + kF16A[i], b_lo + kF16B[i], idesc16, (Lp | ce | i) ? 1u : 0u);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -273,7 +283,8 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
                         __syncwarp();
                         if (act) {
                             *reinterpret_cast<uint2*>(row + ((((chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = hi;
-                            *reinterpret_cast<uint2*>(row + (((4 + (chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = lo;
+                            if constexpr (MODE != 2)
+                                *reinterpret_cast<uint2*>(row + (((4 + (chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = lo;
                         }
                         __syncwarp();
                     }
@@ -415,27 +426,29 @@ typedef CUresult (*HEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int BN, bool F16>
+template <int BN, int MODE>
 static int launch_halo(const HaloParams& p, const CUtensorMap& tmA, const float* wk, HEncodeTiledFn encode, cudaStream_t st) {
-    using Cfg = HaloCfg<BN>;
+    using Cfg = HaloCfg<BN, MODE>;
+    constexpr int HL_NPL = Cfg::NPL;
     alignas(64) CUtensorMap tmB;
     cuuint64_t gdim[2] = {(cuuint64_t)p.Cin, (cuuint64_t)9 * p.KD * p.CoutP};
     cuuint64_t gstr[1] = {(cuuint64_t)p.Cin * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)BN};
+    cuuint32_t box[2] = {Cfg::SINGLE ? 16u : 32u, (cuuint32_t)BN};       // single pass: the hi halves = first 64 bytes of every chunk row
     cuuint32_t estr[2] = {1, 1};
     if (encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wk), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+               Cfg::SINGLE ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return set_arg_error("conv_halo: tensor map B");
     const size_t smem = 1024 + (size_t)HL_NPL * HL_PLANE_BYTES + (size_t)Cfg::SB * Cfg::B_BYTES + 2 * BN * sizeof(double) +
                         (3 * HL_NPL + 2 * Cfg::SB + 1) * sizeof(uint64_t) + 16 + 32 + 2 * (size_t)p.Cin * sizeof(float);
     static thread_local size_t configured = 0;
     if (smem > configured) {
-        SS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid((unsigned)((long long)p.B * p.D * p.nTH * p.nTW), (unsigned)((p.CoutP + BN - 1) / BN), 1);
-    conv_halo_kernel<BN, F16><<<grid, HL_THREADS, smem, st>>>(p, tmA, tmB);
-    return check_launch(F16 ? "conv_halo_f16x3_kernel" : "conv_halo_kernel");
+    conv_halo_kernel<BN, MODE><<<grid, HL_THREADS, smem, st>>>(p, tmA, tmB);
+    return check_launch(MODE == 2 ? "conv_halo_f16_kernel" : MODE == 1 ? "conv_halo_f16x3_kernel" : "conv_halo_kernel");
 }
 
 // returns 1 if the layer was handled here
@@ -495,7 +508,8 @@ int try_conv_halo(const ss_conv3d_desc* d, const float* x, const float* in_scale
         if (cp % 160 == 0 && cost(160) < bc) { best = 160; bc = cost(160); }
     }
 #define SS_HALO_LAUNCH(BN_)                                                                        \
-    *rc = ps.f16 ? launch_halo<BN_, true>(p, tmA, w_kmajor, encode, st) : launch_halo<BN_, false>(p, tmA, w_kmajor, encode, st)
+    *rc = !ps.f16 ? launch_halo<BN_, 0>(p, tmA, w_kmajor, encode, st)                              \
+                  : (ps.f16_n == 2 ? launch_halo<BN_, 2>(p, tmA, w_kmajor, encode, st) : launch_halo<BN_, 1>(p, tmA, w_kmajor, encode, st))
     if (best == 64) SS_HALO_LAUNCH(64);
     else if (best == 128) SS_HALO_LAUNCH(128);
     else if (best == 160) SS_HALO_LAUNCH(160);

@@ -69,12 +69,11 @@ def default_math() -> int:
 # ``math_scope(group)`` around their stage.
 MATH_POLICIES = {
     "tf32": {},                                                                          # every stage plain TF32
-    # the parity-green product mode (CA3D sits on a residual branch: leaving it in TF32 moves the logits error 6.8e-4 -> 7.4e-4)
-    "mixed": {"depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_TF32},
-    # "mixed" / "tf32" with the uncompensated halo / box layers on fp16 operands (SS_MATH_F16: TF32's 11-bit significand, hence
-    # TF32's error -- measured -- at half the MMA count).  Measured NO faster (9.70 vs 9.83 ms): the fp32 planes still stream
-    # through a 2-slot ring and half of every weight row (the lo halves) is loaded unused, so the layers turn from tensor-bound
-    # into L2->SM bound; a real gain needs fp16 storage (64 channels per 128-byte row).  Kept for the tests and that follow-up.
+    # the parity-green product mode (CA3D sits on a residual branch: leaving it in TF32 moves the logits error 6.8e-4 -> 7.4e-4);
+    # the voxel stack's halo-resident layers (encoder blocks, head) multiply fp16 operands: TF32's significand, half the MMAs
+    "mixed": {"depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_TF32, "voxel": SS_MATH_F16},
+    "mixed_tf32voxel": {"depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_TF32},
+    # every uncompensated halo-resident layer on fp16 operands (stereo branch included)
     "mixed16": {"stereo": SS_MATH_F16, "depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_F16, "voxel": SS_MATH_F16},
     "f16": {g: SS_MATH_F16 for g in ("stereo", "depthnet", "mie", "voxel")},
     "tf32x3": {g: SS_MATH_TF32X3 for g in ("stereo", "depthnet", "mie", "voxel")},
@@ -389,6 +388,15 @@ def _halo_or_march_layer(pc: "PackedConv", Din: int, Hin: int, Win: int, Cin: in
     return Hin * Win / (256.0 * min(tiles(Hin, Win), tiles(Win, Hin))) >= 0.7
 
 
+def _halo_layer(pc: "PackedConv", Din: int, Hin: int, Win: int, Cin: int) -> bool:
+    """Does this layer run on the halo-resident kernel (conv3d_halo.cu:try_conv_halo)?  The fp16 single pass (SS_MATH_F16) is
+    only a gain there (weight tiles of half the size in a deeper ring, a third plane slot): every other kernel keeps TF32,
+    which has the same significand."""
+    if Cin == 32 and pc.CoutP == 32:
+        return False
+    return pc.CoutP >= 64 and _halo_or_march_layer(pc, Din, Hin, Win, Cin)
+
+
 _MATERIALIZE_BYTES = 16 << 20
 
 
@@ -439,8 +447,8 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
         d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pad_eff, *pc.d,
                           1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP, sd0, sd1)
         d.acc_scale = 1.0
-    if mm == SS_MATH_F16 and not (tc and lib.ss_conv3d_tc_f16x3_supported(C.byref(d)) == 1):
-        mm = SS_MATH_TF32            # kernels without an fp16 operand path: TF32 has the same 11-bit significand
+    if mm == SS_MATH_F16 and not (tc and pad is None and _halo_layer(pc, Din, Hin, Win, Cin)):
+        mm = SS_MATH_TF32            # only the halo-resident kernel gains from fp16 operands; TF32 has the same 11-bit significand
         d.math = mm
     if tc and ((mm == SS_MATH_TF32X3 and _USE_F16X3 and lib.ss_conv3d_tc_f16x3_supported(C.byref(d)) == 1) or mm == SS_MATH_F16):
         # the halo-resident / box kernels take fp16 operands in ONE launch: the compensated hi/lo split (1.5x the TF32 tensor

@@ -80,8 +80,9 @@ class BEVDepthOccupancy(nn.Module):
 
     # ---- the volumetric path ---------------------------------------------------------------
     def bev_encoder_vol(self, bev: torch.Tensor) -> Vol:
-        with ops.math_scope("voxel"):
+        with ops.math_scope("voxel.encoder"):
             levels = self.img_bev_encoder_backbone.forward_vol(Vol(bev))
+        with ops.math_scope("voxel.neck"):
             neck = self.img_bev_encoder_neck.forward_vol(levels)
         st = self.img_view_transformer.stage_outputs
         if st is not None:          # per-stage capture for the parity tests (logical NCDHW views, neck materialised)
@@ -103,7 +104,7 @@ class BEVDepthOccupancy(nn.Module):
         geo_r = [right[k] for k in keys] + [mr]
         bev, depth = vt([x_left] + geo_l + [x_right] + geo_r + [calib, None, None])
         neck = self.bev_encoder_vol(bev.permute(0, 2, 3, 4, 1))
-        with ops.math_scope("voxel"):
+        with ops.math_scope("voxel.head"):
             logits = self.pts_bbox_head.forward_voxel_vol([neck])[0]        # [B,X,Y,Z,classes]
         labels = None
         if occ_size is not None:
@@ -130,7 +131,7 @@ class BEVDepthOccupancy(nn.Module):
     def simple_test(self, img_metas, img=None, rescale=False, points_occ=None, gt_occ=None, points_uv=None):
         """bevdepth_occupancy.py:275-297."""
         voxel_feats, depth, img_feats = self.extract_img_feat(img, img_metas)
-        with ops.math_scope("voxel"):
+        with ops.math_scope("voxel.head"):
             logits = self.pts_bbox_head.forward_voxel_vol(voxel_feats)[0]
         up, _ = ops.trilinear(logits, tuple(gt_occ.shape[1:]))
         return {"output_voxels": up.permute(0, 4, 1, 2, 3), "output_points": None, "evaluation_semantic": 0,
