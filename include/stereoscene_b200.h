@@ -159,10 +159,11 @@ int ss_gn_finalize_gated(const double* stats, const float* gamma, const float* b
 /* ASPP image-pooling branch (ViewTransformerLSSBEVDepth.py:373-379, 394-406) folded into the pending shift of the fusing conv's
  * BatchNorm: shift_out[b][j] = bn_shift[b][j] + bn_scale[b][j] * (Wp relu(GroupNorm(W1 mean_x)))[j], where mean_x comes from the
  * per-channel sums of the ASPP input (stats: double[B][C][2] as written by ss_channel_sums_fwd, count voxels each).
- * w1: float[mid][C] (the branch's 1x1 conv), w_pool: float[mid][mid] (conv1's columns that multiply the pooled branch). */
+ * w1: float[mid][C] (the branch's 1x1 conv), w_pool: float[mid][mid] (conv1's columns that multiply the pooled branch);
+ * t_ws: workspace float[B*mid]. */
 int ss_aspp_pool_shift(const double* stats, double count, const float* w1, const float* gamma, const float* beta, int groups,
                        float eps, const float* w_pool, const float* bn_scale, const float* bn_shift, float* shift_out,
-                       int B, int C, int mid, void* stream);
+                       float* t_ws, int B, int C, int mid, void* stream);
 
 /* CA3D squeeze-excite folded into the pending affine (attention.py:98-107, 113-118):
  * pool[b,c] = scale*mean_raw + shift (mean of the GroupNorm output), s = GELU(W2*GELU(W1*pool+b1)+b2),

@@ -47,7 +47,7 @@ SIGNATURES = {
     "ss_conv3d_tc_join_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvJoin), _vp, _vp]),
     "ss_gn_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _f, _vp, _vp, _i, _vp]),
     "ss_gn_finalize_gated": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "ss_aspp_pool_shift": (_i, [_vp, _d, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ss_aspp_pool_shift": (_i, [_vp, _d, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ss_ca3d_gate": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ss_affine_join_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _i, _vp, _vp]),
     "ss_channel_sums_fwd": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _i, _vp, _vp]),

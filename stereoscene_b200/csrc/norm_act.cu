@@ -224,50 +224,84 @@ __global__ void gn_finalize_gated_kernel(const double* __restrict__ stats, const
 // 373-379, 394-406): the branch is constant over the map, so its share of conv1 is a per-(batch, channel) vector.
 //   pooled[c] = sum_x[b][c] / count;  t = W1 pooled;  g = relu(GroupNorm_groups(t));  u = Wp g;
 //   shift_out[b][j] = bn_shift[b][j] + bn_scale[b][j] * u[j]
-// One CTA per sample; W1: [mid][C], Wp: [mid][mid] (conv1's columns of the pooled branch), row-major.
-__global__ void __launch_bounds__(1024)
-aspp_pool_shift_kernel(const double* __restrict__ stats, double count, const float* __restrict__ w1, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, int groups, float eps, const float* __restrict__ wp,
-                       const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ shift_out,
-                       int C, int mid) {
+// Two launches of (B x mid/32) CTAs, 8 warps each, a warp computes 4 outputs at a time with float4 loads (the two 640 x 640
+// matrix-vector products are bound by streaming 3.3 MB of weights: one CTA per sample took 0.11 ms, 20 per sample take ~5 us).
+constexpr int AP_ROWS = 32;      // outputs per CTA
+
+__device__ __forceinline__ void ap_matvec_rows(const float* __restrict__ w, const float* __restrict__ x_s, int K, int row0, int nrows,
+                                               float* out4 /* [4] per warp-iteration */, int warp, int lane, float* dst_s) {
+    // rows row0 + warp*4 .. +3 of w (row-major [.][K]) times x_s[K]
+    for (int r = 0; r < 4; ++r) {
+        const int o = row0 + warp * 4 + r;
+        float a = 0.f;
+        if (warp * 4 + r < nrows) {
+            const float* wr = w + (size_t)o * K;
+            if ((K & 3) == 0) {
+                for (int c = lane * 4; c < K; c += 128) {
+                    const float4 wv = ldg_f4(wr + c);
+                    a = fmaf(wv.x, x_s[c], a); a = fmaf(wv.y, x_s[c + 1], a); a = fmaf(wv.z, x_s[c + 2], a); a = fmaf(wv.w, x_s[c + 3], a);
+                }
+            } else {
+                for (int c = lane; c < K; c += 32) a = fmaf(__ldg(wr + c), x_s[c], a);
+            }
+        }
+        out4[r] = warp_sum(a);
+    }
+    if (lane == 0)
+        for (int r = 0; r < 4; ++r)
+            if (warp * 4 + r < nrows) dst_s[warp * 4 + r] = out4[r];
+}
+
+__global__ void __launch_bounds__(256)
+aspp_pool_t_kernel(const double* __restrict__ stats, double count, const float* __restrict__ w1, float* __restrict__ t, int C, int mid) {
     extern __shared__ float sm[];
     float* pooled = sm;                 // [C]
-    float* t = sm + C;                  // [mid]
-    float* red = t + mid;               // [2 * groups]
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    float* res = sm + C;                // [AP_ROWS]
+    const int b = blockIdx.y, row0 = blockIdx.x * AP_ROWS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int c = tid; c < C; c += blockDim.x) pooled[c] = (float)(stats[((size_t)b * C + c) * 2] / count);
     __syncthreads();
-    for (int o = warp; o < mid; o += nwarp) {
-        float a = 0.f;
-        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + (size_t)o * C + c), pooled[c], a);
-        a = warp_sum(a);
-        if (lane == 0) t[o] = a;
-    }
+    float o4[4];
+    ap_matvec_rows(w1, pooled, C, row0, min(AP_ROWS, mid - row0), o4, warp, lane, res);
+    __syncthreads();
+    if (tid < AP_ROWS && row0 + tid < mid) t[(size_t)b * mid + row0 + tid] = res[tid];
+}
+
+__global__ void __launch_bounds__(256)
+aspp_pool_shift_kernel(const float* __restrict__ t, const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                       const float* __restrict__ wp, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                       float* __restrict__ shift_out, int mid) {
+    extern __shared__ float sm[];
+    float* g = sm;                      // [mid]   relu(GroupNorm(t))
+    float* red = sm + mid;              // [2 * groups]
+    float* res = red + 2 * groups;      // [AP_ROWS]
+    const int b = blockIdx.y, row0 = blockIdx.x * AP_ROWS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int o = tid; o < mid; o += blockDim.x) g[o] = t[(size_t)b * mid + o];
     __syncthreads();
     const int cpg = mid / groups;
-    if (warp < groups) {                // one warp per group: mean and variance over its channels
+    for (int gi = warp; gi < groups; gi += blockDim.x >> 5) {      // one warp per group: mean and variance over its channels
         float s = 0.f, q = 0.f;
-        for (int k = lane; k < cpg; k += 32) { const float v = t[warp * cpg + k]; s += v; q = fmaf(v, v, q); }
+        for (int k = lane; k < cpg; k += 32) { const float v = g[gi * cpg + k]; s += v; q = fmaf(v, v, q); }
         s = warp_sum(s); q = warp_sum(q);
         if (lane == 0) {
             const float mean = s / cpg;
             float var = q / cpg - mean * mean;
             if (var < 0.f) var = 0.f;
-            red[2 * warp] = mean;
-            red[2 * warp + 1] = rsqrtf(var + eps);
+            red[2 * gi] = mean;
+            red[2 * gi + 1] = rsqrtf(var + eps);
         }
     }
     __syncthreads();
     for (int o = tid; o < mid; o += blockDim.x) {
-        const int g = o / cpg;
-        t[o] = fmaxf((t[o] - red[2 * g]) * red[2 * g + 1] * __ldg(gamma + o) + __ldg(beta + o), 0.f);
+        const int gi = o / cpg;
+        g[o] = fmaxf((g[o] - red[2 * gi]) * red[2 * gi + 1] * __ldg(gamma + o) + __ldg(beta + o), 0.f);
     }
     __syncthreads();
-    for (int j = warp; j < mid; j += nwarp) {
-        float a = 0.f;
-        for (int o = lane; o < mid; o += 32) a = fmaf(__ldg(wp + (size_t)j * mid + o), t[o], a);
-        a = warp_sum(a);
-        if (lane == 0) shift_out[(size_t)b * mid + j] = fmaf(__ldg(bn_scale + (size_t)b * mid + j), a, __ldg(bn_shift + (size_t)b * mid + j));
+    float o4[4];
+    ap_matvec_rows(wp, g, mid, row0, min(AP_ROWS, mid - row0), o4, warp, lane, res);
+    __syncthreads();
+    if (tid < AP_ROWS && row0 + tid < mid) {
+        const size_t j = (size_t)b * mid + row0 + tid;
+        shift_out[j] = fmaf(__ldg(bn_scale + j), res[tid], __ldg(bn_shift + j));
     }
 }
 
@@ -285,13 +319,18 @@ extern "C" int ss_gn_finalize_gated(const double* stats, const float* gamma, con
 
 extern "C" int ss_aspp_pool_shift(const double* stats, double count, const float* w1, const float* gamma, const float* beta, int groups,
                                   float eps, const float* w_pool, const float* bn_scale, const float* bn_shift, float* shift_out,
-                                  int B, int C, int mid, void* stream) {
-    SS_REQUIRE(stats && w1 && gamma && beta && w_pool && bn_scale && bn_shift && shift_out, "ss_aspp_pool_shift: null pointer");
+                                  float* t_ws, int B, int C, int mid, void* stream) {
+    SS_REQUIRE(stats && w1 && gamma && beta && w_pool && bn_scale && bn_shift && shift_out && t_ws, "ss_aspp_pool_shift: null pointer");
     SS_REQUIRE(B > 0 && C > 0 && mid > 0 && groups > 0 && groups <= 32 && mid % groups == 0 && count > 0, "ss_aspp_pool_shift: shape");
-    const size_t smem = ((size_t)C + mid + 2 * groups) * sizeof(float);
-    SS_REQUIRE(smem <= 48 * 1024, "ss_aspp_pool_shift: channel counts too large");
-    aspp_pool_shift_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(stats, count, w1, gamma, beta, groups, eps, w_pool, bn_scale, bn_shift,
-                                                                     shift_out, C, mid);
+    SS_REQUIRE(((size_t)C + AP_ROWS) * 4 <= 48 * 1024 && ((size_t)mid + 2 * groups + AP_ROWS) * 4 <= 48 * 1024,
+               "ss_aspp_pool_shift: channel counts too large");
+    dim3 grid((mid + AP_ROWS - 1) / AP_ROWS, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    aspp_pool_t_kernel<<<grid, 256, ((size_t)C + AP_ROWS) * sizeof(float), st>>>(stats, count, w1, t_ws, C, mid);
+    int rc = check_launch("aspp_pool_t_kernel");
+    if (rc != SS_OK) return rc;
+    aspp_pool_shift_kernel<<<grid, 256, ((size_t)mid + 2 * groups + AP_ROWS) * sizeof(float), st>>>(t_ws, gamma, beta, groups, eps, w_pool,
+                                                                                                  bn_scale, bn_shift, shift_out, mid);
     return check_launch("aspp_pool_shift_kernel");
 }
 

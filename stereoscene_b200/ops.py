@@ -586,10 +586,11 @@ def aspp_pool_shift(stats: torch.Tensor, count: int, w1: torch.Tensor, gn: torch
     lib = cabi.load()
     B, Cc = stats.shape[0], stats.shape[1]
     mid = w_pool.shape[0]
-    out = torch.empty((B, mid), dtype=torch.float32, device=stats.device)
+    out = torch.empty((2, B, mid), dtype=torch.float32, device=stats.device)
     rc = lib.ss_aspp_pool_shift(stats.data_ptr(), float(count), w1.data_ptr(), gn.weight.data_ptr(), gn.bias.data_ptr(), gn.num_groups,
-                                float(gn.eps), w_pool.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), out.data_ptr(), B, Cc, mid,
-                                _stream())
+                                float(gn.eps), w_pool.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), out[0].data_ptr(),
+                                out[1].data_ptr(), B, Cc, mid, _stream())
+    out = out[0]
     cabi.check(rc, "ss_aspp_pool_shift")
     return out
 
