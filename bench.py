@@ -36,7 +36,7 @@ import torch  # noqa: E402
 
 # roofline.traffic of the dominant kernel comes from the ncu --set full capture committed this round; tools/prof_kernels.sh
 # writes the two DRAM counters of that capture into profiles/r02_head_conv_traffic.json next to the raw page
-TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_head_conv_traffic.json")
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_head_conv_traffic.json")          # {"tf32": {...}, "f16": {...}}
 
 VOXELS = {"config1": 128 * 128 * 16, "config2": 256 * 256 * 32, "config0": 64 * 64 * 8, "tiny": 32 * 32 * 8,
           "config4": 512 * 512 * 64}
@@ -545,8 +545,10 @@ def run_ours(args):
     # slow everything timed after them
     time.sleep(1.0)
     pk["tf32_tflops_cublas"] = measure_tf32_peak(dev)
-    roof["peak"] = pk["tf32_tflops_cublas"]
-    roof["frac"] = roof["achieved"] / roof["peak"]
+    if roof["peak"] is None:                       # TF32 kernel: against the TF32 GEMM peak measured just now
+        roof["peak"] = pk["tf32_tflops_cublas"]
+        roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["tf32_gemm_tflops_measured_in_run"] = pk["tf32_tflops_cublas"]
 
     line = {
         "metric": "voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
@@ -599,11 +601,14 @@ def stage_breakdown(model, xl, xr, left, right, calib, occ, iters=7):
             ev[0].record()
             bev, _ = vt([xl] + [left[k] for k in keys] + [ml] + [xr] + [right[k] for k in keys] + [mr] + [calib, None, None])
             ev[1].record()
-            levels = model.img_bev_encoder_backbone.forward_vol(ops.Vol(bev.permute(0, 2, 3, 4, 1)))
+            with ops.math_scope("voxel.encoder"):
+                levels = model.img_bev_encoder_backbone.forward_vol(ops.Vol(bev.permute(0, 2, 3, 4, 1)))
             ev[2].record()
-            neck = model.img_bev_encoder_neck.forward_vol(levels)
+            with ops.math_scope("voxel.neck"):
+                neck = model.img_bev_encoder_neck.forward_vol(levels)
             ev[3].record()
-            logits = model.pts_bbox_head.forward_voxel_vol([neck])[0]
+            with ops.math_scope("voxel.head"):
+                logits = model.pts_bbox_head.forward_voxel_vol([neck])[0]
             ops.trilinear(logits, occ, want_labels=True)
             ev[4].record()
             torch.cuda.synchronize()
@@ -644,9 +649,14 @@ def dominant_kernel_roofline(model, mc, dev, pk):
     y = torch.empty((1, nx[0], nx[1], nx[2], head.out_channels), device=dev)
     vin = Vol(x, sc, sh, ops.SS_ACT_RELU)
 
+    with ops.math_scope("voxel.head"):
+        head_mode = ops.default_math()                    # the mode the active policy runs this layer in
+    if head_mode not in (ops.SS_MATH_TF32, ops.SS_MATH_F16):
+        head_mode = ops.SS_MATH_TF32
+
     def head_conv():
         ops.arena(dev).reset()
-        ops.conv(vin, head, out=y, want_stats=True, math_mode=ops.SS_MATH_TF32)
+        ops.conv(vin, head, out=y, want_stats=True, math_mode=head_mode)
     t = _time_launches(head_conv)
     V = nx[0] * nx[1] * nx[2]
     flops = 2.0 * V * 27 * head.in_channels * head.out_channels
@@ -654,18 +664,24 @@ def dominant_kernel_roofline(model, mc, dev, pk):
     traffic, traffic_src = None, "no ncu capture of this round found (profiles/r02_head_conv_traffic.json)"
     if os.path.exists(TRAFFIC_JSON):
         with open(TRAFFIC_JSON) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
-    tf32_peak = pk.get("tf32_tflops_cublas") or pk["tflops"] / 2
-    roof = {"bound": "tensor", "kernel": "conv_halo_kernel<192> (OccHead conv 384->192 k3 on the 128x128x16 grid; "
-                                         "TMA halo planes + tcgen05.mma kind::tf32, TMEM accumulators)",
-            "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+            tj = json.load(f).get("f16" if head_mode == ops.SS_MATH_F16 else "tf32")
+        if tj:
+            traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+    f16 = head_mode == ops.SS_MATH_F16
+    roof = {"bound": "tensor",
+            "kernel": ("conv_halo_kernel<192, 2> (OccHead conv 384->192 k3 on the 128x128x16 grid; TMA halo planes, fp32 planes rewritten "
+                       "in place as fp16 by the fix-up warps, tcgen05.mma kind::f16 with SWIZZLE_64B weight tiles, TMEM accumulators)") if f16 else
+                      ("conv_halo_kernel<192, 0> (OccHead conv 384->192 k3 on the 128x128x16 grid; TMA halo planes + tcgen05.mma kind::tf32, "
+                       "TMEM accumulators)"),
+            "math": "fp16 operands (11-bit significand = TF32's), fp32 accumulate" if f16 else "tf32",
+            "achieved": ach, "peak": pk["tflops"] if f16 else None, "unit": "TFLOP/s", "frac": ach / pk["tflops"] if f16 else None,
             "peak_bf16": pk["tflops"], "frac_of_bf16_peak": ach / pk["tflops"],
             "traffic": traffic, "traffic_source": traffic_src,
             "launch_ms": t * 1e3, "algorithmic_flops": flops,
             "algorithmic_bytes": (x.numel() + y.numel()) * 4.0,
-            "peak_source": "peak = cuBLAS TF32 GEMM (8192^3) measured in this run on this GPU: the kernel multiplies in TF32; "
-                           f"peak_bf16 = MEASURED_PEAKS.json bf16 burst ({pk['source']}) for reference"}
+            "peak_source": (f"peak = MEASURED_PEAKS.json dense bf16 burst ({pk['source']}): kind::f16 and kind::bf16 share the 16-bit tensor rate"
+                            if f16 else "peak = cuBLAS TF32 GEMM (8192^3) measured at the end of this run on this GPU (the kernel multiplies in "
+                                        f"TF32); peak_bf16 = MEASURED_PEAKS.json bf16 burst ({pk['source']}) beside it")}
     kernels.append({"name": "occ_head conv3d 384->192 k3", "bound": "tensor", "ms": t * 1e3, "tflops": ach,
                     "frac": ach / pk["tflops"]})
     # (2) full-res 32->32 k3 frustum conv (HBM-bound in the algorithmic accounting: in + out once)

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--what", default="step", choices=["step", "head_conv", "frustum_conv", "enc_conv", "bri", "gwc", "splat", "redir1x1", "depth_conv", "aspp_dil", "mie_redir1", "frustum_conv_pending", "stage2_conv", "tpose32", "hg_conv1", "neck_k4", "hg_redir2", "stage2_conv_plain", "hg_conv4", "hg_conv4_plain", "hg_conv3", "hg_conv3_plain", "hourglass", "pw_proj"])
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--math", default="mixed", help="math policy (ops.MATH_POLICIES); single-kernel cases run plain TF32 unless --kernel-math says otherwise")
-    ap.add_argument("--kernel-math", default="tf32", choices=["tf32", "tf32x3", "3xtf32"])
+    ap.add_argument("--kernel-math", default="tf32", choices=["tf32", "f16", "tf32x3", "3xtf32"])
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--time-one", action="store_true")
     ap.add_argument("--time", action="store_true", help="time every kernel case with CUDA events instead of profiling one")
