@@ -78,6 +78,14 @@ __device__ __forceinline__ void split_f16x4(float4 v, uint2& hi, uint2& lo) {
     hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
     lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
+// two floats -> packed fp16 pair (lo half = a), round-to-nearest, saturating to +-65504 (one F2FP instruction)
+__device__ __forceinline__ uint32_t f2h2_sat(float a, float b) {
+    uint32_t r;
+    asm volatile("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ uint2 hi_f16x4(const float4& v) { return make_uint2(f2h2_sat(v.x, v.y), f2h2_sat(v.z, v.w)); }
+
 // cute::UMMA::InstrDescriptor for kind::f16 with fp16 operands: c_format F32 (1) at [4,6), a/b format F16 (0), K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -104,6 +104,9 @@ __device__ __forceinline__ uint64_t h_desc(uint32_t saddr, uint32_t sbo_bytes) {
     return ((uint64_t)hi << 32) | lo;
 }
 
+// (Measured and dropped in round 2: a persistent variant of MODE 2 with double-buffered TMEM accumulators and dedicated epilogue
+// warps -- 0.273 vs 0.274 ms on the 128 -> 128 encoder layers: after the fix-up loops were trimmed the kernel streams 1.4 GB of TMA
+// loads in 0.24 ms, i.e. it is bound by the L2 -> SM stream of weight tiles every CTA re-fetches, not by prologue / epilogue.)
 // MODE 0: TF32.  MODE 1: fp16 hi/lo split, six MMAs per chunk (SS_MATH_F16X3).  MODE 2: fp16 single pass (SS_MATH_F16): only the
 // hi halves are multiplied, so the weight tiles are the FIRST 64 bytes of every 128-byte row (TMA box of 16 floats, SWIZZLE_64B
 // in shared memory): half the L2->SM bytes and twice as many tiles in flight for the same shared memory, and a third plane slot.
@@ -120,6 +123,73 @@ struct HaloCfg {
                                             : ((1024u >> 4) | (1u << 14) | (2u << 29));
     static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
+
+// ---- fix-up of a landed plane by the 256 worker threads ---------------------------------------------------------------------
+// Item `it` of a thread is row (tid >> 3) + 32 it, 16-byte chunk tid & 7 (4 channels); row & 7 == (tid >> 3) & 7 for every item, so
+// the swizzled read / write offsets inside the row are per-thread constants and only the validity of the rows depends on the tile.
+constexpr int HL_FIX_ITERS = (HL_PLANE_ROWS * 8 + HL_WORKERS - 1) / HL_WORKERS;      // 11
+struct FixMap { uint32_t rd, wr_hi, wr_lo, vmask; };
+__device__ __forceinline__ FixMap make_fixmap(int tid, int h0, int w0, int H, int W) {
+    FixMap m;
+    const int r0 = tid >> 3, chunk = tid & 7, rsw = r0 & 7;
+    m.rd = (uint32_t)(r0 * 128 + ((chunk ^ rsw) << 4));
+    m.wr_hi = (uint32_t)(r0 * 128 + (((chunk >> 1) ^ rsw) << 4) + ((chunk & 1) << 3));
+    m.wr_lo = (uint32_t)(r0 * 128 + (((4 + (chunk >> 1)) ^ rsw) << 4) + ((chunk & 1) << 3));
+    m.vmask = 0;
+#pragma unroll
+    for (int it = 0; it < HL_FIX_ITERS; ++it) {
+        const int r = r0 + 32 * it;
+        const int hh = h0 - 1 + r / HL_HW, ww = w0 - 1 + r % HL_HW;
+        if (r < HL_PLANE_ROWS && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W) m.vmask |= 1u << it;
+    }
+    return m;
+}
+__device__ __forceinline__ float4 fix_value(float4 v, const float4& sc, const float4& sh, bool has_aff, bool in_relu) {
+    if (has_aff) { v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w); }
+    if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+}
+// MODE 0: TF32 (hi, or the lo part when LO) written back in place.  MODE 1 / 2: the row becomes [hi(32 fp16) | lo(32 fp16)] (MODE 2: hi
+// only); the 8 lanes of a row read their chunks of a batch of rows, sync, then overwrite -- two batches, two warp syncs per plane.
+template <int MODE, bool LO>
+__device__ __forceinline__ void fix_plane(unsigned char* pl, const FixMap& m, const float4& sc, const float4& sh, bool has_aff, bool in_relu) {
+    if constexpr (MODE == 0) {
+#pragma unroll
+        for (int it = 0; it < HL_FIX_ITERS; ++it)
+            if ((m.vmask >> it) & 1u) {
+                float4* ptr = reinterpret_cast<float4*>(pl + m.rd + it * 4096);
+                const float4 v = fix_value(*ptr, sc, sh, has_aff, in_relu);
+                uint4 o;
+                o.x = f2tf32_part<LO>(v.x); o.y = f2tf32_part<LO>(v.y); o.z = f2tf32_part<LO>(v.z); o.w = f2tf32_part<LO>(v.w);
+                *reinterpret_cast<uint4*>(ptr) = o;
+            }
+    } else {
+        constexpr int HALF = (HL_FIX_ITERS + 1) / 2;
+#pragma unroll
+        for (int b0 = 0; b0 < HL_FIX_ITERS; b0 += HALF) {
+            uint2 hi[HALF], lo[HALF];
+#pragma unroll
+            for (int k = 0; k < HALF; ++k) {
+                const int it = b0 + k;
+                if (it < HL_FIX_ITERS && ((m.vmask >> it) & 1u)) {
+                    const float4 v = fix_value(*reinterpret_cast<const float4*>(pl + m.rd + it * 4096), sc, sh, has_aff, in_relu);
+                    if constexpr (MODE == 2) hi[k] = hi_f16x4(v);
+                    else split_f16x4(v, hi[k], lo[k]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < HALF; ++k) {
+                const int it = b0 + k;
+                if (it < HL_FIX_ITERS && ((m.vmask >> it) & 1u)) {
+                    *reinterpret_cast<uint2*>(pl + m.wr_hi + it * 4096) = hi[k];
+                    if constexpr (MODE != 2) *reinterpret_cast<uint2*>(pl + m.wr_lo + it * 4096) = lo[k];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
 
 // F16 = the single-launch fp16-split compensated variant (SS_MATH_F16X3, see common.cuh:split_f16x4): the workers rewrite
 // every landed fp32 plane row in place as [hi | lo] fp16 halves and each (chunk, tap) issues six kind::f16 MMAs.
@@ -252,66 +322,26 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         umma_commit_elect(accum_bar);
         __syncwarp();
     } else if (fixup) {
-        // ======================= WORKERS: pending affine / ReLU, once per landed plane, in place =====
+        // ======================= WORKERS: pending affine / ReLU / operand conversion, once per landed plane, in place =====
+        const FixMap fm = make_fixmap(tid, h0, w0, p.H, p.W);
+        const int chunk = tid & 7;
         for (int L = 0; L < kchunks * KD; ++L) {
             const int slot = L % HL_NPL;
             h_mbar_wait(pa_full0 + 8 * slot, (uint32_t)(L / HL_NPL) & 1u);
             const int dpl = d - KD / 2 + (L % KD), c0 = (L / KD) * 32;
-            if constexpr (F16) {
-                if ((unsigned)dpl < (unsigned)p.D) {
-                    unsigned char* pl = planes + slot * HL_PLANE_BYTES;
-                    // the 8 lanes that share a row read their fp32 chunks, then (after a warp sync) overwrite the row
-                    // with its fp16 halves: chunk j (channels 4j..4j+3) -> 8 bytes of hi at 8j, 8 bytes of lo at 64 + 8j
-                    constexpr int ITERS = (HL_PLANE_ROWS * 8 + HL_WORKERS - 1) / HL_WORKERS;
-                    for (int it = 0; it < ITERS; ++it) {
-                        const int idx = tid + it * HL_WORKERS;
-                        const int r = idx >> 3, chunk = idx & 7;
-                        const int hh = h0 - 1 + r / HL_HW, ww = w0 - 1 + r % HL_HW;
-                        const bool act = idx < HL_PLANE_ROWS * 8 && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
-                        unsigned char* row = pl + r * 128;
-                        uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
-                        if (act) {
-                            float4 v = *reinterpret_cast<const float4*>(row + ((chunk ^ (r & 7)) << 4));
-                            if (has_aff) {
-                                const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
-                                const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
-                                v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                            }
-                            if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                            split_f16x4(v, hi, lo);
-                        }
-                        __syncwarp();
-                        if (act) {
-                            *reinterpret_cast<uint2*>(row + ((((chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = hi;
-                            if constexpr (MODE != 2)
-                                *reinterpret_cast<uint2*>(row + (((4 + (chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = lo;
-                        }
-                        __syncwarp();
-                    }
-                }
-            } else if ((unsigned)dpl < (unsigned)p.D) {
+            if ((unsigned)dpl < (unsigned)p.D) {
                 unsigned char* pl = planes + slot * HL_PLANE_BYTES;
-                auto fix = [&](auto lo_tag) {
-                    constexpr bool LO = decltype(lo_tag)::value;
-                    for (int idx = tid; idx < HL_PLANE_ROWS * 8; idx += HL_WORKERS) {
-                        const int r = idx >> 3, chunk = idx & 7;
-                        const int hh = h0 - 1 + r / HL_HW, ww = w0 - 1 + r % HL_HW;
-                        if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
-                            float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
-                            float4 v = *ptr;
-                            if (has_aff) {
-                                const float4 sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
-                                const float4 sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
-                                v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                            }
-                            if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                            uint4 o;
-                            o.x = f2tf32_part<LO>(v.x); o.y = f2tf32_part<LO>(v.y); o.z = f2tf32_part<LO>(v.z); o.w = f2tf32_part<LO>(v.w);
-                            *reinterpret_cast<uint4*>(ptr) = o;
-                        }
-                    }
-                };
-                SS_UNSWITCH_LO(p.a_lo, fix);
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_aff) {
+                    sc = *reinterpret_cast<const float4*>(ssc + c0 + chunk * 4);
+                    sh = *reinterpret_cast<const float4*>(ssc + p.Cin + c0 + chunk * 4);
+                }
+                if constexpr (F16) {
+                    fix_plane<MODE, false>(pl, fm, sc, sh, has_aff, in_relu);
+                } else {
+                    if (p.a_lo) fix_plane<0, true>(pl, fm, sc, sh, has_aff, in_relu);
+                    else fix_plane<0, false>(pl, fm, sc, sh, has_aff, in_relu);
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             h_mbar_arrive(pa_ready0 + 8 * slot);

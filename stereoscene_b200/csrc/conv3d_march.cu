@@ -527,58 +527,72 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
                     sc = ldg_f4(p.in_scale + (size_t)c.b * 32 + chunk * 4);
                     sh = ldg_f4(p.in_shift + (size_t)c.b * 32 + chunk * 4);
                 }
+                // item `it` of this thread = row (ft >> 3) + 16 it, chunk ft & 7; row & 7 is the same for all its items, so the swizzled
+                // offsets inside a row are thread constants and the row validity (a bit mask) only depends on the tile column
+                constexpr int ITERS = (MR_PLANE_ROWS + 15) / 16;
+                const int r0 = ft >> 3, rsw = r0 & 7;
+                const uint32_t rd = (uint32_t)(r0 * 128 + ((chunk ^ rsw) << 4));
+                const uint32_t wr_hi = (uint32_t)(r0 * 128 + (((chunk >> 1) ^ rsw) << 4) + ((chunk & 1) << 3));
+                const uint32_t wr_lo = (uint32_t)(r0 * 128 + (((4 + (chunk >> 1)) ^ rsw) << 4) + ((chunk & 1) << 3));
+                uint32_t vmask = 0;
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    const int r = r0 + 16 * it;
+                    const int hh = c.th * MR_TH - PAD + r / MR_HW, ww = c.tw * MR_TW - PAD + r % MR_HW;
+                    if (r < MR_PLANE_ROWS && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) vmask |= 1u << it;
+                }
+                auto fixv = [&](float4 v) {
+                    if (has_aff) {
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    }
+                    if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    return v;
+                };
                 for (int s = 0; s < run + KS - 1; ++s, ++L) {
                     const int slot = (int)(L % MR_NP);
                     m_mbar_wait(p_full0 + 8 * slot, (uint32_t)(L / MR_NP) & 1u);
                     const int dpl = c.d - PAD + s;
-                    if constexpr (F16) {
-                        if ((unsigned)dpl < (unsigned)p.D) {
-                            unsigned char* pl = planes + slot * MR_PLANE_BYTES;
-                            constexpr int ITERS = (MR_PLANE_ROWS + 15) / 16;
-                            for (int it = 0; it < ITERS; ++it) {       // the 8 lanes of a row read, sync, then overwrite it with [hi | lo]
-                                const int r = (ft >> 3) + 16 * it;
-                                const int hh = c.th * MR_TH - PAD + r / MR_HW, ww = c.tw * MR_TW - PAD + r % MR_HW;
-                                const bool actv = r < MR_PLANE_ROWS && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
-                                unsigned char* row = pl + r * 128;
-                                uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
-                                if (actv) {
-                                    float4 v = *reinterpret_cast<const float4*>(row + ((chunk ^ (r & 7)) << 4));
-                                    if (has_aff) {
-                                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                                    }
-                                    if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                                    split_f16x4(v, hi, lo);
-                                }
-                                __syncwarp();
-                                if (actv) {
-                                    *reinterpret_cast<uint2*>(row + (((chunk >> 1) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = hi;
-                                    *reinterpret_cast<uint2*>(row + (((4 + (chunk >> 1)) ^ (r & 7)) << 4) + ((chunk & 1) << 3)) = lo;
-                                }
-                                __syncwarp();
-                            }
-                        }
-                    } else if ((unsigned)dpl < (unsigned)p.D) {    // planes outside the volume are all padding
+                    if ((unsigned)dpl < (unsigned)p.D) {           // planes outside the volume are all padding
                         unsigned char* pl = planes + slot * MR_PLANE_BYTES;
-                        auto fix = [&](auto lo_tag) {
-                            constexpr bool LO = decltype(lo_tag)::value;
-                            for (int r = ft >> 3; r < MR_PLANE_ROWS; r += 16) {
-                                const int hh = c.th * MR_TH - PAD + r / MR_HW, ww = c.tw * MR_TW - PAD + r % MR_HW;
-                                if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) {
-                                    float4* ptr = reinterpret_cast<float4*>(pl + r * 128 + ((chunk ^ (r & 7)) << 4));
-                                    float4 v = *ptr;
-                                    if (has_aff) {
-                                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        if constexpr (F16) {
+                            // the 8 lanes of a row read their chunks of a batch of rows, sync, then overwrite the rows with [hi | lo]
+                            constexpr int HALF = (ITERS + 1) / 2;
+#pragma unroll
+                            for (int b0 = 0; b0 < ITERS; b0 += HALF) {
+                                uint2 hi[HALF], lo[HALF];
+#pragma unroll
+                                for (int k = 0; k < HALF; ++k) {
+                                    const int it = b0 + k;
+                                    if (it < ITERS && ((vmask >> it) & 1u))
+                                        split_f16x4(fixv(*reinterpret_cast<const float4*>(pl + rd + it * 2048)), hi[k], lo[k]);
+                                }
+                                __syncwarp();
+#pragma unroll
+                                for (int k = 0; k < HALF; ++k) {
+                                    const int it = b0 + k;
+                                    if (it < ITERS && ((vmask >> it) & 1u)) {
+                                        *reinterpret_cast<uint2*>(pl + wr_hi + it * 2048) = hi[k];
+                                        *reinterpret_cast<uint2*>(pl + wr_lo + it * 2048) = lo[k];
                                     }
-                                    if (in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                                    uint4 o;
-                                    o.x = f2tf32_part<LO>(v.x); o.y = f2tf32_part<LO>(v.y); o.z = f2tf32_part<LO>(v.z); o.w = f2tf32_part<LO>(v.w);
-                                    *reinterpret_cast<uint4*>(ptr) = o;
                                 }
                             }
-                        };
-                        SS_UNSWITCH_LO(p.a_lo, fix);
+                            __syncwarp();
+                        } else {
+                            auto fix = [&](auto lo_tag) {
+                                constexpr bool LO = decltype(lo_tag)::value;
+#pragma unroll
+                                for (int it = 0; it < ITERS; ++it)
+                                    if ((vmask >> it) & 1u) {
+                                        float4* ptr = reinterpret_cast<float4*>(pl + rd + it * 2048);
+                                        const float4 v = fixv(*ptr);
+                                        uint4 o;
+                                        o.x = f2tf32_part<LO>(v.x); o.y = f2tf32_part<LO>(v.y); o.z = f2tf32_part<LO>(v.z); o.w = f2tf32_part<LO>(v.w);
+                                        *reinterpret_cast<uint4*>(ptr) = o;
+                                    }
+                            };
+                            SS_UNSWITCH_LO(p.a_lo, fix);
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     m_mbar_arrive(p_ready0 + 8 * slot);
