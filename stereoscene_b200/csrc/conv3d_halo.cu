@@ -106,7 +106,10 @@ __device__ __forceinline__ uint64_t h_desc(uint32_t saddr, uint32_t sbo_bytes) {
 
 // (Measured and dropped in round 2: a persistent variant of MODE 2 with double-buffered TMEM accumulators and dedicated epilogue
 // warps -- 0.273 vs 0.274 ms on the 128 -> 128 encoder layers: after the fix-up loops were trimmed the kernel streams 1.4 GB of TMA
-// loads in 0.24 ms, i.e. it is bound by the L2 -> SM stream of weight tiles every CTA re-fetches, not by prologue / epilogue.)
+// loads in 0.24 ms, i.e. it is bound by the L2 -> SM stream of weight tiles every CTA re-fetches, not by prologue / epilogue.  Also
+// dropped: a "depth pair" variant in which a CTA owns two output planes (4 M-tiles share every weight tile, 4 input planes instead of
+// 2 x 3 per chunk: -44 % L2 -> SM bytes) -- 0.30 vs 0.22 ms on the same layer: with two of three plane slots pinned by the current
+// step only one plane prefetches, and 512 double-size CTAs leave the last of 3.5 waves half empty.)
 // MODE 0: TF32.  MODE 1: fp16 hi/lo split, six MMAs per chunk (SS_MATH_F16X3).  MODE 2: fp16 single pass (SS_MATH_F16): only the
 // hi halves are multiplied, so the weight tiles are the FIRST 64 bytes of every 128-byte row (TMA box of 16 floats, SWIZZLE_64B
 // in shared memory): half the L2->SM bytes and twice as many tiles in flight for the same shared memory, and a third plane slot.
