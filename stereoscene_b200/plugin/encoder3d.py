@@ -91,8 +91,9 @@ class CustomResNet3D(nn.Module):
         v = ops.gn_pending(y, st, self.input_proj[1], SS_ACT_RELU)
         res = []
         for i, layer in enumerate(self.layers):
-            for blk in layer:
-                v = Vol(blk.run(v))
+            with ops.math_scope(f"voxel.stage{i}"):          # per-stage math policy entry (falls back to "voxel")
+                for blk in layer:
+                    v = Vol(blk.run(v))
             if i in self.out_indices:
                 res.append(v.data)
         return res

@@ -9,10 +9,12 @@ from stereoscene_b200 import ops, presets, synth
 
 M = {"tf32": ops.SS_MATH_TF32, "f16": ops.SS_MATH_F16, "x3": ops.SS_MATH_TF32X3}
 dev = torch.device("cuda", 0)
-model, mc = presets.build("config2")
-synth.randomize_weights_(model, 0)
+WL = os.environ.get("WORKLOAD", "config2")
+SEED = json.load(open(os.path.join(ROOT, "tests", "golden", f"golden_{WL}.json")))["seed"]
+model, mc = presets.build(WL)
+synth.randomize_weights_(model, SEED)
 model = model.to(dev).eval()
-xl, xr = synth.stereo_features(1, mc["input_size"], 8, seed=0, device=dev)
+xl, xr = synth.stereo_features(1, mc["input_size"], 8, seed=SEED, device=dev)
 left, right, calib = synth.kitti_calibration(1, mc["input_size"], device=dev)
 occ = mc["occ_size"]
 
@@ -42,7 +44,7 @@ for spec in specs:
         g.replay()
     b.record()
     torch.cuda.synchronize()
-    par = bench.golden_parity("config2", o, 0)
+    par = bench.golden_parity(WL, o, SEED)
     print(f"{name:28s} {a.elapsed_time(b) / 20:7.3f} ms   logits {par['logits']['max_rel']:.2e}/{par['logits']['rms_rel']:.2e}  "
           f"logits_up {par['logits_up']['max_rel']:.2e}/{par['logits_up']['rms_rel']:.2e}", flush=True)
     del g
