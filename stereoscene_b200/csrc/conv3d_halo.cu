@@ -109,7 +109,13 @@ __device__ __forceinline__ uint64_t h_desc(uint32_t saddr, uint32_t sbo_bytes) {
 // loads in 0.24 ms, i.e. it is bound by the L2 -> SM stream of weight tiles every CTA re-fetches, not by prologue / epilogue.  Also
 // dropped: a "depth pair" variant in which a CTA owns two output planes (4 M-tiles share every weight tile, 4 input planes instead of
 // 2 x 3 per chunk: -44 % L2 -> SM bytes) -- 0.30 vs 0.22 ms on the same layer: with two of three plane slots pinned by the current
-// step only one plane prefetches, and 512 double-size CTAs leave the last of 3.5 waves half empty.)
+// step only one plane prefetches, and 512 double-size CTAs leave the last of 3.5 waves half empty.  Also dropped: two-CTA clusters
+// in which each CTA fetches half of every weight tile and multicasts it into both rings (cp.async.bulk.tensor .multicast::cluster,
+// slot release through tcgen05.commit .multicast::cluster) -- correct, and no faster (head 0.725 vs 0.715 ms, encoder 0.29 vs 0.27):
+// the L2 -> SM stream is not the limit either.  What is: the shared-memory port.  An fp16 MMA of M = 128, N = 128, K = 16 reads
+// 4 KB of A and 4 KB of B in its 64 cycles = the port's 128 B/clk, and the TMA writes (115 KB per plane and chunk) and the fix-up
+// (64 KB) share that port: 467 KB per plane = 3650 clk against 2304 clk of MMA.  The next step is therefore cta_group::2 (M = 256
+// across an SM pair, each SM reading half of B) or fp16 storage (no fix-up pass, half the plane bytes), not more pipelining.)
 // MODE 0: TF32.  MODE 1: fp16 hi/lo split, six MMAs per chunk (SS_MATH_F16X3).  MODE 2: fp16 single pass (SS_MATH_F16): only the
 // hi halves are multiplied, so the weight tiles are the FIRST 64 bytes of every 128-byte row (TMA box of 16 floats, SWIZZLE_64B
 // in shared memory): half the L2->SM bytes and twice as many tiles in flight for the same shared memory, and a third plane slot.
