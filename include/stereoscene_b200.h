@@ -266,7 +266,8 @@ int ss_trilinear_fwd(const float* x, float* y, uint8_t* labels, int B, int C, in
  *                        in place (ssc_metric.py:147-148)
  *   counts[C*C + 0..2] += completion tp, fp, fn over voxels with target != ignore_label (and nonempty, nonsurface),
  *                        occupied = label > 0
- * Per-class tp = counts[j*C+j], fp = column sum - tp, fn = row sum - tp.  counts: int64[C*C + 3], the caller
+ *   counts[C*C + 3 + t] += voxels of target t whose prediction lies outside [0, C): misses of class t that are nobody's false positive
+ * Per-class tp = counts[j*C+j], fp = column sum - tp, fn = row sum - tp + counts[C*C+3+j].  counts: int64[C*C + 3 + C], the caller
  * zeroes it (or keeps accumulating across samples).  pred: uint8[n]; target: uint8[n] or int64[n]
  * (target_elem_bytes = 1 / 8); nonempty / nonsurface: uint8[n] or NULL.  C <= 32.
  * ------------------------------------------------------------------------------------------- */

@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(SSC_THREADS)
 ssc_confusion_kernel(const uint8_t* __restrict__ pred, const TT* __restrict__ target, const uint8_t* __restrict__ nonempty,
                      const uint8_t* __restrict__ nonsurface, long long n, int C, int ignore,
                      unsigned long long* __restrict__ counts) {
-    __shared__ unsigned int hist[SSC_MAX_C * SSC_MAX_C + 3];
-    for (int i = threadIdx.x; i < C * C + 3; i += SSC_THREADS) hist[i] = 0u;
+    __shared__ unsigned int hist[SSC_MAX_C * SSC_MAX_C + 3 + SSC_MAX_C];
+    for (int i = threadIdx.x; i < C * C + 3 + C; i += SSC_THREADS) hist[i] = 0u;
     __syncthreads();
     unsigned int ctp = 0, cfp = 0, cfn = 0;
     for (long long i = (long long)blockIdx.x * SSC_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * SSC_THREADS) {
@@ -39,7 +39,10 @@ ssc_confusion_kernel(const uint8_t* __restrict__ pred, const TT* __restrict__ ta
             const bool bt = t > 0, bp = pr > 0;
             ctp += (bt && bp); cfp += (!bt && bp); cfn += (bt && !bp);
         }
-        if (ne && (unsigned)t < (unsigned)C && (unsigned)pr < (unsigned)C) atomicAdd(&hist[t * C + pr], 1u);
+        if (ne && (unsigned)t < (unsigned)C) {
+            if ((unsigned)pr < (unsigned)C) atomicAdd(&hist[t * C + pr], 1u);
+            else atomicAdd(&hist[C * C + 3 + t], 1u);       // prediction outside the class range: a miss (fn) of the target class,
+        }                                                   // a false positive of none (ssc_metric.py:157-163 counts it the same way)
     }
     // completion counts: warp reduce, then one shared atomic per warp
 #pragma unroll
@@ -52,7 +55,7 @@ ssc_confusion_kernel(const uint8_t* __restrict__ pred, const TT* __restrict__ ta
         atomicAdd(&hist[C * C + 0], ctp); atomicAdd(&hist[C * C + 1], cfp); atomicAdd(&hist[C * C + 2], cfn);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C * C + 3; i += SSC_THREADS)
+    for (int i = threadIdx.x; i < C * C + 3 + C; i += SSC_THREADS)
         if (hist[i]) atomicAdd(counts + i, (unsigned long long)hist[i]);
 }
 

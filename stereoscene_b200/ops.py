@@ -889,7 +889,8 @@ def bev_pool(feats: torch.Tensor, coords: torch.Tensor, B, D, H, W) -> torch.Ten
 def ssc_confusion(pred: torch.Tensor, target: torch.Tensor, n_classes: int, nonempty: Optional[torch.Tensor] = None,
                   nonsurface: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
                   ignore_label: int = 255) -> torch.Tensor:
-    """int64[C*C+3]: confusion matrix [target][prediction] of the remapped labels + completion (tp, fp, fn);
+    """int64[C*C+3+C]: confusion matrix [target][prediction] of the remapped labels + completion (tp, fp, fn) + per-target count of
+    predictions outside the class range;
     ``counts`` (zeroed by the caller) lets several samples accumulate into one tensor."""
     lib = cabi.load()
     if not pred.is_cuda or not target.is_cuda:
@@ -912,7 +913,7 @@ def ssc_confusion(pred: torch.Tensor, target: torch.Tensor, n_classes: int, none
 
     ne, ns = mask(nonempty, "nonempty"), mask(nonsurface, "nonsurface")
     if counts is None:
-        counts = torch.zeros(n_classes * n_classes + 3, dtype=torch.int64, device=pred.device)
+        counts = torch.zeros(n_classes * n_classes + 3 + n_classes, dtype=torch.int64, device=pred.device)
     rc = lib.ss_ssc_confusion_fwd(pred.data_ptr(), target.data_ptr(), target.element_size(), _ptr(ne), _ptr(ns), pred.numel(),
                                   n_classes, ignore_label, counts.data_ptr(), _stream())
     cabi.check(rc, "ss_ssc_confusion_fwd")

@@ -33,7 +33,8 @@ class SSCMetrics(nn.Module):
         counts = ops.ssc_confusion(y_pred, y_true, C, nonempty=nonempty, nonsurface=nonsurface)
         M = counts[:C * C].view(C, C)                     # [target][prediction]
         tps = M.diagonal().clone()
-        return counts[C * C:], tps, M.sum(0) - tps, M.sum(1) - tps
+        # predictions outside the class range are misses of their target class and false positives of none (ssc_metric.py:157-163)
+        return counts[C * C:C * C + 3], tps, M.sum(0) - tps, M.sum(1) - tps + counts[C * C + 3:]
 
     def compute_single(self, y_pred, y_true, nonempty=None, nonsurface=None):
         comp, tps, fps, fns = self.scores(y_pred, y_true, nonempty, nonsurface)
@@ -59,11 +60,28 @@ class SSCMetrics(nn.Module):
         _, tps, fps, fns = self.scores(predict, target, nonempty, None)
         return tps.float(), fps.float(), fns.float()
 
+    def synced_state(self):
+        """The six accumulators summed over the ranks of the default process group (the reference's torchmetrics states use
+        dist_reduce_fx='sum', ssc_metric.py:24-35); the local buffers are left untouched, so compute() may be called repeatedly."""
+        names = ("completion_tp", "completion_fp", "completion_fn", "tps", "fps", "fns")
+        vals = [getattr(self, n) for n in names]
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            flat = torch.cat([v.reshape(-1).double() for v in vals])
+            torch.distributed.all_reduce(flat)
+            out, off = [], 0
+            for v in vals:
+                out.append(flat[off:off + v.numel()].to(v.dtype).view_as(v))
+                off += v.numel()
+            vals = out
+        return dict(zip(names, vals))
+
     def compute(self):
-        precision = self.completion_tp / (self.completion_tp + self.completion_fp)
-        recall = self.completion_tp / (self.completion_tp + self.completion_fn)
-        iou = self.completion_tp / (self.completion_tp + self.completion_fp + self.completion_fn)
-        iou_ssc = self.tps / (self.tps + self.fps + self.fns + 1e-5)
+        s = self.synced_state()
+        ctp, cfp, cfn, tps, fps, fns = (s[k] for k in ("completion_tp", "completion_fp", "completion_fn", "tps", "fps", "fns"))
+        precision = ctp / (ctp + cfp)
+        recall = ctp / (ctp + cfn)
+        iou = ctp / (ctp + cfp + cfn)
+        iou_ssc = tps / (tps + fps + fns + 1e-5)
         return {"precision": precision, "recall": recall, "iou": iou.item(), "iou_ssc": iou_ssc,
                 "iou_ssc_mean": iou_ssc[1:].mean().item()}
 

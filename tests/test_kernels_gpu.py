@@ -656,6 +656,13 @@ def test_ssc_metrics_kernel_matches_reference(ops):
     # empty input is a no-op
     z = ops.ssc_confusion(pred.cuda()[:0], true.cuda()[:0], 20)
     assert int(z.sum()) == 0
+    # predictions outside the class range: misses of their target class, false positives of no class (the oracle's loops agree)
+    pred2 = pred.clone()
+    pred2[torch.rand(shape, generator=gen) < 0.05] = 37
+    want = O.ssc_scores(pred2, true)
+    comp, tps, fps, fns = SSCMetrics().cuda().scores(pred2.cuda(), true.cuda())
+    assert torch.equal(comp.cpu(), want["completion"]) and torch.equal(tps.cpu(), want["tps"])
+    assert torch.equal(fps.cpu(), want["fps"]) and torch.equal(fns.cpu(), want["fns"])
 
 
 def test_errors_are_loud(ops):
