@@ -39,6 +39,8 @@ extern "C" {
 #define SS_ACT_NONE 0
 #define SS_ACT_RELU 1
 #define SS_ACT_GELU 2                  /* exact erf GELU (nn.GELU default) */
+#define SS_ACT_SWISH 3                 /* x * sigmoid(x): the image encoder's activation (efficientnet.py:374) */
+#define SS_ACT_SIGMOID 4               /* ss_se_fc_fwd only (the SE gate) */
 
 #define SS_MATH_TF32 0                 /* tensor-core TF32 multiply, fp32 accumulate */
 #define SS_MATH_3XTF32 1               /* error-compensated split (hi/lo) TF32 on the mma.sync kernels: ~fp32 accuracy */
@@ -53,7 +55,7 @@ extern "C" {
                                           rate.  Same packing and availability as SS_MATH_F16X3 (only the hi halves are multiplied) */
 
 /* ABI version of this header; ss_abi_version() of the library must match. */
-#define SS_ABI_VERSION 5
+#define SS_ABI_VERSION 6
 int ss_abi_version(void);
 /* Text of the last CUDA error seen by the calling thread (host pointer, never NULL). */
 const char* ss_last_error_string(void);
@@ -184,6 +186,29 @@ int ss_affine_join_fwd(const float* x, const float* x_scale, const float* x_shif
  * DepthNet's ASPP (image2bev/ViewTransformerLSSBEVDepth.py:373-379, 394) without a pass through ATen. */
 int ss_channel_sums_fwd(const float* x, const float* x_scale, const float* x_shift, int x_act, int B,
                         long long V, int C, int x_ldc, double* stats, void* stream);
+
+/* ---- 2-D image encoder (CustomEfficientNet-B7, backbones/efficientnet.py:113-231, 274-534).
+ * Its pointwise convolutions run through ss_conv3d_tc_fwd / ss_conv3d_fwd as depth-1 volumes; these three entries are the rest.
+ *
+ * Stem (efficientnet.py:396-405): K x K stride-S convolution of a few-channel image with TensorFlow "SAME" padding
+ * (mmcv Conv2dAdaptivePadding: total = max((ceil(H/S)-1)*S + K - H, 0), the smaller half in front), bias (the folded BatchNorm)
+ * and activation.  x: float[N][Cin][H][W] (Cin <= 4); w: float[K*K*Cin][Cout] ordered (ky, kx, ci); y: channels-last
+ * float[N][ceil(H/S)][ceil(W/S)][Cout]. */
+int ss_stem_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int N, int Cin, int H, int W, int Cout,
+                       int K, int S, int out_act, void* stream);
+
+/* Depthwise K x K convolution (K = 3 | 5, stride 1 | 2, "SAME" padding as above) of a channels-last image
+ * float[N][H][W][C] (pixel stride in_ldc) with bias and activation (InvertedResidual.depthwise_conv, efficientnet.py:181-190);
+ * w: float[K*K][C].  pool (optional): double[N][C][2], slot 0 += the per-image sum of the activated output -- the global
+ * average pool of the squeeze-excite block that follows (mmdet SELayer), taken in the same pass. */
+int ss_dwconv2d_fwd(const float* x, const float* w, const float* bias, float* y, double* pool, int N, int H, int W, int C,
+                    int in_ldc, int out_ldc, int K, int S, int out_act, void* stream);
+
+/* One fully connected layer of the squeeze-excite block: out[n][o] = act(bias[o] + in_mul * sum_c in[n][c] * w[o][c]),
+ * w: float[Cout][Cin]; act may be SS_ACT_SIGMOID.  in_is_stats != 0: in = double[N][Cin][2] channel sums (slot 0 read), so
+ * in_mul = 1 / pixels makes it the pooled mean; otherwise in = float[N][Cin]. */
+int ss_se_fc_fwd(const void* in, int in_is_stats, const float* w, const float* bias, float* out, int N, int Cin, int Cout,
+                 float in_mul, int act, void* stream);
 
 /* Softmax over the depth axis of a [B][D][P] volume (P = H*W pixels, contiguous), batch strides
  * in floats.  Replaces F.softmax(dim=1) at ViewTransformerLSSVoxel.py:222, 267 and

@@ -137,7 +137,8 @@ class _DCN(nn.Module):
 def _build_conv_layer(cfg, *args, **kwargs):
     cfg = dict(cfg) if cfg is not None else dict(type="Conv2d")
     t = cfg.pop("type")
-    table = {"Conv1d": nn.Conv1d, "Conv2d": nn.Conv2d, "Conv3d": nn.Conv3d, "Conv": nn.Conv2d, "DCN": _DCN}
+    table = {"Conv1d": nn.Conv1d, "Conv2d": nn.Conv2d, "Conv3d": nn.Conv3d, "Conv": nn.Conv2d, "DCN": _DCN,
+             "Conv2dAdaptivePadding": _Conv2dAdaptivePadding}
     return table[t](*args, **kwargs, **cfg)
 
 
@@ -146,6 +147,150 @@ def _build_upsample_layer(cfg, *args, **kwargs):
     t = cfg.pop("type")
     table = {"deconv": nn.ConvTranspose2d, "deconv3d": nn.ConvTranspose3d}
     return table[t](*args, **kwargs, **cfg)
+
+
+# --------------------------------------------------------------------------------------
+# the 2-D image encoder's third-party bricks (row N2).  mmcv 1.4.0 / mmdet 2.14.0 / mmdet3d 0.17.1
+# are the versions the reference pins (docs/install.md); none is vendored under /root/reference, so
+# their PUBLISHED behaviour is restated here, only as far as efficientnet.py and SECONDFPN use it.
+# --------------------------------------------------------------------------------------
+class _Conv2dAdaptivePadding(nn.Conv2d):
+    """mmcv.cnn.bricks.Conv2dAdaptivePadding: TensorFlow 'SAME' padding computed per call from the input
+    size -- total = max((ceil(H/s)-1)*s + (k-1)*d + 1 - H, 0), the smaller half in front; the constructor's
+    ``padding`` argument is ignored (the layer is built with padding 0)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride, 0, dilation, groups, bias)
+
+    def forward(self, x):
+        import math
+        import torch.nn.functional as F
+        ih, iw = x.shape[-2:]
+        kh, kw = self.weight.shape[-2:]
+        sh, sw = self.stride
+        oh, ow = math.ceil(ih / sh), math.ceil(iw / sw)
+        ph = max((oh - 1) * sh + (kh - 1) * self.dilation[0] + 1 - ih, 0)
+        pw = max((ow - 1) * sw + (kw - 1) * self.dilation[1] + 1 - iw, 0)
+        if ph > 0 or pw > 0:
+            x = F.pad(x, [pw // 2, pw - pw // 2, ph // 2, ph - ph // 2])
+        return F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+
+class _Swish(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(x)
+
+
+def _build_activation_layer(cfg):
+    cfg = dict(cfg)
+    t = cfg.pop("type")
+    if t == "ReLU":
+        cfg.setdefault("inplace", True)
+    table = {"ReLU": nn.ReLU, "Swish": _Swish, "Sigmoid": nn.Sigmoid, "GELU": nn.GELU}
+    return table[t](**cfg)
+
+
+class _ConvModule(nn.Module):
+    """mmcv.cnn.bricks.ConvModule with the default order (conv, norm, act): bias='auto' means "no bias when a
+    norm layer follows"; attribute names ``conv`` / ``bn`` / ``activate`` give the reference's state_dict keys."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias="auto", conv_cfg=None, norm_cfg=None, act_cfg=dict(type="ReLU"), inplace=True, **kw):
+        super().__init__()
+        self.with_norm = norm_cfg is not None
+        self.with_activation = act_cfg is not None
+        if bias == "auto":
+            bias = not self.with_norm
+        self.conv = _build_conv_layer(conv_cfg, in_channels, out_channels, kernel_size, stride=stride,
+                                      padding=padding, dilation=dilation, groups=groups, bias=bias)
+        if self.with_norm:
+            self.norm_name, norm = _build_norm_layer(norm_cfg, out_channels)
+            self.add_module(self.norm_name, norm)
+        if self.with_activation:
+            self.activate = _build_activation_layer(act_cfg)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.with_norm:
+            x = getattr(self, self.norm_name)(x)
+        if self.with_activation:
+            x = self.activate(x)
+        return x
+
+
+class _DropPath(nn.Module):
+    """Stochastic depth: the identity outside training (the path here is inference)."""
+
+    def __init__(self, drop_prob=0.1):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        assert not self.training
+        return x
+
+
+class _Sequential(_BaseModule, nn.Sequential):
+    def __init__(self, *args, init_cfg=None):
+        _BaseModule.__init__(self, init_cfg)
+        nn.Sequential.__init__(self, *args)
+
+
+class _SELayer(_BaseModule):
+    """mmdet.models.utils.SELayer: global average pool -> 1x1 conv (bias) + act[0] -> 1x1 conv (bias) + act[1]
+    -> channel gate multiplied onto the input."""
+
+    def __init__(self, channels, ratio=16, conv_cfg=None, act_cfg=(dict(type="ReLU"), dict(type="Sigmoid")),
+                 init_cfg=None):
+        super().__init__(init_cfg)
+        self.global_avgpool = nn.AdaptiveAvgPool2d(1)
+        self.conv1 = _ConvModule(channels, int(channels / ratio), 1, stride=1, conv_cfg=conv_cfg, act_cfg=act_cfg[0])
+        self.conv2 = _ConvModule(int(channels / ratio), channels, 1, stride=1, conv_cfg=conv_cfg, act_cfg=act_cfg[1])
+
+    def forward(self, x):
+        return x * self.conv2(self.conv1(self.global_avgpool(x)))
+
+
+def _make_divisible(value, divisor, min_value=None, min_ratio=0.9):
+    if min_value is None:
+        min_value = divisor
+    new_value = max(min_value, int(value + divisor / 2) // divisor * divisor)
+    if new_value < min_ratio * value:
+        new_value += divisor
+    return new_value
+
+
+class SECONDFPN(_BaseModule):
+    """mmdet3d.models.necks.SECONDFPN (0.17.1), restated: one deblock per input level -- ConvTranspose2d with
+    kernel = stride for upsample_strides >= 1 (a stride of exactly 1 is still a 1x1 transposed conv because
+    use_conv_for_no_stride defaults to False), Conv2d with kernel = stride = round(1/s) below 1 -- each without
+    bias and followed by BatchNorm2d(eps 1e-3, momentum 0.01) + ReLU; outputs concatenated over channels and
+    returned as a one-element list."""
+
+    def __init__(self, in_channels=[128, 128, 256], out_channels=[256, 256, 256], upsample_strides=[1, 2, 4],
+                 norm_cfg=dict(type="BN", eps=1e-3, momentum=0.01), upsample_cfg=dict(type="deconv", bias=False),
+                 conv_cfg=dict(type="Conv2d", bias=False), use_conv_for_no_stride=False, init_cfg=None):
+        super().__init__(init_cfg)
+        assert len(out_channels) == len(upsample_strides) == len(in_channels)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        deblocks = []
+        for i, oc in enumerate(out_channels):
+            stride = upsample_strides[i]
+            if stride > 1 or (stride == 1 and not use_conv_for_no_stride):
+                up = _build_upsample_layer(upsample_cfg, in_channels=in_channels[i], out_channels=oc,
+                                           kernel_size=upsample_strides[i], stride=upsample_strides[i])
+            else:
+                stride = int(round(1 / stride))
+                up = _build_conv_layer(conv_cfg, in_channels=in_channels[i], out_channels=oc, kernel_size=stride,
+                                       stride=stride)
+            deblocks.append(nn.Sequential(up, _build_norm_layer(norm_cfg, oc)[1], nn.ReLU(inplace=True)))
+        self.deblocks = nn.ModuleList(deblocks)
+
+    def forward(self, x):
+        assert len(x) == len(self.in_channels)
+        ups = [deblock(x[i]) for i, deblock in enumerate(self.deblocks)]
+        out = torch.cat(ups, dim=1) if len(ups) > 1 else ups[0]
+        return [out]
 
 
 class _BasicBlock2d(nn.Module):
@@ -297,11 +442,13 @@ def install():
     necks, backbones, heads, detectors = (_Registry(n) for n in ("neck", "backbone", "head", "detector"))
     _mk("mmcv")
     _mk("mmcv.runner", BaseModule=_BaseModule, force_fp32=_identity_decorator_factory,
-        auto_fp16=_identity_decorator_factory, get_dist_info=lambda: (0, 1))
+        auto_fp16=_identity_decorator_factory, get_dist_info=lambda: (0, 1), Sequential=_Sequential)
     _mk("mmcv.cnn", build_norm_layer=_build_norm_layer, build_conv_layer=_build_conv_layer,
-        build_upsample_layer=_build_upsample_layer)
+        build_upsample_layer=_build_upsample_layer, ConvModule=_ConvModule)
+    _mk("mmcv.cnn.bricks", ConvModule=_ConvModule, DropPath=_DropPath)
     _mk("mmdet")
     _mk("mmdet.models", NECKS=necks, HEADS=heads, DETECTORS=detectors, BACKBONES=backbones)
+    _mk("mmdet.models.utils", SELayer=_SELayer, make_divisible=_make_divisible)
     _mk("mmdet.models.backbones")
     _mk("mmdet.models.backbones.resnet", BasicBlock=_BasicBlock2d)
     _mk("mmdet3d")
@@ -344,6 +491,11 @@ def resnet3d_module():
 
 def neck_module():
     return _imp("projects.mmdet3d_plugin.occupancy.necks.second_fpn_3d")
+
+
+def efficientnet_module():
+    """The reference's CustomEfficientNet file (unmodified), on the restated mmcv / mmdet bricks above."""
+    return _imp("projects.mmdet3d_plugin.occupancy.backbones.efficientnet")
 
 
 def occhead_module():

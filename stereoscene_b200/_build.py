@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "lib", "obj")
 LIBNAME = "libstereoscene_b200.so"
-SOURCES = ["api.cu", "conv3d.cu", "conv3d_tc.cu", "conv3d_march.cu", "conv3d_halo.cu", "conv3d_tpose.cu", "conv_small.cu", "conv_pw.cu", "deform.cu", "norm_act.cu", "gwc_warp.cu", "lift_splat.cu", "upsample.cu", "bri_attn.cu", "bri_attn_tc.cu", "ssc_metric.cu", "peer.cu"]
+SOURCES = ["api.cu", "conv3d.cu", "conv3d_tc.cu", "conv3d_march.cu", "conv3d_halo.cu", "conv3d_tpose.cu", "conv_small.cu", "conv_pw.cu", "deform.cu", "norm_act.cu", "gwc_warp.cu", "lift_splat.cu", "upsample.cu", "bri_attn.cu", "bri_attn_tc.cu", "ssc_metric.cu", "peer.cu", "image2d.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

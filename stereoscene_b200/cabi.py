@@ -10,9 +10,9 @@ import os
 
 from . import _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
-SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU = 0, 1, 2
+SS_ACT_NONE, SS_ACT_RELU, SS_ACT_GELU, SS_ACT_SWISH, SS_ACT_SIGMOID = 0, 1, 2, 3, 4
 SS_MATH_TF32, SS_MATH_3XTF32, SS_MATH_TF32X3, SS_MATH_F16X3, SS_MATH_F16 = 0, 1, 2, 3, 4
 
 
@@ -51,6 +51,9 @@ SIGNATURES = {
     "ss_ca3d_gate": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ss_affine_join_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _i, _vp, _vp]),
     "ss_channel_sums_fwd": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _i, _vp, _vp]),
+    "ss_stem_conv2d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ss_dwconv2d_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ss_se_fc_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, C.c_float, _i, _vp]),
     "ss_softmax_d_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "ss_gwc_warp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ss_bri_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -115,9 +115,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+__device__ __forceinline__ float swish_f(float x) { return x / (1.0f + expf(-x)); }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == SS_ACT_RELU) return fmaxf(v, 0.0f);
     if (act == SS_ACT_GELU) return gelu_erf(v);
+    if (act == SS_ACT_SWISH) return swish_f(v);
     return v;
 }
 

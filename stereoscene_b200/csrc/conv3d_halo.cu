@@ -411,6 +411,9 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
             } else if (act == SS_ACT_GELU) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = gelu_erf(v[k]);
+            } else if (act == SS_ACT_SWISH) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = swish_f(v[k]);
             }
             if (valid) {
                 float* dst = p.y + ov * p.out_ldc + cbase;

@@ -295,6 +295,9 @@ __device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t
         } else if (act == SS_ACT_GELU) {
 #pragma unroll
             for (int k = 0; k < NCOL; ++k) v[k] = gelu_erf(v[k]);
+        } else if (act == SS_ACT_SWISH) {
+#pragma unroll
+            for (int k = 0; k < NCOL; ++k) v[k] = swish_f(v[k]);
         }
         const int oh = c.th * MR_TH + lh, ow = c.tw * MR_TW + lw;
         if (oh < p.H && ow < p.W) {

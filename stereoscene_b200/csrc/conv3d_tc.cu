@@ -477,6 +477,9 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             } else if (act == SS_ACT_GELU) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = gelu_erf(v[k]);
+            } else if (act == SS_ACT_SWISH) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = swish_f(v[k]);
             }
             if (ov >= 0) {
                 float* dst = p.y + (size_t)ov * p.out_ldc + cbase;

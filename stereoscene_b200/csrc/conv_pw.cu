@@ -310,6 +310,9 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
                 } else if (act == SS_ACT_GELU) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) x[k] = gelu_erf(x[k]);
+                } else if (act == SS_ACT_SWISH) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) x[k] = swish_f(x[k]);
                 }
                 if (valid) {
                     float* dst = p.y + ov * p.out_ldc + cbase;

@@ -1,0 +1,229 @@
+// The CUDA-core kernels of the 2-D image encoder (CustomEfficientNet-B7, reference
+// projects/mmdet3d_plugin/occupancy/backbones/efficientnet.py:113-231, 274-534).  The pointwise convolutions of the
+// MBConv blocks (expand 1x1, linear 1x1, the 1x1 head, the SECONDFPN deblocks) are GEMMs and run on the tcgen05 kernels
+// of conv3d_tc.cu as depth-1 volumes; what is left is HBM-bound and lives here:
+//
+//   stem_conv_kernel      3 -> Cout, 3x3 stride 2, TF-"SAME" padding, NCHW fp32 images in, channels-last out, folded
+//                         BatchNorm bias + Swish (efficientnet.py:396-405).  K = 27: CUDA cores, weights in shared memory.
+//   dwconv2d_kernel<K,S>  depthwise K x K (3 or 5), stride S (1 or 2), TF-"SAME" padding, channels-last, folded BatchNorm
+//                         bias + Swish (efficientnet.py:181-190) and, in the same pass, the per-(image, channel) sums that
+//                         the squeeze-excite block's global average pool needs (mmdet SELayer) -- the activation is read
+//                         once and written once.  One thread owns 4 channels x TW neighbouring output columns, so an input
+//                         value is loaded once per (TW-1)*S+K columns instead of once per tap.
+//   se_fc_kernel          the two tiny fully connected layers of the SE block (C -> C/24 Swish, C/24 -> C sigmoid): one warp
+//                         per output, coalesced weight rows.  The resulting gate [image, channel] is NOT multiplied into the
+//                         activation: it travels as the pending per-(batch, channel) scale of the linear 1x1 convolution's
+//                         input and is applied by that kernel's operand fix-up (no extra pass).
+#include "common.cuh"
+
+namespace ss {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stem: block = (Cout/4 channel quads) x PX output pixels of one output row
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int STEM_PX = 16;
+
+__global__ void __launch_bounds__(512)
+stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                 int Cin, int H, int W, int Ho, int Wo, int Cout, int K, int S, int pt, int pl, int out_act) {
+    extern __shared__ float stem_smem[];
+    const int taps = K * K * Cin;
+    float* sw = stem_smem;                                   // [taps][Cout]
+    float* sx = stem_smem + (size_t)taps * Cout;             // [Cin][K][span]
+    const int span = (STEM_PX - 1) * S + K;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * STEM_PX;
+    for (int i = tid; i < taps * Cout; i += nthr) sw[i] = __ldg(w + i);
+    const int ix0 = ox0 * S - pl, iy0 = oy * S - pt;
+    for (int i = tid; i < Cin * K * span; i += nthr) {
+        const int c = i / (K * span), r = (i / span) % K, j = i % span;
+        const int iy = iy0 + r, ix = ix0 + j;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((size_t)n * Cin + c) * H + iy) * W + ix);
+        sx[i] = v;
+    }
+    __syncthreads();
+    const int cq = threadIdx.x, px = threadIdx.y, ox = ox0 + px;
+    if (ox >= Wo || cq * 4 >= Cout) return;
+    float4 acc = ldg_f4(bias + cq * 4);
+    for (int ky = 0; ky < K; ++ky)
+        for (int kx = 0; kx < K; ++kx)
+            for (int c = 0; c < Cin; ++c) {
+                const float v = sx[(c * K + ky) * span + px * S + kx];
+                const float4 wv = *reinterpret_cast<const float4*>(sw + (size_t)((ky * K + kx) * Cin + c) * Cout + cq * 4);
+                acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y); acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+            }
+    acc.x = apply_act(acc.x, out_act); acc.y = apply_act(acc.y, out_act); acc.z = apply_act(acc.z, out_act); acc.w = apply_act(acc.w, out_act);
+    *reinterpret_cast<float4*>(y + (((size_t)n * Ho + oy) * Wo + ox) * Cout + cq * 4) = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// depthwise: block = 32 channel quads x DW_G column groups; a block walks DW_ROWS output rows
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int DW_G = 8;
+constexpr int DW_ROWS = 4;
+
+template <int K, int S, int TW>
+__global__ void __launch_bounds__(32 * DW_G)
+dwconv2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                double* __restrict__ pool, int H, int W, int C, int in_ldc, int Ho, int Wo, int out_ldc, int pt, int pl, int out_act,
+                int row_blocks) {
+    constexpr int SPAN = (TW - 1) * S + K;
+    __shared__ float4 red[DW_G][32];
+    const int cq = blockIdx.x * 32 + threadIdx.x;            // channel quad
+    const int n = blockIdx.z / row_blocks, rb = blockIdx.z % row_blocks;
+    const int ox0 = (blockIdx.y * DW_G + threadIdx.y) * TW;
+    const bool live = (cq * 4 < C) && (ox0 < Wo);
+    float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        const int c = cq * 4;
+        const float4 bv = ldg_f4(bias + c);
+        const int ix0 = ox0 * S - pl;
+        for (int r = 0; r < DW_ROWS; ++r) {
+            const int oy = rb * DW_ROWS + r;
+            if (oy >= Ho) break;
+            float4 acc[TW];
+#pragma unroll
+            for (int t = 0; t < TW; ++t) acc[t] = bv;
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const int iy = oy * S - pt + ky;
+                if (iy < 0 || iy >= H) continue;
+                const float* xr = x + (((size_t)n * H + iy) * W) * in_ldc + c;
+                float4 wv[K];
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) wv[kx] = ldg_f4(w + (size_t)(ky * K + kx) * C + c);
+#pragma unroll
+                for (int j = 0; j < SPAN; ++j) {
+                    const int ix = ix0 + j;
+                    if (ix < 0 || ix >= W) continue;
+                    const float4 v = ldg_f4(xr + (size_t)ix * in_ldc);
+#pragma unroll
+                    for (int t = 0; t < TW; ++t) {
+                        const int kx = j - t * S;             // compile-time after unrolling
+                        if (kx >= 0 && kx < K) {
+                            acc[t].x = fmaf(v.x, wv[kx].x, acc[t].x); acc[t].y = fmaf(v.y, wv[kx].y, acc[t].y);
+                            acc[t].z = fmaf(v.z, wv[kx].z, acc[t].z); acc[t].w = fmaf(v.w, wv[kx].w, acc[t].w);
+                        }
+                    }
+                }
+            }
+            float* yr = y + (((size_t)n * Ho + oy) * Wo) * out_ldc + c;
+#pragma unroll
+            for (int t = 0; t < TW; ++t) {
+                if (ox0 + t < Wo) {
+                    float4 o = acc[t];
+                    o.x = apply_act(o.x, out_act); o.y = apply_act(o.y, out_act); o.z = apply_act(o.z, out_act); o.w = apply_act(o.w, out_act);
+                    *reinterpret_cast<float4*>(yr + (size_t)(ox0 + t) * out_ldc) = o;
+                    psum.x += o.x; psum.y += o.y; psum.z += o.z; psum.w += o.w;
+                }
+            }
+        }
+    }
+    if (pool == nullptr) return;
+    red[threadIdx.y][threadIdx.x] = psum;
+    __syncthreads();
+    if (threadIdx.y == 0 && cq * 4 < C) {
+        float4 s = red[0][threadIdx.x];
+#pragma unroll
+        for (int g = 1; g < DW_G; ++g) {
+            const float4 t = red[g][threadIdx.x];
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        double* dst = pool + ((size_t)n * C + cq * 4) * 2;    // double[B][C][2] like the GroupNorm sums: slot 0 = sum
+        atomicAdd(dst + 0, (double)s.x); atomicAdd(dst + 2, (double)s.y); atomicAdd(dst + 4, (double)s.z); atomicAdd(dst + 6, (double)s.w);
+    }
+}
+
+template <int K, int S, int TW>
+static int launch_dw(const float* x, const float* w, const float* bias, float* y, double* pool, int N, int H, int W, int C, int in_ldc,
+                     int Ho, int Wo, int out_ldc, int pt, int pl, int out_act, cudaStream_t st) {
+    const int rbk = (Ho + DW_ROWS - 1) / DW_ROWS;
+    dim3 grid((unsigned)((C / 4 + 31) / 32), (unsigned)((Wo + DW_G * TW - 1) / (DW_G * TW)), (unsigned)(N * rbk)), block(32, DW_G);
+    dwconv2d_kernel<K, S, TW><<<grid, block, 0, st>>>(x, w, bias, y, pool, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, rbk);
+    return check_launch("dwconv2d_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SE fully connected layer: out[n][o] = act(bias[o] + in_mul * sum_c in[n][c] * w[o][c]); one warp per output
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool IN_DOUBLE>
+__global__ void __launch_bounds__(256)
+se_fc_kernel(const void* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+             int Cin, int Cout, float in_mul, int act) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + warp, n = blockIdx.y;
+    if (o >= Cout) return;
+    const float* wr = w + (size_t)o * Cin;
+    float acc = 0.f;
+    for (int c = lane; c < Cin; c += 32) {
+        float v;
+        if constexpr (IN_DOUBLE) v = (float)(reinterpret_cast<const double*>(in)[((size_t)n * Cin + c) * 2] * (double)in_mul);
+        else v = reinterpret_cast<const float*>(in)[(size_t)n * Cin + c] * in_mul;
+        acc = fmaf(v, __ldg(wr + c), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        float v = acc + (bias ? __ldg(bias + o) : 0.f);
+        if (act == SS_ACT_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+        else v = apply_act(v, act);
+        out[(size_t)n * Cout + o] = v;
+    }
+}
+
+}  // namespace ss
+
+// x: float[N][Cin][H][W] (the reference's image layout); w: float[K*K*Cin][Cout] ordered (ky, kx, ci); y: channels-last
+// float[N][Ho][Wo][Cout] with Ho = ceil(H/S), Wo = ceil(W/S) (TF "SAME": pad_top = total/2, the rest at the bottom).
+extern "C" int ss_stem_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int N, int Cin, int H, int W, int Cout,
+                                  int K, int S, int out_act, void* stream) {
+    using namespace ss;
+    SS_REQUIRE(x && w && bias && y, "ss_stem_conv2d_fwd: null pointer");
+    SS_REQUIRE(N > 0 && N <= 65535 && Cin > 0 && Cin <= 4 && H > 0 && W > 0 && K >= 1 && K <= 7 && S >= 1 && S <= 4,
+               "ss_stem_conv2d_fwd: shape");
+    SS_REQUIRE(Cout % 4 == 0 && Cout >= 4 && Cout <= 128, "ss_stem_conv2d_fwd: Cout must be a multiple of 4, at most 128");
+    const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
+    SS_REQUIRE(Ho <= 65535, "ss_stem_conv2d_fwd: too many rows");
+    const int th = max((Ho - 1) * S + K - H, 0), tw = max((Wo - 1) * S + K - W, 0);
+    const int span = (STEM_PX - 1) * S + K;
+    const size_t smem = ((size_t)K * K * Cin * Cout + (size_t)Cin * K * span) * sizeof(float);
+    SS_REQUIRE(smem <= 48 * 1024, "ss_stem_conv2d_fwd: weights do not fit in shared memory");
+    dim3 grid((unsigned)((Wo + STEM_PX - 1) / STEM_PX), (unsigned)Ho, (unsigned)N), block((unsigned)(Cout / 4), STEM_PX);
+    stem_conv_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(x, w, bias, y, Cin, H, W, Ho, Wo, Cout, K, S, th / 2, tw / 2, out_act);
+    return check_launch("stem_conv_kernel");
+}
+
+// x: channels-last float[N][H][W][C] (pixel stride in_ldc); w: float[K*K][C]; y: float[N][Ho][Wo][C] (pixel stride out_ldc);
+// pool (optional): double[N][C][2], slot 0 += sum over the image of the activated output (slot 1 untouched).
+extern "C" int ss_dwconv2d_fwd(const float* x, const float* w, const float* bias, float* y, double* pool, int N, int H, int W, int C,
+                               int in_ldc, int out_ldc, int K, int S, int out_act, void* stream) {
+    using namespace ss;
+    SS_REQUIRE(x && w && bias && y, "ss_dwconv2d_fwd: null pointer");
+    SS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "ss_dwconv2d_fwd: shape (C must be a multiple of 4)");
+    SS_REQUIRE(in_ldc >= C && out_ldc >= C && in_ldc % 4 == 0 && out_ldc % 4 == 0, "ss_dwconv2d_fwd: ldc");
+    SS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w) |
+                 reinterpret_cast<uintptr_t>(bias)) & 15) == 0, "ss_dwconv2d_fwd: 16-byte alignment");
+    SS_REQUIRE((K == 3 || K == 5) && (S == 1 || S == 2), "ss_dwconv2d_fwd: kernel 3 or 5, stride 1 or 2");
+    const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
+    const int th = max((Ho - 1) * S + K - H, 0), tw = max((Wo - 1) * S + K - W, 0);
+    const int pt = th / 2, pl = tw / 2;
+    SS_REQUIRE((long long)N * ((Ho + DW_ROWS - 1) / DW_ROWS) <= 65535, "ss_dwconv2d_fwd: too many row blocks");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 3 && S == 1) return launch_dw<3, 1, 4>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
+    if (K == 3 && S == 2) return launch_dw<3, 2, 2>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
+    if (K == 5 && S == 1) return launch_dw<5, 1, 4>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
+    return launch_dw<5, 2, 2>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
+}
+
+// out[n][o] = act(bias[o] + in_mul * sum_c in[n][c] * w[o][c]).  in_is_stats != 0: ``in`` is a double[N][Cin][2] block of
+// channel sums (slot 0 is read) -- with in_mul = 1 / pixels that is the SE block's global average pool.
+extern "C" int ss_se_fc_fwd(const void* in, int in_is_stats, const float* w, const float* bias, float* out, int N, int Cin, int Cout,
+                            float in_mul, int act, void* stream) {
+    using namespace ss;
+    SS_REQUIRE(in && w && out, "ss_se_fc_fwd: null pointer");
+    SS_REQUIRE(N > 0 && N <= 65535 && Cin > 0 && Cout > 0, "ss_se_fc_fwd: shape");
+    dim3 grid((unsigned)((Cout + 7) / 8), (unsigned)N);
+    if (in_is_stats) se_fc_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(in, w, bias, out, Cin, Cout, in_mul, act);
+    else se_fc_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, w, bias, out, Cin, Cout, in_mul, act);
+    return check_launch("se_fc_kernel");
+}

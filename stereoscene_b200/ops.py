@@ -23,7 +23,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import cabi
-from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_MATH_3XTF32, SS_MATH_F16, SS_MATH_F16X3, SS_MATH_TF32, SS_MATH_TF32X3  # noqa: F401
+from .cabi import SS_ACT_GELU, SS_ACT_NONE, SS_ACT_RELU, SS_ACT_SIGMOID, SS_ACT_SWISH, SS_MATH_3XTF32, SS_MATH_F16, SS_MATH_F16X3, SS_MATH_TF32, SS_MATH_TF32X3  # noqa: F401
 
 _DEFAULT_MATH = SS_MATH_TF32
 _USE_TCGEN05 = os.environ.get("STEREOSCENE_B200_NO_TCGEN05", "0") != "1"
@@ -71,13 +71,15 @@ MATH_POLICIES = {
     "tf32": {},                                                                          # every stage plain TF32
     # the parity-green product mode (CA3D sits on a residual branch: leaving it in TF32 moves the logits error 6.8e-4 -> 7.4e-4);
     # the voxel stack's halo-resident layers (encoder blocks, head) multiply fp16 operands: TF32's significand, half the MMAs
-    "mixed": {"depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_TF32, "voxel": SS_MATH_F16},
-    "mixed_tf32voxel": {"depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_TF32},
+    # "image" = the 2-D image encoder in front of the path (row N2): ~110 chained pointwise GEMMs -- plain TF32 leaves its output
+    # features at 8e-4 of the reference before the volumetric stages add theirs, so it runs compensated
+    "mixed": {"image": SS_MATH_TF32X3, "depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_TF32, "voxel": SS_MATH_F16},
+    "mixed_tf32voxel": {"image": SS_MATH_TF32X3, "depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_TF32},
     # every uncompensated halo-resident layer on fp16 operands (stereo branch included)
-    "mixed16": {"stereo": SS_MATH_F16, "depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_F16, "voxel": SS_MATH_F16},
-    "f16": {g: SS_MATH_F16 for g in ("stereo", "depthnet", "mie", "voxel")},
-    "tf32x3": {g: SS_MATH_TF32X3 for g in ("stereo", "depthnet", "mie", "voxel")},
-    "3xtf32": {g: SS_MATH_3XTF32 for g in ("stereo", "depthnet", "mie", "voxel")},
+    "mixed16": {"image": SS_MATH_TF32X3, "stereo": SS_MATH_F16, "depthnet": SS_MATH_TF32X3, "mie": SS_MATH_TF32X3, "mie.ca3d": SS_MATH_F16, "voxel": SS_MATH_F16},
+    "f16": {g: SS_MATH_F16 for g in ("image", "stereo", "depthnet", "mie", "voxel")},
+    "tf32x3": {g: SS_MATH_TF32X3 for g in ("image", "stereo", "depthnet", "mie", "voxel")},
+    "3xtf32": {g: SS_MATH_3XTF32 for g in ("image", "stereo", "depthnet", "mie", "voxel")},
 }
 DEFAULT_POLICY = "mixed"
 _POLICY: Optional[dict] = dict(MATH_POLICIES[DEFAULT_POLICY])
@@ -661,6 +663,61 @@ def channel_sums(x: Vol) -> torch.Tensor:
                                  st.data_ptr(), _stream())
     cabi.check(rc, "ss_channel_sums_fwd")
     return st
+
+
+# ------------------------------------------------------------------------------------------
+# 2-D image encoder (row N2): the CUDA-core kernels next to the pointwise GEMMs that ``conv`` serves
+# ------------------------------------------------------------------------------------------
+def stem_conv2d(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, k: int, stride: int, out_act: int = SS_ACT_NONE) -> torch.Tensor:
+    """img [N,Cin<=4,H,W] (the reference's layout) -> channels-last [N,1,ceil(H/s),ceil(W/s),Cout]; TF "SAME" padding;
+    w: [k*k*Cin, Cout] ordered (ky, kx, ci), bias [Cout] (BatchNorm folded by the caller)."""
+    lib = cabi.load()
+    _need_cuda_f32(img, "stem_conv2d")
+    img = img.contiguous()
+    N, Cin, H, W = img.shape
+    Cout = w.shape[1]
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    y = torch.empty((N, 1, Ho, Wo, Cout), dtype=torch.float32, device=img.device)
+    rc = lib.ss_stem_conv2d_fwd(img.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), N, Cin, H, W, Cout, k, stride,
+                                out_act, _stream())
+    cabi.check(rc, "ss_stem_conv2d_fwd")
+    return y
+
+
+def dwconv2d(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, k: int, stride: int, out_act: int = SS_ACT_NONE,
+             want_pool: bool = False, out: Optional[torch.Tensor] = None):
+    """Depthwise k x k conv (TF "SAME" padding) of a channels-last [N,1,H,W,C] image; w [k*k, C], bias [C].  Returns
+    (y [N,1,ceil(H/s),ceil(W/s),C], pool) with pool = double[N,C,2] whose slot 0 holds the per-image channel sums of y."""
+    lib = cabi.load()
+    in_ldc = _vol_ldc(x, "dwconv2d input")
+    N, D, H, W, Cc = x.shape
+    if D != 1:
+        raise RuntimeError("dwconv2d: expected a depth-1 volume [N,1,H,W,C]")
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    if out is None:
+        out = torch.empty((N, 1, Ho, Wo, Cc), dtype=torch.float32, device=x.device)
+    out_ldc = _vol_ldc(out, "dwconv2d output")
+    pool = arena(x.device).take(N, Cc) if want_pool else None
+    rc = lib.ss_dwconv2d_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(pool), N, H, W, Cc, in_ldc, out_ldc,
+                             k, stride, out_act, _stream())
+    cabi.check(rc, "ss_dwconv2d_fwd")
+    return out, pool
+
+
+def se_fc(inp: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int, in_mul: float = 1.0) -> torch.Tensor:
+    """out[n,o] = act(bias[o] + in_mul * sum_c in[n,c] w[o,c]); ``inp`` is float[N,Cin] or a double[N,Cin,2] block of channel
+    sums (slot 0 is read: with in_mul = 1/pixels that is the squeeze-excite block's pooled mean)."""
+    lib = cabi.load()
+    stats = inp.dtype == torch.float64
+    N, Cin = inp.shape[0], inp.shape[1]
+    Cout = w.shape[0]
+    if w.shape[1] != Cin or not w.is_contiguous() or not inp.is_contiguous():
+        raise RuntimeError(f"se_fc: weight {tuple(w.shape)} does not match input {tuple(inp.shape)}")
+    out = torch.empty((N, Cout), dtype=torch.float32, device=inp.device)
+    rc = lib.ss_se_fc_fwd(inp.data_ptr(), 1 if stats else 0, w.data_ptr(), _ptr(bias), out.data_ptr(), N, Cin, Cout, float(in_mul),
+                          act, _stream())
+    cabi.check(rc, "ss_se_fc_fwd")
+    return out
 
 
 def softmax_d(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -2,11 +2,12 @@
 (projects/mmdet3d_plugin/occupancy/detectors/bevdepth_occupancy.py:23-297 on top of
 bevdepth.py:14-34) around the B200 volumetric modules.
 
-The 2-D image encoder (CustomEfficientNet-B7 + SECONDFPN, stereoscene.py:59-74) is upstream of
-the accelerated path and out of scope: the config entries are accepted
-and kept, an externally built encoder can be attached with ``set_image_encoder``, and the
-volumetric path is entered with backbone features through ``forward_features`` -- the call
-``bench.py`` and the parity tests make.
+The volumetric path is entered with backbone features through ``forward_features`` -- the call ``bench.py`` and
+the parity tests make (BASELINE.json's metric starts after the 2-D image encoder).  The encoder itself
+(CustomEfficientNet-B7 + SECONDFPN, stereoscene.py:59-74) is plugin/image_encoder.py:
+when the config carries ``img_backbone`` / ``img_neck`` the detector runs from images (``forward_images``,
+``extract_img_feat``, ``simple_test``) and hands the view transformer the channels-last feature pair directly; an
+externally built encoder can still be attached with ``set_image_encoder``.
 """
 from __future__ import annotations
 
@@ -17,30 +18,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import Vol
-from ..registry import BACKBONES, DETECTORS, HEADS, NECKS, build_backbone, build_head, build_neck
-
-
-class _ExternalComponent(nn.Module):
-    """Placeholder for a config entry whose implementation lives outside the accelerated path."""
-
-    def __init__(self, **cfg):
-        super().__init__()
-        self.cfg = cfg
-
-    def forward(self, *a, **k):
-        raise NotImplementedError(
-            f"{type(self).__name__} (2-D image encoder) is out of scope for the volumetric hot path; attach an "
-            "implementation with BEVDepthOccupancy.set_image_encoder() or call forward_features() with backbone features")
-
-
-@BACKBONES.register_module()
-class CustomEfficientNet(_ExternalComponent):
-    pass
-
-
-@NECKS.register_module()
-class SECONDFPN(_ExternalComponent):
-    pass
+from ..registry import DETECTORS, build_backbone, build_head, build_neck
 
 
 @DETECTORS.register_module()
@@ -71,12 +49,27 @@ class BEVDepthOccupancy(nn.Module):
         """fn(imgs[B*N,3,H,W]) -> features [B*N,C,fH,fW]."""
         self._image_encoder = fn
 
-    def image_encoder(self, img):
+    def image_encoder_cl(self, img) -> torch.Tensor:
+        """bevdepth_occupancy.py:42-59 on [B,N,3,H,W], result as the channels-last buffer [B*N,1,h,w,C]."""
         B, N, Cc, H, W = img.shape
-        if self._image_encoder is None:
-            raise NotImplementedError("no image encoder attached (out of scope); use forward_features()")
-        x = self._image_encoder(img.view(B * N, Cc, H, W))
-        return x.view(B, N, *x.shape[1:])
+        flat = img.reshape(B * N, Cc, H, W)
+        if self._image_encoder is not None:
+            x = self._image_encoder(flat)                                   # [B*N,C,h,w]
+            return ops.to_channels_last(x.contiguous()).unsqueeze(1)
+        if self.img_backbone is None:
+            raise NotImplementedError("the model was built without img_backbone / img_neck; use forward_features() with "
+                                      "backbone features or attach an encoder with set_image_encoder()")
+        ops.arena(img.device).reset()
+        levels = self.img_backbone.forward_vol(flat)
+        if self.with_img_neck:
+            return self.img_neck.forward_vol(levels)
+        buf, cc = levels[-1]
+        return buf[..., :cc].contiguous()
+
+    def image_encoder(self, img):
+        """Reference contract: [B,N,3,H,W] -> [B,N,C,h,w] (a channels_last view)."""
+        B, N = img.shape[:2]
+        return self.image_encoder_cl(img).squeeze(1).permute(0, 3, 1, 2).unflatten(0, (B, N))
 
     # ---- the volumetric path ---------------------------------------------------------------
     def bev_encoder_vol(self, bev: torch.Tensor) -> Vol:
@@ -90,7 +83,15 @@ class BEVDepthOccupancy(nn.Module):
                       **{f"enc{i}": t.permute(0, 4, 1, 2, 3) for i, t in enumerate(levels)})
         return neck
 
-    def forward_features(self, x_left, x_right, left, right, calib, occ_size=None, want_labels=False):
+    def forward_images(self, img_left, img_right, left, right, calib, occ_size=None, want_labels=False):
+        """End to end from the stereo images [B,1,3,H,W] x 2 (bevdepth_occupancy.py:83-128, 275-297): image encoder on the
+        concatenated pair (DET:94), then ``forward_features`` on its channels-last output."""
+        B = img_left.shape[0]
+        cl = self.image_encoder_cl(torch.cat([img_left, img_right], 0))                     # [2B,1,h,w,C]
+        feats = cl.squeeze(1).permute(0, 3, 1, 2).unsqueeze(1)                                # logical [2B,1,C,h,w]
+        return self.forward_features(feats[:B], feats[B:], left, right, calib, occ_size, want_labels, pair_cl=cl)
+
+    def forward_features(self, x_left, x_right, left, right, calib, occ_size=None, want_labels=False, pair_cl=None):
         """Volumetric forward from image-backbone features.
         x_left/x_right: [B,1,Cin,fH,fW]; left/right: calibration dicts (rots, trans, intrins,
         post_rots, post_trans, bda); calib: [B,1].  Returns dict(output_voxels = logical
@@ -102,7 +103,7 @@ class BEVDepthOccupancy(nn.Module):
         mr = ops.cached_const("mlp_input", [right[k] for k in keys], lambda: vt.get_mlp_input(*[right[k] for k in keys]).contiguous())
         geo_l = [left[k] for k in keys] + [ml]
         geo_r = [right[k] for k in keys] + [mr]
-        bev, depth = vt([x_left] + geo_l + [x_right] + geo_r + [calib, None, None])
+        bev, depth = vt([x_left] + geo_l + [x_right] + geo_r + [calib, None, None], pair_cl=pair_cl)
         neck = self.bev_encoder_vol(bev.permute(0, 2, 3, 4, 1))
         with ops.math_scope("voxel.head"):
             logits = self.pts_bbox_head.forward_voxel_vol([neck])[0]        # [B,X,Y,Z,classes]
@@ -116,15 +117,16 @@ class BEVDepthOccupancy(nn.Module):
 
     # ---- reference-signature entry points ----------------------------------------------------
     def extract_img_feat(self, img, img_metas=None):
-        """bevdepth_occupancy.py:83-128; needs an attached image encoder."""
+        """bevdepth_occupancy.py:83-128."""
         left, right = img[0], img[1]
         B = left[0].shape[0]
-        feats = self.image_encoder(torch.cat([left[0], right[0]], 0))
+        cl = self.image_encoder_cl(torch.cat([left[0], right[0]], 0))
+        feats = cl.squeeze(1).permute(0, 3, 1, 2).unsqueeze(1)
         x, x2 = feats[:B], feats[B:]
         vt = self.img_view_transformer
         ml = vt.get_mlp_input(*left[1:7])
         mr = vt.get_mlp_input(*right[1:7])
-        bev, depth = vt([x] + list(left[1:7]) + [ml] + [x2] + list(right[1:7]) + [mr] + [left[-1], left, right])
+        bev, depth = vt([x] + list(left[1:7]) + [ml] + [x2] + list(right[1:7]) + [mr] + [left[-1], left, right], pair_cl=cl)
         neck = self.bev_encoder_vol(bev.permute(0, 2, 3, 4, 1))
         return [neck], depth, x
 

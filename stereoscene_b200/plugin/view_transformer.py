@@ -574,7 +574,7 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         return out.permute(0, 1, 3, 4, 2)
 
     # ---- forward -------------------------------------------------------------------------------
-    def frustum_forward(self, input):
+    def frustum_forward(self, input, pair_cl=None):
         """Stages (i), (N1), (iii) -- everything up to the MIE boundary: returns (depth_prob [B,D,fH,fW],
         img_feat [B,fH,fW,C] channels-last, depth_logits, lss, stereo).  ``forward`` = this + lift (x) splat; the X-slab
         sharded mode (stereoscene_b200.xshard) all-gathers the first two tensors here and splats slabs."""
@@ -588,7 +588,11 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         if N != 1:
             raise NotImplementedError("the stereo path is defined for one camera per side (N=1)")
         # one channels-last copy of the feature pair serves the stereo branch (both maps) and depth_net (left)
-        pair_cl = self.pair_channels_last(feat_left, feat_right)                                # [2B,1,H,W,Cin]
+        # (``pair_cl``: the image encoder of this package already produces exactly that buffer, plugin/image_encoder.py)
+        if pair_cl is None:
+            pair_cl = self.pair_channels_last(feat_left, feat_right)                            # [2B,1,H,W,Cin]
+        elif tuple(pair_cl.shape) != (2 * B, 1, H, W, Cin) or not pair_cl.is_contiguous():
+            raise RuntimeError(f"pair_cl must be a contiguous [2B,1,H,W,Cin] tensor, got {tuple(pair_cl.shape)}")
         with ops.math_scope("stereo"):
             stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
 
@@ -619,9 +623,9 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         with ops.math_scope("mie"):
             return self.mutual_interactive_ensemble(stereo, lss)
 
-    def forward(self, input):
+    def forward(self, input, pair_cl=None):
         rots, trans, intrins, post_rots, post_trans, bda = input[1:7]
-        depth_prob, img_feat, depth_logits, lss, stereo = self.frustum_forward(input)
+        depth_prob, img_feat, depth_logits, lss, stereo = self.frustum_forward(input, pair_cl)
         index = self.splat_index(rots, trans, intrins, post_rots, post_trans, bda)
         bev = ops.lift_splat(depth_prob, img_feat, index)                         # [B,X,Y,Z,C]
         if self.stage_outputs is not None:

@@ -30,11 +30,18 @@ def shipped_config() -> dict:
         return json.load(f)
 
 
-def model_config(workload: str = "config2") -> dict:
-    """Model dict for a named workload; returns dict(model=..., occ_size=..., input_size=...)."""
+def model_config(workload: str = "config2", image_encoder: bool = False) -> dict:
+    """Model dict for a named workload; returns dict(model=..., occ_size=..., input_size=...).  ``image_encoder`` keeps the
+    config's img_backbone / img_neck (EfficientNet-B7 + SECONDFPN, 64 M parameters); by default they are dropped and the
+    model is entered with backbone features, which is where BASELINE.json's metric starts."""
     occ_size, input_size, dbound = WORKLOADS[workload]
     cfg = shipped_config()
     model = copy.deepcopy(cfg["model"])
+    if not image_encoder:
+        model.pop("img_backbone", None)
+        model.pop("img_neck", None)
+    else:
+        model["img_backbone"].pop("init_cfg", None)        # 'Pretrained' checkpoint path: weights are loaded by the caller
     ds = cfg["lss_downsample"]
     pcr = cfg["point_cloud_range"]
     vox = [(pcr[3 + i] - pcr[i]) / occ_size[i] for i in range(3)]
@@ -50,11 +57,11 @@ def model_config(workload: str = "config2") -> dict:
     return dict(model=model, occ_size=list(occ_size), input_size=tuple(input_size), workload=workload)
 
 
-def build(workload: str = "config2"):
+def build(workload: str = "config2", image_encoder: bool = False):
     """Build ``BEVDepthOccupancy`` for a workload through the registry (random init, eval mode)."""
     from . import plugin  # noqa: F401  (registers the modules)
     from .registry import build_model
-    mc = model_config(workload)
+    mc = model_config(workload, image_encoder)
     m = build_model(mc["model"])
     m.eval()
     return m, mc

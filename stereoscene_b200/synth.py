@@ -83,6 +83,24 @@ def stereo_features(batch: int, input_size=(384, 1280), downsample=8, channels=6
     return xl.to(device), xr.to(device)
 
 
+def stereo_images(batch: int, input_size=(384, 1280), seed=0, device="cpu", pin=False):
+    """Left/right normalised camera images [B,1,3,H,W] (the reference feeds mean/std-normalised RGB,
+    loading_semkitti.py:30-34): smooth low-frequency content plus N(0, 0.25) texture, so that neighbouring
+    pixels are correlated like an image's and every pyramid level of the encoder sees signal."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    H, W = input_size
+
+    def one():
+        low = torch.randn(batch, 3, max(H // 16, 1), max(W // 16, 1), generator=g)
+        img = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False)
+        return (img + 0.5 * torch.randn(batch, 3, H, W, generator=g)).unsqueeze(1).contiguous()
+
+    left, right = one(), one()
+    if pin:
+        left, right = left.pin_memory(), right.pin_memory()
+    return left.to(device), right.to(device)
+
+
 _GEOMETRY_KEYS = ("dx", "bx", "nx", "frustum")
 
 
@@ -143,6 +161,10 @@ def randomize_state_dict(sd: dict, seed: int = 0) -> dict:
             v = normal(math.sqrt(2.0 / fan_in))
         elif leaf == "weight" and t.dim() == 2:
             v = normal(math.sqrt(1.0 / shape[1]))
+        elif key.endswith("linear_conv.bn.weight") and key.split(".")[-4] != "0":
+            # image encoder (efficientnet.py:197-205): the residual branches of ~50 stacked MBConv blocks are
+            # damped, otherwise eval-mode BatchNorm lets the activations grow by 1.3x per block
+            v = uniform(0.15, 0.45)
         elif leaf == "weight":                      # GroupNorm / BatchNorm scale
             v = uniform(0.5, 1.5)
         elif leaf == "bias":

@@ -67,11 +67,14 @@ def test_bev_pool_restatement_edge_cases():
 def test_state_dict_contract_matches_reference_spec():
     """Our registry-built model exposes exactly the reference's state_dict keys and shapes."""
     from stereoscene_b200 import presets
-    model, _ = presets.build("config2")
+    model, _ = presets.build("config2", image_encoder=True)
     with open(os.path.join(GOLDEN, "state_dict_spec.json")) as f:
         spec = json.load(f)
     mine = {k: list(v.shape) for k, v in model.state_dict().items()}
     assert mine == spec
+    # the default build enters the path with backbone features: same keys minus the 2-D image encoder
+    feats_only, _ = presets.build("config2")
+    assert set(feats_only.state_dict()) == {k for k in spec if not k.startswith(("img_backbone.", "img_neck."))}
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/projects"), reason="reference tree not present")

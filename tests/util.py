@@ -77,3 +77,27 @@ def stage_error(got_sample, want_sample, stat) -> dict:
     assert a.shape == b.shape, (a.shape, b.shape)
     d = a - b
     return dict(max=float(np.abs(d).max() / stat["absmax"]), rms=float(np.sqrt((d * d).mean()) / stat["rms"]))
+
+
+# ---- 2-D image encoder fixtures (tests/golden/golden_image_{tiny,full}.npz, written by oracle/make_golden_image.py) ----
+def golden_image(case: str):
+    with open(os.path.join(GOLDEN, f"golden_image_{case}.json")) as f:
+        meta = json.load(f)
+    return meta, np.load(os.path.join(GOLDEN, f"golden_image_{case}.npz"))
+
+
+def image_inputs(meta, device="cpu"):
+    """The seeded stereo pair of the fixture as the reference feeds it: torch.cat([left, right], 0) -> [2,1,3,H,W]."""
+    left, right = synth.stereo_images(meta["batch"], tuple(meta["input_size"]), seed=meta["seed"])
+    return torch.cat([left, right], 0).to(device)
+
+
+def build_image_encoder(seed: int, device="cpu"):
+    """Our CustomEfficientNet-B7 + SECONDFPN from the shipped config, with the seeded key-addressed weights under the
+    detector's prefixes (img_backbone. / img_neck.)."""
+    from stereoscene_b200 import plugin  # noqa: F401
+    from stereoscene_b200.registry import build_backbone, build_neck
+    cfg = presets.model_config("config2", image_encoder=True)["model"]
+    enc = torch.nn.ModuleDict(dict(img_backbone=build_backbone(cfg["img_backbone"]), img_neck=build_neck(cfg["img_neck"])))
+    synth.randomize_weights_(enc, seed)
+    return enc.to(device).eval()
