@@ -92,6 +92,9 @@ typedef struct ss_conv3d_desc {
                                          GroupNorm sums cover the slab only (the halo outputs are overwritten by the next exchange). */
     float acc_scale;                  /* SS_MATH_F16X3 only: power of two the accumulator is multiplied by (the packed weights were
                                          multiplied by its inverse so that their lo halves stay out of the fp16 subnormals) */
+    int32_t accumulate;               /* ss_conv3d_tc_fwd only: y = act(conv + bias + y_old) -- the identity shortcut of a residual block whose
+                                         branch ends in this convolution, taken in place on the block's input (efficientnet.py:219-222);
+                                         not combined with `stats` */
 } ss_conv3d_desc;
 
 /* w_packed: float[taps][Cin][cout_packed], taps = kd*kh*kw in (kd,kh,kw) row-major order, i.e.

@@ -115,7 +115,10 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-__device__ __forceinline__ float swish_f(float x) { return x / (1.0f + expf(-x)); }
+// x * sigmoid(x) on the fast-math SFU path (ex2.approx + rcp.approx, ~4e-7 relative): an IEEE division here costs a ~100-instruction
+// slow path per element and made the Swish epilogues of the image encoder 5x slower than the GEMMs in front of them
+__device__ __forceinline__ float swish_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == SS_ACT_RELU) return fmaxf(v, 0.0f);

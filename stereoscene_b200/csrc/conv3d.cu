@@ -421,6 +421,7 @@ extern "C" int ss_conv3d_fwd(const ss_conv3d_desc* d, const float* x, const floa
     SS_REQUIRE(d->in_ldc >= d->Cin && d->out_ldc >= d->Cout, "ss_conv3d_fwd: ldc");
     SS_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "ss_conv3d_fwd: scale/shift must come together");
     SS_REQUIRE(d->in_act == SS_ACT_NONE || d->in_act == SS_ACT_RELU, "ss_conv3d_fwd: in_act");
+    SS_REQUIRE(!d->accumulate, "ss_conv3d_fwd: accumulate is offered by ss_conv3d_tc_fwd only");
     SS_REQUIRE(!(in_scale && d->Cin > 4096), "ss_conv3d_fwd: pending affine limited to 4096 channels");
     SS_REQUIRE((long long)d->B * d->Dout * d->Hout * d->Wout < (1ll << 31), "ss_conv3d_fwd: output too large");
     SS_REQUIRE(!stats || d->stats_d1 <= d->stats_d0 || (d->stats_d0 <= 0 && d->stats_d1 >= d->Dout),

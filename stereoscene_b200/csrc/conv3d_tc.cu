@@ -418,10 +418,19 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
 
     // ======================= EPILOGUE: 8 warps drain TMEM ========================================
     if (warp < TC_WORKERS / 32) {
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int half = warp >> 2;                    // column half handled by this warp
+        // bias of this warp's column chunks, one coalesced load per chunk issued BEFORE the accumulator wait (lane = column;
+        // broadcast by shuffle below): 32 scalar loads per chunk after the wait were a serial L2 round trip each -- 1.3 us of
+        // every chunk on the image encoder's 1x1 layers
+        float bias_l[(BN / 32 + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < (BN / 32 + 1) / 2; ++i) {
+            const int c = n0 + (half * ((BN / 32 + 1) / 2) + i) * 32 + lane;
+            bias_l[i] = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+        }
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
         const int row = q * 32 + lane;
         const int qd = q0d + row / (p.TW * p.TH), qh = q0h + (row / p.TW) % p.TH, qw = q0w + row % p.TW;
         int ov = -1;
@@ -437,6 +446,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
         // column sums through a per-warp 32x33 scratch tile in the (now idle) operand ring
         float* scratch = reinterpret_cast<float*>(ring) + warp * (32 * 33);
         float* part = reinterpret_cast<float*>(ring) + 8 * 32 * 33 + q * (2 * BN);           // per-quarter column sums (no atomics: fixed summation order)
+        float* trans = reinterpret_cast<float*>(ring) + 8 * 32 * 33 + 4 * 2 * 256 + warp * (32 * 36);   // store transposition tile (the ring is >= 80 KB)
         const int act = p.out_act;
         const bool has_bias = p.bias != nullptr;
         const bool want_stats = p.stats != nullptr;
@@ -467,9 +477,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
                 }
             }
             if (has_bias) {
+                float bl = 0.f;
 #pragma unroll
-                for (int k = 0; k < 32; ++k)
-                    if (cbase + k < p.Cout) v[k] += __ldg(p.bias + cbase + k);
+                for (int i = 0; i < CPH; ++i)
+                    if (i == ci - half * CPH) bl = bias_l[i];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] += __shfl_sync(0xffffffffu, bl, k);
             }
             if (act == SS_ACT_RELU) {
 #pragma unroll
@@ -481,16 +494,28 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = swish_f(v[k]);
             }
-            if (ov >= 0) {
-                float* dst = p.y + (size_t)ov * p.out_ldc + cbase;
-                if (vec_ok && cbase + 32 <= p.Cout) {
+            if (vec_ok && cbase + 32 <= p.Cout) {
+                // A lane holds 32 columns of ITS row: storing them directly makes every STG.128 touch 32 different rows (32
+                // LSU wavefronts per instruction; measured 6 us of a 9 us CTA on the 1x1 layers of the image encoder).  The
+                // chunk is transposed through a per-warp 32 x 36 tile instead, so that 8 neighbouring lanes write one row's
+                // 128 bytes and an instruction covers 4 full lines.
+                float* tr = trans + lane * 36;
 #pragma unroll
-                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-                } else {
+                for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(tr + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (cbase + k < p.Cout) dst[k] = v[k];
+                for (int j = 0; j < 8; ++j) {
+                    const int rr = 4 * j + (lane >> 3);
+                    const int ovr = __shfl_sync(0xffffffffu, ov, rr);
+                    const float4 t4 = *reinterpret_cast<const float4*>(trans + rr * 36 + (lane & 7) * 4);
+                    if (ovr >= 0) *reinterpret_cast<float4*>(p.y + (size_t)ovr * p.out_ldc + cbase + (lane & 7) * 4) = t4;
                 }
+                __syncwarp();
+            } else if (ov >= 0) {
+                float* dst = p.y + (size_t)ov * p.out_ldc + cbase;
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (cbase + k < p.Cout) dst[k] = v[k];
             }
             if (want_stats) {
 #pragma unroll
@@ -664,6 +689,9 @@ static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_
         double bc = cost(256) * 0.9;
         if (cp % 128 == 0 && cost(128) <= bc * 1.0001 / 0.9) { best = 128; bc = cost(128); }
         if (cp % 160 == 0 && cost(160) < bc) { best = 160; bc = cost(160); }
+        if (cp % 128 != 0 && cp % 160 != 0)              // 288- and 1344-wide layers of the image encoder: a partial last tile of 160
+            for (int bn : {160, 192})                    // or 192 columns wastes less than 256-column tiles
+                if (cost(bn) < bc) { best = bn; bc = cost(bn); }
     }
 #define SS_TC_LAUNCH(BN_)                                                                                          \
     return ps.f16 ? launch_tc<BN_, true>(p, x, d->in_ldc, w_kmajor, ntaps_total, st) : launch_tc<BN_, false>(p, x, d->in_ldc, w_kmajor, ntaps_total, st)
@@ -683,9 +711,10 @@ static int tc_three_pass(const ss_conv3d_desc* d, const float* w_kmajor, F&& lau
     ss_conv3d_desc t = *d;
     t.math = SS_MATH_TF32;
     const size_t wn = (size_t)d->kd * d->kh * d->kw * d->cout_packed * d->Cin;
-    if (d->math == SS_MATH_TF32) return launch(&t, w_kmajor, ConvPass{0, 0}, true);
+    const int acc = d->accumulate ? 1 : 0;           // in-place residual: the first (or only) pass adds what y already holds
+    if (d->math == SS_MATH_TF32) return launch(&t, w_kmajor, ConvPass{0, acc}, true);
     if (d->math == SS_MATH_F16X3 || d->math == SS_MATH_F16) {      // single launch on fp16 operands (split inside the kernel)
-        ConvPass ps{0, 0};
+        ConvPass ps{0, acc};
         ps.f16 = 1;
         ps.f16_n = d->math == SS_MATH_F16 ? 2 : 6;
         ps.acc_scale = d->acc_scale;
@@ -693,7 +722,7 @@ static int tc_three_pass(const ss_conv3d_desc* d, const float* w_kmajor, F&& lau
     }
     ss_conv3d_desc part = t;
     part.out_act = SS_ACT_NONE;
-    int rc = launch(&part, w_kmajor, ConvPass{1, 0}, false);                 // lo(x) * hi(w)
+    int rc = launch(&part, w_kmajor, ConvPass{1, acc}, false);               // lo(x) * hi(w)
     if (rc != SS_OK) return rc;
     rc = launch(&part, w_kmajor + wn, ConvPass{0, 1}, false);                // hi(x) * lo(w)
     if (rc != SS_OK) return rc;
@@ -707,7 +736,10 @@ extern "C" int ss_conv3d_tc_f16x3_supported(const ss_conv3d_desc* d) {
     if (!d || d->Cin % 32 != 0 || d->in_ldc % 4 != 0) return 0;
     ss_conv3d_desc t = *d;
     t.math = SS_MATH_TF32;
-    if (ss::conv_pw_eligible(&t)) return 0;          // the pointwise streaming kernel has no fp16 operand path
+    // the pointwise streaming kernel has no fp16 operand path; for the 3-D layers it serves (hourglass redir, neck deblocks) three
+    // streaming passes beat the box kernel, for the 2-D ones of the image encoder (depth-1 volumes of 10^5 pixels, N = 32) one
+    // box-kernel launch beats three passes that re-read and re-write the output
+    if (ss::conv_pw_eligible(&t) && d->Din > 1) return 0;
     return 1;
 }
 
@@ -730,6 +762,7 @@ extern "C" int ss_conv3d_tc_fwd(const ss_conv3d_desc* d, const float* x, const f
     SS_REQUIRE((long long)d->B * d->Dout * d->Hout * d->Wout < (1ll << 31), "ss_conv3d_tc_fwd: output too large");
     SS_REQUIRE(d->math == SS_MATH_TF32 || d->math == SS_MATH_TF32X3 || d->math == SS_MATH_F16X3 || d->math == SS_MATH_F16,
                "ss_conv3d_tc_fwd: TF32 / TF32X3 / F16X3 / F16 only (use ss_conv3d_fwd for 3xTF32 on mma.sync)");
+    SS_REQUIRE(!(d->accumulate && stats), "ss_conv3d_tc_fwd: accumulate is not combined with statistics");
     if (d->math == SS_MATH_F16X3 || d->math == SS_MATH_F16) SS_REQUIRE(ss_conv3d_tc_f16x3_supported(d) == 1 && d->acc_scale > 0.f, "ss_conv3d_tc_fwd: F16X3 not offered for this layer (ask ss_conv3d_tc_f16x3_supported)");
     if (d->transposed) SS_REQUIRE(d->dd == 1 && d->dh == 1 && d->dw == 1, "ss_conv3d_tc_fwd: dilated transposed conv unsupported");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

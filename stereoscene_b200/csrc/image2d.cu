@@ -58,29 +58,39 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// depthwise: block = 32 channel quads x DW_G column groups; a block walks DW_ROWS output rows
+// depthwise: block = qx channel quads x gy column groups (qx = the largest divisor of C/4 that is <= 32, so no lane idles on
+// 288- or 1344-channel tensors); a block walks ``rows`` output rows.  Loads use clamped addresses and a zero mask instead of
+// branches, so the (TW-1)*S+K loads of a row are issued back to back.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int DW_G = 8;
-constexpr int DW_ROWS = 4;
+constexpr int DW_MAX_THREADS = 320;
 
 template <int K, int S, int TW>
-__global__ void __launch_bounds__(32 * DW_G)
+__global__ void __launch_bounds__(DW_MAX_THREADS)
 dwconv2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
                 double* __restrict__ pool, int H, int W, int C, int in_ldc, int Ho, int Wo, int out_ldc, int pt, int pl, int out_act,
-                int row_blocks) {
+                int row_blocks, int rows) {
     constexpr int SPAN = (TW - 1) * S + K;
-    __shared__ float4 red[DW_G][32];
-    const int cq = blockIdx.x * 32 + threadIdx.x;            // channel quad
+    __shared__ float4 red[DW_MAX_THREADS];
+    const int qx = blockDim.x, gy = blockDim.y;
+    const int cq = blockIdx.x * qx + threadIdx.x;            // channel quad (always < C/4: qx divides C/4)
     const int n = blockIdx.z / row_blocks, rb = blockIdx.z % row_blocks;
-    const int ox0 = (blockIdx.y * DW_G + threadIdx.y) * TW;
-    const bool live = (cq * 4 < C) && (ox0 < Wo);
+    const int ox0 = (blockIdx.y * gy + threadIdx.y) * TW;
+    const int c = cq * 4;
     float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-        const int c = cq * 4;
+    if (ox0 < Wo) {
         const float4 bv = ldg_f4(bias + c);
         const int ix0 = ox0 * S - pl;
-        for (int r = 0; r < DW_ROWS; ++r) {
-            const int oy = rb * DW_ROWS + r;
+        int xoff[SPAN];
+        float xm[SPAN];
+#pragma unroll
+        for (int j = 0; j < SPAN; ++j) {
+            const int ix = ix0 + j;
+            const bool ok = ix >= 0 && ix < W;
+            xoff[j] = (ok ? ix : 0) * in_ldc;
+            xm[j] = ok ? 1.f : 0.f;
+        }
+        for (int r = 0; r < rows; ++r) {
+            const int oy = rb * rows + r;
             if (oy >= Ho) break;
             float4 acc[TW];
 #pragma unroll
@@ -88,22 +98,24 @@ dwconv2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
                 const int iy = oy * S - pt + ky;
-                if (iy < 0 || iy >= H) continue;
+                if (iy < 0 || iy >= H) continue;              // uniform over the block
                 const float* xr = x + (((size_t)n * H + iy) * W) * in_ldc + c;
+                float4 v[SPAN];
+#pragma unroll
+                for (int j = 0; j < SPAN; ++j) v[j] = ldg_f4(xr + xoff[j]);
                 float4 wv[K];
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) wv[kx] = ldg_f4(w + (size_t)(ky * K + kx) * C + c);
 #pragma unroll
                 for (int j = 0; j < SPAN; ++j) {
-                    const int ix = ix0 + j;
-                    if (ix < 0 || ix >= W) continue;
-                    const float4 v = ldg_f4(xr + (size_t)ix * in_ldc);
+                    const float m = xm[j];
+                    const float4 u = make_float4(v[j].x * m, v[j].y * m, v[j].z * m, v[j].w * m);
 #pragma unroll
                     for (int t = 0; t < TW; ++t) {
                         const int kx = j - t * S;             // compile-time after unrolling
                         if (kx >= 0 && kx < K) {
-                            acc[t].x = fmaf(v.x, wv[kx].x, acc[t].x); acc[t].y = fmaf(v.y, wv[kx].y, acc[t].y);
-                            acc[t].z = fmaf(v.z, wv[kx].z, acc[t].z); acc[t].w = fmaf(v.w, wv[kx].w, acc[t].w);
+                            acc[t].x = fmaf(u.x, wv[kx].x, acc[t].x); acc[t].y = fmaf(u.y, wv[kx].y, acc[t].y);
+                            acc[t].z = fmaf(u.z, wv[kx].z, acc[t].z); acc[t].w = fmaf(u.w, wv[kx].w, acc[t].w);
                         }
                     }
                 }
@@ -121,16 +133,15 @@ dwconv2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
         }
     }
     if (pool == nullptr) return;
-    red[threadIdx.y][threadIdx.x] = psum;
+    red[threadIdx.y * qx + threadIdx.x] = psum;
     __syncthreads();
-    if (threadIdx.y == 0 && cq * 4 < C) {
-        float4 s = red[0][threadIdx.x];
-#pragma unroll
-        for (int g = 1; g < DW_G; ++g) {
-            const float4 t = red[g][threadIdx.x];
+    if (threadIdx.y == 0) {
+        float4 s = red[threadIdx.x];
+        for (int g = 1; g < gy; ++g) {
+            const float4 t = red[g * qx + threadIdx.x];
             s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
         }
-        double* dst = pool + ((size_t)n * C + cq * 4) * 2;    // double[B][C][2] like the GroupNorm sums: slot 0 = sum
+        double* dst = pool + ((size_t)n * C + c) * 2;         // double[B][C][2] like the GroupNorm sums: slot 0 = sum
         atomicAdd(dst + 0, (double)s.x); atomicAdd(dst + 2, (double)s.y); atomicAdd(dst + 4, (double)s.z); atomicAdd(dst + 6, (double)s.w);
     }
 }
@@ -138,37 +149,59 @@ dwconv2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 template <int K, int S, int TW>
 static int launch_dw(const float* x, const float* w, const float* bias, float* y, double* pool, int N, int H, int W, int C, int in_ldc,
                      int Ho, int Wo, int out_ldc, int pt, int pl, int out_act, cudaStream_t st) {
-    const int rbk = (Ho + DW_ROWS - 1) / DW_ROWS;
-    dim3 grid((unsigned)((C / 4 + 31) / 32), (unsigned)((Wo + DW_G * TW - 1) / (DW_G * TW)), (unsigned)(N * rbk)), block(32, DW_G);
-    dwconv2d_kernel<K, S, TW><<<grid, block, 0, st>>>(x, w, bias, y, pool, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, rbk);
+    const int Q = C / 4;
+    int qx = 1;
+    for (int d = 1; d <= 32; ++d)
+        if (Q % d == 0) qx = d;
+    const int groups = (Wo + TW - 1) / TW;
+    int gy = min(max(256 / qx, 1), groups);
+    gy = (groups + (groups + gy - 1) / gy - 1) / ((groups + gy - 1) / gy);       // same block count, least idle groups
+    // rows per block: enough blocks for ~4 waves of 148 SMs x 2 resident blocks, at most 4 rows (L1 re-use of the K-row window)
+    const long long per_row = (long long)(Q / qx) * ((groups + gy - 1) / gy) * N;
+    int rows = 4;
+    while (rows > 1 && per_row * ((Ho + rows - 1) / rows) < 148LL * 8) rows >>= 1;
+    const int rbk = (Ho + rows - 1) / rows;
+    if ((long long)N * rbk > 65535) return set_arg_error("ss_dwconv2d_fwd: too many row blocks");
+    dim3 grid((unsigned)(Q / qx), (unsigned)((groups + gy - 1) / gy), (unsigned)(N * rbk)), block(qx, gy);
+    dwconv2d_kernel<K, S, TW><<<grid, block, 0, st>>>(x, w, bias, y, pool, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, rbk, rows);
     return check_launch("dwconv2d_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// SE fully connected layer: out[n][o] = act(bias[o] + in_mul * sum_c in[n][c] * w[o][c]); one warp per output
+// SE fully connected layer: out[n][o] = act(bias[o] + in_mul * sum_c in[n][c] * w[o][c]).  WIDE = one 256-thread block per
+// output (the squeeze layer: few outputs, thousands of inputs), else one warp per output (the excite layer).
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool IN_DOUBLE>
+template <bool IN_DOUBLE, bool WIDE>
 __global__ void __launch_bounds__(256)
 se_fc_kernel(const void* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
              int Cin, int Cout, float in_mul, int act) {
+    __shared__ float part[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o = blockIdx.x * 8 + warp, n = blockIdx.y;
+    const int o = WIDE ? blockIdx.x : blockIdx.x * 8 + warp, n = blockIdx.y;
     if (o >= Cout) return;
     const float* wr = w + (size_t)o * Cin;
     float acc = 0.f;
-    for (int c = lane; c < Cin; c += 32) {
+    for (int c = WIDE ? threadIdx.x : lane; c < Cin; c += WIDE ? 256 : 32) {
         float v;
         if constexpr (IN_DOUBLE) v = (float)(reinterpret_cast<const double*>(in)[((size_t)n * Cin + c) * 2] * (double)in_mul);
         else v = reinterpret_cast<const float*>(in)[(size_t)n * Cin + c] * in_mul;
         acc = fmaf(v, __ldg(wr + c), acc);
     }
     acc = warp_sum(acc);
-    if (lane == 0) {
-        float v = acc + (bias ? __ldg(bias + o) : 0.f);
-        if (act == SS_ACT_SIGMOID) v = 1.0f / (1.0f + expf(-v));
-        else v = apply_act(v, act);
-        out[(size_t)n * Cout + o] = v;
+    if constexpr (WIDE) {
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x != 0) return;
+        acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += part[i];
+    } else if (lane != 0) {
+        return;
     }
+    float v = acc + (bias ? __ldg(bias + o) : 0.f);
+    if (act == SS_ACT_SIGMOID) v = sigmoid_f(v);
+    else v = apply_act(v, act);
+    out[(size_t)n * Cout + o] = v;
 }
 
 }  // namespace ss
@@ -207,7 +240,7 @@ extern "C" int ss_dwconv2d_fwd(const float* x, const float* w, const float* bias
     const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
     const int th = max((Ho - 1) * S + K - H, 0), tw = max((Wo - 1) * S + K - W, 0);
     const int pt = th / 2, pl = tw / 2;
-    SS_REQUIRE((long long)N * ((Ho + DW_ROWS - 1) / DW_ROWS) <= 65535, "ss_dwconv2d_fwd: too many row blocks");
+    SS_REQUIRE(N <= 65535, "ss_dwconv2d_fwd: batch");
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 3 && S == 1) return launch_dw<3, 1, 4>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
     if (K == 3 && S == 2) return launch_dw<3, 2, 2>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
@@ -222,8 +255,16 @@ extern "C" int ss_se_fc_fwd(const void* in, int in_is_stats, const float* w, con
     using namespace ss;
     SS_REQUIRE(in && w && out, "ss_se_fc_fwd: null pointer");
     SS_REQUIRE(N > 0 && N <= 65535 && Cin > 0 && Cout > 0, "ss_se_fc_fwd: shape");
-    dim3 grid((unsigned)((Cout + 7) / 8), (unsigned)N);
-    if (in_is_stats) se_fc_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(in, w, bias, out, Cin, Cout, in_mul, act);
-    else se_fc_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, w, bias, out, Cin, Cout, in_mul, act);
+    SS_REQUIRE(Cout <= 65535 * 8, "ss_se_fc_fwd: too many outputs");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool wide = Cin >= 512 && Cout <= 1024;          // squeeze: a block per output; excite: a warp per output
+    dim3 grid((unsigned)(wide ? Cout : (Cout + 7) / 8), (unsigned)N);
+    if (in_is_stats) {
+        if (wide) se_fc_kernel<true, true><<<grid, 256, 0, st>>>(in, w, bias, out, Cin, Cout, in_mul, act);
+        else se_fc_kernel<true, false><<<grid, 256, 0, st>>>(in, w, bias, out, Cin, Cout, in_mul, act);
+    } else {
+        if (wide) se_fc_kernel<false, true><<<grid, 256, 0, st>>>(in, w, bias, out, Cin, Cout, in_mul, act);
+        else se_fc_kernel<false, false><<<grid, 256, 0, st>>>(in, w, bias, out, Cin, Cout, in_mul, act);
+    }
     return check_launch("se_fc_kernel");
 }

@@ -404,8 +404,10 @@ _MATERIALIZE_BYTES = 16 << 20
 
 def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, out_act: int = SS_ACT_NONE,
          want_stats: bool = False, math_mode: Optional[int] = None, use_bias: bool = True,
-         pad: Optional[Sequence[int]] = None, stats_planes: Optional[Tuple[int, int]] = None):
+         pad: Optional[Sequence[int]] = None, stats_planes: Optional[Tuple[int, int]] = None, accumulate: bool = False):
     """y = act_out(conv(act_in(x*scale+shift)) + bias); returns (y [B,D',H',W',Cout], stats or None).
+    ``accumulate``: y = act_out(conv + bias + out) in place on ``out`` (the identity shortcut of a residual block, taken in the
+    epilogue of the tcgen05 kernels; on the mma.sync kernels it is a separate join).
     ``out`` may be a channel slice of a concatenation buffer.  ``pad`` overrides the module's padding and
     ``stats_planes`` = (d0, d1) restricts the GroupNorm sums to output planes d0 <= d < d1: both serve the X-slab
     sharded mode (stereoscene_b200.xshard), where a rank convolves its slab plus halo planes."""
@@ -436,6 +438,14 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
     tc = (_USE_TCGEN05 and mm in (SS_MATH_TF32, SS_MATH_TF32X3, SS_MATH_F16) and Cin % 32 == 0 and ((pc.Cout % 4 == 0 and pc.Cout >= 32) or pc.Cout < 32)
           and in_ldc % 4 == 0 and xin.data_ptr() % 16 == 0)
     d.acc_scale = 1.0
+    if accumulate:
+        if out is None or want_stats:
+            raise RuntimeError("conv: accumulate needs an explicit out tensor and is not combined with statistics")
+        if not tc or mm == SS_MATH_3XTF32:     # mma.sync kernels: convolve into a temporary, then one join
+            tmp, _ = conv(x, module, None, SS_ACT_NONE, False, math_mode, use_bias, pad)
+            join(Vol(tmp), Vol(out), out_act=out_act, out=out)
+            return out, None
+        d.accumulate = 1
     if mm == SS_MATH_TF32X3 and not tc:        # layers the tcgen05 kernels do not take (Cin = 2, odd strides): mma.sync split TF32
         mm = SS_MATH_3XTF32
         d.math = mm
@@ -449,6 +459,7 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
         d = cabi.ConvDesc(B, Din, Hin, Win, Cin, Do, Ho, Wo, pc.Cout, *pc.k, *pc.s, *pad_eff, *pc.d,
                           1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP, sd0, sd1)
         d.acc_scale = 1.0
+        d.accumulate = 1 if accumulate else 0
     if mm == SS_MATH_F16 and not (tc and pad is None and _halo_layer(pc, Din, Hin, Win, Cin)):
         mm = SS_MATH_TF32            # only the halo-resident kernel gains from fp16 operands; TF32 has the same 11-bit significand
         d.math = mm

@@ -177,11 +177,12 @@ class InvertedResidual(nn.Module):
         z, pool = ops.dwconv2d(y, w, b, self.k, self.stride, SS_ACT_SWISH, want_pool=True)
         N, _, Ho, Wo, _ = z.shape
         gate = self.se.gate(pool, Ho * Wo)
+        zg = Vol(z, gate, bufs.zeros_like(gate))
+        if self.with_res_shortcut:       # x += linear(z * gate): the shortcut is taken in the GEMM's epilogue, in place on the block input
+            ops.conv(zg, self.linear_conv.pointwise(), out=x[..., :self.cout], accumulate=True)
+            return x
         out = bufs.take(N, Ho, Wo, self.cout, avoid=x)
-        lin = out[..., :self.cout]
-        ops.conv(Vol(z, gate, bufs.zeros_like(gate)), self.linear_conv.pointwise(), out=lin)
-        if self.with_res_shortcut:
-            ops.join(Vol(lin), Vol(x[..., :self.cout]), out=lin)          # elementwise, in place on the branch output
+        ops.conv(zg, self.linear_conv.pointwise(), out=out[..., :self.cout])
         return out
 
 

@@ -117,9 +117,21 @@ def test_swish_epilogue_and_se_gate_as_pending_scale(ops):
         ops.conv(ops.Vol(z, gate.cuda(), torch.zeros(N, 288, device="cuda")), lin.cuda(), out=out[..., :48], math_mode=mode)
         assert rel_err(_nchw(out[..., :48]), want2) < tol, mode
         assert float(out[..., 48:].abs().max()) == 0.0
-    res = out.clone()
-    ops.join(ops.Vol(res[..., :48]), ops.Vol(xb[..., :48]), out=res[..., :48])           # in-place residual join on a slice
-    assert rel_err(_nchw(res[..., :48]), _nchw(out[..., :48]) + x) < 1e-6 and float(res[..., 48:].abs().max()) == 0.0
+    # identity shortcut taken in the GEMM epilogue, in place on the (channel-padded) block input
+    for mode, tol in ((ops.SS_MATH_TF32X3, 2e-5), (ops.SS_MATH_TF32, 2e-3), (ops.SS_MATH_3XTF32, 2e-5)):
+        res = xb.clone()
+        ops.conv(ops.Vol(z, gate.cuda(), torch.zeros(N, 288, device="cuda")), lin.cuda(), out=res[..., :48], math_mode=mode,
+                 accumulate=True)
+        assert rel_err(_nchw(res[..., :48]), want2 + x) < tol, mode
+        assert float(res[..., 48:].abs().max()) == 0.0
+    ops.use_f16x3(False)                     # the three-launch compensated mode accumulates too
+    try:
+        res = xb.clone()
+        ops.conv(ops.Vol(z, gate.cuda(), torch.zeros(N, 288, device="cuda")), lin.cuda(), out=res[..., :48],
+                 math_mode=ops.SS_MATH_TF32X3, accumulate=True)
+    finally:
+        ops.use_f16x3(True)
+    assert rel_err(_nchw(res[..., :48]), want2 + x) < 2e-5
 
 
 @pytest.fixture(scope="module")

@@ -33,6 +33,17 @@ def timed(fn, n=20):
     return a.elapsed_time(b) / n
 
 
+if os.environ.get("PROFILE_ONE"):           # under ncu --profile-from-start off: one warm forward in the given policy
+    ops.set_math_policy(os.environ["PROFILE_ONE"])
+    with torch.no_grad():
+        fwd(); fwd()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        fwd()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    sys.exit(0)
+
 for pol in (sys.argv[1:] or ["mixed", "tf32"]):
     ops.set_math_policy(pol)
     with torch.no_grad():
