@@ -95,6 +95,11 @@ typedef struct ss_conv3d_desc {
     int32_t accumulate;               /* ss_conv3d_tc_fwd only: y = act(conv + bias + y_old) -- the identity shortcut of a residual block whose
                                          branch ends in this convolution, taken in place on the block's input (efficientnet.py:219-222);
                                          not combined with `stats` */
+    void* splitk_ws;                  /* ss_conv3d_tc_fwd only, optional: device workspace the layer may use to split its K range over several
+                                         CTAs per output tile (partial tiles float[k][voxels][Cout], then one reduce kernel that adds bias /
+                                         shortcut / activation in a fixed order).  Taken when the tiles alone fill less than half of the SMs and
+                                         K is long: the 1x1 projections of the image encoder's late stages.  NULL: never split. */
+    int64_t splitk_ws_bytes;          /* size of splitk_ws */
 } ss_conv3d_desc;
 
 /* w_packed: float[taps][Cin][cout_packed], taps = kd*kh*kw in (kd,kh,kw) row-major order, i.e.

@@ -20,7 +20,8 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "B", "Din", "Hin", "Win", "Cin", "Dout", "Hout", "Wout", "Cout",
         "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw", "dd", "dh", "dw",
-        "transposed", "in_ldc", "out_ldc", "in_act", "out_act", "math", "cout_packed", "stats_d0", "stats_d1")] + [("acc_scale", C.c_float), ("accumulate", C.c_int32)]
+        "transposed", "in_ldc", "out_ldc", "in_act", "out_act", "math", "cout_packed", "stats_d0", "stats_d1")] + [("acc_scale", C.c_float), ("accumulate", C.c_int32),
+                                                                                                      ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
 
 
 class ConvJoin(C.Structure):

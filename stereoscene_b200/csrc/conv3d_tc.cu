@@ -23,6 +23,7 @@
 //     add bias / activation, store 128-byte rows and reduce per-channel sums with a shuffle butterfly.
 //   * STAGES-deep smem ring (A 16 KB + B BN*128 B per stage), full / ready / empty mbarriers.
 #include <cuda.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace ss {
@@ -48,6 +49,9 @@ struct TcParams {
     int a_lo, accumulate;      // ConvPass (common.cuh)
     float acc_scale;           // F16 variant: accumulator scale (power of two)
     int f16_n;                 // F16 variant: MMAs per K step (6 = compensated, 2 = fp16 single pass)
+    int ksplit;                // > 1: blockIdx.y = column tile * ksplit + K slice; raw partial tiles go to ws, splitk_reduce_kernel finishes
+    float* ws;                 // float[ksplit][B*Dout*Hout*Wout][Cout]
+    long long ws_slab;
     StatsRange sr;             // output planes that contribute to stats
 };
 
@@ -214,7 +218,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
     const int ncls = p.cls_d * p.cls_h * p.cls_w;
     const int b = blockIdx.z / ncls, cls = blockIdx.z % ncls;
     const int rd = cls / (p.cls_h * p.cls_w), rh = (cls / p.cls_w) % p.cls_h, rw = cls % p.cls_w;
-    const int n0 = blockIdx.y * BN;
+    const int n0 = (int)(blockIdx.y / p.ksplit) * BN;
     const int Dc = (p.Dout - rd + p.cls_d - 1) / p.cls_d, Hc = (p.Hout - rh + p.cls_h - 1) / p.cls_h,
               Wc = (p.Wout - rw + p.cls_w - 1) / p.cls_w;
     const int isd = p.transposed ? 1 : p.sd, ish = p.transposed ? 1 : p.sh, isw = p.transposed ? 1 : p.sw;
@@ -268,7 +272,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
     const uint32_t tmem_base = *tmem_slot;
     const int ntaps = *s_ntaps;
     const int kchunks = p.Cin / TC_BK;
-    const int nsteps = ntaps * kchunks;
+    // split-K: this CTA runs K steps [s0, s0 + nsteps) of the layer's ntaps * kchunks (the host makes every slice non-empty)
+    const int ks = (int)(blockIdx.y % p.ksplit);
+    const int per_slice = (ntaps * kchunks + p.ksplit - 1) / p.ksplit;
+    const int s0 = ks * per_slice;
+    const int nsteps = min(ntaps * kchunks, s0 + per_slice) - s0;
     const uint32_t ring_u32 = smem_u32(ring);
 
     if (warp == TC_WORKERS / 32) {
@@ -277,7 +285,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             const int slot = step % STAGES;
             const uint32_t use = (uint32_t)(step / STAGES);
             mbar_wait(empty0 + 8 * slot, (use & 1u) ^ 1u);
-            const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;     // taps innermost: the box stays hot in L2
+            const int tap = (s0 + step) % ntaps, c0 = ((s0 + step) / ntaps) * TC_BK;     // taps innermost: the box stays hot in L2
             const int4 tp = taps[tap];
             const uint32_t a_dst = ring_u32 + slot * Cfg::STAGE_BYTES;
             const uint32_t bar = full0 + 8 * slot;
@@ -346,7 +354,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             for (int step = grp; step < nsteps; step += 2) {
                 const int slot = step % STAGES;
                 const uint32_t use = (uint32_t)(step / STAGES);
-                const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
+                const int tap = (s0 + step) % ntaps, c0 = ((s0 + step) / ntaps) * TC_BK;
                 mbar_wait(full0 + 8 * slot, use & 1u);
                 const unsigned char* a_src = ring + slot * Cfg::STAGE_BYTES;
                 const bool ok = (vmask >> tap) & 1ull;
@@ -383,7 +391,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             for (int step = grp; step < nsteps; step += 2) {
                 const int slot = step % STAGES;
                 const uint32_t use = (uint32_t)(step / STAGES);
-                const int tap = step % ntaps, c0 = (step / ntaps) * TC_BK;
+                const int tap = (s0 + step) % ntaps, c0 = ((s0 + step) / ntaps) * TC_BK;
                 mbar_wait(full0 + 8 * slot, use & 1u);
                 const unsigned char* a_src = ring + slot * Cfg::STAGE_BYTES;
                 const bool ok = (vmask >> tap) & 1ull;
@@ -461,6 +469,20 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
             if constexpr (F16) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] *= p.acc_scale;
+            }
+            if (p.ksplit > 1) {                                // split-K: the raw partial tile; bias / shortcut / activation in splitk_reduce_kernel
+                if (ov >= 0) {
+                    float* dst = p.ws + (size_t)ks * p.ws_slab + (size_t)ov * p.Cout + cbase;
+                    if ((p.Cout & 3) == 0 && cbase + 32 <= p.Cout) {
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            if (cbase + k < p.Cout) dst[k] = v[k];
+                    }
+                }
+                continue;
             }
             if (p.accumulate && ov >= 0) {                     // later pass of the compensated mode: add the partial result
                 const float* src = p.y + (size_t)ov * p.out_ldc + cbase;
@@ -555,6 +577,26 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
     }
 }
 
+// y[r][c] = act(bias[c] + sum_s ws[s][r][c] (+ y[r][c] when accumulate)): the second half of a split-K layer (fixed summation order)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, long long slab, int S, const float* __restrict__ bias, float* __restrict__ y,
+                     long long rows, int Cout, int out_ldc, int accumulate, int act) {
+    const int cq = Cout >> 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cq) return;
+    const long long r = i / cq;
+    const int c = (int)(i % cq) * 4;
+    float4 a = bias ? ldg_f4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+        const float4 t = *reinterpret_cast<const float4*>(ws + (size_t)s * slab + (size_t)r * Cout + c);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(y + (size_t)r * out_ldc + c);
+    if (accumulate) { const float4 t = *dst; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
+    *dst = a;
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -586,7 +628,7 @@ static void choose_box(int Dc, int Hc, int Wc, int sd, int sh, int sw, int& TD, 
 }
 
 template <int BN, bool F16 = false>
-static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, int ntaps_total, cudaStream_t st) {
+static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, int ntaps_total, cudaStream_t st, float* ws, size_t ws_bytes) {
     using Cfg = TcCfg<BN>;
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return set_arg_error("ss_conv3d_tc_fwd: cuTensorMapEncodeTiled is not available from the driver");
@@ -628,9 +670,32 @@ static int launch_tc(TcParams& p, const float* x, int in_ldc, const float* wk, i
         SS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid((unsigned)(p.nTD * p.nTH * p.nTW), (unsigned)((p.CoutP + BN - 1) / BN), (unsigned)(p.B * ncls));
+    // split-K (the caller lent a workspace): layers whose tiles fill less than half of the SMs while each walks a long K -- the
+    // 1x1 projections of the image encoder's late stages (960 pixels x 2304..3840 channels -> 30..50 CTAs of 72..120 K steps)
+    const int ntiles = (p.CoutP + BN - 1) / BN;
+    const long long tiles = (long long)p.nTD * p.nTH * p.nTW * ntiles * p.B * ncls;
+    const int nsteps_all = ntaps_total * (p.Cin / TC_BK);
+    p.ksplit = 1;
+    if (ws && ncls == 1 && !p.stats && !p.a_lo && tiles * 2 <= 148 && nsteps_all >= 16 && (p.Cout & 3) == 0 && (p.out_ldc & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+        const long long rows = (long long)p.B * p.Dout * p.Hout * p.Wout;
+        int k = (int)std::min<long long>(std::min<long long>(148 / tiles, nsteps_all / 6), 8);
+        while (k > 1 && (size_t)k * rows * p.Cout * sizeof(float) > ws_bytes) --k;
+        if (k > 1) {
+            const int per = (nsteps_all + k - 1) / k;
+            p.ksplit = (nsteps_all + per - 1) / per;
+            p.ws = ws;
+            p.ws_slab = rows * p.Cout;
+        }
+    }
+    dim3 grid((unsigned)(p.nTD * p.nTH * p.nTW), (unsigned)(ntiles * p.ksplit), (unsigned)(p.B * ncls));
     conv_tc_kernel<BN, F16><<<grid, TC_THREADS, smem, st>>>(p, tmA, tmB);
-    return check_launch(F16 ? "conv_tc_f16x3_kernel" : "conv_tc_kernel");
+    int rc = check_launch(F16 ? "conv_tc_f16x3_kernel" : "conv_tc_kernel");
+    if (rc != SS_OK || p.ksplit == 1) return rc;
+    const long long rows = (long long)p.B * p.Dout * p.Hout * p.Wout, items = rows * (p.Cout / 4);
+    splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(p.ws, p.ws_slab, p.ksplit, p.bias, p.y, rows, p.Cout, p.out_ldc,
+                                                                         p.accumulate, p.out_act);
+    return check_launch("splitk_reduce_kernel");
 }
 
 }  // namespace ss
@@ -660,6 +725,9 @@ static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_
     p.cls_d = d->transposed ? d->sd : 1; p.cls_h = d->transposed ? d->sh : 1; p.cls_w = d->transposed ? d->sw : 1;
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
     p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale; p.sr = stats_range_of(d); p.f16_n = ps.f16_n;
+    p.ksplit = 1; p.ws = nullptr; p.ws_slab = 0;
+    float* ws = reinterpret_cast<float*>(d->splitk_ws);
+    const size_t ws_bytes = d->splitk_ws ? (size_t)d->splitk_ws_bytes : 0;
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");
     {
         int rcm = 0;
@@ -682,19 +750,24 @@ static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_
     else {  // wide layers: the column tile that minimises (waves of CTAs on 148 SMs) x (work per CTA ~ BN); 256-column tiles
         // leave SMs idle on small grids, 160 columns turn the 300-CTA grid of the 640-channel 2-D layers into 240
         const int ncls = p.cls_d * p.cls_h * p.cls_w;
-        const long long rows = ((long long)(p.Dout + p.cls_d - 1) / p.cls_d) * ((p.Hout + p.cls_h - 1) / p.cls_h) *
-                               ((p.Wout + p.cls_w - 1) / p.cls_w);
-        const long long mt = ((rows + TC_BM - 1) / TC_BM) * p.B * ncls;
+        const int Dc = (p.Dout + p.cls_d - 1) / p.cls_d, Hc = (p.Hout + p.cls_h - 1) / p.cls_h, Wc = (p.Wout + p.cls_w - 1) / p.cls_w;
+        long long mt = (((long long)Dc * Hc * Wc + TC_BM - 1) / TC_BM) * p.B * ncls;
+        if (p.Din == 1 && ntaps_total == 1) {            // 2-D pointwise layers: count the boxes the launch will really use (a 12 x 40
+            int td, th, tw;                              // image is 3.75 tiles of 128 pixels but 5 boxes)
+            choose_box(Dc, Hc, Wc, 1, 1, 1, td, th, tw);
+            mt = (long long)((Dc + td - 1) / td) * ((Hc + th - 1) / th) * ((Wc + tw - 1) / tw) * p.B * ncls;
+        }
         auto cost = [&](int bn) { const long long ctas = mt * ((cp + bn - 1) / bn); return (double)((ctas + 147) / 148) * bn; };
         double bc = cost(256) * 0.9;
         if (cp % 128 == 0 && cost(128) <= bc * 1.0001 / 0.9) { best = 128; bc = cost(128); }
         if (cp % 160 == 0 && cost(160) < bc) { best = 160; bc = cost(160); }
+        if (p.Din == 1 && ntaps_total == 1 && cp % 192 == 0 && cost(192) < bc) { best = 192; bc = cost(192); }
         if (cp % 128 != 0 && cp % 160 != 0)              // 288- and 1344-wide layers of the image encoder: a partial last tile of 160
             for (int bn : {160, 192})                    // or 192 columns wastes less than 256-column tiles
                 if (cost(bn) < bc) { best = bn; bc = cost(bn); }
     }
 #define SS_TC_LAUNCH(BN_)                                                                                          \
-    return ps.f16 ? launch_tc<BN_, true>(p, x, d->in_ldc, w_kmajor, ntaps_total, st) : launch_tc<BN_, false>(p, x, d->in_ldc, w_kmajor, ntaps_total, st)
+    return ps.f16 ? launch_tc<BN_, true>(p, x, d->in_ldc, w_kmajor, ntaps_total, st, ws, ws_bytes) : launch_tc<BN_, false>(p, x, d->in_ldc, w_kmajor, ntaps_total, st, ws, ws_bytes)
     if (best == 32) SS_TC_LAUNCH(32);
     if (best == 64) SS_TC_LAUNCH(64);
     if (best == 128) SS_TC_LAUNCH(128);

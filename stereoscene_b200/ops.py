@@ -404,10 +404,12 @@ _MATERIALIZE_BYTES = 16 << 20
 
 def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, out_act: int = SS_ACT_NONE,
          want_stats: bool = False, math_mode: Optional[int] = None, use_bias: bool = True,
-         pad: Optional[Sequence[int]] = None, stats_planes: Optional[Tuple[int, int]] = None, accumulate: bool = False):
+         pad: Optional[Sequence[int]] = None, stats_planes: Optional[Tuple[int, int]] = None, accumulate: bool = False,
+         splitk_ws: Optional[torch.Tensor] = None):
     """y = act_out(conv(act_in(x*scale+shift)) + bias); returns (y [B,D',H',W',Cout], stats or None).
     ``accumulate``: y = act_out(conv + bias + out) in place on ``out`` (the identity shortcut of a residual block, taken in the
-    epilogue of the tcgen05 kernels; on the mma.sync kernels it is a separate join).
+    epilogue of the tcgen05 kernels; on the mma.sync kernels it is a separate join).  ``splitk_ws``: a float32 scratch tensor the
+    tcgen05 box kernel may use to split a long K over several CTAs per tile (small-M layers of the image encoder).
     ``out`` may be a channel slice of a concatenation buffer.  ``pad`` overrides the module's padding and
     ``stats_planes`` = (d0, d1) restricts the GroupNorm sums to output planes d0 <= d < d1: both serve the X-slab
     sharded mode (stereoscene_b200.xshard), where a rank convolves its slab plus halo planes."""
@@ -446,6 +448,8 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
             join(Vol(tmp), Vol(out), out_act=out_act, out=out)
             return out, None
         d.accumulate = 1
+    if splitk_ws is not None and tc:
+        d.splitk_ws, d.splitk_ws_bytes = splitk_ws.data_ptr(), splitk_ws.numel() * 4
     if mm == SS_MATH_TF32X3 and not tc:        # layers the tcgen05 kernels do not take (Cin = 2, odd strides): mma.sync split TF32
         mm = SS_MATH_3XTF32
         d.math = mm
@@ -460,6 +464,8 @@ def conv(x: Vol, module: torch.nn.Module, out: Optional[torch.Tensor] = None, ou
                           1 if pc.transposed else 0, in_ldc, out_ldc, x.act, out_act, mm, pc.CoutP, sd0, sd1)
         d.acc_scale = 1.0
         d.accumulate = 1 if accumulate else 0
+        if splitk_ws is not None:
+            d.splitk_ws, d.splitk_ws_bytes = splitk_ws.data_ptr(), splitk_ws.numel() * 4
     if mm == SS_MATH_F16 and not (tc and pad is None and _halo_layer(pc, Din, Hin, Win, Cin)):
         mm = SS_MATH_TF32            # only the halo-resident kernel gains from fp16 operands; TF32 has the same 11-bit significand
         d.math = mm

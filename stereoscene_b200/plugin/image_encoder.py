@@ -178,11 +178,12 @@ class InvertedResidual(nn.Module):
         N, _, Ho, Wo, _ = z.shape
         gate = self.se.gate(pool, Ho * Wo)
         zg = Vol(z, gate, bufs.zeros_like(gate))
+        ws = bufs.workspace(x.device)
         if self.with_res_shortcut:       # x += linear(z * gate): the shortcut is taken in the GEMM's epilogue, in place on the block input
-            ops.conv(zg, self.linear_conv.pointwise(), out=x[..., :self.cout], accumulate=True)
+            ops.conv(zg, self.linear_conv.pointwise(), out=x[..., :self.cout], accumulate=True, splitk_ws=ws)
             return x
         out = bufs.take(N, Ho, Wo, self.cout, avoid=x)
-        ops.conv(zg, self.linear_conv.pointwise(), out=out[..., :self.cout])
+        ops.conv(zg, self.linear_conv.pointwise(), out=out[..., :self.cout], splitk_ws=ws)
         return out
 
 
@@ -203,6 +204,13 @@ class _Buffers:
         if pair is None:
             pair = self.padded[(N, H, W, cp, dev)] = [torch.zeros((N, 1, H, W, cp), dtype=torch.float32, device=dev) for _ in range(2)]
         return pair[1] if avoid.data_ptr() == pair[0].data_ptr() else pair[0]
+
+    def workspace(self, dev) -> torch.Tensor:
+        """Split-K scratch for the long-K projections of the late stages (8 slices x 960 pixels x 640 channels fit)."""
+        w = self.zero.get(("ws", dev))
+        if w is None:
+            w = self.zero[("ws", dev)] = torch.empty(8 << 20, dtype=torch.float32, device=dev)
+        return w
 
     def zeros_like(self, t: torch.Tensor) -> torch.Tensor:
         key = (tuple(t.shape), t.device)

@@ -211,3 +211,39 @@ def test_reference_tensor_contract_and_end_to_end_from_images(ops):
                                    want_labels=True)
     assert torch.equal(a["output_voxels"], b["output_voxels"]) and torch.equal(a["labels"], b["labels"])
     assert torch.isfinite(a["output_voxels"]).all()
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_split_k_projection_matches_oracle(ops, accumulate):
+    """Late-stage projection (960 pixels, K = 2304): 30 tiles on 148 SMs -> the box kernel splits K over CTAs when lent a workspace;
+    the partial tiles are summed in a fixed order, so two runs agree bit for bit and the result equals the unsplit kernel's to rounding."""
+    import torch.nn as nn
+    from stereoscene_b200 import cabi
+    g = torch.Generator().manual_seed(8)
+    N, H, W, ci, co = 2, 12, 40, 2304, 384
+    x = torch.randn(N, ci, H, W, generator=g)
+    gate = torch.rand(N, ci, generator=g)
+    lin = nn.Conv2d(ci, co, 1, bias=True)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(co, ci, 1, 1, generator=g) * 0.03)
+    res = torch.randn(N, co, H, W, generator=g)
+    want = F.conv2d(x.double() * gate.double().view(N, ci, 1, 1), lin.weight.double(), lin.bias.double()).float().detach()
+    if accumulate:
+        want = want + res
+    ws = torch.empty(8 << 20, device="cuda")
+    v = ops.Vol(_nhwc(x), gate.cuda(), torch.zeros(N, ci, device="cuda"))
+    outs = []
+    for use_ws in (ws, ws, None):
+        out = _nhwc(res) if accumulate else torch.zeros((N, 1, H, W, co), device="cuda")
+        c0 = cabi.kernel_census().get("splitk_reduce_kernel", 0)
+        ops.conv(v, lin.cuda(), out=out, math_mode=ops.SS_MATH_TF32X3, accumulate=accumulate, splitk_ws=use_ws)
+        assert cabi.kernel_census().get("splitk_reduce_kernel", 0) - c0 == (1 if use_ws is not None else 0)
+        outs.append(_nchw(out))
+    assert rel_err(outs[0], want) < 2e-5 and rel_err(outs[2], want) < 2e-5
+    assert torch.equal(outs[0], outs[1])
+    # a large-M layer ignores the workspace (its tiles already fill the GPU)
+    big = nn.Conv2d(64, 96, 1, bias=True).cuda()
+    xb = torch.randn(2, 1, 96, 320, 64, device="cuda")
+    c0 = cabi.kernel_census().get("splitk_reduce_kernel", 0)
+    ops.conv(ops.Vol(xb), big, math_mode=ops.SS_MATH_TF32X3, splitk_ws=ws)
+    assert cabi.kernel_census().get("splitk_reduce_kernel", 0) == c0
