@@ -109,6 +109,64 @@ def golden_parity(workload: str, out: dict, seed: int):
     return res
 
 
+def image_encoder_extra(model, mc, dev, left, right, calib, occ, seed):
+    """SURVEY.md section 8 row N2, outside the metric (BASELINE.json's path starts from backbone features): the 2-D image
+    encoder (EfficientNet-B7 + SECONDFPN) on one stereo pair -- time alone, time of the whole detector from images, parity of
+    its output features against the reference's own efficientnet.py (tests/golden/golden_image_full.npz, same seed)."""
+    import json as _json
+    import numpy as np
+    from stereoscene_b200 import cabi, presets, synth
+    from stereoscene_b200.registry import build_backbone, build_neck
+    cfg = presets.model_config("config2", image_encoder=True)["model"]
+    enc = torch.nn.ModuleDict(dict(img_backbone=build_backbone(cfg["img_backbone"]), img_neck=build_neck(cfg["img_neck"])))
+    synth.randomize_weights_(enc, seed)
+    enc = enc.to(dev).eval()
+    model.img_backbone, model.img_neck = enc["img_backbone"], enc["img_neck"]
+    il, ir = synth.stereo_images(1, mc["input_size"], seed=seed, device=dev)
+    pair = torch.cat([il, ir], 0)
+
+    def timed_graph(fn, n=10):
+        with torch.no_grad():
+            fn(); fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out = {"model": "CustomEfficientNet-b7 + SECONDFPN (stereoscene.py:59-74), 2 x 3 x %d x %d" % tuple(mc["input_size"]),
+           "in_metric": False}
+    with torch.no_grad():
+        c0 = cabi.launch_count()
+        feat = model.image_encoder_cl(pair)
+        out["gpu_launches"] = int(cabi.launch_count() - c0)
+    out["ms_per_pair"] = timed_graph(lambda: model.image_encoder_cl(pair))
+    out["from_images_ms_per_step"] = timed_graph(lambda: model.forward_images(il, ir, left, right, calib, occ_size=occ, want_labels=True))
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden")
+    meta_p = os.path.join(gdir, "golden_image_full.json")
+    if os.path.exists(meta_p) and tuple(mc["input_size"]) == (384, 1280):
+        meta = _json.load(open(meta_p))
+        if meta["seed"] == seed:
+            gold = np.load(os.path.join(gdir, "golden_image_full.npz"))["img_feat"].astype(np.float64)
+            sl = tuple(slice(*x) for x in meta["samplers"]["img_feat"])
+            got = feat.squeeze(1).permute(0, 3, 1, 2)[sl].double().cpu().numpy()
+            d = got - gold
+            st = meta["stats"]["img_feat"]
+            out["parity_img_feat"] = {"max_rel": float(np.abs(d).max() / st["absmax"]), "rms_rel": float(np.sqrt((d * d).mean()) / st["rms"]),
+                                      "against": "tests/golden/golden_image_full.npz (reference's own efficientnet.py, seed 0)"}
+    model.img_backbone = model.img_neck = None
+    return out
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -541,6 +599,10 @@ def run_ours(args):
             finally:
                 ops.set_math_policy(args.math)
 
+    image_enc = None
+    if world == 1 and B == 1 and not args.no_other_modes:
+        image_enc = image_encoder_extra(model, mc, dev, left, right, calib, occ, seed)
+
     # the cuBLAS TF32 GEMM peak is measured LAST: 60 back-to-back 8192^3 GEMMs push the chip to its power cap and would
     # slow everything timed after them
     time.sleep(1.0)
@@ -571,6 +633,7 @@ def run_ours(args):
         "peaks": pk,
         "parity": parity,
         "other_math_policies": other_modes,
+        "image_encoder": image_enc,
     }
     if args.workload == "config2":
         # whole-step algorithmic totals of SURVEY.md section 8(a) (B=1, fp32 storage, incl. depth_net): 3,986 GFLOP and 9,139 MB

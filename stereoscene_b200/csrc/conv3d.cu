@@ -328,8 +328,8 @@ conv_igemm_kernel(const ConvParams p) {
                 const int r = moff + i * 16 + g + 8 * h;
                 const int ov = rowinfo[r].w;
                 if (ov < 0) continue;
-                const float v0 = apply_act(acc[i][j][2 * h] + bias0, p.out_act);
-                const float v1 = apply_act(acc[i][j][2 * h + 1] + bias1, p.out_act);
+                const float v0 = apply_act_sw(acc[i][j][2 * h] + bias0, p.out_act);
+                const float v1 = apply_act_sw(acc[i][j][2 * h + 1] + bias1, p.out_act);
                 float* dst = p.y + (size_t)ov * p.out_ldc + c;
                 if (c + 1 < p.Cout && vec2) {
                     *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);

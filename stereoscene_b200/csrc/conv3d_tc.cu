@@ -24,6 +24,7 @@
 //   * STAGES-deep smem ring (A 16 KB + B BN*128 B per stage), full / ready / empty mbarriers.
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ss {
@@ -49,6 +50,7 @@ struct TcParams {
     int a_lo, accumulate;      // ConvPass (common.cuh)
     float acc_scale;           // F16 variant: accumulator scale (power of two)
     int f16_n;                 // F16 variant: MMAs per K step (6 = compensated, 2 = fp16 single pass)
+    int direct_store;          // A/B switch (STEREOSCENE_B200_TC_DIRECT_STORE=1): every lane stores its own row, as before round 2's transposed epilogue
     int ksplit;                // > 1: blockIdx.y = column tile * ksplit + K slice; raw partial tiles go to ws, splitk_reduce_kernel finishes
     float* ws;                 // float[ksplit][B*Dout*Hout*Wout][Cout]
     long long ws_slab;
@@ -516,7 +518,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = swish_f(v[k]);
             }
-            if (vec_ok && cbase + 32 <= p.Cout) {
+            if (p.direct_store && vec_ok && cbase + 32 <= p.Cout) {
+                if (ov >= 0) {
+                    float* dst = p.y + (size_t)ov * p.out_ldc + cbase;
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                }
+            } else if (vec_ok && cbase + 32 <= p.Cout) {
                 // A lane holds 32 columns of ITS row: storing them directly makes every STG.128 touch 32 different rows (32
                 // LSU wavefronts per instruction; measured 6 us of a 9 us CTA on the 1x1 layers of the image encoder).  The
                 // chunk is transposed through a per-warp 32 x 36 tile instead, so that 8 neighbouring lanes write one row's
@@ -593,7 +601,7 @@ splitk_reduce_kernel(const float* __restrict__ ws, long long slab, int S, const 
     }
     float4* dst = reinterpret_cast<float4*>(y + (size_t)r * out_ldc + c);
     if (accumulate) { const float4 t = *dst; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-    a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
+    a.x = apply_act_sw(a.x, act); a.y = apply_act_sw(a.y, act); a.z = apply_act_sw(a.z, act); a.w = apply_act_sw(a.w, act);
     *dst = a;
 }
 
@@ -726,6 +734,8 @@ static int tc_dispatch(const ss_conv3d_desc* d, const float* x, const float* in_
     p.in_scale = in_scale; p.in_shift = in_shift; p.bias = bias; p.y = y; p.stats = stats;
     p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.acc_scale = ps.acc_scale; p.sr = stats_range_of(d); p.f16_n = ps.f16_n;
     p.ksplit = 1; p.ws = nullptr; p.ws_slab = 0;
+    static const int direct_store = [] { const char* e = getenv("STEREOSCENE_B200_TC_DIRECT_STORE"); return (e && e[0] == '1') ? 1 : 0; }();
+    p.direct_store = direct_store;
     float* ws = reinterpret_cast<float*>(d->splitk_ws);
     const size_t ws_bytes = d->splitk_ws ? (size_t)d->splitk_ws_bytes : 0;
     SS_REQUIRE((long long)p.B * p.cls_d * p.cls_h * p.cls_w <= 65535, "ss_conv3d_tc_fwd: batch x parity classes > 65535");

@@ -491,6 +491,7 @@ int conv_tpose_join_supported(const ss_conv3d_desc* d) { return tpose_eligible(d
 int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift, const float* w_kmajor,
                    const float* bias, float* y, double* stats, cudaStream_t st, int* rc, const ss_conv3d_join* join, const ConvPass& ps) {
     if (!d->transposed || d->Cin % 32 != 0 || d->kd != 3 || d->kh != 3 || d->kw != 3) return 0;
+    if (d->out_act == SS_ACT_SWISH) return 0;             // Swish epilogues live in the box / pointwise / plane kernels only
     if (d->sd != 2 || d->sh != 2 || d->sw != 2 || d->pd != 1 || d->ph != 1 || d->pw != 1) return 0;
     if (d->math != SS_MATH_TF32 || (d->cout_packed != 32 && d->cout_packed != 64)) return 0;
     if (d->Dout > 2 * d->Din || d->Hout > 2 * d->Hin || d->Wout > 2 * d->Win) return 0;

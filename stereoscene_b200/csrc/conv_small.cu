@@ -86,7 +86,7 @@ conv_cout1_kernel(const C1Params p, int w_ld) {
 // used by ss_conv3d_fwd for eligible layers; returns 1 if the layer was handled here
 int try_conv_cout1(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                    const float* w_packed, const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
-    if (d->Cout != 1 || d->transposed || stats || d->Cin % 32 != 0 || d->math != SS_MATH_TF32) return 0;
+    if (d->Cout != 1 || d->transposed || stats || d->Cin % 32 != 0 || d->math != SS_MATH_TF32 || d->out_act == SS_ACT_SWISH) return 0;
     if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1 || d->kw > 3) return 0;
     if (d->Dout != d->Din || d->Hout != d->Hin || d->Wout != d->Win) return 0;
     C1Params p;
@@ -251,7 +251,7 @@ conv_cin_small_kernel(const CsParams p) {
 // used by ss_conv3d_fwd for eligible layers; returns 1 if the layer was handled here
 int try_conv_cin_small(const ss_conv3d_desc* d, const float* x, const float* in_scale, const float* in_shift,
                        const float* w_packed, const float* bias, float* y, double* stats, cudaStream_t st, int* rc) {
-    if (d->transposed || d->Cin > 2 || d->cout_packed != 32 || in_scale || d->in_act != SS_ACT_NONE) return 0;
+    if (d->transposed || d->Cin > 2 || d->cout_packed != 32 || in_scale || d->in_act != SS_ACT_NONE || d->out_act == SS_ACT_SWISH) return 0;
     if (d->math != SS_MATH_TF32 && d->math != SS_MATH_3XTF32) return 0;
     const bool precise = d->math == SS_MATH_3XTF32;
     if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 1 || d->sh != 1 || d->sw != 1 || d->pd != 1 || d->ph != 1 || d->pw != 1) return 0;

@@ -53,7 +53,7 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
                 const float4 wv = *reinterpret_cast<const float4*>(sw + (size_t)((ky * K + kx) * Cin + c) * Cout + cq * 4);
                 acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y); acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
             }
-    acc.x = apply_act(acc.x, out_act); acc.y = apply_act(acc.y, out_act); acc.z = apply_act(acc.z, out_act); acc.w = apply_act(acc.w, out_act);
+    acc.x = apply_act_sw(acc.x, out_act); acc.y = apply_act_sw(acc.y, out_act); acc.z = apply_act_sw(acc.z, out_act); acc.w = apply_act_sw(acc.w, out_act);
     *reinterpret_cast<float4*>(y + (((size_t)n * Ho + oy) * Wo + ox) * Cout + cq * 4) = acc;
 }
 
@@ -89,6 +89,13 @@ dwconv2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
             xoff[j] = (ok ? ix : 0) * in_ldc;
             xm[j] = ok ? 1.f : 0.f;
         }
+        // K = 3: the nine weight vectors stay in registers over the block's rows; K = 5 (25 vectors) reloads the row's five per ky
+        constexpr bool HOIST = (K == 3);
+        float4 wall[HOIST ? K * K : 1];
+        if constexpr (HOIST) {
+#pragma unroll
+            for (int i = 0; i < K * K; ++i) wall[i] = ldg_f4(w + (size_t)i * C + c);
+        }
         for (int r = 0; r < rows; ++r) {
             const int oy = rb * rows + r;
             if (oy >= Ho) break;
@@ -105,7 +112,10 @@ dwconv2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
                 for (int j = 0; j < SPAN; ++j) v[j] = ldg_f4(xr + xoff[j]);
                 float4 wv[K];
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) wv[kx] = ldg_f4(w + (size_t)(ky * K + kx) * C + c);
+                for (int kx = 0; kx < K; ++kx) {
+                    if constexpr (HOIST) wv[kx] = wall[ky * K + kx];
+                    else wv[kx] = ldg_f4(w + (size_t)(ky * K + kx) * C + c);
+                }
 #pragma unroll
                 for (int j = 0; j < SPAN; ++j) {
                     const float m = xm[j];
@@ -125,7 +135,7 @@ dwconv2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
             for (int t = 0; t < TW; ++t) {
                 if (ox0 + t < Wo) {
                     float4 o = acc[t];
-                    o.x = apply_act(o.x, out_act); o.y = apply_act(o.y, out_act); o.z = apply_act(o.z, out_act); o.w = apply_act(o.w, out_act);
+                    o.x = apply_act_sw(o.x, out_act); o.y = apply_act_sw(o.y, out_act); o.z = apply_act_sw(o.z, out_act); o.w = apply_act_sw(o.w, out_act);
                     *reinterpret_cast<float4*>(yr + (size_t)(ox0 + t) * out_ldc) = o;
                     psum.x += o.x; psum.y += o.y; psum.z += o.z; psum.w += o.w;
                 }
@@ -200,7 +210,7 @@ se_fc_kernel(const void* __restrict__ in, const float* __restrict__ w, const flo
     }
     float v = acc + (bias ? __ldg(bias + o) : 0.f);
     if (act == SS_ACT_SIGMOID) v = sigmoid_f(v);
-    else v = apply_act(v, act);
+    else v = apply_act_sw(v, act);
     out[(size_t)n * Cout + o] = v;
 }
 
@@ -242,6 +252,9 @@ extern "C" int ss_dwconv2d_fwd(const float* x, const float* w, const float* bias
     const int pt = th / 2, pl = tw / 2;
     SS_REQUIRE(N <= 65535, "ss_dwconv2d_fwd: batch");
     cudaStream_t st = (cudaStream_t)stream;
+    // 5 x 5 on mid-sized maps (24 x 80 x 1344 channels): 8 output columns per thread re-use an input vector for up to 5 outputs
+    // (measured 36 -> 29 us); on the large maps of stages 2-3 the 4-column variant's extra parallelism wins (57 vs 70 us)
+    if (K == 5 && S == 1 && Wo >= 64 && Wo < 128) return launch_dw<5, 1, 8>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
     if (K == 3 && S == 1) return launch_dw<3, 1, 4>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
     if (K == 3 && S == 2) return launch_dw<3, 2, 2>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);
     if (K == 5 && S == 1) return launch_dw<5, 1, 4>(x, w, bias, y, pool, N, H, W, C, in_ldc, Ho, Wo, out_ldc, pt, pl, out_act, st);

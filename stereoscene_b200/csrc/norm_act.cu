@@ -358,6 +358,7 @@ extern "C" int ss_affine_join_fwd(const float* x, const float* x_scale, const fl
                                   const float* alpha, int out_act, int B, long long V, int C, int x_ldc, int r_ldc,
                                   int out_ldc, float* out, void* stream) {
     SS_REQUIRE(x && out, "ss_affine_join_fwd: null pointer");
+    SS_REQUIRE(x_act <= SS_ACT_GELU && r_act <= SS_ACT_GELU && out_act <= SS_ACT_GELU, "ss_affine_join_fwd: activations NONE | RELU | GELU");
     SS_REQUIRE(B > 0 && B <= 65535 && V > 0 && C > 0, "ss_affine_join_fwd: shape");
     SS_REQUIRE((x_scale == nullptr) == (x_shift == nullptr) && (r_scale == nullptr) == (r_shift == nullptr),
                "ss_affine_join_fwd: scale/shift must come together");
