@@ -369,8 +369,13 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         // column sums go through a per-warp 32x33 scratch tile (the plane ring is free once accum_bar fired): one
         // store + one load + two FP ops per value instead of the 5-round shuffle transpose
-        float* scratch = reinterpret_cast<float*>(planes) + warp * (32 * 33);
-        float* part = reinterpret_cast<float*>(planes) + 8 * 32 * 33 + warp * (2 * BN);      // per-warp column sums (no atomics: fixed summation order)
+        // (stride 36: rows stay 16-byte aligned, so the same tile also transposes the chunk for the stores -- a lane holds 32
+        // columns of ITS row, and storing them directly makes every STG.128 touch 32 different rows; through the tile 8 neighbouring
+        // lanes write one row's 128 bytes and an instruction covers 4 full lines)
+        float* scratch = reinterpret_cast<float*>(planes) + warp * (32 * 36);
+        float* part = reinterpret_cast<float*>(planes) + 8 * 32 * 36 + warp * (2 * BN);      // per-warp column sums (no atomics: fixed summation order)
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const long long ov_ll = valid ? (long long)ov : -1;
         const int act = p.out_act;
         const bool has_bias = p.bias != nullptr;
         const bool want_stats = p.stats != nullptr && p.sr.has(d);
@@ -415,32 +420,38 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = swish_f(v[k]);
             }
-            if (valid) {
-                float* dst = p.y + ov * p.out_ldc + cbase;
-                if (vec_ok && cbase + 32 <= p.Cout) {
+            const bool full = vec_ok && cbase + 32 <= p.Cout;
+            if (full || want_stats) {
 #pragma unroll
-                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-                } else {
+                for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(scratch + lane * 36 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                __syncwarp();
+            }
+            if (full) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (cbase + k < p.Cout) dst[k] = v[k];
+                for (int j = 0; j < 8; ++j) {
+                    const int rr = 4 * j + (lane >> 3);
+                    const long long ovr = __shfl_sync(0xffffffffu, ov_ll, rr);
+                    const float4 t4 = *reinterpret_cast<const float4*>(scratch + rr * 36 + (lane & 7) * 4);
+                    if (ovr >= 0) *reinterpret_cast<float4*>(p.y + (size_t)ovr * p.out_ldc + cbase + (lane & 7) * 4) = t4;
                 }
+            } else if (valid) {
+                float* dst = p.y + ov * p.out_ldc + cbase;
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (cbase + k < p.Cout) dst[k] = v[k];
             }
             if (want_stats) {
-#pragma unroll
-                for (int k = 0; k < 32; ++k) scratch[lane * 33 + k] = valid ? v[k] : 0.f;
-                __syncwarp();
                 float cs = 0.f, cq = 0.f;
 #pragma unroll
                 for (int rr = 0; rr < 32; ++rr) {
-                    const float x = scratch[rr * 33 + lane];
+                    const float x = ((vmask >> rr) & 1u) ? scratch[rr * 36 + lane] : 0.f;
                     cs += x;
                     cq = fmaf(x, x, cq);
                 }
-                __syncwarp();
                 part[2 * (ci * 32 + lane) + 0] = cs;
                 part[2 * (ci * 32 + lane) + 1] = cq;
             }
+            if (full || want_stats) __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -449,7 +460,7 @@ conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap tmA, co
         for (int i = tid; i < BN; i += HL_THREADS) {
             const int c = n0 + i;
             if (c < p.Cout) {
-                const float* part0 = reinterpret_cast<const float*>(planes) + 8 * 32 * 33;
+                const float* part0 = reinterpret_cast<const float*>(planes) + 8 * 32 * 36;
                 double ts = 0.0, tq = 0.0;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) { ts += (double)part0[w * 2 * BN + 2 * i + 0]; tq += (double)part0[w * 2 * BN + 2 * i + 1]; }
