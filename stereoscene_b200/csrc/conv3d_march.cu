@@ -209,7 +209,11 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const MarchParams&
 // GroupNorm sums are per-thread running sums that are transposed / reduced once per (CTA, sample).
 template <int NCOL, bool F16>
 __device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t_begin, long long t_end, int q, int lane, int col0,
-                                               uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0) {
+                                               uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0, float* tr) {
+    // tr: this warp's 32 x (NCOL + 4) float transposition tile.  A lane holds NCOL columns of ITS row; stored directly, every
+    // STG.128 touches 32 different rows (32 LSU wavefronts per instruction).  Through the tile NCOL/4 neighbouring lanes write one
+    // row's NCOL * 4 bytes, and the rows of a tile line are adjacent in memory: an instruction covers 512 contiguous bytes.
+    constexpr int TS = NCOL + 4, LPR = NCOL / 4, RPI = 32 / LPR;
     if (t_begin >= t_end) return;
     const int row = q * 32 + lane;
     const int lh = row / MR_TW, lw = row % MR_TW;
@@ -300,12 +304,24 @@ __device__ __forceinline__ void march_epilogue(const MarchParams& p, long long t
             for (int k = 0; k < NCOL; ++k) v[k] = swish_f(v[k]);
         }
         const int oh = c.th * MR_TH + lh, ow = c.tw * MR_TW + lw;
-        if (oh < p.H && ow < p.W) {
-            float* dst = p.y + ((((size_t)c.b * p.D + c.d) * p.H + oh) * p.W + ow) * p.out_ldc + col0;
-            if (vec_ok) {
+        if (vec_ok) {
 #pragma unroll
-                for (int k = 0; k < NCOL; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-            } else {
+            for (int k = 0; k < NCOL; k += 4) *reinterpret_cast<float4*>(tr + lane * TS + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+            __syncwarp();
+            float* plane = p.y + (((size_t)c.b * p.D + c.d) * p.H) * p.W * p.out_ldc + col0 + (lane % LPR) * 4;
+#pragma unroll
+            for (int j = 0; j < LPR; ++j) {
+                const int rr = RPI * j + lane / LPR;
+                const int r2 = q * 32 + rr;
+                const int oh2 = c.th * MR_TH + r2 / MR_TW, ow2 = c.tw * MR_TW + r2 % MR_TW;
+                const float4 t4 = *reinterpret_cast<const float4*>(tr + rr * TS + (lane % LPR) * 4);
+                if (oh2 < p.H && ow2 < p.W) *reinterpret_cast<float4*>(plane + ((size_t)oh2 * p.W + ow2) * p.out_ldc) = t4;
+            }
+            __syncwarp();
+        }
+        if (oh < p.H && ow < p.W) {
+            if (!vec_ok) {
+                float* dst = p.y + ((((size_t)c.b * p.D + c.d) * p.H + oh) * p.W + ow) * p.out_ldc + col0;
 #pragma unroll
                 for (int k = 0; k < NCOL; ++k)
                     if (col0 + k < p.Cout) dst[k] = v[k];
@@ -606,8 +622,9 @@ conv_march32_kernel(const MarchParams p, const __grid_constant__ CUtensorMap tmA
     } else {
         // ======================= EPILOGUE WARPS (0..3, plus 4..7 when there is no fix-up work) =======
         // warps sharing a TMEM lane quarter split the 32 output columns when all 8 worker warps drain
-        if (fixup) march_epilogue<32, F16>(p, t_begin, t_end, warp & 3, lane, 0, tmem_base, t_full0, t_empty0);
-        else march_epilogue<16, F16>(p, t_begin, t_end, warp & 3, lane, (warp >> 2) * 16, tmem_base, t_full0, t_empty0);
+        float* trbase = reinterpret_cast<float*>(aux + 512);
+        if (fixup) march_epilogue<32, F16>(p, t_begin, t_end, warp & 3, lane, 0, tmem_base, t_full0, t_empty0, trbase + warp * (32 * 36));
+        else march_epilogue<16, F16>(p, t_begin, t_end, warp & 3, lane, (warp >> 2) * 16, tmem_base, t_full0, t_empty0, trbase + warp * (32 * 20));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -645,7 +662,7 @@ static int launch_march(const MarchParams& p, const ss_conv3d_desc* d, const flo
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return set_arg_error("conv_march32: tensor map W");
     }
-    const size_t smem = 1024 + Cfg::W_BYTES + MR_NP * Cfg::PLANE_BYTES + 32 * sizeof(uint64_t) + 64;
+    const size_t smem = 1024 + Cfg::W_BYTES + MR_NP * Cfg::PLANE_BYTES + 512 + 8 * 32 * 20 * sizeof(float);   // barriers, then the epilogue warps' transposition tiles
     static thread_local bool configured = false;
     if (!configured) {
         SS_CUDA(cudaFuncSetAttribute(conv_march32_kernel<KS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
