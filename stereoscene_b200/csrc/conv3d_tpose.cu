@@ -402,16 +402,27 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                         v[k] = apply_act(f, p.out_act);
                     }
                 }
-                if (valid) {
-                    float* dst = p.y + ov * p.out_ldc + cbase;
-                    if (vec_ok && cbase + 32 <= p.Cout) {
+                if (vec_ok && cbase + 32 <= p.Cout) {
+                    // transposed through a per-warp 32 x 36 tile in the (idle) plane ring: 8 neighbouring lanes store one output
+                    // voxel's 128 bytes instead of every lane storing its own row (32 wavefronts per STG.128)
+                    float* trw = reinterpret_cast<float*>(planes) + warp * (32 * 36);
 #pragma unroll
-                        for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-                    } else {
+                    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(trw + lane * 36 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                    __syncwarp();
+                    const long long ov_ll = valid ? (long long)ov : -1;
 #pragma unroll
-                        for (int k = 0; k < 32; ++k)
-                            if (cbase + k < p.Cout) dst[k] = v[k];
+                    for (int j = 0; j < 8; ++j) {
+                        const int r2 = 4 * j + (lane >> 3);
+                        const long long ovr = __shfl_sync(0xffffffffu, ov_ll, r2);
+                        const float4 t4 = *reinterpret_cast<const float4*>(trw + r2 * 36 + (lane & 7) * 4);
+                        if (ovr >= 0) *reinterpret_cast<float4*>(p.y + (size_t)ovr * p.out_ldc + cbase + (lane & 7) * 4) = t4;
                     }
+                    __syncwarp();
+                } else if (valid) {
+                    float* dst = p.y + ov * p.out_ldc + cbase;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cbase + k < p.Cout) dst[k] = v[k];
                 }
                 if (p.stats) {
                     float s[32], sq[32];

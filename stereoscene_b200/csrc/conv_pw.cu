@@ -84,7 +84,7 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
     unsigned char* wres = base;                                   // KC chunks of [NP rows][128 B]
     unsigned char* ring = base + W_BYTES;                         // RS chunks of [128 rows][128 B]
     unsigned char* aux = ring + (size_t)RS * CH_BYTES;
-    float* scratch = reinterpret_cast<float*>(aux);               // 8 warps x 32 x 32 floats, XOR-swizzled (GroupNorm column sums); 0 without stats
+    float* scratch = reinterpret_cast<float*>(aux);               // 8 warps x 32 x 32 floats, XOR-swizzled by float4: store transposition + GroupNorm column sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + p.scratch_floats);
     // barriers: w_full, w_empty, c_full[MAXRS], c_ready[MAXRS], c_empty[MAXRS], t_full[ACC], t_empty[ACC]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 3 * PW_MAXRS + 2 * PW_ACC);
@@ -314,32 +314,43 @@ conv_pw_kernel(const PwParams p, const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
                     for (int k = 0; k < 32; ++k) x[k] = swish_f(x[k]);
                 }
-                if (valid) {
-                    float* dst = p.y + ov * p.out_ldc + cbase;
-                    if (vec_ok && cbase + 32 <= p.Cout) {
+                // the chunk goes through a 32 x 36 tile: 8 neighbouring lanes then store one row's 128 bytes (a lane storing its own
+                // row makes every STG.128 touch 32 rows), and the GroupNorm column sums read the same tile
+                const bool full = vec_ok && cbase + 32 <= p.Cout;
+                if (full || want_stats) {
 #pragma unroll
-                        for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
-                    } else {
+                    for (int k = 0; k < 32; k += 4)      // float4 k/4 of row `lane` sits at slot (k/4) ^ (lane & 7): every access below is conflict-free
+                        *reinterpret_cast<float4*>(sc + lane * 32 + (((k >> 2) ^ (lane & 7)) << 2)) = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
+                    __syncwarp();
+                }
+                if (full) {
+                    const long long ov_ll = valid ? (long long)ov : -1;
 #pragma unroll
-                        for (int k = 0; k < 32; ++k)
-                            if (cbase + k < p.Cout) dst[k] = x[k];
+                    for (int j = 0; j < 8; ++j) {
+                        const int rr = 4 * j + (lane >> 3);
+                        const long long ovr = __shfl_sync(0xffffffffu, ov_ll, rr);
+                        const float4 t4 = *reinterpret_cast<const float4*>(sc + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+                        if (ovr >= 0) *reinterpret_cast<float4*>(p.y + (size_t)ovr * p.out_ldc + cbase + (lane & 7) * 4) = t4;
                     }
+                } else if (valid) {
+                    float* dst = p.y + ov * p.out_ldc + cbase;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cbase + k < p.Cout) dst[k] = x[k];
                 }
                 if (want_stats) {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) sc[lane * 32 + (k ^ lane)] = st_row ? x[k] : 0.f;     // bank = k ^ lane: conflict-free
-                    __syncwarp();
+                    const unsigned smask = __ballot_sync(0xffffffffu, st_row);
                     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};      // four independent chains
 #pragma unroll
                     for (int rr = 0; rr < 32; ++rr) {
-                        const float e = sc[rr * 32 + (lane ^ rr)];
+                        const float e = ((smask >> rr) & 1u) ? sc[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))] : 0.f;
                         cs[rr & 3] += e;
                         cq[rr & 3] = fmaf(e, e, cq[rr & 3]);
                     }
-                    __syncwarp();
                     run_s[gi] += (cs[0] + cs[1]) + (cs[2] + cs[3]);
                     run_q[gi] += (cq[0] + cq[1]) + (cq[2] + cq[3]);
                 }
+                if (full || want_stats) __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             pw_mbar_arrive(t_empty0 + 8 * acc);                     // accumulator may be overwritten
@@ -401,7 +412,7 @@ int try_conv_pw(const ss_conv3d_desc* d, const float* x, const float* in_scale, 
     if (s > 1 && d->cout_packed % 32 != 0) return 0;
     const int KC = d->Cin / 32;
     int NP = (d->cout_packed + 31) / 32 * 32, NH = 1;
-    const int scratch_floats = stats ? 8 * 32 * 32 : 0;
+    const int scratch_floats = 8 * 32 * 32;
     auto fixed_bytes = [&](int np) { return (size_t)1024 + (size_t)KC * np * 128 + (size_t)scratch_floats * sizeof(float) +
                                             (2 + 3 * PW_MAXRS + 2 * PW_ACC) * sizeof(uint64_t) + 64; };
     const size_t min_ring = (size_t)(KC < 4 ? 4 : (KC > 6 ? 4 : KC)) * PW_TILE * 128;              // at least 4 chunks in flight
