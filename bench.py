@@ -174,7 +174,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(VOXELS))
-    ap.add_argument("--math", default="mixed", choices=["mixed", "mixed16", "tf32", "f16", "tf32x3", "3xtf32"],
+    ap.add_argument("--math", default="mixed", choices=["mixed", "mixed_tf32stereo", "mixed16", "tf32", "f16", "tf32x3", "3xtf32"],
                     help="per-stage math policy (stereoscene_b200.ops.MATH_POLICIES); 'mixed' = plain TF32 tensor-core math with "
                          "the error-compensated TF32x3 mode on depth_net and the MIE block: the cheapest policy whose logits "
                          "are within 1e-3 of the reference's forward")

@@ -37,7 +37,9 @@ def test_math_policy_scopes_and_substages():
         ops.set_math_policy(None)                                 # back to the product default
         assert ops.math_policy() == ops.MATH_POLICIES[ops.DEFAULT_POLICY]
         mixed = ops.MATH_POLICIES["mixed"]
-        assert mixed["depthnet"] == ops.SS_MATH_TF32X3 and mixed["mie"] == ops.SS_MATH_TF32X3 and "stereo" not in mixed
+        assert mixed["depthnet"] == ops.SS_MATH_TF32X3 and mixed["mie"] == ops.SS_MATH_TF32X3 and mixed["image"] == ops.SS_MATH_TF32X3
+        assert mixed["stereo"] == ops.SS_MATH_F16 and mixed["voxel"] == ops.SS_MATH_F16      # fp16 operands = TF32's significand
+        assert "stereo" not in ops.MATH_POLICIES["mixed_tf32stereo"] and ops.MATH_POLICIES["mixed16"] == mixed
     finally:
         ops.set_math_policy(None)
 

@@ -14,7 +14,7 @@ def main(src, dst):
     for p in sorted(glob.glob(os.path.join(src, "parity_config*_*.json"))):
         r = json.load(open(p))
         runs.setdefault(r["workload"], {})[r["mode"]] = r
-    order = ["tf32", "f16", "mixed", "mixed16", "tf32x3", "3xtf32"]
+    order = ["tf32", "f16", "mixed", "mixed_tf32stereo", "mixed16", "tf32x3", "3xtf32"]
     out = ["# Full-size parity of the product forward against the reference's own forward (round 2, measured on B200)", "",
            "Source: `tests/test_parity_fullsize_gpu.py` (fixtures `tests/golden/golden_config{1,2}.npz` written by the unmodified",
            "reference modules, `oracle/make_golden_full.py`).  Each cell is `max|d|/max|ref|` / `rms(d)/rms(ref)` of the stage's strided",
