@@ -10,6 +10,7 @@
 // shifted UMMA descriptor (start + (off_h*9 + off_w) rows, SBO = 9 rows), weight tiles stream through
 // a TMA ring, and the 8 class accumulators (8 x BN fp32 columns) live side by side in TMEM.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ss {
@@ -40,6 +41,7 @@ struct TposeParams {
     int res_ldc, res_act, has_join;
     int a_lo, accumulate;            // ConvPass (common.cuh)
     StatsRange sr;                   // output planes that contribute to stats
+    int gather;                      // residual read through the transposition tile (default; STEREOSCENE_B200_TPOSE_GATHER=0: every lane reads its own row)
     float acc_scale;                 // F16 variant: accumulator scale (power of two)
     int f16_n;                       // F16 variant: MMAs per chunk and tap (6 = compensated, 2 = fp16 single pass)
 };
@@ -349,6 +351,27 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
             const int od = 2 * q + (cls >> 2), oh = 2 * ih + ((cls >> 1) & 1), ow = 2 * iw + (cls & 1);
             const bool valid = ih < p.Hin && iw < p.Win && od < p.Dout && oh < p.Hout && ow < p.Wout;
             const size_t ov = (((size_t)b * p.Dout + od) * p.Hout + oh) * p.Wout + ow;
+            const long long ov_ll = valid ? (long long)ov : -1;
+            float* trw = reinterpret_cast<float*>(planes) + warp * (32 * 36);      // per-warp 32 x 36 tile in the (idle) plane ring
+            // rows of this warp x 32 columns of a global tensor -> out[32] of the lane's own row, read with full 128-byte lines
+            // (8 neighbouring lanes per row) instead of 32 rows per load instruction
+            auto gather_rows = [&](const float* gbase, int ldc, int cb, float (&out)[32]) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r2 = 4 * j + (lane >> 3);
+                    const long long ovr = __shfl_sync(0xffffffffu, ov_ll, r2);
+                    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ovr >= 0) t4 = *reinterpret_cast<const float4*>(gbase + (size_t)ovr * ldc + cb + (lane & 7) * 4);
+                    *reinterpret_cast<float4*>(trw + r2 * 36 + (lane & 7) * 4) = t4;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(trw + lane * 36 + k);
+                    out[k] = t4.x; out[k + 1] = t4.y; out[k + 2] = t4.z; out[k + 3] = t4.w;
+                }
+                __syncwarp();
+            };
 #pragma unroll 1
             for (int ci = 0; ci < BN / 32; ++ci) {
                 uint32_t r[32];
@@ -370,10 +393,15 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                     const bool rvec = valid && p.res && ((p.res_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) &&
                                       cbase + 32 <= p.Cout;
                     const float* rsrc = p.res ? p.res + ov * p.res_ldc + cbase : nullptr;
+                    const bool rvec_w = p.gather && p.res && ((p.res_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) && cbase + 32 <= p.Cout;
+                    float resv[32];
+                    if (rvec_w) gather_rows(p.res, p.res_ldc, cbase, resv);        // warp-uniform condition
 #pragma unroll
                     for (int k4 = 0; k4 < 8; ++k4) {
                         float rr[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (rvec) {
+                        if (rvec_w) {
+                            rr[0] = resv[4 * k4]; rr[1] = resv[4 * k4 + 1]; rr[2] = resv[4 * k4 + 2]; rr[3] = resv[4 * k4 + 3];
+                        } else if (rvec) {
                             const float4 t4 = ldg_f4(rsrc + 4 * k4);
                             rr[0] = t4.x; rr[1] = t4.y; rr[2] = t4.z; rr[3] = t4.w;
                         } else if (valid && p.res) {
@@ -405,11 +433,9 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                 if (vec_ok && cbase + 32 <= p.Cout) {
                     // transposed through a per-warp 32 x 36 tile in the (idle) plane ring: 8 neighbouring lanes store one output
                     // voxel's 128 bytes instead of every lane storing its own row (32 wavefronts per STG.128)
-                    float* trw = reinterpret_cast<float*>(planes) + warp * (32 * 36);
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(trw + lane * 36 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
                     __syncwarp();
-                    const long long ov_ll = valid ? (long long)ov : -1;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int r2 = 4 * j + (lane >> 3);
@@ -527,6 +553,8 @@ int try_conv_tpose(const ss_conv3d_desc* d, const float* x, const float* in_scal
     p.res = join ? join->res : nullptr; p.r_scale = join ? join->res_scale : nullptr; p.r_shift = join ? join->res_shift : nullptr;
     p.res_ldc = join ? join->res_ldc : 0; p.res_act = join ? join->res_act : 0;
     p.a_lo = ps.a_lo; p.accumulate = ps.accumulate; p.sr = stats_range_of(d); p.acc_scale = ps.acc_scale; p.f16_n = ps.f16_n;
+    static const int gather = [] { const char* e = getenv("STEREOSCENE_B200_TPOSE_GATHER"); return (e && e[0] == '0') ? 0 : 1; }();
+    p.gather = gather;
     const bool fixup = (in_scale != nullptr) || (d->in_act == SS_ACT_RELU) || ps.a_lo || ps.f16;
     alignas(64) CUtensorMap tmA;
     cuuint64_t gdim[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.Din, (cuuint64_t)p.B};
