@@ -346,34 +346,50 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
         const int row = qq * 32 + lane;
         const int ih = h0 + row / TP_TW, iw = w0 + row % TP_TW;
         const bool vec_ok = ((p.out_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        // The residual of the fused join does not depend on the MMAs and is the epilogue's longest wait (ncu: 38 % of the stall samples
+        // were long-scoreboard on these loads): the 32 rows x 32 columns of the NEXT (class, chunk) item are copied global -> shared
+        // memory with cp.async (8 neighbouring lanes per 128-byte row: full lines) while the current item is computed and stored.
+        // Two per-warp 32 x 36-float tiles in the idle plane ring alternate; an item's tile is then re-used to transpose its stores.
+        constexpr int CH = BN / 32, ITEMS = 4 * CH;
+        float* tiles = reinterpret_cast<float*>(planes) + warp * (2 * 32 * 36);
+        const bool res_async = p.gather && p.has_join && p.res != nullptr && ((p.res_ldc & 3) == 0) &&
+                               ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) && p.Cout >= BN;
+        auto issue_res = [&](int item, float* buf) {
+            const int cls2 = chalf * 4 + item / CH, cb = (item % CH) * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r2 = 4 * j + (lane >> 3), rowq = qq * 32 + r2;
+                const int ih2 = h0 + rowq / TP_TW, iw2 = w0 + rowq % TP_TW;
+                const int od2 = 2 * q + (cls2 >> 2), oh2 = 2 * ih2 + ((cls2 >> 1) & 1), ow2 = 2 * iw2 + (cls2 & 1);
+                float* dst = buf + r2 * 36 + (lane & 7) * 4;
+                if (ih2 < p.Hin && iw2 < p.Win && od2 < p.Dout && oh2 < p.Hout && ow2 < p.Wout) {
+                    const size_t ov2 = (((size_t)b * p.Dout + od2) * p.Hout + oh2) * p.Wout + ow2;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(t_smem_u32(dst)), "l"(p.res + ov2 * p.res_ldc + cb + (lane & 7) * 4) : "memory");
+                } else {
+                    *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (res_async) issue_res(0, tiles);
 #pragma unroll 1
-        for (int cls = chalf * 4; cls < chalf * 4 + 4; ++cls) {
+        for (int item = 0; item < ITEMS; ++item) {
+            const int cls = chalf * 4 + item / CH, ci = item % CH;
             const int od = 2 * q + (cls >> 2), oh = 2 * ih + ((cls >> 1) & 1), ow = 2 * iw + (cls & 1);
             const bool valid = ih < p.Hin && iw < p.Win && od < p.Dout && oh < p.Hout && ow < p.Wout;
             const size_t ov = (((size_t)b * p.Dout + od) * p.Hout + oh) * p.Wout + ow;
             const long long ov_ll = valid ? (long long)ov : -1;
-            float* trw = reinterpret_cast<float*>(planes) + warp * (32 * 36);      // per-warp 32 x 36 tile in the (idle) plane ring
-            // rows of this warp x 32 columns of a global tensor -> out[32] of the lane's own row, read with full 128-byte lines
-            // (8 neighbouring lanes per row) instead of 32 rows per load instruction
-            auto gather_rows = [&](const float* gbase, int ldc, int cb, float (&out)[32]) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r2 = 4 * j + (lane >> 3);
-                    const long long ovr = __shfl_sync(0xffffffffu, ov_ll, r2);
-                    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ovr >= 0) t4 = *reinterpret_cast<const float4*>(gbase + (size_t)ovr * ldc + cb + (lane & 7) * 4);
-                    *reinterpret_cast<float4*>(trw + r2 * 36 + (lane & 7) * 4) = t4;
+            float* trw = tiles + (item & 1) * (32 * 36);
+            if (res_async) {
+                if (item + 1 < ITEMS) {
+                    issue_res(item + 1, tiles + ((item + 1) & 1) * (32 * 36));
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
                 __syncwarp();
-#pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(trw + lane * 36 + k);
-                    out[k] = t4.x; out[k + 1] = t4.y; out[k + 2] = t4.z; out[k + 3] = t4.w;
-                }
-                __syncwarp();
-            };
-#pragma unroll 1
-            for (int ci = 0; ci < BN / 32; ++ci) {
+            }
+            {
                 uint32_t r[32];
                 t_tmem_ld32(tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(cls * BN + ci * 32), r);
                 const int cbase = ci * 32;
@@ -393,14 +409,13 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                     const bool rvec = valid && p.res && ((p.res_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) &&
                                       cbase + 32 <= p.Cout;
                     const float* rsrc = p.res ? p.res + ov * p.res_ldc + cbase : nullptr;
-                    const bool rvec_w = p.gather && p.res && ((p.res_ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) && cbase + 32 <= p.Cout;
-                    float resv[32];
-                    if (rvec_w) gather_rows(p.res, p.res_ldc, cbase, resv);        // warp-uniform condition
+                    const bool rvec_w = res_async;                                 // warp-uniform: this item's residual rows are in trw
 #pragma unroll
                     for (int k4 = 0; k4 < 8; ++k4) {
                         float rr[4] = {0.f, 0.f, 0.f, 0.f};
                         if (rvec_w) {
-                            rr[0] = resv[4 * k4]; rr[1] = resv[4 * k4 + 1]; rr[2] = resv[4 * k4 + 2]; rr[3] = resv[4 * k4 + 3];
+                            const float4 t4 = *reinterpret_cast<const float4*>(trw + lane * 36 + 4 * k4);
+                            rr[0] = t4.x; rr[1] = t4.y; rr[2] = t4.z; rr[3] = t4.w;
                         } else if (rvec) {
                             const float4 t4 = ldg_f4(rsrc + 4 * k4);
                             rr[0] = t4.x; rr[1] = t4.y; rr[2] = t4.z; rr[3] = t4.w;
@@ -433,6 +448,7 @@ conv_tpose_kernel(const TposeParams p, const __grid_constant__ CUtensorMap tmA, 
                 if (vec_ok && cbase + 32 <= p.Cout) {
                     // transposed through a per-warp 32 x 36 tile in the (idle) plane ring: 8 neighbouring lanes store one output
                     // voxel's 128 bytes instead of every lane storing its own row (32 wavefronts per STG.128)
+                    __syncwarp();                                  // every lane has read its residual row from this tile
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(trw + lane * 36 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
                     __syncwarp();
