@@ -118,8 +118,11 @@ struct CsParams {
 
 // PRECISE: error-compensated split TF32 (SS_MATH_3XTF32 / the Cin <= 2 layer of an SS_MATH_TF32X3 forward): the halo tile is
 // kept in fp32, A and B fragments are split hi/lo in registers and every k-step issues lo*hi + hi*lo + hi*hi.
+// (its B fragments -- hi and lo halves of the whole weight matrix, 112 registers per thread -- live in shared memory instead, one
+// conflict-free 64-bit load per MMA: the kernel keeps two CTAs per SM like the TF32 variant; with the fragments in registers it
+// ran one CTA per SM and took 0.20 ms against 0.10 ms)
 template <int CIN, bool PRECISE>
-__global__ void __launch_bounds__(CS_THREADS, PRECISE ? 1 : 2)
+__global__ void __launch_bounds__(CS_THREADS, 2)
 conv_cin_small_kernel(const CsParams p) {
     constexpr int K = 27 * CIN, KSTEPS = (K + 7) / 8;
     constexpr int HH = CS_TH + 2, HW = CS_TW + 2;
@@ -145,8 +148,8 @@ conv_cin_small_kernel(const CsParams p) {
         xs[idx] = PRECISE ? v : __uint_as_float(f2tf32(v));
     }
     // B fragments of the whole [K x 32] weight matrix and the tap offsets of this lane's two K columns
-    uint32_t breg[KSTEPS][4][2];
-    uint32_t blo[PRECISE ? KSTEPS : 1][4][2];
+    uint32_t breg[PRECISE ? 1 : KSTEPS][4][2];
+    __shared__ uint2 sbh[PRECISE ? KSTEPS * 4 * 32 : 1], sbl[PRECISE ? KSTEPS * 4 * 32 : 1];     // [ks][nt][lane]: (e = 0, e = 1)
     int koff[KSTEPS][2];
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks)
@@ -159,14 +162,31 @@ conv_cin_small_kernel(const CsParams p) {
                 off = (((tap / 9) * HH + (tap / 3) % 3) * HW + tap % 3) * CIN + c;
             }
             koff[ks][e] = off;
+            if constexpr (!PRECISE) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int n = nt * 8 + g;
-                const float wv = (k < K) ? __ldg(p.w + (size_t)k * p.CoutP + n) : 0.f;
-                breg[ks][nt][e] = f2tf32(wv);
-                if constexpr (PRECISE) blo[ks][nt][e] = f2tf32(wv - __uint_as_float(breg[ks][nt][e]));
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int n = nt * 8 + g;
+                    const float wv = (k < K) ? __ldg(p.w + (size_t)k * p.CoutP + n) : 0.f;
+                    breg[ks][nt][e] = f2tf32(wv);
+                }
             }
         }
+    if constexpr (PRECISE) {        // every warp would build the same fragments: warp w fills the K steps w, w + 8, ...
+        for (int ks = warp; ks < KSTEPS; ks += CS_THREADS / 32)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                uint32_t hi[2], lo[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = ks * 8 + t + 4 * e, n = nt * 8 + g;
+                    const float wv = (k < K) ? __ldg(p.w + (size_t)k * p.CoutP + n) : 0.f;
+                    hi[e] = f2tf32(wv);
+                    lo[e] = f2tf32(wv - __uint_as_float(hi[e]));
+                }
+                sbh[(ks * 4 + nt) * 32 + lane] = make_uint2(hi[0], hi[1]);
+                sbl[(ks * 4 + nt) * 32 + lane] = make_uint2(lo[0], lo[1]);
+            }
+    }
     float bias_r[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -198,9 +218,11 @@ conv_cin_small_kernel(const CsParams p) {
                 for (int i = 0; i < 4; ++i) { a[i] = f2tf32(af[i]); al[i] = f2tf32(af[i] - __uint_as_float(a[i])); }
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
-                    mma_tf32(acc[nt], al, breg[ks][nt]);
-                    mma_tf32(acc[nt], a, blo[ks][nt]);
-                    mma_tf32(acc[nt], a, breg[ks][nt]);
+                    const uint2 h2 = sbh[(ks * 4 + nt) * 32 + lane], l2 = sbl[(ks * 4 + nt) * 32 + lane];
+                    const uint32_t bh[2] = {h2.x, h2.y}, bl[2] = {l2.x, l2.y};
+                    mma_tf32(acc[nt], al, bh);
+                    mma_tf32(acc[nt], a, bl);
+                    mma_tf32(acc[nt], a, bh);
                 }
             } else {
                 const uint32_t a[4] = {__float_as_uint(xs[rb0 + koff[ks][0]]), __float_as_uint(xs[rb1 + koff[ks][0]]),
