@@ -65,6 +65,38 @@ lift_splat_kernel(const float* __restrict__ depth_prob, const float* __restrict_
     const int b = (int)(v / nvox_per_batch);
     const int s = __ldg(start + v), e = __ldg(start + v + 1);
     const long long P = (long long)D * HW;
+    if (C <= 128) {
+        // The point ids and their depth probabilities are fetched lane-parallel, 32 points at a time, and handed round by shuffle:
+        // the loop body is then left with ONE dependent load (the feature row) instead of a chain of three, and consecutive
+        // iterations overlap.  Same ascending-point summation order as before.
+        const int c0 = lane * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = s; base < e; base += 32) {
+            const int cnt = min(32, e - base);
+            int n_l = 0;
+            float dp_l = 0.f;
+            if (lane < cnt) {
+                n_l = __ldg(order + base + lane);           // global point id = b*P + d*HW + pix
+                dp_l = __ldg(depth_prob + n_l);
+            }
+            const int pix_l = (int)((n_l - b * P) % HW);
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const int pix = __shfl_sync(0xffffffffu, pix_l, i);
+                const float dp = __shfl_sync(0xffffffffu, dp_l, i);
+                if (c0 < C) {
+                    const float4 f = ldg_f4(img_feat + ((size_t)b * HW + pix) * C + c0);
+                    // separate multiply and add (no fma): reproduces "materialise the product, then sum"
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(dp, f.x));
+                    acc.y = __fadd_rn(acc.y, __fmul_rn(dp, f.y));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(dp, f.z));
+                    acc.w = __fadd_rn(acc.w, __fmul_rn(dp, f.w));
+                }
+            }
+        }
+        if (c0 < C) st_cs_f4(out + (size_t)v * C + c0, acc);
+        return;
+    }
     for (int c0 = lane * 4; c0 < C; c0 += 128) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = s; i < e; ++i) {
