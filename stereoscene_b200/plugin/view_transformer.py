@@ -21,6 +21,7 @@ Stages and the kernels that run them (all through the C ABI, stereoscene_b200.op
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -35,6 +36,18 @@ from .layers import HourglassParams, MlpParams, SEParams, conv_gn, conv_gn3d, ho
 # ------------------------------------------------------------------------------------------
 # parameter containers of the stereo branch and the MIE block
 # ------------------------------------------------------------------------------------------
+_STREAM_OVERLAP = os.environ.get("STEREOSCENE_B200_STREAM_OVERLAP", "0") == "1"      # experimental: depth_net beside the stereo branch
+_side_streams = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index)
+    s = _side_streams.get(key)
+    if s is None:
+        s = _side_streams[key] = torch.cuda.Stream(device)
+    return s
+
+
 class StereoFeatureParams(nn.Module):
     """keys: reduce_conv.{0,1}, depth_mlp, depth_se, depth_conv.0 (ViewTransformerLSSVoxel.py:32-58)."""
 
@@ -593,13 +606,33 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
             pair_cl = self.pair_channels_last(feat_left, feat_right)                            # [2B,1,H,W,Cin]
         elif tuple(pair_cl.shape) != (2 * B, 1, H, W, Cin) or not pair_cl.is_contiguous():
             raise RuntimeError(f"pair_cl must be a contiguous [2B,1,H,W,Cin] tensor, got {tuple(pair_cl.shape)}")
-        with ops.math_scope("stereo"):
-            stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
+        def depth_stage():
+            with ops.math_scope("depthnet"):
+                d_cl, c_cl = self.depth_net.forward_vol(pair_cl[:B], mlp_input)
+            logits = ops.to_channels_first(d_cl.squeeze(1))                       # [B,D,H,W]
+            return d_cl, c_cl, logits, ops.softmax_d(logits)
 
-        with ops.math_scope("depthnet"):
-            depth_cl, ctx_cl = self.depth_net.forward_vol(pair_cl[:B], mlp_input)
-        depth_logits = ops.to_channels_first(depth_cl.squeeze(1))                 # [B,D,H,W]
-        lss = ops.softmax_d(depth_logits)
+        if _STREAM_OVERLAP and x.is_cuda:
+            # EXPERIMENTAL, KNOWN TO FAIL (STEREOSCENE_B200_STREAM_OVERLAP=1, off by default; DESIGN.md section 8 item 4b,
+            # tools/overlap_repro.py): the stereo branch and depth_net only meet at the MIE block and depth_net's 2-D layers (7680
+            # pixels: 60-240 CTAs) leave most SMs idle, so it runs on a side stream (fork / join by events) underneath the stereo
+            # branch's full-grid kernels.  Eager forwards and a first graph replay are correct; repeated replays at config2 die with a
+            # launch failure unless depth_net stays off the tcgen05 kernels (OVERLAP_DEPTH_NO_TC=1).
+            main, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.arena(x.device).reset()                                      # the GroupNorm-sum arena is per stream
+                if os.environ.get("OVERLAP_DEPTH_NO_TC") == "1":
+                    ops.use_tcgen05(False)
+                depth_cl, ctx_cl, depth_logits, lss = depth_stage()
+                ops.use_tcgen05(True)
+            with ops.math_scope("stereo"):
+                stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
+            main.wait_stream(side)
+        else:
+            with ops.math_scope("stereo"):
+                stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
+            depth_cl, ctx_cl, depth_logits, lss = depth_stage()
         img_feat = ctx_cl.squeeze(1)                                              # [B,H,W,C] channels-last
 
         with ops.math_scope("mie"):
