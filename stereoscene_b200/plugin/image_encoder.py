@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..ops import SS_ACT_NONE, SS_ACT_RELU, SS_ACT_SIGMOID, SS_ACT_SWISH, Vol
+from ..ops import SS_ACT_RELU, SS_ACT_SIGMOID, SS_ACT_SWISH, Vol
 from ..registry import BACKBONES, NECKS
 
 BN_EPS = 1e-3
@@ -45,11 +45,6 @@ def _round8(v: float) -> int:
 
 def _pad32(c: int) -> int:
     return (c + 31) // 32 * 32
-
-
-def _same_pad(size: int, k: int, s: int):
-    total = max((math.ceil(size / s) - 1) * s + k - size, 0)
-    return total // 2, total - total // 2
 
 
 def layer_plan(arch: str):

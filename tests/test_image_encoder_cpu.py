@@ -3,7 +3,6 @@ efficientnet.py wrote (and against the reference run live when /root/reference i
 plugin/image_encoder.py (layer plan, BatchNorm folding, channel padding) against plain torch."""
 import os
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

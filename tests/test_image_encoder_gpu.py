@@ -9,7 +9,6 @@ held to 5e-3.
 import json
 import os
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
