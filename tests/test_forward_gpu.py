@@ -203,3 +203,37 @@ def test_engine_graphs_survive_cache_eviction_by_another_calibration():
     del junk
     again = eng1.infer(a, b)
     assert (again != want).float().mean().item() < 1e-3
+
+
+def test_two_stream_frustum_stage_survives_graph_replays():
+    """depth_net runs on a side stream beside the stereo branch (plugin/view_transformer.py).  At the shipped size two
+    kernels of different streams then really run at once, which once exposed a barrier-phase race of the box kernel
+    (conv3d_tc.cu, TcCfg::STAGES must be even): 60 replays of the step's CUDA graph must reproduce the eager output bit for bit,
+    and the serialised forward (STEREOSCENE_B200_STREAM_OVERLAP=0 semantics) must give the same result."""
+    from stereoscene_b200 import ops, synth
+    from stereoscene_b200.plugin import view_transformer as VT
+    ops.set_math_policy(None)
+    model, mc = build_model("config2", 0, device="cuda")
+    xl, xr = synth.stereo_features(1, mc["input_size"], 8, seed=0, device="cuda")
+    left, right, calib = synth.kitti_calibration(1, mc["input_size"], device="cuda")
+    f = lambda: model.forward_features(xl, xr, left, right, calib, occ_size=mc["occ_size"], want_labels=True)   # noqa: E731
+    assert VT._STREAM_OVERLAP
+    with torch.no_grad():
+        a = f()
+        b = f()
+        torch.cuda.synchronize()
+        assert torch.equal(a["output_voxels"], b["output_voxels"])
+        VT._STREAM_OVERLAP = False
+        try:
+            serial = f()
+        finally:
+            VT._STREAM_OVERLAP = True
+        torch.cuda.synchronize()
+        assert torch.equal(serial["output_voxels"], a["output_voxels"]) and torch.equal(serial["labels"], a["labels"])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = f()
+        for _ in range(60):
+            g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out["output_voxels"], a["output_voxels"]) and torch.equal(out["labels"], a["labels"])
